@@ -1,0 +1,135 @@
+"""Generate tests/golden/*.npz from the REFERENCE'S OWN CLASSES run under oracle/shim.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+    python oracle/make_golden.py
+The fixtures travel to the GPU box (which has no /root/reference); the parity tests compare the
+CUDA path and oracle/restate.py with them.  Inputs are seeded (random / numpy / torch = 1234)
+because the reference never seeds; weights are the shipped checkpoints
+where one matches the script (quantum/new_model/epoch{1,3}, classical/model/epoch18), otherwise
+the script's own seeded initialisation.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _run_case(name, script, program, consts, raw_subs=(), ckpt=None, loader="test_loader", T=None,
+              seed=1234):
+    subdir = os.path.dirname(script)
+    with ref_loader.reference_session(subdir):
+        ns = ref_loader.load_reference(script, consts=consts, raw_subs=raw_subs, seed=seed)
+        rows, cols = int(ns.rows), int(ns.cols)
+        B = int(ns.BATCH_SIZE)
+        Nc = int(ns.Nc) if T is None else T
+        torch.manual_seed(seed + 1)
+        dec = ns.GNNI(Nc)
+        if ckpt is not None:
+            dec.load_state_dict(torch.load(ckpt))
+        dec.eval()
+        batch = next(iter(getattr(ns, loader)))
+        assert batch.x.size(0) == B * (rows + cols), (batch.x.shape, B, rows, cols)
+        with torch.no_grad():
+            pred = dec(batch)                                  # [B*V, 1]
+            # single phases on a random edge state, through the reference's GraphConv.forward
+            ei_b = torch.cat([batch.edge_index[0].unsqueeze(0),
+                              batch.edge_index[1].unsqueeze(0).add(rows)], 0)
+            g = torch.Generator().manual_seed(seed + 2)
+            m0 = torch.randn(ei_b.size(1), 1, generator=g, dtype=torch.float64).to(pred.dtype) * 1.5
+            ph_var = dec.ggc1(m0, ei_b, batch.x)
+            if program in ("cgnni", "bp_classical"):
+                ph_chk = dec.ggc2(m0, ei_b)
+            else:
+                ph_chk = dec.ggc2(m0, ei_b, batch.x)
+        E = ei_b.size(1) // B
+        ei = batch.edge_index[:, :E].clone()                   # per-graph, check ids un-offset
+        H = ns.H                                               # [V, C] (transposed PCM)
+        assert torch.equal(ei, H.to_sparse()._indices())
+        sd = {k: _np(v) for k, v in dec.state_dict().items()}
+        out = dict(program=program, script=script, V=rows, C=cols, E=E, B=B, T=Nc,
+                   dtype=str(pred.dtype).replace("torch.", ""),
+                   edge_index=_np(ei).astype(np.int64), H=_np(H).astype(np.uint8),
+                   x=_np(batch.x.reshape(B, rows + cols)),
+                   y=_np(batch.y.reshape(B, -1)) if batch.y is not None else np.zeros(0),
+                   prob=_np(pred.reshape(B, rows)),
+                   m0=_np(m0.reshape(B, E)), phase_var=_np(ph_var.reshape(B, E)),
+                   phase_chk=_np(ph_chk.reshape(B, E)))
+        for k, v in sd.items():
+            out["w:" + k] = v
+        if hasattr(ns, "logical"):
+            out["logical"] = _np(ns.logical).astype(np.uint8)
+            out["H_prep"] = _np(ns.H_prep).astype(np.uint8)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote %s  (V=%d C=%d E=%d B=%d T=%d, prob range %.3g..%.3g)" %
+              (path, rows, cols, E, B, Nc, pred.min().item(), pred.max().item()))
+
+
+def _codes():
+    """Code-construction fixtures: toric H / H_prep / logical from error_generate.py."""
+    eg = ref_loader.load_error_generate()
+    out = {}
+    for L in (3, 4, 5, 6, 7):
+        H, H_one = eg.generate_PCM(2 * L * L - 2, L)
+        out["toric_H_L%d" % L] = H.astype(np.uint8)
+        if L in (4, 5):
+            hp = eg.H_Prep(torch.from_numpy(H))
+            H_prep = torch.from_numpy(hp.get_H_Prep())
+            assert hp.symplectic_product(H_prep, torch.from_numpy(H)).sum() == 0   # error_generate.py:311
+            logical, stab = hp.get_logical(H_prep)
+            out["toric_Hprep_L%d" % L] = _np(H_prep).astype(np.uint8)
+            out["toric_logical_L%d" % L] = _np(logical).astype(np.uint8)
+    out["bch_63_45_H"] = np.loadtxt(os.path.join(ref_loader.REF_ROOT, "classical", "BCH(63,45).txt")).astype(np.uint8)
+    # gen_syn layout sample (seeded): x = [prior | (-1)^syn], y = err  (error_generate.py:252-278)
+    ref_loader.seed_all(1234)
+    L = 4
+    H = torch.from_numpy(eg.generate_PCM(2 * L * L - 2, L)[0]).t()
+    ds = eg.gen_syn([0.05, 0.1], L, H, 8)
+    out["gen_syn_L4_x"] = np.concatenate([_np(d) for d in ds[0::2]], 0)
+    out["gen_syn_L4_y"] = np.concatenate([_np(d) for d in ds[1::2]], 0)
+    path = os.path.join(OUT, "codes.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    R = ref_loader.REF_ROOT
+    q_small = {"BATCH_SIZE": "16", "run1": "16", "run2": "16"}
+    _run_case("v2_4_toricL5_epoch3", "quantum/decoder_v2_4.py", "v2_4", dict(q_small, L="5"),
+              ckpt=R + "/quantum/new_model/decoder_parameters_epoch3.pkl", loader="train_loader")
+    _run_case("v2_4_toricL4_epoch1", "quantum/decoder_v2_4.py", "v2_4", dict(q_small, L="4"),
+              ckpt=R + "/quantum/new_model/decoder_parameters_epoch1.pkl", loader="train_loader")
+    _run_case("v2_4_toricL7_epoch3_T5", "quantum/decoder_v2_4.py", "v2_4",
+              dict(q_small, L="7", BATCH_SIZE="8", run1="8", run2="8"),
+              ckpt=R + "/quantum/new_model/decoder_parameters_epoch3.pkl", loader="train_loader", T=5)
+    _run_case("qgnni_toricL4_seeded", "quantum/QGNNI.py", "qgnni", dict(q_small, L="4"),
+              loader="train_loader")
+    _run_case("bp_quantum_toricL4", "quantum/BP.py", "bp_quantum",
+              {"BATCH_SIZE": "32", "run2": "32", "L": "4", "P2": "[0.03, 0.08]"})
+    c_small = {"num": "4", "batch_num": "1", "BATCH_SIZE": "24"}
+    _run_case("cgnni_bch_epoch18", "classical/CGNNI.py", "cgnni", c_small,
+              ckpt=R + "/classical/model/decoder_parameters_epoch18.pkl", loader="train_loader")
+    _run_case("cgnni_ldpc_epoch18", "classical/CGNNI.py", "cgnni", c_small,
+              raw_subs=[("H = H_BCH\n", "H = H_LDPC\n"),
+                        ("x = torch.ones((1, 63))", "x = torch.zeros((1, 8))")],
+              ckpt=R + "/classical/model/decoder_parameters_epoch18.pkl", loader="train_loader")
+    _run_case("cgnni_bch_seeded", "classical/CGNNI.py", "cgnni", c_small, loader="train_loader", seed=4321)
+    _run_case("bp_classical_bch", "classical/BP.py", "bp_classical",
+              {"num": "4", "BATCH_SIZE": "24", "SNR2": "[1, 2, 3, 4, 5, 6]"})
+    _codes()
+
+
+if __name__ == "__main__":
+    main()
