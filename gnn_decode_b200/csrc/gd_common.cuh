@@ -1,0 +1,78 @@
+// Shared internals of libgnn_decode_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <vector>
+#include <mutex>
+
+#include "../../include/gnn_decode.h"
+
+namespace gd {
+
+void set_error(const char* fmt, ...);
+
+#define GD_CHECK_ARG(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            gd::set_error(__VA_ARGS__);         \
+            return GD_ERR_INVALID;              \
+        }                                       \
+    } while (0)
+
+#define GD_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            gd::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                 \
+                          cudaGetErrorString(e__));                                          \
+            return GD_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+// Device blob layout (int32 words): all tables of one Tanner graph, uploaded once.
+struct GraphTables {
+    const int32_t* edge_var;   // [E]   variable endpoint of edge e
+    const int32_t* edge_chk;   // [E]   check endpoint of edge e (un-offset)
+    const int32_t* var_ptr;    // [V+1] CSR row pointers
+    const int32_t* var_edges;  // [E]   edge ids of each variable, ascending
+    const int32_t* chk_ptr;    // [C+1]
+    const int32_t* chk_edges;  // [E]
+};
+
+}  // namespace gd
+
+struct gd_graph {
+    int32_t V, C, N;
+    int64_t E;
+    int32_t max_var_deg, max_chk_deg;
+    int device;
+    int sm_count;
+    int max_smem_optin;
+    int32_t* blob_dev;          // single allocation holding all tables
+    gd::GraphTables t;          // device pointers into blob_dev
+    std::vector<int32_t> h_edge_var, h_edge_chk, h_var_ptr, h_var_edges, h_chk_ptr, h_chk_edges;
+    // lazily grown scratch (guarded by mu): global edge-state workspace for codes too large
+    // for shared memory, and pinned/device staging for gd_decode_host.
+    std::mutex mu;
+    float* gstate;
+    size_t gstate_bytes;
+    void* host_ctx;             // gd_decode_host pipeline state (see gd_host.cu)
+};
+
+static inline bool gd_model_valid(const gd_model* m) {
+    if (!m) return false;
+    if (m->flags != 0 || m->iters < 0) return false;
+    switch (m->program) {
+        case GD_PROG_CGNNI:
+        case GD_PROG_QGNNI:
+        case GD_PROG_V2_4:
+            return m->hidden >= 1 && m->hidden <= 256;
+        case GD_PROG_BP_QUANTUM:
+        case GD_PROG_BP_CLASSICAL:
+            return true;
+        default:
+            return false;
+    }
+}

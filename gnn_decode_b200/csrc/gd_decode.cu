@@ -1,0 +1,519 @@
+// The fused decoder: GNNI.forward of the reference (quantum/decoder_v2_4.py:272-294,
+// classical/CGNNI.py:259-284, quantum/QGNNI.py:228-252, quantum/BP.py:199-219,
+// classical/BP.py:239-259) as ONE persistent kernel.
+//
+// Design (B200-first, not a translation of the reference's ~25 eager ops per iteration):
+//   * one CTA per SM loops over tiles of `tile` syndromes; the tile's edge state m[E][tile],
+//     t[E][tile] lives in shared memory for all T iterations (RESIDENT) or, for codes whose
+//     state does not fit 227 KB, in a per-CTA global slab that stays L2-resident (STREAMED);
+//   * lanes of a warp are SYNDROMES (the batch dimension): every shared/global access of the
+//     state is unit-stride across lanes (conflict-free / coalesced), the graph tables and MLP
+//     weights are warp-uniform broadcasts, and there is no divergence and no atomic anywhere;
+//   * thread (s, r) owns syndrome s and the edges / nodes e == r (mod R): node sums are
+//     computed in ascending edge order (deterministic, same order as the CPU index_add_ of
+//     the reference), the per-edge MLPs are evaluated for EB edges at a time in registers;
+//   * the tile's input slab x[tile][V+C] is fetched with one bulk async copy (TMA, UBLKCP)
+//     completing on an mbarrier; outputs go out as 128-bit coalesced stores.
+#include "gd_common.cuh"
+#include "gd_math.cuh"
+
+namespace gd {
+
+constexpr int kMaxThreads = 512;
+constexpr int kEB = 4;  // edges evaluated together per thread (register blocking of the MLP)
+
+struct DecodeParams {
+    const float* x;
+    float* prob;
+    float* logit;
+    uint8_t* hard;
+    const float* weights;
+    GraphTables tb;
+    float* gstate;
+    long long B;
+    int T, V, C, E, N;
+    int tile, R, hid, hp, n_tiles, maxvc;
+    int off_w, off_tab, off_x, off_node, off_m, off_t;
+};
+
+// ---------------- PTX helpers: mbarrier + bulk async copy (TMA 1-D) ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Graph tables: 16-bit copies in shared memory (RESIDENT) or the int32 originals in global
+// memory read through the read-only path (STREAMED; warp-uniform, so L1 broadcasts).
+template <bool RESIDENT>
+struct Tables;
+template <>
+struct Tables<true> {
+    const uint16_t *edge_var, *edge_chk, *var_ptr, *var_edges, *chk_ptr, *chk_edges;
+    __device__ __forceinline__ static int ld(const uint16_t* p, int i) { return p[i]; }
+};
+template <>
+struct Tables<false> {
+    const int32_t *edge_var, *edge_chk, *var_ptr, *var_edges, *chk_ptr, *chk_edges;
+    __device__ __forceinline__ static int ld(const int32_t* p, int i) { return __ldg(p + i); }
+};
+
+__device__ __forceinline__ void stage_mlp(float* dst, int hp, int hid, const float* w1, int w1_stride,
+                                          bool two_in, const float* b1, const float* w2, float s1, float s2,
+                                          int tid, int nthr) {
+    // dst rows: w1a[hp] | w1b[hp] | b1[hp] | w2[hp]
+    for (int k = tid; k < hp; k += nthr) {
+        const bool in = k < hid;
+        dst[k] = in ? w1[k * w1_stride] * s1 : 0.f;
+        dst[hp + k] = (in && two_in) ? w1[k * w1_stride + 1] * s1 : 0.f;
+        dst[2 * hp + k] = in ? b1[k] * s1 : 0.f;
+        dst[3 * hp + k] = in ? w2[k] * s2 : 0.f;
+    }
+}
+
+template <int PROG, bool RESIDENT>
+__global__ void __launch_bounds__(kMaxThreads, 1) decode_kernel(const DecodeParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr bool kIsBP = (PROG == GD_PROG_BP_QUANTUM || PROG == GD_PROG_BP_CLASSICAL);
+    constexpr bool kSoftplus = (PROG == GD_PROG_V2_4);
+
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    float* wsm = reinterpret_cast<float*>(smem + p.off_w);
+    float* xs = reinterpret_cast<float*>(smem + p.off_x);
+    float* node = reinterpret_cast<float*>(smem + p.off_node);
+    const int tile = p.tile, R = p.R, E = p.E, V = p.V, C = p.C, N = p.N, hp = p.hp;
+    float* node2 = node + (size_t)p.maxvc * tile;  // BP only (allocated only then)
+    float* m_st;
+    float* t_st;
+    if (RESIDENT) {
+        m_st = reinterpret_cast<float*>(smem + p.off_m);
+        t_st = reinterpret_cast<float*>(smem + p.off_t);
+    } else {
+        m_st = p.gstate + (size_t)blockIdx.x * 2 * (size_t)E * tile;
+        t_st = m_st + (size_t)E * tile;
+    }
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int s = tid % tile, r = tid / tile;
+
+    // ---- prologue: tables and (pre-scaled) weights into shared memory ----
+    Tables<RESIDENT> tb;
+    if constexpr (RESIDENT) {
+        uint16_t* tab = reinterpret_cast<uint16_t*>(smem + p.off_tab);
+        uint16_t* d_ev = tab;
+        uint16_t* d_ec = d_ev + E;
+        uint16_t* d_vp = d_ec + E;
+        uint16_t* d_ve = d_vp + (V + 1);
+        uint16_t* d_cp = d_ve + E;
+        uint16_t* d_ce = d_cp + (C + 1);
+        for (int i = tid; i < E; i += nthr) {
+            d_ev[i] = (uint16_t)p.tb.edge_var[i];
+            d_ec[i] = (uint16_t)p.tb.edge_chk[i];
+            d_ve[i] = (uint16_t)p.tb.var_edges[i];
+            d_ce[i] = (uint16_t)p.tb.chk_edges[i];
+        }
+        for (int i = tid; i <= V; i += nthr) d_vp[i] = (uint16_t)p.tb.var_ptr[i];
+        for (int i = tid; i <= C; i += nthr) d_cp[i] = (uint16_t)p.tb.chk_ptr[i];
+        tb.edge_var = d_ev; tb.edge_chk = d_ec; tb.var_ptr = d_vp;
+        tb.var_edges = d_ve; tb.chk_ptr = d_cp; tb.chk_edges = d_ce;
+    } else {
+        tb.edge_var = p.tb.edge_var; tb.edge_chk = p.tb.edge_chk; tb.var_ptr = p.tb.var_ptr;
+        tb.var_edges = p.tb.var_edges; tb.chk_ptr = p.tb.chk_ptr; tb.chk_edges = p.tb.chk_edges;
+    }
+    MlpSmem W1{}, W2{}, W3{};
+    if constexpr (!kIsBP) {
+        const float* w = p.weights;
+        const int h = p.hid;
+        const float s1 = kSoftplus ? kLog2e : 1.f, s2 = kSoftplus ? kLn2 : 1.f;
+        float* slot = wsm;
+        if constexpr (PROG == GD_PROG_V2_4) {  // ggc1.mlp: 2 -> h -> 1
+            stage_mlp(slot, hp, h, w, 2, true, w + 2 * h, w + 3 * h, s1, s2, tid, nthr);
+            W1 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[4 * h]};
+            w += 4 * h + 1;
+            slot += 4 * hp;
+        }
+        stage_mlp(slot, hp, h, w, 1, false, w + h, w + 2 * h, s1, s2, tid, nthr);  // check-phase MLP
+        W2 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
+        w += 3 * h + 1;
+        slot += 4 * hp;
+        stage_mlp(slot, hp, h, w, 1, false, w + h, w + 2 * h, s1, s2, tid, nthr);  // read-out MLP
+        W3 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint32_t parity = 0;
+    const int n_iter = (E + R - 1) / R;  // edges per thread (interleaved ownership e = r + i*R)
+
+    for (int tix = blockIdx.x; tix < p.n_tiles; tix += gridDim.x) {
+        const long long s0 = (long long)tix * tile;
+        const int nvalid = (int)min((long long)tile, p.B - s0);
+        const float* xg = p.x + s0 * N;
+        const int n_in = nvalid * N;
+        const uint32_t bulk_bytes = ((uint32_t)n_in * 4u) & ~15u;
+        // ---- input slab: one bulk async copy (TMA) + scalar tail; zero the state ----
+        if (tid == 0) {
+            fence_proxy_async();  // order earlier generic reads of xs before the async write
+            mbar_arrive_expect_tx(bar, bulk_bytes);
+            if (bulk_bytes) bulk_g2s(xs, xg, bulk_bytes, bar);
+        }
+        for (int i = (int)(bulk_bytes >> 2) + tid; i < tile * N; i += nthr) xs[i] = i < n_in ? __ldg(xg + i) : 0.f;
+        for (int i = 0; i < n_iter; ++i) {
+            const int e = r + i * R;
+            if (e < E) m_st[(size_t)e * tile + s] = 0.f;
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        __syncthreads();
+        const float* xrow = xs + (size_t)s * N;  // prior = xrow[0..V), check input = xrow[V..V+C)
+
+        for (int it = 0; it < p.T; ++it) {
+            // ---- V1: per-variable sums of m (ascending edge id) ----
+            for (int v = r; v < V; v += R) {
+                const int b = tb.ld(tb.var_ptr, v), e_end = tb.ld(tb.var_ptr, v + 1);
+                float acc = 0.f;
+                for (int i = b; i < e_end; ++i) acc += m_st[(size_t)tb.ld(tb.var_edges, i) * tile + s];
+                node[v * tile + s] = acc;
+            }
+            __syncthreads();
+            // ---- V2: variable-phase message + the `pre` of the check phase, per edge ----
+            if constexpr (PROG == GD_PROG_V2_4) {
+                for (int i0 = 0; i0 < n_iter; i0 += kEB) {
+                    float x0[kEB], x1[kEB], o[kEB];
+                    int ee[kEB];
+#pragma unroll
+                    for (int j = 0; j < kEB; ++j) {
+                        const int e = r + (i0 + j) * R;
+                        ee[j] = e;
+                        const int ec = e < E ? e : E - 1;
+                        const int v = tb.ld(tb.edge_var, ec);
+                        x0[j] = node[v * tile + s] - m_st[(size_t)ec * tile + s];
+                        x1[j] = xrow[v];
+                    }
+                    mlp_softplus<kEB, true>(W1, hp, x0, x1, o);
+#pragma unroll
+                    for (int j = 0; j < kEB; ++j)
+                        if (ee[j] < E) t_st[(size_t)ee[j] * tile + s] = tanh_half(o[j]);
+                }
+            } else {
+                for (int i = 0; i < n_iter; ++i) {
+                    const int e = r + i * R;
+                    if (e < E) {
+                        const int v = tb.ld(tb.edge_var, e);
+                        const float a = node[v * tile + s] - m_st[(size_t)e * tile + s] + xrow[v];
+                        if constexpr (kIsBP) {
+                            const float le1 = PROG == GD_PROG_BP_QUANTUM ? -46.0517019f : -16.1180957f;
+                            t_st[(size_t)e * tile + s] = bp_log_abs_tanh_half(a, le1);
+                            m_st[(size_t)e * tile + s] = a < 0.f ? 1.f : 0.f;  // sign flag (m is dead here)
+                        } else {
+                            t_st[(size_t)e * tile + s] = tanh_half(a);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- C1: per-check sums ----
+            for (int c = r; c < C; c += R) {
+                const int b = tb.ld(tb.chk_ptr, c), e_end = tb.ld(tb.chk_ptr, c + 1);
+                float acc = 0.f, cnt = 0.f;
+                for (int i = b; i < e_end; ++i) {
+                    const int e = tb.ld(tb.chk_edges, i);
+                    acc += t_st[(size_t)e * tile + s];
+                    if constexpr (kIsBP) cnt += m_st[(size_t)e * tile + s];
+                }
+                node[c * tile + s] = acc;
+                if constexpr (kIsBP) node2[c * tile + s] = cnt;
+            }
+            __syncthreads();
+            // ---- C2: check-phase message, residual ----
+            if constexpr (kIsBP) {
+                for (int i = 0; i < n_iter; ++i) {
+                    const int e = r + i * R;
+                    if (e < E) {
+                        const int c = tb.ld(tb.edge_chk, e);
+                        const float ext = node[c * tile + s] - t_st[(size_t)e * tile + s];
+                        int cnt = (int)(node2[c * tile + s] - m_st[(size_t)e * tile + s]);
+                        if constexpr (PROG == GD_PROG_BP_QUANTUM) cnt += xrow[V + c] < 0.f ? 1 : 0;
+                        const float eps2 = PROG == GD_PROG_BP_QUANTUM ? 1e-12f : 1e-7f;
+                        m_st[(size_t)e * tile + s] = bp_check_out(ext, cnt & 1, eps2);
+                    }
+                }
+            } else {
+                for (int i0 = 0; i0 < n_iter; i0 += kEB) {
+                    float x0[kEB], o[kEB], sg[kEB];
+                    int ee[kEB];
+#pragma unroll
+                    for (int j = 0; j < kEB; ++j) {
+                        const int e = r + (i0 + j) * R;
+                        ee[j] = e;
+                        const int ec = e < E ? e : E - 1;
+                        const int c = tb.ld(tb.edge_chk, ec);
+                        x0[j] = node[c * tile + s] - t_st[(size_t)ec * tile + s];
+                        sg[j] = PROG == GD_PROG_CGNNI ? 1.f : xrow[V + c];
+                    }
+                    if constexpr (kSoftplus) mlp_softplus<kEB, false>(W2, hp, x0, x0, o);
+                    else mlp_relu<kEB>(W2, hp, x0, o);
+#pragma unroll
+                    for (int j = 0; j < kEB; ++j)
+                        if (ee[j] < E) {
+                            float* mp = m_st + (size_t)ee[j] * tile + s;
+                            *mp = o[j] * sg[j] + *mp;
+                        }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- read-out: logits staged as [tile][V] in the node region ----
+        if constexpr (PROG == GD_PROG_V2_4) {  // per-EDGE MLP, then sum at the variable
+            for (int i0 = 0; i0 < n_iter; i0 += kEB) {
+                float x0[kEB], o[kEB];
+                int ee[kEB];
+#pragma unroll
+                for (int j = 0; j < kEB; ++j) {
+                    const int e = r + (i0 + j) * R;
+                    ee[j] = e;
+                    x0[j] = m_st[(size_t)(e < E ? e : E - 1) * tile + s];
+                }
+                mlp_softplus<kEB, false>(W3, hp, x0, x0, o);
+#pragma unroll
+                for (int j = 0; j < kEB; ++j)
+                    if (ee[j] < E) t_st[(size_t)ee[j] * tile + s] = o[j];
+            }
+            __syncthreads();
+        }
+        float* stage = node;  // [tile][V]
+        for (int v = r; v < V; v += R) {
+            const int b = tb.ld(tb.var_ptr, v), e_end = tb.ld(tb.var_ptr, v + 1);
+            const float* src = PROG == GD_PROG_V2_4 ? t_st : m_st;
+            float acc = 0.f;
+            for (int i = b; i < e_end; ++i) acc += src[(size_t)tb.ld(tb.var_edges, i) * tile + s];
+            float lg = acc + xrow[v];
+            if constexpr (PROG == GD_PROG_CGNNI || PROG == GD_PROG_QGNNI) {
+                float xi[1] = {lg}, oo[1];
+                mlp_relu<1>(W3, hp, xi, oo);
+                lg = oo[0];
+            }
+            stage[(size_t)s * V + v] = lg;
+        }
+        __syncthreads();
+        // ---- outputs: coalesced 128-bit stores of prob / logit, 32-bit stores of hard bytes ----
+        {
+            const int total = nvalid * V;
+            const long long g0 = s0 * V;  // multiple of 8 elements: tile % 8 == 0
+            constexpr bool kClamp = (PROG == GD_PROG_CGNNI || PROG == GD_PROG_BP_CLASSICAL);
+            for (int i = tid * 4; i < total; i += nthr * 4) {
+                float l[4], pr[4];
+                const int n = min(4, total - i);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    l[j] = j < n ? stage[i + j] : 0.f;
+                    pr[j] = sigmoid_neg(l[j]);
+                    if (kClamp) pr[j] = fminf(fmaxf(pr[j], 1e-7f), 1.0f - 1e-7f);
+                }
+                if (n == 4) {
+                    if (p.prob) *reinterpret_cast<float4*>(p.prob + g0 + i) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+                    if (p.logit) *reinterpret_cast<float4*>(p.logit + g0 + i) = make_float4(l[0], l[1], l[2], l[3]);
+                    if (p.hard)
+                        *reinterpret_cast<uchar4*>(p.hard + g0 + i) =
+                            make_uchar4(pr[0] > 0.5f, pr[1] > 0.5f, pr[2] > 0.5f, pr[3] > 0.5f);
+                } else {
+                    for (int j = 0; j < n; ++j) {
+                        if (p.prob) p.prob[g0 + i + j] = pr[j];
+                        if (p.logit) p.logit[g0 + i + j] = l[j];
+                        if (p.hard) p.hard[g0 + i + j] = pr[j] > 0.5f;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // xs / node / state are rewritten by the next tile
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct DecodePlan {
+    DecodeParams p;
+    int threads, grid, smem, resident;
+};
+
+static int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePlan* out) {
+    const int V = g->V, C = g->C, N = g->N;
+    const int64_t E64 = g->E;
+    const bool bp = m->program == GD_PROG_BP_QUANTUM || m->program == GD_PROG_BP_CLASSICAL;
+    const int hid = bp ? 0 : m->hidden;
+    const int hp = align_up(hid, 4);
+    const int n_slots = bp ? 0 : (m->program == GD_PROG_V2_4 ? 3 : 2);
+    const int maxvc = V > C ? V : C;
+    DecodeParams& p = out->p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.T = m->iters; p.V = V; p.C = C; p.E = (int)E64; p.N = N; p.hid = hid; p.hp = hp; p.maxvc = maxvc;
+    p.tb = g->t;
+
+    const int smem_max = g->max_smem_optin;
+    int off = 16;                                  // mbarrier
+    p.off_w = off; off += n_slots * 4 * hp * 4; off = align_up(off, 16);
+    const bool fits16 = E64 < 65536 && V < 65535 && C < 65535;
+    const int tab_bytes = (int)(4 * E64 + V + C + 2) * 2;
+    // resident layout first
+    int tile = 0, resident = 0;
+    if (fits16 && off + tab_bytes < smem_max) {
+        const int fixed = align_up(off + tab_bytes, 128);
+        const int64_t per_syn = ((int64_t)N + (int64_t)maxvc * (bp ? 2 : 1) + 2 * E64) * 4;
+        int64_t tmax = (smem_max - fixed) / per_syn;
+        if (tmax >= 32) { tile = (int)(tmax / 32) * 32; if (tile > kMaxThreads) tile = kMaxThreads; }
+        else if (tmax >= 16) tile = 16;
+        else if (tmax >= 8) tile = 8;
+        if (tile) {
+            resident = 1;
+            p.off_tab = off;
+            if (tile >= 32) {  // balance the rounds over the SMs: fewest rounds, then smallest tile
+                const int64_t slots = g->sm_count;
+                const int64_t rounds = (B + slots * tile - 1) / (slots * tile);
+                int64_t t = (B + slots * rounds - 1) / (slots * rounds);
+                t = (t + 31) / 32 * 32;
+                if (t < tile) tile = (int)t;
+            }
+            int o2 = fixed;
+            p.off_x = o2; o2 += tile * N * 4; o2 = align_up(o2, 16);
+            p.off_node = o2; o2 += maxvc * tile * 4 * (bp ? 2 : 1);
+            p.off_m = o2; o2 += (int)E64 * tile * 4;
+            p.off_t = o2; o2 += (int)E64 * tile * 4;
+            out->smem = o2;
+        }
+    }
+    if (!resident) {  // streamed: edge state in a per-CTA global slab, tables read from global
+        tile = 64;
+        while (tile > 8 && align_up(off, 128) + (int64_t)tile * (N + maxvc * (bp ? 2 : 1)) * 4 > smem_max) tile >>= 1;
+        const int fixed = align_up(off, 128);
+        if (fixed + (int64_t)tile * (N + maxvc * (bp ? 2 : 1)) * 4 > smem_max) {
+            set_error("gd_decode: code too large (V+C=%d) for this build's shared-memory staging", N);
+            return GD_ERR_UNSUPPORTED;
+        }
+        p.off_tab = 0;
+        int o2 = fixed;
+        p.off_x = o2; o2 += tile * N * 4; o2 = align_up(o2, 16);
+        p.off_node = o2; o2 += maxvc * tile * 4 * (bp ? 2 : 1);
+        out->smem = o2;
+    }
+    p.tile = tile;
+    int R = kMaxThreads / tile;
+    if (R < 1) R = 1;
+    if ((int64_t)R > E64) R = (int)E64;
+    if (tile < 32) { const int q = 32 / tile; R = R / q * q; if (R < q) R = q; }
+    p.R = R;
+    out->threads = R * tile;
+    p.n_tiles = (int)((B + tile - 1) / tile);
+    out->grid = p.n_tiles < g->sm_count ? p.n_tiles : g->sm_count;
+    out->resident = resident;
+    return GD_OK;
+}
+
+template <int PROG>
+static int launch_decode(const DecodePlan& pl, cudaStream_t st) {
+    auto kr = decode_kernel<PROG, true>;
+    auto ks = decode_kernel<PROG, false>;
+    auto k = pl.resident ? kr : ks;
+    GD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+    k<<<pl.grid, pl.threads, pl.smem, st>>>(pl.p);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+}  // namespace gd
+
+extern "C" int gd_decode_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out) {
+    GD_CHECK_ARG(g && out, "gd_decode_launch_info: NULL argument");
+    GD_CHECK_ARG(gd_model_valid(model), "gd_decode_launch_info: invalid model");
+    GD_CHECK_ARG(B > 0, "gd_decode_launch_info: B must be positive");
+    gd::DecodePlan pl;
+    int rc = gd::plan_decode(g, model, B, &pl);
+    if (rc != GD_OK) return rc;
+    out->tile = pl.p.tile; out->threads = pl.threads; out->grid = pl.grid; out->smem_bytes = pl.smem;
+    out->resident = pl.resident; out->n_tiles = pl.p.n_tiles;
+    return GD_OK;
+}
+
+extern "C" int gd_decode_fwd(const gd_graph* gc, const gd_model* model, const float* weights_dev,
+                             const float* x_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, int64_t B,
+                             void* stream) {
+    gd_graph* g = const_cast<gd_graph*>(gc);
+    GD_CHECK_ARG(g != nullptr, "gd_decode_fwd: graph is NULL");
+    GD_CHECK_ARG(gd_model_valid(model), "gd_decode_fwd: invalid model (program=%d hidden=%d iters=%d)",
+                 model ? model->program : -1, model ? model->hidden : -1, model ? model->iters : -1);
+    GD_CHECK_ARG(B >= 0 && B < ((int64_t)1 << 31), "gd_decode_fwd: B=%lld out of range", (long long)B);
+    if (B == 0) return GD_OK;  // empty batch: nothing to do (the reference would crash; we return cleanly)
+    GD_CHECK_ARG(x_dev != nullptr, "gd_decode_fwd: x is NULL");
+    GD_CHECK_ARG(gd_weights_size(model) == 0 || weights_dev != nullptr, "gd_decode_fwd: weights is NULL");
+    GD_CHECK_ARG(((uintptr_t)x_dev & 15) == 0, "gd_decode_fwd: x must be 16-byte aligned");
+    GD_CHECK_ARG(((uintptr_t)prob_dev & 15) == 0 && ((uintptr_t)logit_dev & 15) == 0 && ((uintptr_t)hard_dev & 3) == 0,
+                 "gd_decode_fwd: outputs must be 16-byte (prob, logit) / 4-byte (hard) aligned");
+    gd::DecodePlan pl;
+    int rc = gd::plan_decode(g, model, B, &pl);
+    if (rc != GD_OK) return rc;
+    pl.p.x = x_dev; pl.p.prob = prob_dev; pl.p.logit = logit_dev; pl.p.hard = hard_dev; pl.p.weights = weights_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    int prev = 0;
+    GD_CUDA(cudaGetDevice(&prev));
+    if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
+    if (!pl.resident) {
+        const size_t need = (size_t)pl.grid * 2 * (size_t)g->E * pl.p.tile * sizeof(float);
+        std::lock_guard<std::mutex> lk(g->mu);
+        if (need > g->gstate_bytes) {
+            if (g->gstate) cudaFree(g->gstate);
+            g->gstate = nullptr; g->gstate_bytes = 0;
+            cudaError_t e = cudaMalloc((void**)&g->gstate, need);
+            if (e != cudaSuccess) {
+                gd::set_error("gd_decode_fwd: cudaMalloc of %zu-byte edge-state workspace failed: %s", need,
+                              cudaGetErrorString(e));
+                if (prev != g->device) cudaSetDevice(prev);
+                return GD_ERR_CUDA;
+            }
+            g->gstate_bytes = need;
+        }
+        pl.p.gstate = g->gstate;
+    }
+    switch (model->program) {
+        case GD_PROG_CGNNI: rc = gd::launch_decode<GD_PROG_CGNNI>(pl, st); break;
+        case GD_PROG_QGNNI: rc = gd::launch_decode<GD_PROG_QGNNI>(pl, st); break;
+        case GD_PROG_V2_4: rc = gd::launch_decode<GD_PROG_V2_4>(pl, st); break;
+        case GD_PROG_BP_QUANTUM: rc = gd::launch_decode<GD_PROG_BP_QUANTUM>(pl, st); break;
+        default: rc = gd::launch_decode<GD_PROG_BP_CLASSICAL>(pl, st); break;
+    }
+    if (prev != g->device) cudaSetDevice(prev);
+    return rc;
+}

@@ -1,0 +1,128 @@
+// Per-edge arithmetic of the phase programs: the k->h->1 MLPs (evaluated as FMA + MUFU in
+// registers -- they are scalar->scalar functions, not GEMMs: SURVEY.md section 7 "hard parts"),
+// tanh(m/2), and the sum-product check update.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gd {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One k->h->1 MLP staged in shared memory as SoA rows padded to a multiple of 4 hidden units
+// (padding units have w2 == 0).  For Softplus MLPs the rows are PRE-SCALED when staged:
+//   w1*log2(e), b1*log2(e), w2*ln(2)   so that
+//   w2*softplus(w1 x + b1) == (w2 ln2) * [ max(z',0) + lg2(1 + 2^-|z'|) ],  z' = (w1 log2e) x + b1 log2e
+// which needs exactly one ex2 and one lg2 (MUFU) per hidden unit.
+struct MlpSmem {
+    const float* w1a;  // [hp] weight of input 0
+    const float* w1b;  // [hp] weight of input 1 (2-input MLPs only)
+    const float* b1;   // [hp]
+    const float* w2;   // [hp]
+    float b2;
+};
+
+// floats needed in shared memory for one MLP slot
+__host__ __device__ constexpr int mlp_smem_floats(int hp) { return 4 * hp; }
+
+// Evaluate a Softplus MLP for EB independent edges at once (weights are loaded once per 4
+// hidden units as 128-bit broadcast LDS and reused across the EB edges).
+template <int EB, bool TWO_IN>
+__device__ __forceinline__ void mlp_softplus(const MlpSmem& W, int hp, const float (&x0)[EB],
+                                             const float (&x1)[EB], float (&out)[EB]) {
+    float acc[EB];
+#pragma unroll
+    for (int j = 0; j < EB; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < hp; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(W.w1a + k);
+        const float4 b4 = *reinterpret_cast<const float4*>(W.b1 + k);
+        const float4 c4 = *reinterpret_cast<const float4*>(W.w2 + k);
+        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TWO_IN) d4 = *reinterpret_cast<const float4*>(W.w1b + k);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < EB; ++j) {
+                float z = fmaf(a[u], x0[j], b[u]);
+                if (TWO_IN) z = fmaf(d[u], x1[j], z);
+                const float t = ex2_approx(-fabsf(z));
+                const float l = lg2_approx(1.0f + t);
+                const float s = fmaxf(z, 0.f) + l;
+                acc[j] = fmaf(c[u], s, acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < EB; ++j) out[j] = acc[j] + W.b2;
+}
+
+// ReLU MLP (CGNNI / QGNNI, hidden 10): 3 instructions per hidden unit, no MUFU.
+template <int EB>
+__device__ __forceinline__ void mlp_relu(const MlpSmem& W, int hp, const float (&x0)[EB], float (&out)[EB]) {
+    float acc[EB];
+#pragma unroll
+    for (int j = 0; j < EB; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < hp; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(W.w1a + k);
+        const float4 b4 = *reinterpret_cast<const float4*>(W.b1 + k);
+        const float4 c4 = *reinterpret_cast<const float4*>(W.w2 + k);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < EB; ++j) {
+                const float z = fmaf(a[u], x0[j], b[u]);
+                acc[j] = fmaf(c[u], fmaxf(z, 0.f), acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < EB; ++j) out[j] = acc[j] + W.b2;
+}
+
+// tanh(a/2): one per edge-iteration, so the full-accuracy libm version is affordable.
+// (tanh.approx.f32 has ~5e-4 relative error: too coarse for the 1e-4 logit bar)
+__device__ __forceinline__ float tanh_half(float a) { return tanhf(0.5f * a); }
+
+// P(flip) = sigmoid(-logit) = 1 / (1 + e^logit)
+__device__ __forceinline__ float sigmoid_neg(float logit) { return 1.0f / (1.0f + expf(logit)); }
+
+// ---- sum-product (BP) pieces, written so that fp32 keeps the accuracy the fp64 reference has
+// in the saturated regime (reference quantum/BP.py:103-117, classical/BP.py:101-116) ----
+// log|tanh(a/2)| after clamp(a, -10, 10), clamped below at log(eps1):
+//   |tanh(a/2)| = (1 - q) / (1 + q), q = e^{-|a|}  ->  log(-expm1(-|a|)) - log1p(q)
+__device__ __forceinline__ float bp_log_abs_tanh_half(float a, float log_eps1) {
+    const float aa = fminf(fabsf(a), 10.0f);
+    const float q = expf(-aa);
+    const float v = logf(-expm1f(-aa)) - log1pf(q);   // aa == 0 -> -inf
+    return fmaxf(v, log_eps1);
+}
+// m = log((1+o)/(1-o)), o = sign * exp(ext) clamped to [-1+eps2, 1-eps2]; ext <= 0.
+__device__ __forceinline__ float bp_check_out(float ext, bool odd, float eps2) {
+    const float p = fminf(expf(ext), 1.0f);
+    const float one_minus = fmaxf(-expm1f(ext), eps2);
+    const float mag = log1pf(fminf(p, 1.0f - eps2)) - logf(one_minus);
+    return odd ? -mag : mag;
+}
+
+}  // namespace gd

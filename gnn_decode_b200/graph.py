@@ -1,0 +1,186 @@
+"""TannerGraph: Python owner of the opaque gd_graph* (destination-sorted CSR/CSC tables on the GPU).
+
+Replaces what the reference rebuilds for every batch: `H.to_sparse()._indices()` in
+CustomDataset.__init__ (quantum/decoder_v2_4.py:164-165), the PyG DataLoader collate that
+replicates edge_index block-diagonally (:205-206) and the `+rows` offset (:277).
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _dev_index(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _cabi.GdError("gnn_decode_b200 runs on CUDA devices only (got %s); there is no CPU fallback" % device)
+    return torch.cuda.current_device() if device.index is None else device.index
+
+
+class TannerGraph(object):
+    """Immutable device-resident tables of one Tanner graph.
+
+    edge_index: [2, E] integer tensor / array of ONE graph -- row 0 variable ids in [0, V),
+    row 1 check ids in [0, C) (un-offset, exactly `data.edge_index` of a single reference sample).
+    """
+
+    def __init__(self, edge_index, V, C, device="cuda"):
+        ei = torch.as_tensor(edge_index).detach().to("cpu", torch.int64).contiguous()
+        if ei.dim() != 2 or ei.size(0) != 2:
+            raise ValueError("edge_index must have shape [2, E], got %s" % (tuple(ei.shape),))
+        self.V, self.C, self.E = int(V), int(C), int(ei.size(1))
+        self.N = self.V + self.C
+        self.device = torch.device("cuda", _dev_index(device))
+        self.edge_index = ei
+        handle = C.c_void_p()
+        lib = _cabi.lib()
+        _cabi.check(lib.gd_graph_create(C.c_void_p(ei.data_ptr()), self.E, self.V, self.C, self.device.index,
+                                        C.byref(handle)), "gd_graph_create")
+        self._h = handle
+        self._finalizer = weakref.finalize(self, lib.gd_graph_destroy, handle)
+        mv, mc = C.c_int32(), C.c_int32()
+        _cabi.check(lib.gd_graph_dims(self._h, None, None, None, C.byref(mv), C.byref(mc)))
+        self.max_var_deg, self.max_chk_deg = mv.value, mc.value
+        self._logical_dev = {}
+
+    # ---- constructors -------------------------------------------------------------------------
+    @classmethod
+    def from_H(cls, H, device="cuda"):
+        """H in the REFERENCE's orientation: [V, C] (the transposed parity-check matrix, as in
+        `H = torch.from_numpy(generate_PCM(...)).t()`, decoder_v2_4.py:189).  Edge order =
+        `H.to_sparse()._indices()`: row-major, i.e. sorted by variable then check."""
+        Ht = torch.as_tensor(np.asarray(H) if not torch.is_tensor(H) else H).to("cpu")
+        idx = torch.nonzero(Ht != 0, as_tuple=False).t().contiguous()   # row-major order == coalesced COO
+        return cls(idx, Ht.size(0), Ht.size(1), device)
+
+    @classmethod
+    def from_pcm(cls, pcm, device="cuda"):
+        """pcm: the parity-check matrix itself, [C, V]."""
+        p = torch.as_tensor(np.asarray(pcm) if not torch.is_tensor(pcm) else pcm)
+        return cls.from_H(p.t(), device)
+
+    # ---- introspection ------------------------------------------------------------------------
+    @property
+    def handle(self):
+        return self._h
+
+    def tables(self):
+        """Host copies of the device tables (used by the parity tests)."""
+        lib = _cabi.lib()
+        out = {k: np.empty(n, np.int32) for k, n in
+               (("var_ptr", self.V + 1), ("var_edges", self.E), ("chk_ptr", self.C + 1),
+                ("chk_edges", self.E), ("edge_var", self.E), ("edge_chk", self.E))}
+        ptr = lambda a: C.c_void_p(a.ctypes.data)
+        _cabi.check(lib.gd_graph_tables(self._h, ptr(out["var_ptr"]), ptr(out["var_edges"]), ptr(out["chk_ptr"]),
+                                        ptr(out["chk_edges"]), ptr(out["edge_var"]), ptr(out["edge_chk"])))
+        return out
+
+    def check_batched(self, edge_index, B, chk_offset):
+        """Number of entries of a PyG-batched [2, B*E] int64 CUDA edge_index that differ from the
+        block-diagonal replication of this graph (0 == it is the replication)."""
+        ei = edge_index
+        if ei.dtype != torch.int64 or not ei.is_cuda or not ei.is_contiguous():
+            ei = ei.to(self.device, torch.int64).contiguous()
+        if ei.dim() != 2 or ei.size(0) != 2 or ei.size(1) != B * self.E:
+            raise ValueError("batched edge_index must be [2, %d], got %s" % (B * self.E, tuple(ei.shape)))
+        bad = C.c_int64(-1)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _cabi.check(_cabi.lib().gd_graph_check_batched(self._h, C.c_void_p(ei.data_ptr()), B, int(chk_offset),
+                                                       C.c_void_p(st), C.byref(bad)))
+        return bad.value
+
+    def launch_info(self, model, B):
+        info = _cabi.GdLaunchInfo()
+        _cabi.check(_cabi.lib().gd_decode_launch_info(self._h, C.byref(model), int(B), C.byref(info)))
+        return {k: getattr(info, k) for k, _ in info._fields_}
+
+
+# ---- resolving the graph behind a PyG-batched edge_index ---------------------------------------
+_batched_cache = {}
+
+
+def _infer_dims(ei_cpu_head, total_edges, n_node_rows, chk_is_offset):
+    """Infer (V, C, E) of the per-graph Tanner graph from a batched edge_index and the number of
+    node rows of x, assuming every variable and check touches at least one edge."""
+    r0, r1 = ei_cpu_head[0], ei_cpu_head[1]
+    n = r0.numel()
+    for E in range(1, n + 1):
+        if total_edges % E:
+            continue
+        B = total_edges // E
+        if n_node_rows % B:
+            continue
+        N = n_node_rows // B
+        if B > 1:
+            if E >= n:
+                break
+            if int(r0[E] - r0[0]) != N or int(r1[E] - r1[0]) != N:
+                continue
+        V = int(r0[:E].max()) + 1
+        cmax = int(r1[:E].max()) + 1
+        C = cmax - V if chk_is_offset else cmax
+        if C > 0 and V + C == N:
+            return V, C, E
+    return None
+
+
+def graph_from_batched(edge_index, n_node_rows, rows=None, cols=None, chk_is_offset=False, device=None):
+    """Return (TannerGraph, B) for a PyG-batched edge_index [2, B*E].
+
+    rows/cols (= V, C; the reference's module globals) are used when given, otherwise inferred.
+    The result is cached per edge_index storage, and the batched tensor is verified ONCE on the
+    device to be the block-diagonal replication of the first graph (the reference silently
+    assumes it)."""
+    device = edge_index.device if device is None else torch.device(device)
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, n_node_rows, rows, cols,
+           bool(chk_is_offset), str(device))
+    hit = _batched_cache.get(key)
+    if hit is not None:
+        return hit
+    total = int(edge_index.size(1))
+    if rows is not None and cols is not None:
+        V, Cn = int(rows), int(cols)
+        if n_node_rows % (V + Cn):
+            raise ValueError("x has %d rows, not a multiple of rows+cols=%d" % (n_node_rows, V + Cn))
+        B = n_node_rows // (V + Cn)
+        if B == 0 or total % B:
+            raise ValueError("edge_index has %d edges, not a multiple of the batch size %d" % (total, B))
+        E = total // B
+    else:
+        head = edge_index[:, :min(total, 1 << 16)].detach().to("cpu", torch.int64)
+        dims = _infer_dims(head, total, n_node_rows, chk_is_offset)
+        if dims is None:
+            raise ValueError("cannot infer (rows, cols) of the Tanner graph from edge_index; pass rows=/cols= "
+                             "to the decoder constructor")
+        V, Cn, E = dims
+        B = total // E
+    per = edge_index[:, :E].detach().to("cpu", torch.int64).clone()
+    if chk_is_offset:
+        per[1] -= V
+    g = _graph_intern(per, V, Cn, device)
+    if B > 1 or chk_is_offset:
+        bad = g.check_batched(edge_index, B, V if chk_is_offset else 0)
+        if bad:
+            raise ValueError("edge_index is not the block-diagonal replication of its first graph "
+                             "(%d mismatching entries)" % bad)
+    if len(_batched_cache) > 64:
+        _batched_cache.clear()
+    _batched_cache[key] = (g, B)
+    return g, B
+
+
+_graph_cache = {}
+
+
+def _graph_intern(per_graph_ei, V, C, device):
+    key = (V, C, str(torch.device("cuda", _dev_index(device))), per_graph_ei.numpy().tobytes())
+    g = _graph_cache.get(key)
+    if g is None:
+        g = TannerGraph(per_graph_ei, V, C, device)
+        if len(_graph_cache) > 32:
+            _graph_cache.clear()
+        _graph_cache[key] = g
+    return g

@@ -1,0 +1,177 @@
+/*
+ * gnn_decode.h -- C ABI of the B200-native message-passing decoder (libgnn_decode_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of ironmanaudi/GNN-decode: the forked PyG
+ * MessagePassing.propagate() -> scatter "sum over siblings minus self" -> per-edge update(),
+ * iterated Nc times by GNNI.forward over a PyG-batched (block-diagonal) Tanner graph.
+ * The reference has no FFI (pure Python); each entry point cites the reference interface it
+ * replaces.  Paths are relative to the reference tree (GNN-decode/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns an int status (GD_OK == 0); gd_last_error() gives the thread-local
+ *     message of the last failure; no C++ exception crosses the boundary;
+ *   - "dev" pointers are CUDA device pointers on the graph's device, "host" pointers are host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all device
+ *     entry points are asynchronous on that stream and allocate nothing on the hot path
+ *     (exception: the global-state workspace of very large codes is grown lazily, once);
+ *   - tensors are fp32, row-major, BATCH-MAJOR exactly like the reference's flattened tensors:
+ *       x      [B, V+C]   == data.x [B*(V+C), 1]   (prior LLR of the V variable nodes, then the
+ *                                                   C check-node inputs: (-1)^syndrome, or 0)
+ *       m      [B, E]     == edge-resident messages [B*E, 1], edges in the order of the
+ *                            per-graph edge_index (H.to_sparse()._indices(): by variable, then check)
+ *       prob   [B, V]     == GNNI.forward output [B*V, 1] = P(bit/qubit flipped)
+ */
+#ifndef GNN_DECODE_H_
+#define GNN_DECODE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GD_ABI_VERSION 1
+
+enum gd_status {
+    GD_OK = 0,
+    GD_ERR_INVALID = 1,      /* bad argument (the Python layer raises ValueError)          */
+    GD_ERR_CUDA = 2,         /* CUDA runtime failure (RuntimeError)                         */
+    GD_ERR_UNSUPPORTED = 3   /* valid request this build has no kernel for (RuntimeError)   */
+};
+
+/* The five phase programs on the hot path. */
+enum gd_program {
+    GD_PROG_CGNNI = 0,        /* classical/CGNNI.py:212-284      hidden 10 ReLU              */
+    GD_PROG_QGNNI = 1,        /* quantum/QGNNI.py:186-252        hidden 10 ReLU, x syndrome  */
+    GD_PROG_V2_4 = 2,         /* quantum/decoder_v2_4.py:230-294 hidden 128 Softplus         */
+    GD_PROG_BP_QUANTUM = 3,   /* quantum/BP.py:101-124,191-219   sum-product, syndrome sign  */
+    GD_PROG_BP_CLASSICAL = 4  /* classical/BP.py:99-123,231-259  sum-product                 */
+};
+
+/* flow of one propagate(): which node type the reduce runs over. */
+enum gd_phase {
+    GD_PHASE_VAR = 0,  /* flow='source_to_target': reduce over edge_index[0] (variable nodes) */
+    GD_PHASE_CHK = 1   /* flow='target_to_source': reduce over edge_index[1] (check nodes)    */
+};
+
+/* Opaque, immutable, device-resident Tanner-graph tables (destination-sorted CSR by variable
+ * and CSC by check, per-edge endpoints).  Replaces the per-batch int64 edge_index gathers /
+ * scatters of MessagePassing.propagate (decoder_v2_4.py:136-144). */
+typedef struct gd_graph gd_graph;
+
+/* Model description for the fused decoder.  `weights` buffers are packed fp32 in state_dict
+ * order of the tensors the reference's forward actually uses:
+ *   V2_4       : ggc1.mlp.{0.weight[h,2],0.bias[h],2.weight[1,h],2.bias[1]},
+ *                ggc2.mlp.{0.weight[h,1],0.bias[h],2.weight[1,h],2.bias[1]}, mlp.{same}   (10h+3)
+ *   CGNNI      : ggc2.mlp2.{...}, mlp.{...}                                                (6h+2)
+ *   QGNNI      : ggc2.mlp.{...},  mlp.{...}                                                (6h+2)
+ *   BP_*       : none (weights may be NULL)
+ */
+typedef struct gd_model {
+    int32_t program;   /* enum gd_program                                   */
+    int32_t hidden;    /* h: 128 for V2_4, 10 for CGNNI/QGNNI, 0 for BP     */
+    int32_t iters;     /* Nc (T) message-passing iterations                  */
+    int32_t flags;     /* reserved, must be 0                                */
+} gd_model;
+
+const char* gd_last_error(void);
+int gd_abi_version(void);
+
+/* Number of floats in the packed weight buffer of `model` (0 for BP); <0 on invalid model. */
+int64_t gd_weights_size(const gd_model* model);
+
+/* ---- graph preprocessing (replaces CustomDataset.__init__ `H.to_sparse()._indices()` +
+ *      PyG DataLoader collate + the `+rows` offset: decoder_v2_4.py:164-165,205-206,277) ---- */
+
+/* edge_index_host: [2, E] int64 row-major, row 0 = variable id in [0,V), row 1 = check id in
+ * [0,C) (un-offset, as in data.edge_index of ONE graph).  device: CUDA ordinal. */
+int gd_graph_create(const int64_t* edge_index_host, int64_t E, int32_t V, int32_t C, int device,
+                    gd_graph** out);
+void gd_graph_destroy(gd_graph* g);
+int gd_graph_dims(const gd_graph* g, int32_t* V, int32_t* C, int64_t* E, int32_t* max_var_deg,
+                  int32_t* max_chk_deg);
+/* Copy the tables back to host int32 arrays (any pointer may be NULL):
+ *   var_ptr[V+1], var_edges[E] : CSR, edges of each variable in ascending edge id
+ *   chk_ptr[C+1], chk_edges[E] : CSC, edges of each check in ascending edge id
+ *   edge_var[E], edge_chk[E]   : endpoints of each edge                                  */
+int gd_graph_tables(const gd_graph* g, int32_t* var_ptr, int32_t* var_edges, int32_t* chk_ptr,
+                    int32_t* chk_edges, int32_t* edge_var, int32_t* edge_chk);
+/* Verify on the device that a PyG-batched edge_index_dev [2, B*E] int64 is the block-diagonal
+ * replication of the graph: ei[0][g*E+e] == var[e] + g*(V+C), ei[1][g*E+e] == chk[e] + g*(V+C)
+ * + chk_offset (chk_offset = V after GNNI.forward's `.add(rows)`, 0 for raw data.edge_index).
+ * Writes the number of mismatching entries to *mismatches_host (synchronises the stream). */
+int gd_graph_check_batched(const gd_graph* g, const int64_t* edge_index_dev, int64_t B,
+                           int32_t chk_offset, void* stream, int64_t* mismatches_host);
+
+/* ---- one propagate() (decoder_v2_4.py:85-148, CGNNI.py:52-112, QGNNI.py:54-116,
+ *      quantum/BP.py:54-124, classical/BP.py:52-123) fused with GraphConv.update
+ *      (decoder_v2_4.py:253-257, CGNNI.py:238-242, QGNNI.py:207-214) ----
+ * m_dev [B,E] in, out_dev [B,E] out.  weights_dev is the packed k->h->1 MLP of THIS GraphConv
+ * only ({0.weight, 0.bias, 2.weight, 2.bias}; NULL where the phase has no MLP).
+ * x_dev [B,V+C] may be NULL only where the reference
+ * passes post=None (CGNNI check phase).  With fuse_update == 0 the kernel stops before
+ * update() and writes the tensor the reference hands to self.update(): out_dev is [B,E,F]
+ * with F = gd_propagate_features(program, phase) (2 where the reference `cat`s extra). */
+int gd_propagate_features(int32_t program, int32_t phase);
+int gd_propagate_fwd(const gd_graph* g, const gd_model* model, int32_t phase, int32_t fuse_update,
+                     const float* m_dev, const float* x_dev, const float* weights_dev,
+                     float* out_dev, int64_t B, void* stream);
+
+/* ---- the fused decoder: GNNI.forward (decoder_v2_4.py:272-294, CGNNI.py:259-284,
+ *      QGNNI.py:228-252, quantum/BP.py:199-219, classical/BP.py:239-259) ----
+ * One persistent kernel keeps a tile of syndromes' edge state on chip for all `iters`
+ * iterations.  Outputs (any may be NULL): prob_dev [B,V] fp32 = sigmoid(-logit) (clamped to
+ * [1e-7,1-1e-7] for the classical programs as the reference does), logit_dev [B,V] fp32,
+ * hard_dev [B,V] uint8 = (prob > 0.5) (neural_BP.py:338 semantics). */
+int gd_decode_fwd(const gd_graph* g, const gd_model* model, const float* weights_dev,
+                  const float* x_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev,
+                  int64_t B, void* stream);
+
+/* Same computation with HOST buffers: host->device copy of x, the kernel, device->host copy of
+ * the requested outputs, pipelined in chunks over internal streams; returns when the outputs
+ * are complete.  Replaces `datas.to(device); pred = decoder(datas)` (decoder_v2_4.py:332-334)
+ * followed by reading the prediction back. weights_host is the packed buffer on the host. */
+int gd_decode_host(const gd_graph* g, const gd_model* model, const float* weights_host,
+                   const float* x_host, float* prob_host, uint8_t* hard_host, int64_t B);
+
+/* Launch geometry the library picked for (graph, model, B): for benchmarks / roofline. */
+typedef struct gd_launch_info {
+    int32_t tile;            /* syndromes per CTA tile                          */
+    int32_t threads;         /* threads per CTA                                 */
+    int32_t grid;            /* CTAs                                            */
+    int32_t smem_bytes;      /* dynamic shared memory per CTA                   */
+    int32_t resident;        /* 1 = edge state in shared memory, 0 = in global  */
+    int32_t n_tiles;
+} gd_launch_info;
+int gd_decode_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out);
+
+/* ---- synthetic input: on-GPU Philox4x32-10 sampler with the layout and distribution of
+ *      gen_syn (error_generate.py:252-278): per sample s, p = p_list[philox(seed, s) % n_p];
+ *      x = [log((1-p)/p)]*V | (-1)^(H^T e mod 2);  y = e.
+ *      noise: 0 = reference iid X/Z flips (each of the V slots flips w.p. p);
+ *             1 = depolarizing on V/2 qubits (X,Y,Z each p/3; slot j = X part, j+V/2 = Z part,
+ *                 prior = log((1-2p/3)/(2p/3))). */
+int gd_sample(const gd_graph* g, int32_t noise, const float* p_list_host, int32_t n_p,
+              uint64_t seed, uint64_t first_sample, float* x_dev, uint8_t* err_dev, int64_t B,
+              void* stream);
+
+/* ---- evaluation (neural_BP.py:338-348 semantics): counts, over B samples, how many decodes
+ *      leave a non-zero residual syndrome (H^T (e xor ehat) != 0) and how many flip a logical
+ *      (logical_dev [K, V] uint8 row-major ON THE DEVICE, may be NULL with K = 0; rows are applied
+ *      to (e xor ehat) directly, exactly as `logical` from H_Prep.get_logical is used).  counts_dev[0] = residual
+ *      syndrome failures, counts_dev[1] = logical failures among syndrome-satisfying decodes,
+ *      counts_dev[2] = total failures (either). counts are ADDED to (uint64). */
+int gd_eval_failures(const gd_graph* g, const uint8_t* logical_dev, int32_t K,
+                     const uint8_t* err_dev, const uint8_t* hard_dev, int64_t B,
+                     unsigned long long* counts_dev, void* stream);
+
+/* ---- measurement support: throughput of the pipes that bound the resident decoders
+ *      (kind 0 MUFU ex2, 1 ex2+lg2, 2 FFMA, 3 one Softplus hidden unit, 4 packed FFMA2).
+ *      result[0] = units / s over the whole GPU, result[1] = ms of the timed launch. ---- */
+int gd_microbench(int32_t kind, int32_t iters, int device, double* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNN_DECODE_H_ */

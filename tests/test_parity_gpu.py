@@ -1,0 +1,201 @@
+"""GPU suite: the CUDA path, called through the C ABI, against the oracle and the golden vectors.
+
+Bars (BASELINE.json north_star):
+  * graph / index tables: bit-exact;
+  * hard decisions: bit-exact wherever the reference's own logit is not within LOGIT_TIE of 0;
+  * soft logits: |cuda_fp32 - reference| <= RTOL * |reference| + ATOL, RTOL = 1e-4, with the
+    absolute floor ATOL = 1e-4 * (1 + rms of the reference logits of that case) for values near 0.
+    The sum-product (BP) programs are ill-conditioned in the saturated regime (the fp32 reference
+    itself is ~1e-2 away from the fp64 evaluation of its own formulas there), so for them the bar is
+    RTOL_BP against the fp64 oracle plus hard-decision equality.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, golden_cases, make_decoder
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+
+RTOL, RTOL_BP, LOGIT_TIE = 1e-4, 2e-3, 1e-3
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _logit_close(got, want, rtol):
+    want = want.double()
+    got = got.double().cpu()
+    atol = 1e-4 * (1.0 + want.pow(2).mean().sqrt().item())
+    err = (got - want).abs()
+    bound = rtol * want.abs() + atol
+    worst = (err / bound).max().item()
+    return worst, err.max().item()
+
+
+class _Data(object):
+    def __init__(self, g, dev, dtype=None):
+        self.x = g.x.reshape(-1, 1).to(dev, dtype or g.dtype)
+        self.edge_index = g.batched_edge_index().to(dev)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_graph_tables_bit_exact(name):
+    from gnn_decode_b200.graph import TannerGraph
+    g = Golden(name)
+    tg = TannerGraph(g.edge_index, g.V, g.C, _dev())
+    t = tg.tables()
+    ei = g.edge_index.numpy()
+    assert np.array_equal(t["edge_var"], ei[0]) and np.array_equal(t["edge_chk"], ei[1])
+    for ptr, ids, key, n in ((t["var_ptr"], t["var_edges"], ei[0], g.V), (t["chk_ptr"], t["chk_edges"], ei[1], g.C)):
+        order = np.argsort(key, kind="stable")            # destination-sorted, ascending edge id inside
+        assert np.array_equal(ids, order.astype(np.int32))
+        assert np.array_equal(ptr, np.concatenate([[0], np.cumsum(np.bincount(key, minlength=n))]).astype(np.int32))
+    # H.to_sparse()._indices() route gives the same graph
+    tg2 = TannerGraph.from_H(g.H, _dev())
+    assert torch.equal(tg2.edge_index, g.edge_index)
+
+
+def test_batched_edge_index_check():
+    from gnn_decode_b200.graph import TannerGraph
+    g = Golden("v2_4_toricL4_epoch1")
+    dev = _dev()
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    ei = g.batched_edge_index().to(dev)
+    assert tg.check_batched(ei, g.B, 0) == 0
+    ei2 = ei.clone()
+    ei2[1] += g.V
+    assert tg.check_batched(ei2, g.B, g.V) == 0
+    ei2[0, 5] += 1
+    assert tg.check_batched(ei2, g.B, g.V) == 1
+    dec = make_decoder(g)[1].to(dev)
+    d = _Data(g, dev)
+    d.edge_index = ei2 - torch.tensor([[0], [g.V]], device=dev)
+    with pytest.raises(ValueError):
+        dec(d)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_fused_decoder_matches_reference(name):
+    g = Golden(name)
+    dev = _dev()
+    mod, dec = make_decoder(g)
+    dec = dec.to(dev).eval()
+    ref = restate.decode(g.program, g.edge_index, g.V, g.C, g.x, g.weights, T=g.T, dtype=torch.float64)
+    with torch.no_grad():
+        pred = dec(_Data(g, dev))                                   # the reference's entry point
+    assert pred.shape == (g.B * g.V, 1) and pred.dtype == g.dtype
+    from gnn_decode_b200.graph import TannerGraph
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    prob, logit, hard = dec.decode(g.x.to(dev), graph=tg, return_logits=True, return_hard=True)
+    assert torch.equal(pred.reshape(g.B, g.V).float(), prob)
+    bp = g.program.startswith("bp")
+    worst, max_err = _logit_close(logit, ref["logit"], RTOL_BP if bp else RTOL)
+    assert worst <= 1.0, "logit mismatch: %.3g x bound (max abs err %.3g)" % (worst, max_err)
+    # probabilities against the golden output of the reference's own code (its dtype)
+    assert (prob.double().cpu() - g.prob.double()).abs().max().item() <= (2e-3 if bp else 1e-5)
+    # hard decisions bit-exact away from ties
+    want_hard = (g.prob > 0.5)
+    decided = ref["logit"].abs() > LOGIT_TIE
+    assert torch.equal(hard.cpu().bool()[decided], want_hard[decided])
+    assert torch.equal(hard.bool(), prob > 0.5)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_single_propagate_matches_reference(name):
+    """GraphConv.forward == propagate + update, through gd_propagate_fwd."""
+    g = Golden(name)
+    dev = _dev()
+    mod, dec = make_decoder(g)
+    dec = dec.to(dev).eval()
+    dec.bind_code(g.V, g.C)
+    ei = g.batched_edge_index().to(dev)
+    ei[1] += g.V                                                    # what GNNI.forward hands to GraphConv
+    x = g.x.reshape(-1, 1).to(dev, g.dtype)
+    m0 = g.m0.reshape(-1, 1).to(dev, g.dtype)
+    bp = g.program.startswith("bp")
+    with torch.no_grad():
+        got_var = dec.ggc1(m0, ei, x)
+        got_chk = dec.ggc2(m0, ei) if g.program in ("cgnni", "bp_classical") else dec.ggc2(m0, ei, x)
+    for got, want in ((got_var, g.phase_var), (got_chk, g.phase_chk)):
+        assert got.shape == (g.B * g.E, 1) and got.dtype == g.dtype
+        worst, max_err = _logit_close(got.reshape(g.B, g.E), want, RTOL_BP if bp else RTOL)
+        assert worst <= 1.0, "phase mismatch %.3g x bound (max abs %.3g)" % (worst, max_err)
+
+
+def test_custom_update_override_runs_unfused():
+    """A user subclass overriding update() gets the reference's pre/reduce/post tensor."""
+    from gnn_decode_b200.quantum import decoder_v2_4 as q
+    g = Golden("v2_4_toricL4_epoch1")
+    dev = _dev()
+    seen = {}
+
+    class MyConv(q.GraphConv):
+        def update(self, aggr_out):
+            seen["shape"] = tuple(aggr_out.shape)
+            return aggr_out[:, :1] * 2 + aggr_out[:, 1:]
+
+    conv = MyConv("target_to_source").to(dev)
+    ei = g.batched_edge_index().to(dev)
+    ei[1] += g.V
+    x = g.x.reshape(-1, 1).to(dev)
+    m0 = g.m0.reshape(-1, 1).to(dev)
+    out = conv(m0, ei, x)
+    assert seen["shape"] == (g.B * g.E, 2)
+    t = torch.tanh(g.m0.double() / 2)
+    chk = g.edge_index[1]
+    S = torch.zeros(g.B, g.C, dtype=torch.float64).index_add_(1, chk, t)
+    want = (S[:, chk] - t) * 2 + g.x[:, g.V:][:, chk]
+    assert (out.reshape(g.B, g.E).double().cpu() - want).abs().max().item() < 1e-5
+
+
+def test_deterministic_and_partial_tiles():
+    """Bit-repeatable (atomic-free reductions) and independent of how the batch is tiled."""
+    g = Golden("v2_4_toricL5_epoch3")
+    dev = _dev()
+    mod, dec = make_decoder(g)
+    dec = dec.to(dev).eval()
+    from gnn_decode_b200.graph import TannerGraph
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    gen = torch.Generator().manual_seed(5)
+    reps = 37                                                       # 37*16 = 592 syndromes: ragged last tile
+    x = g.x.repeat(reps, 1).to(dev)
+    a = dec.decode(x, graph=tg)
+    b = dec.decode(x, graph=tg)
+    assert torch.equal(a, b)
+    small = dec.decode(g.x.to(dev), graph=tg)
+    assert torch.equal(a.reshape(reps, g.B, g.V), small.unsqueeze(0).expand(reps, -1, -1))
+    one = dec.decode(g.x[3:4].to(dev), graph=tg)                     # B = 1
+    assert torch.equal(one, small[3:4])
+    empty = dec.decode(g.x[:0].to(dev), graph=tg)                    # B = 0
+    assert empty.shape == (0, g.V)
+
+
+def test_decode_host_matches_device_path():
+    g = Golden("v2_4_toricL4_epoch1")
+    dev = _dev()
+    mod, dec = make_decoder(g)
+    dec = dec.to(dev).eval()
+    from gnn_decode_b200.graph import TannerGraph
+    dec.bind_graph(TannerGraph(g.edge_index, g.V, g.C, dev))
+    reps = 1100                                                      # 17600 syndromes: several chunks
+    xh = g.x.float().repeat(reps, 1).contiguous().pin_memory()
+    prob_h = torch.empty(xh.size(0), g.V, dtype=torch.float32).pin_memory()
+    hard_h = torch.empty(xh.size(0), g.V, dtype=torch.uint8).pin_memory()
+    dec.decode_host(xh, prob_h, hard_h)
+    prob_d, hard_d = dec.decode(xh.to(dev), return_hard=True)
+    assert torch.equal(prob_h, prob_d.cpu()) and torch.equal(hard_h, hard_d.cpu())
+
+
+def test_fp32_and_fp64_inputs_agree():
+    g = Golden("qgnni_toricL4_seeded")
+    dev = _dev()
+    mod, dec = make_decoder(g)
+    dec = dec.to(dev).eval()
+    p64 = dec(_Data(g, dev, torch.float64))
+    p32 = dec(_Data(g, dev, torch.float32))
+    assert p64.dtype == torch.float64 and p32.dtype == torch.float32
+    assert torch.equal(p64.float(), p32)
