@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- decoded syndromes/s of the fused message-passing decoder (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path (GNNI.forward: T message-passing iterations + read-out +
+hard decision) over one batch of synthetic syndromes.  N = 1 workload = BASELINE.json configs[1]:
+the decoder_v2_4 program (hidden 128 Softplus, T = 15) on the rotated surface code d = 5 under
+depolarizing noise, batch 65536 per GPU, sampled on the GPU by the Philox sampler before the timed
+region.  N > 1 (torchrun, one rank per GPU): every rank decodes its own shard of the batch, no
+data-path collective -> "scaling": "weak".
+
+`value`  : syndromes/s with inputs resident in HBM (CUDA events around each step, L2 flushed
+           between steps, max over ranks).
+`e2e`    : the same metric through the reference-facing call with HOST buffers
+           (decoder.decode_host -> C ABI gd_decode_host): pinned host x -> device, kernel,
+           prob + hard bits -> pinned host, all inside the timed region.
+`roofline`: HBM roofline of the decode kernel (algorithmic bytes / measured duration vs
+           MEASURED_PEAKS.json) -- tiny by construction, the fused kernel moves ~0.8 KB per
+           syndrome -- plus `pipe`: the pipe that actually binds it (MUFU ex2+lg2 for Softplus),
+           with its peak measured live by gd_microbench.
+`cpu_baseline` / `--impl reference`: the oracle port of the reference's CPU path (same ATen op
+           sequence, torch threads = all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (program, code builder, T, per-GPU batch, noise, p list)
+    "v2_4_rotated_d5_depol_B65536": ("v2_4", ("rotated", 5), 15, 65536, 1, [0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.1]),
+    "v2_4_toric_L5_iidxz_B65536": ("v2_4", ("toric", 5), 15, 65536, 0, [0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.1]),
+    "v2_4_toric_L11_iidxz_B65536": ("v2_4", ("toric", 11), 15, 65536, 0, [0.01, 0.02, 0.03, 0.04, 0.05]),
+    "v2_4_rotated_d11_depol_B65536": ("v2_4", ("rotated", 11), 15, 65536, 1, [0.01, 0.02, 0.03, 0.04, 0.05]),
+}
+DEFAULT_WORKLOAD = "v2_4_rotated_d5_depol_B65536"
+
+
+def build_pcm(spec):
+    from gnn_decode_b200 import codes
+    kind, size = spec
+    return codes.rotated_surface_pcm(size) if kind == "rotated" else codes.toric_pcm(size)
+
+
+def load_v2_4_weights():
+    """The shipped trained checkpoint (quantum/new_model/epoch3), carried in the golden fixture."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "v2_4_toricL5_epoch3.npz"))
+    return {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_rate(program, pcm, T, weights, x_sample, chunk, budget_s, threads):
+    """Time the oracle port (the reference's CPU arithmetic) on a bounded sample; returns
+    (syndromes/s, syndromes timed, seconds)."""
+    from gnn_decode_b200 import codes
+    from oracle import restate
+    torch.set_num_threads(threads)
+    ei = torch.from_numpy(codes.edge_index_of(pcm))
+    C_, V = pcm.shape
+    done, t_used = 0, 0.0
+    restate.decode(program, ei, V, C_, x_sample[:min(chunk, 8)], weights, T=T)     # warm-up
+    i = 0
+    while done < x_sample.size(0) and t_used < budget_s:
+        xb = x_sample[i:i + chunk]
+        if xb.size(0) == 0:
+            break
+        t0 = time.perf_counter()
+        restate.decode(program, ei, V, C_, xb, weights, T=T)
+        t_used += time.perf_counter() - t0
+        done += xb.size(0)
+        i += chunk
+    return done / t_used, done, t_used
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    program, code_spec, T, B, noise, p_list = WORKLOADS[args.workload]
+    pcm = build_pcm(code_spec)
+    Cn, V = pcm.shape
+    N = V + Cn
+    E = int(pcm.sum())
+    weights = load_v2_4_weights()
+    cores = os.cpu_count() or 1
+    config = {"workload": args.workload, "program": "quantum/decoder_v2_4.GNNI (h=128 Softplus)", "code": "%s-%d" % code_spec,
+              "V": V, "C": Cn, "E": E, "T": T, "batch_per_gpu": B, "noise": "depolarizing" if noise else "iid-xz",
+              "l2": "L2 flushed (256 MiB write) between timed steps", "weights": "reference checkpoint epoch3"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from gnn_decode_b200 import codes  # noqa: F401  (host-side code builders only)
+        rng = np.random.RandomState(1234)
+        # bounded sample of the same workload: synthetic syndromes with the same layout/statistics
+        est_rate, _, _ = cpu_reference_rate(program, pcm, T, weights, _host_sample(pcm, noise, p_list, 128, rng), 128, 5.0, cores)
+        total_budget = 150.0
+        per_step = int(max(128, min(4096, est_rate * total_budget / max(1, args.steps + args.warmup))) // 128 * 128)
+        xs = _host_sample(pcm, noise, p_list, per_step, rng)
+        for _ in range(args.warmup):
+            cpu_reference_rate(program, pcm, T, weights, xs, 128, 1e9, cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_reference_rate(program, pcm, T, weights, xs, 128, 1e9, cores)
+        dt = time.perf_counter() - t0
+        value = per_step * args.steps / dt
+        line = {"impl": "reference", "metric": "decoded syndromes/sec", "value": value, "unit": "syndromes/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": value, "unit": "syndromes/s", "cores": cores, "kind": "port",
+                                 "sample": "%d syndromes per step in chunks of 128 (the reference's BATCH_SIZE), fp64, "
+                                           "torch CPU %d threads, oracle/restate.py" % (per_step, cores)},
+                "e2e": {"value": value, "unit": "syndromes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch.distributed as dist
+    from gnn_decode_b200 import _cabi
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.quantum import decoder_v2_4
+    from gnn_decode_b200.sampler import sample_syndromes
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g = TannerGraph.from_pcm(pcm, dev)
+    dec = decoder_v2_4.GNNI(T)
+    dec.load_state_dict(weights)
+    dec = dec.to(dev).eval()
+    dec.bind_graph(g)
+    model = dec.gd_model()
+    info = g.launch_info(model, B)
+
+    # synthetic inputs, resident in HBM before the timed region; each rank its own Philox range
+    x, err = sample_syndromes(g, B, p_list, noise=noise, seed=1234, first_sample=rank * B)
+    prob = torch.empty((B, V), dtype=torch.float32, device=dev)
+    hard = torch.empty((B, V), dtype=torch.uint8, device=dev)
+    wdev = dec.packed_weights(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _cabi.lib()
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        _cabi.check(lib.gd_decode_fwd(g.handle, C.byref(model), C.c_void_p(wdev.data_ptr()), C.c_void_p(x.data_ptr()),
+                                      C.c_void_p(prob.data_ptr()), None, C.c_void_p(hard.data_ptr()), B,
+                                      C.c_void_p(stream.cuda_stream)))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in evs:
+        flush.fill_(1)                       # evict the inputs from L2 (untimed)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+    barrier()
+    kernel_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = sum(kernel_ms)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = t.item()
+    ms_per_step = total_ms_max / args.steps
+    value = world * B * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end-to-end through the host-buffer call ----
+    xh = x.cpu().pin_memory()
+    prob_h = torch.empty((B, V), dtype=torch.float32).pin_memory()
+    hard_h = torch.empty((B, V), dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        dec.decode_host(xh, prob_h, hard_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dec.decode_host(xh, prob_h, hard_h)     # returns when the host outputs are complete
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / t.item()
+    clk = clocks.stop() if rank == 0 else None
+    same = bool(torch.equal(prob_h, prob.cpu()) and torch.equal(hard_h, hard.cpu()))
+
+    if rank == 0:
+        # ---- rooflines ----
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        else:
+            hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = B * (4 * N + 4 * V + V)                      # x in, prob + hard out, per launch
+        med_ms = statistics.median(kernel_ms)
+        achieved = alg_bytes / (med_ms * 1e-3) / 1e9
+        r = (C.c_double * 2)()
+        _cabi.check(lib.gd_microbench(1, 4096, local_rank, r))   # ex2+lg2 pairs / s: the Softplus unit rate
+        unit_peak = r[0]
+        units = B * E * (T * 256 + 128)                          # Softplus hidden-unit evaluations per launch
+        unit_rate = units / (med_ms * 1e-3)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_decode_kernel_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel": "gd::decode_kernel<V2_4, resident>",
+                    "kernel_ms": med_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                    "note": "fused resident kernel: ~%d B/syndrome, so HBM is not the binding resource" % (alg_bytes // B),
+                    "pipe": {"name": "xu (MUFU ex2+lg2, one pair per Softplus hidden unit)", "achieved": unit_rate / 1e12,
+                             "peak": unit_peak / 1e12, "unit": "T Softplus units/s", "frac": unit_rate / unit_peak,
+                             "peak_source": "gd_microbench kind=1, measured live on this GPU",
+                             "units_per_launch": units}}
+        line = {"metric": "decoded syndromes/sec", "value": value, "unit": "syndromes/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config, launch=info, parallelism="batch-sharded x%d, no collective" % world),
+                "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "syndromes/s", "h2d_bytes_per_step": B * N * 4,
+                        "d2h_bytes_per_step": B * V * 5, "api": "GNNI.decode_host -> gd_decode_host (pinned host buffers)",
+                        "matches_device_path": same},
+                "gpu_launches": args.steps * 1,
+                "roofline": roofline}
+        if not args.no_cpu_baseline and world == 1:
+            rng = np.random.RandomState(1234)
+            n_s = 2048
+            rate, n_done, secs = cpu_reference_rate(program, pcm, T, weights, x[:n_s].cpu().double(), 128, 20.0, cores)
+            line["cpu_baseline"] = {"value": rate, "unit": "syndromes/s", "cores": cores, "kind": "port",
+                                    "sample": "%d syndromes of this workload in chunks of 128 (the reference's BATCH_SIZE), "
+                                              "fp64, %.1f s, oracle/restate.py on %d torch threads" % (n_done, secs, cores)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _host_sample(pcm, noise, p_list, n, rng):
+    """Host-side synthetic syndromes with gen_syn's layout (quantum/error_generate.py:252-278)."""
+    Cn, V = pcm.shape
+    p = np.asarray(p_list)[rng.randint(0, len(p_list), n)]
+    if noise == 0:
+        err = (rng.random_sample((n, V)) < p[:, None]).astype(np.uint8)
+        pm = p
+    else:
+        nq = V // 2
+        u = rng.random_sample((n, nq))
+        err = np.concatenate([(u < 2 * p[:, None] / 3), (u >= p[:, None] / 3) & (u < p[:, None])], 1).astype(np.uint8)
+        pm = 2 * p / 3
+    syn = (err.astype(np.int64) @ pcm.T.astype(np.int64)) % 2
+    x = np.concatenate([np.repeat(np.log((1 - pm) / pm)[:, None], V, 1), 1.0 - 2.0 * syn], 1)
+    return torch.from_numpy(x)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

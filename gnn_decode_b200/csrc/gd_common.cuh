@@ -50,6 +50,7 @@ struct gd_graph {
     int device;
     int sm_count;
     int max_smem_optin;
+    int max_smem_sm;
     int32_t* blob_dev;          // single allocation holding all tables
     gd::GraphTables t;          // device pointers into blob_dev
     std::vector<int32_t> h_edge_var, h_edge_chk, h_var_ptr, h_var_edges, h_chk_ptr, h_chk_edges;

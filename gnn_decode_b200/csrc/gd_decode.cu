@@ -4,8 +4,8 @@
 //
 // Design (B200-first, not a translation of the reference's ~25 eager ops per iteration):
 //   * one CTA per SM loops over tiles of `tile` syndromes; the tile's edge state m[E][tile],
-//     t[E][tile] lives in shared memory for all T iterations (RESIDENT) or, for codes whose
-//     state does not fit 227 KB, in a per-CTA global slab that stays L2-resident (STREAMED);
+//     t[E][tile] lives in shared memory for all T iterations (codes whose state does not fit
+//     227 KB take the streamed global-memory kernel in gd_streamed.cu instead);
 //   * lanes of a warp are SYNDROMES (the batch dimension): every shared/global access of the
 //     state is unit-stride across lanes (conflict-free / coalesced), the graph tables and MLP
 //     weights are warp-uniform broadcasts, and there is no divergence and no atomic anywhere;
@@ -16,11 +16,13 @@
 //     completing on an mbarrier; outputs go out as 128-bit coalesced stores.
 #include "gd_common.cuh"
 #include "gd_math.cuh"
+#include "gd_decode.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace gd {
 
-constexpr int kMaxThreads = 512;
-constexpr int kEB = 4;  // edges evaluated together per thread (register blocking of the MLP)
+constexpr int kMaxThreads = 1024;   // largest CTA; kernels are instantiated for 512 (<=128 regs) and 1024 (<=64 regs)
 
 struct DecodeParams {
     const float* x;
@@ -29,7 +31,6 @@ struct DecodeParams {
     uint8_t* hard;
     const float* weights;
     GraphTables tb;
-    float* gstate;
     long long B;
     int T, V, C, E, N;
     int tile, R, hid, hp, n_tiles, maxvc;
@@ -74,19 +75,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// Graph tables: 16-bit copies in shared memory (RESIDENT) or the int32 originals in global
-// memory read through the read-only path (STREAMED; warp-uniform, so L1 broadcasts).
-template <bool RESIDENT>
-struct Tables;
-template <>
-struct Tables<true> {
+// Graph tables: 16-bit copies in shared memory (warp-uniform reads: broadcast, conflict-free).
+struct Tables {
     const uint16_t *edge_var, *edge_chk, *var_ptr, *var_edges, *chk_ptr, *chk_edges;
     __device__ __forceinline__ static int ld(const uint16_t* p, int i) { return p[i]; }
-};
-template <>
-struct Tables<false> {
-    const int32_t *edge_var, *edge_chk, *var_ptr, *var_edges, *chk_ptr, *chk_edges;
-    __device__ __forceinline__ static int ld(const int32_t* p, int i) { return __ldg(p + i); }
 };
 
 __device__ __forceinline__ void stage_mlp(float* dst, int hp, int hid, const float* w1, int w1_stride,
@@ -102,8 +94,10 @@ __device__ __forceinline__ void stage_mlp(float* dst, int hp, int hid, const flo
     }
 }
 
-template <int PROG, bool RESIDENT>
-__global__ void __launch_bounds__(kMaxThreads, 1) decode_kernel(const DecodeParams p) {
+// kEB = edges evaluated together per thread (register blocking of the MLP: weights are loaded
+// once per 4 hidden units and reused for kEB edges).
+template <int PROG, int MAXT, int kEB>
+__global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool kIsBP = (PROG == GD_PROG_BP_QUANTUM || PROG == GD_PROG_BP_CLASSICAL);
     constexpr bool kSoftplus = (PROG == GD_PROG_V2_4);
@@ -114,21 +108,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) decode_kernel(const DecodePara
     float* node = reinterpret_cast<float*>(smem + p.off_node);
     const int tile = p.tile, R = p.R, E = p.E, V = p.V, C = p.C, N = p.N, hp = p.hp;
     float* node2 = node + (size_t)p.maxvc * tile;  // BP only (allocated only then)
-    float* m_st;
-    float* t_st;
-    if (RESIDENT) {
-        m_st = reinterpret_cast<float*>(smem + p.off_m);
-        t_st = reinterpret_cast<float*>(smem + p.off_t);
-    } else {
-        m_st = p.gstate + (size_t)blockIdx.x * 2 * (size_t)E * tile;
-        t_st = m_st + (size_t)E * tile;
-    }
+    float* m_st = reinterpret_cast<float*>(smem + p.off_m);
+    float* t_st = reinterpret_cast<float*>(smem + p.off_t);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int s = tid % tile, r = tid / tile;
 
     // ---- prologue: tables and (pre-scaled) weights into shared memory ----
-    Tables<RESIDENT> tb;
-    if constexpr (RESIDENT) {
+    Tables tb;
+    {
         uint16_t* tab = reinterpret_cast<uint16_t*>(smem + p.off_tab);
         uint16_t* d_ev = tab;
         uint16_t* d_ec = d_ev + E;
@@ -146,9 +133,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) decode_kernel(const DecodePara
         for (int i = tid; i <= C; i += nthr) d_cp[i] = (uint16_t)p.tb.chk_ptr[i];
         tb.edge_var = d_ev; tb.edge_chk = d_ec; tb.var_ptr = d_vp;
         tb.var_edges = d_ve; tb.chk_ptr = d_cp; tb.chk_edges = d_ce;
-    } else {
-        tb.edge_var = p.tb.edge_var; tb.edge_chk = p.tb.edge_chk; tb.var_ptr = p.tb.var_ptr;
-        tb.var_edges = p.tb.var_edges; tb.chk_ptr = p.tb.chk_ptr; tb.chk_edges = p.tb.chk_edges;
     }
     MlpSmem W1{}, W2{}, W3{};
     if constexpr (!kIsBP) {
@@ -366,13 +350,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) decode_kernel(const DecodePara
 // ---------------------------------------------------------------------------------------------
 struct DecodePlan {
     DecodeParams p;
-    int threads, grid, smem, resident;
+    int threads, grid, smem, resident, cps, eb;
 };
 
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePlan* out) {
-    const int V = g->V, C = g->C, N = g->N;
+    const int V = g->V, C = g->C, N = g->N, Cn = g->C;
     const int64_t E64 = g->E;
     const bool bp = m->program == GD_PROG_BP_QUANTUM || m->program == GD_PROG_BP_CLASSICAL;
     const int hid = bp ? 0 : m->hidden;
@@ -381,6 +365,8 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     const int maxvc = V > C ? V : C;
     DecodeParams& p = out->p;
     memset(&p, 0, sizeof(p));
+    out->cps = 1;
+    out->eb = 4;
     p.B = B; p.T = m->iters; p.V = V; p.C = C; p.E = (int)E64; p.N = N; p.hid = hid; p.hp = hp; p.maxvc = maxvc;
     p.tb = g->t;
 
@@ -390,24 +376,59 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     const bool fits16 = E64 < 65536 && V < 65535 && C < 65535;
     const int tab_bytes = (int)(4 * E64 + V + C + 2) * 2;
     // resident layout first
-    int tile = 0, resident = 0;
+    int tile = 0, resident = 0, R = 0;
     if (fits16 && off + tab_bytes < smem_max) {
         const int fixed = align_up(off + tab_bytes, 128);
         const int64_t per_syn = ((int64_t)N + (int64_t)maxvc * (bp ? 2 : 1) + 2 * E64) * 4;
-        int64_t tmax = (smem_max - fixed) / per_syn;
-        if (tmax >= 32) { tile = (int)(tmax / 32) * 32; if (tile > kMaxThreads) tile = kMaxThreads; }
-        else if (tmax >= 16) tile = 16;
-        else if (tmax >= 8) tile = 8;
+        const int64_t tmax = (smem_max - fixed) / per_syn;
+        if (tmax >= 8) {
+            // Pick (tile, R, EB): tile = syndromes per CTA, R = threads per syndrome.  Score =
+            //   (fraction of the SMs' tile slots doing useful work over all rounds)
+            // x (fraction of the EB-blocked edge slots of a thread that hold a real edge)
+            // x w(threads): measured sensitivity of the MUFU-bound inner loop to resident warps
+            //   and to the register blocking (profiles/r01_geometry_sweep.txt).
+            const int E = (int)E64;
+            const int64_t slots = g->sm_count;
+            static const int wx[] = {32, 128, 256, 384, 512, 640, 896, 1024};
+            static const double wy[] = {0.20, 0.62, 0.80, 0.90, 0.96, 0.985, 1.0, 1.0};
+            double best = -1.0;
+            const char* et = getenv("GD_TILE");
+            const char* er = getenv("GD_R");
+            const char* eb = getenv("GD_EB");
+            for (int t = 8; t <= tmax && t <= kMaxThreads; t += 8) {
+                if (et && atoi(et) != t) continue;
+                if (t < 32 && (32 % t)) continue;
+                const int64_t n_t = (B + t - 1) / t;
+                const int64_t rounds = (n_t + slots - 1) / slots;
+                const double eff_round = (double)B / ((double)rounds * (double)slots * t);
+                for (int r = 1; r * t <= kMaxThreads && r <= E; ++r) {
+                    if (er && atoi(er) != r) continue;
+                    const int thr = r * t;
+                    if (thr % 32) continue;
+                    double w = wy[7];
+                    for (int i = 1; i < 8; ++i)
+                        if (thr <= wx[i]) { w = wy[i - 1] + (wy[i] - wy[i - 1]) * (thr - wx[i - 1]) / (wx[i] - wx[i - 1]); break; }
+                    const int n_iter = (E + r - 1) / r;
+                    // per-thread cost of one iteration in issue slots: EB-blocked per-edge update
+                    // (c_edge each) + the node sums this thread owns (c_ld per summed edge)
+                    const double c_edge = m->program == GD_PROG_V2_4 ? 16.0 * hp : (bp ? 200.0 : 40.0 + 6.0 * hp);
+                    const double c_ld = 4.0;
+                    const double node_cost = (double)((V + r - 1) / r) * g->max_var_deg + (double)((Cn + r - 1) / r) * g->max_chk_deg;
+                    const double ideal = E * c_edge + 2.0 * E * c_ld;
+                    for (int ebk = 4; ebk >= 2; ebk -= 2) {
+                        if (eb && atoi(eb) != ebk) continue;
+                        const int blocks = (n_iter + ebk - 1) / ebk;
+                        const double per_thread = (bp ? n_iter : blocks * ebk) * c_edge + node_cost * c_ld;
+                        const double eff_bal = ideal / (r * per_thread);
+                        const double score = eff_round * eff_bal * w * (ebk == 2 ? (thr >= 384 ? 1.0 : 0.92) : (thr >= 384 ? 0.985 : 1.0));
+                        if (score > best + 1e-9) { best = score; tile = t; R = r; out->eb = ebk; }
+                    }
+                }
+            }
+        }
         if (tile) {
             resident = 1;
             p.off_tab = off;
-            if (tile >= 32) {  // balance the rounds over the SMs: fewest rounds, then smallest tile
-                const int64_t slots = g->sm_count;
-                const int64_t rounds = (B + slots * tile - 1) / (slots * tile);
-                int64_t t = (B + slots * rounds - 1) / (slots * rounds);
-                t = (t + 31) / 32 * 32;
-                if (t < tile) tile = (int)t;
-            }
             int o2 = fixed;
             p.off_x = o2; o2 += tile * N * 4; o2 = align_up(o2, 16);
             p.off_node = o2; o2 += maxvc * tile * 4 * (bp ? 2 : 1);
@@ -416,25 +437,11 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
             out->smem = o2;
         }
     }
-    if (!resident) {  // streamed: edge state in a per-CTA global slab, tables read from global
-        tile = 64;
-        while (tile > 8 && align_up(off, 128) + (int64_t)tile * (N + maxvc * (bp ? 2 : 1)) * 4 > smem_max) tile >>= 1;
-        const int fixed = align_up(off, 128);
-        if (fixed + (int64_t)tile * (N + maxvc * (bp ? 2 : 1)) * 4 > smem_max) {
-            set_error("gd_decode: code too large (V+C=%d) for this build's shared-memory staging", N);
-            return GD_ERR_UNSUPPORTED;
-        }
-        p.off_tab = 0;
-        int o2 = fixed;
-        p.off_x = o2; o2 += tile * N * 4; o2 = align_up(o2, 16);
-        p.off_node = o2; o2 += maxvc * tile * 4 * (bp ? 2 : 1);
-        out->smem = o2;
+    if (!resident || getenv("GD_FORCE_STREAMED")) {
+        out->resident = 0;
+        return GD_OK;           // caller takes the streamed kernel (gd_streamed.cu)
     }
     p.tile = tile;
-    int R = kMaxThreads / tile;
-    if (R < 1) R = 1;
-    if ((int64_t)R > E64) R = (int)E64;
-    if (tile < 32) { const int q = 32 / tile; R = R / q * q; if (R < q) R = q; }
     p.R = R;
     out->threads = R * tile;
     p.n_tiles = (int)((B + tile - 1) / tile);
@@ -445,9 +452,9 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
 
 template <int PROG>
 static int launch_decode(const DecodePlan& pl, cudaStream_t st) {
-    auto kr = decode_kernel<PROG, true>;
-    auto ks = decode_kernel<PROG, false>;
-    auto k = pl.resident ? kr : ks;
+    void (*k)(const DecodeParams);
+    if (pl.threads > 512) k = pl.eb == 2 ? decode_kernel<PROG, 1024, 2> : decode_kernel<PROG, 1024, 4>;
+    else k = pl.eb == 2 ? decode_kernel<PROG, 512, 2> : decode_kernel<PROG, 512, 4>;
     GD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     k<<<pl.grid, pl.threads, pl.smem, st>>>(pl.p);
     GD_CUDA(cudaGetLastError());
@@ -463,6 +470,7 @@ extern "C" int gd_decode_launch_info(const gd_graph* g, const gd_model* model, i
     gd::DecodePlan pl;
     int rc = gd::plan_decode(g, model, B, &pl);
     if (rc != GD_OK) return rc;
+    if (!pl.resident) return gd::streamed_launch_info(g, model, B, out);
     out->tile = pl.p.tile; out->threads = pl.threads; out->grid = pl.grid; out->smem_bytes = pl.smem;
     out->resident = pl.resident; out->n_tiles = pl.p.n_tiles;
     return GD_OK;
@@ -491,21 +499,9 @@ extern "C" int gd_decode_fwd(const gd_graph* gc, const gd_model* model, const fl
     GD_CUDA(cudaGetDevice(&prev));
     if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
     if (!pl.resident) {
-        const size_t need = (size_t)pl.grid * 2 * (size_t)g->E * pl.p.tile * sizeof(float);
-        std::lock_guard<std::mutex> lk(g->mu);
-        if (need > g->gstate_bytes) {
-            if (g->gstate) cudaFree(g->gstate);
-            g->gstate = nullptr; g->gstate_bytes = 0;
-            cudaError_t e = cudaMalloc((void**)&g->gstate, need);
-            if (e != cudaSuccess) {
-                gd::set_error("gd_decode_fwd: cudaMalloc of %zu-byte edge-state workspace failed: %s", need,
-                              cudaGetErrorString(e));
-                if (prev != g->device) cudaSetDevice(prev);
-                return GD_ERR_CUDA;
-            }
-            g->gstate_bytes = need;
-        }
-        pl.p.gstate = g->gstate;
+        rc = gd::streamed_decode(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, B, st);
+        if (prev != g->device) cudaSetDevice(prev);
+        return rc;
     }
     switch (model->program) {
         case GD_PROG_CGNNI: rc = gd::launch_decode<GD_PROG_CGNNI>(pl, st); break;

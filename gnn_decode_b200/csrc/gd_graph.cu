@@ -114,6 +114,7 @@ extern "C" int gd_graph_create(const int64_t* ei, int64_t E, int32_t V, int32_t 
     }
     g->sm_count = prop.multiProcessorCount;
     g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    g->max_smem_sm = (int)prop.sharedMemPerMultiprocessor;
     g->t.edge_var = g->blob_dev + o_ev;
     g->t.edge_chk = g->blob_dev + o_ec;
     g->t.var_ptr = g->blob_dev + o_vp;

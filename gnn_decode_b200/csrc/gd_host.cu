@@ -84,6 +84,8 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
     if (e == cudaSuccess) {
         // chunks: multiples of 8 syndromes (output alignment); >= 4096 syndromes each, at most 4
         int n_chunks = (int)std::min<int64_t>(4, std::max<int64_t>(1, B / 8192));
+        gd_launch_info li;
+        if (gd_decode_launch_info(g, model, B, &li) == GD_OK && !li.resident) n_chunks = 1;  // one shared slab
         int64_t per = ((B + n_chunks - 1) / n_chunks + 7) / 8 * 8;
         for (int k = 0; k < n_chunks && e == cudaSuccess && rc == GD_OK; ++k) {
             const int64_t b0 = (int64_t)k * per;

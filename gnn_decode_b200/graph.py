@@ -4,7 +4,7 @@ Replaces what the reference rebuilds for every batch: `H.to_sparse()._indices()`
 CustomDataset.__init__ (quantum/decoder_v2_4.py:164-165), the PyG DataLoader collate that
 replicates edge_index block-diagonally (:205-206) and the `+rows` offset (:277).
 """
-import ctypes as C
+import ctypes as ct
 import weakref
 
 import numpy as np
@@ -35,14 +35,14 @@ class TannerGraph(object):
         self.N = self.V + self.C
         self.device = torch.device("cuda", _dev_index(device))
         self.edge_index = ei
-        handle = C.c_void_p()
+        handle = ct.c_void_p()
         lib = _cabi.lib()
-        _cabi.check(lib.gd_graph_create(C.c_void_p(ei.data_ptr()), self.E, self.V, self.C, self.device.index,
-                                        C.byref(handle)), "gd_graph_create")
+        _cabi.check(lib.gd_graph_create(ct.c_void_p(ei.data_ptr()), self.E, self.V, self.C, self.device.index,
+                                        ct.byref(handle)), "gd_graph_create")
         self._h = handle
         self._finalizer = weakref.finalize(self, lib.gd_graph_destroy, handle)
-        mv, mc = C.c_int32(), C.c_int32()
-        _cabi.check(lib.gd_graph_dims(self._h, None, None, None, C.byref(mv), C.byref(mc)))
+        mv, mc = ct.c_int32(), ct.c_int32()
+        _cabi.check(lib.gd_graph_dims(self._h, None, None, None, ct.byref(mv), ct.byref(mc)))
         self.max_var_deg, self.max_chk_deg = mv.value, mc.value
         self._logical_dev = {}
 
@@ -73,7 +73,7 @@ class TannerGraph(object):
         out = {k: np.empty(n, np.int32) for k, n in
                (("var_ptr", self.V + 1), ("var_edges", self.E), ("chk_ptr", self.C + 1),
                 ("chk_edges", self.E), ("edge_var", self.E), ("edge_chk", self.E))}
-        ptr = lambda a: C.c_void_p(a.ctypes.data)
+        ptr = lambda a: ct.c_void_p(a.ctypes.data)
         _cabi.check(lib.gd_graph_tables(self._h, ptr(out["var_ptr"]), ptr(out["var_edges"]), ptr(out["chk_ptr"]),
                                         ptr(out["chk_edges"]), ptr(out["edge_var"]), ptr(out["edge_chk"])))
         return out
@@ -86,15 +86,15 @@ class TannerGraph(object):
             ei = ei.to(self.device, torch.int64).contiguous()
         if ei.dim() != 2 or ei.size(0) != 2 or ei.size(1) != B * self.E:
             raise ValueError("batched edge_index must be [2, %d], got %s" % (B * self.E, tuple(ei.shape)))
-        bad = C.c_int64(-1)
+        bad = ct.c_int64(-1)
         st = torch.cuda.current_stream(self.device).cuda_stream
-        _cabi.check(_cabi.lib().gd_graph_check_batched(self._h, C.c_void_p(ei.data_ptr()), B, int(chk_offset),
-                                                       C.c_void_p(st), C.byref(bad)))
+        _cabi.check(_cabi.lib().gd_graph_check_batched(self._h, ct.c_void_p(ei.data_ptr()), B, int(chk_offset),
+                                                       ct.c_void_p(st), ct.byref(bad)))
         return bad.value
 
     def launch_info(self, model, B):
         info = _cabi.GdLaunchInfo()
-        _cabi.check(_cabi.lib().gd_decode_launch_info(self._h, C.byref(model), int(B), C.byref(info)))
+        _cabi.check(_cabi.lib().gd_decode_launch_info(self._h, ct.byref(model), int(B), ct.byref(info)))
         return {k: getattr(info, k) for k, _ in info._fields_}
 
 

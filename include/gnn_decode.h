@@ -123,7 +123,10 @@ int gd_propagate_fwd(const gd_graph* g, const gd_model* model, int32_t phase, in
  * One persistent kernel keeps a tile of syndromes' edge state on chip for all `iters`
  * iterations.  Outputs (any may be NULL): prob_dev [B,V] fp32 = sigmoid(-logit) (clamped to
  * [1e-7,1-1e-7] for the classical programs as the reference does), logit_dev [B,V] fp32,
- * hard_dev [B,V] uint8 = (prob > 0.5) (neural_BP.py:338 semantics). */
+ * hard_dev [B,V] uint8 = (prob > 0.5) (neural_BP.py:338 semantics).
+ * Codes whose edge state does not fit shared memory run the streamed global-memory kernel, whose
+ * per-graph state slab is allocated lazily and is NOT re-entrant: serialise streamed decodes of
+ * one gd_graph across streams (gd_decode_launch_info().resident == 0 tells which path is taken). */
 int gd_decode_fwd(const gd_graph* g, const gd_model* model, const float* weights_dev,
                   const float* x_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev,
                   int64_t B, void* stream);

@@ -53,8 +53,9 @@ if __name__ == "__main__":
              ("cgnni bch", CGNNI.GNNI(25), codes.bch_63_45_pcm(), 65536),
              ("cgnni ldpc", CGNNI.GNNI(25), codes.ldpc_toy_pcm(), 1 << 20),
              ("bp_q toric-L5", BP.GNNI(10), codes.toric_pcm(5), 65536),
-             ("bp_q hgp1600", BP.GNNI(20), codes.hgp_pcm(), 4096),
-             ("v2_4 hgp1600", decoder_v2_4.GNNI(3), codes.hgp_pcm(), 2048)]
+             ("bp_q hgp1600", BP.GNNI(20), codes.hgp_pcm(), 16384),
+             ("qgnni hgp1600", QGNNI.GNNI(20), codes.hgp_pcm(), 16384),
+             ("v2_4 hgp1600", decoder_v2_4.GNNI(3), codes.hgp_pcm(), 8192)]
     only = sys.argv[1:] 
     for name, dec, pcm, B in cases:
         if only and not any(o in name for o in only):

@@ -199,3 +199,57 @@ def test_fp32_and_fp64_inputs_agree():
     p32 = dec(_Data(g, dev, torch.float32))
     assert p64.dtype == torch.float64 and p32.dtype == torch.float32
     assert torch.equal(p64.float(), p32)
+
+
+@pytest.mark.parametrize("name", ["v2_4_toricL4_epoch1", "qgnni_toricL4_seeded", "cgnni_bch_seeded", "bp_quantum_toricL4"])
+def test_streamed_kernel_matches_resident_and_reference(name, monkeypatch):
+    """The global-memory (streamed) kernel used for codes too large for shared memory, forced on
+    a small code: same logits as the oracle (same bar) and hard decisions identical to the
+    resident kernel."""
+    g = Golden(name)
+    dev = _dev()
+    mod, dec = make_decoder(g)
+    dec = dec.to(dev).eval()
+    from gnn_decode_b200.graph import TannerGraph
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    x = g.x.repeat(5, 1).to(dev)                                   # 80..160 syndromes: ragged tiles
+    p_res, l_res, h_res = dec.decode(x, graph=tg, return_logits=True, return_hard=True)
+    monkeypatch.setenv("GD_FORCE_STREAMED", "1")
+    assert tg.launch_info(dec.gd_model(), x.size(0))["resident"] == 0
+    p_str, l_str, h_str = dec.decode(x, graph=tg, return_logits=True, return_hard=True)
+    p_str2 = dec.decode(x, graph=tg)
+    monkeypatch.delenv("GD_FORCE_STREAMED")
+    assert torch.equal(p_str, p_str2)                               # deterministic
+    ref = restate.decode(g.program, g.edge_index, g.V, g.C, g.x, g.weights, T=g.T, dtype=torch.float64)
+    bp = g.program.startswith("bp")
+    worst, max_err = _logit_close(l_str[:g.B], ref["logit"], RTOL_BP if bp else RTOL)
+    assert worst <= 1.0, "streamed logit mismatch: %.3g x bound (max abs %.3g)" % (worst, max_err)
+    decided = (ref["logit"].abs() > LOGIT_TIE).repeat(5, 1)
+    assert torch.equal(h_str.cpu()[decided], h_res.cpu()[decided])
+
+
+def test_hgp_1600_streamed_matches_oracle():
+    """BASELINE config 5 shape: hypergraph-product [[1600,64]] (E = 10752) takes the streamed path."""
+    from gnn_decode_b200 import codes
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.quantum import QGNNI, BP
+    from gnn_decode_b200.sampler import sample_syndromes
+    dev = _dev()
+    pcm = codes.hgp_pcm()
+    tg = TannerGraph.from_pcm(pcm, dev)
+    ei = torch.from_numpy(codes.edge_index_of(pcm))
+    x, _ = sample_syndromes(tg, 40, [0.02, 0.05], noise=1, seed=9)
+    torch.manual_seed(0)
+    dec = QGNNI.GNNI(6).to(dev).eval()
+    assert tg.launch_info(dec.gd_model(), 40)["resident"] == 0
+    prob, logit = dec.decode(x, graph=tg, return_logits=True)
+    ref = restate.decode("qgnni", ei, tg.V, tg.C, x.cpu().double(), {k: v.cpu() for k, v in dec.state_dict().items()}, T=6)
+    worst, max_err = _logit_close(logit, ref["logit"], RTOL)
+    assert worst <= 1.0, "HGP qgnni: %.3g x bound (max abs %.3g)" % (worst, max_err)
+    bpd = BP.GNNI(8).to(dev).eval()
+    prob, logit, hard = bpd.decode(x, graph=tg, return_logits=True, return_hard=True)
+    ref = restate.decode("bp_quantum", ei, tg.V, tg.C, x.cpu().double(), {}, T=8)
+    worst, max_err = _logit_close(logit, ref["logit"], RTOL_BP)
+    assert worst <= 1.0, "HGP bp: %.3g x bound (max abs %.3g)" % (worst, max_err)
+    decided = ref["logit"].abs() > LOGIT_TIE
+    assert torch.equal(hard.cpu().bool()[decided], (ref["prob"] > 0.5)[decided])

@@ -1,0 +1,81 @@
+"""GPU suite: Philox sampler (bit-exact vs the NumPy oracle, distribution vs the reference's
+gen_syn) and the failure counters (exact vs the oracle restatement of neural_BP.py:338-348)."""
+import numpy as np
+import pytest
+import torch
+
+from gnn_decode_b200 import codes
+from gnn_decode_b200.evaluate import count_failures
+from gnn_decode_b200.graph import TannerGraph
+from gnn_decode_b200.sampler import sample_syndromes
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("code,noise", [(("toric", 4), 0), (("toric", 5), 0), (("rot", 5), 1), (("rot", 3), 0),
+                                        (("hgp", 0), 1)])
+def test_sampler_bit_exact_vs_oracle(code, noise):
+    pcm = {"toric": codes.toric_pcm, "rot": codes.rotated_surface_pcm}.get(code[0], lambda _: codes.hgp_pcm(6, 8))(code[1])
+    g = TannerGraph.from_pcm(pcm, DEV)
+    P = [0.01, 0.05, 0.1, 0.2]
+    B = 777
+    x, err = sample_syndromes(g, B, P, noise=noise, seed=0x1234567890ABCDEF, first_sample=(1 << 33) + 5)
+    xo, eo = philox.sample(pcm, B, P, noise=noise, seed=0x1234567890ABCDEF, first_sample=(1 << 33) + 5)
+    assert np.array_equal(err.cpu().numpy(), eo)
+    assert np.array_equal(x.cpu().numpy()[:, g.V:], xo[:, g.V:])                 # syndromes bit-exact
+    assert np.allclose(x.cpu().numpy()[:, :g.V], xo[:, :g.V], rtol=1e-6)          # prior: log in double, cast
+    # shards are slices of the full draw
+    x2, e2 = sample_syndromes(g, 100, P, noise=noise, seed=0x1234567890ABCDEF, first_sample=(1 << 33) + 5 + 300)
+    assert torch.equal(e2, err[300:400]) and torch.equal(x2, x[300:400])
+
+
+def test_sampler_distribution_matches_gen_syn_layout(codes_npz):
+    """Layout of the reference's gen_syn output (fixture produced by the reference, seeded) and its
+    flip statistics: every slot flips independently w.p. p, prior = log((1-p)/p), syndrome signs."""
+    L = 4
+    pcm = codes.toric_pcm(L)
+    g = TannerGraph.from_pcm(pcm, DEV)
+    xr, yr = codes_npz["gen_syn_L4_x"], codes_npz["gen_syn_L4_y"]
+    assert xr.shape[1] == g.N and yr.shape[1] == g.V
+    syn = (yr.astype(np.int64) @ pcm.T.astype(np.int64)) % 2                         # reference layout check
+    assert np.array_equal(xr[:, g.V:], 1.0 - 2.0 * syn)
+    B, p = 200000, 0.07
+    x, err = sample_syndromes(g, B, [p], noise=0, seed=7)
+    e = err.float()
+    rate = e.mean().item()
+    assert abs(rate - p) < 5 * np.sqrt(p * (1 - p) / (B * g.V))
+    per_slot = e.mean(0)
+    assert (per_slot - p).abs().max().item() < 6 * np.sqrt(p * (1 - p) / B)
+    c = torch.corrcoef(e[:, :16].t())                                                # independence of slots
+    assert (c - torch.eye(16, device=c.device)).abs().max().item() < 0.02
+    assert np.allclose(x[:, :g.V].cpu().numpy(), np.log((1 - p) / p), rtol=1e-6)
+    # depolarizing marginals: X, Y, Z each p/3
+    gd5 = TannerGraph.from_pcm(codes.rotated_surface_pcm(5), DEV)
+    _, err = sample_syndromes(gd5, B, [0.09], noise=1, seed=11)
+    n = gd5.V // 2
+    ex, ez = err[:, :n].bool(), err[:, n:].bool()
+    for mask in (ex & ~ez, ex & ez, ~ex & ez):
+        assert abs(mask.float().mean().item() - 0.03) < 5 * np.sqrt(0.03 * 0.97 / (B * n))
+
+
+def test_failure_counters_exact():
+    L = 4
+    pcm = codes.toric_pcm(L)
+    n, k = 2 * L * L, L * L - 1
+    logical = codes.css_logicals(pcm[:k, :n], pcm[k:, n:])
+    g = TannerGraph.from_pcm(pcm, DEV)
+    B = 5000
+    _, err = sample_syndromes(g, B, [0.03], seed=3)
+    rng = np.random.RandomState(0)
+    ker = codes.gf2_nullspace(pcm)
+    hard = err.cpu().numpy().copy()
+    # a third: perfect; a third: differ by a random syndrome-free residual; a third: random bits
+    hard[B // 3:2 * B // 3] ^= ((rng.randint(0, 2, (2 * B // 3 - B // 3, ker.shape[0])) @ ker) % 2).astype(np.uint8)
+    hard[2 * B // 3:] = rng.randint(0, 2, hard[2 * B // 3:].shape)
+    want = philox.count_failures(pcm, logical, err.cpu().numpy(), hard)
+    got = count_failures(g, err, torch.from_numpy(hard).to(DEV), logical)
+    assert tuple(got.tolist()) == want and want[1] > 0 and want[0] > 0
+    got2 = count_failures(g, err, err.clone(), logical)
+    assert got2.tolist() == [0, 0, 0]
