@@ -96,7 +96,7 @@ __device__ __forceinline__ void stage_mlp(float* dst, int hp, int hid, const flo
 
 // kEB = edges evaluated together per thread (register blocking of the MLP: weights are loaded
 // once per 4 hidden units and reused for kEB edges).
-template <int PROG, int MAXT, int kEB>
+template <int PROG, int MAXT, int kEB, int NPOLY>
 __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool kIsBP = (PROG == GD_PROG_BP_QUANTUM || PROG == GD_PROG_BP_CLASSICAL);
@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         x0[j] = node[v * tile + s] - m_st[(size_t)ec * tile + s];
                         x1[j] = xrow[v];
                     }
-                    mlp_softplus<kEB, true>(W1, hp, x0, x1, o);
+                    if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, true, (NPOLY > 0 ? NPOLY : 0)>(W1, hp, x0, x1, o);
+                    else mlp_softplus<kEB, true>(W1, hp, x0, x1, o);
 #pragma unroll
                     for (int j = 0; j < kEB; ++j)
                         if (ee[j] < E) t_st[(size_t)ee[j] * tile + s] = tanh_half(o[j]);
@@ -268,7 +269,8 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         x0[j] = node[c * tile + s] - t_st[(size_t)ec * tile + s];
                         sg[j] = PROG == GD_PROG_CGNNI ? 1.f : xrow[V + c];
                     }
-                    if constexpr (kSoftplus) mlp_softplus<kEB, false>(W2, hp, x0, x0, o);
+                    if constexpr (kSoftplus && NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W2, hp, x0, x0, o);
+                    else if constexpr (kSoftplus) mlp_softplus<kEB, false>(W2, hp, x0, x0, o);
                     else mlp_relu<kEB>(W2, hp, x0, o);
 #pragma unroll
                     for (int j = 0; j < kEB; ++j)
@@ -292,7 +294,8 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                     ee[j] = e;
                     x0[j] = m_st[(size_t)(e < E ? e : E - 1) * tile + s];
                 }
-                mlp_softplus<kEB, false>(W3, hp, x0, x0, o);
+                if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W3, hp, x0, x0, o);
+                else mlp_softplus<kEB, false>(W3, hp, x0, x0, o);
 #pragma unroll
                 for (int j = 0; j < kEB; ++j)
                     if (ee[j] < E) t_st[(size_t)ee[j] * tile + s] = o[j];
@@ -360,7 +363,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     const int64_t E64 = g->E;
     const bool bp = m->program == GD_PROG_BP_QUANTUM || m->program == GD_PROG_BP_CLASSICAL;
     const int hid = bp ? 0 : m->hidden;
-    const int hp = align_up(hid, 4);
+    const int hp = align_up(hid, 8);
     const int n_slots = bp ? 0 : (m->program == GD_PROG_V2_4 ? 3 : 2);
     const int maxvc = V > C ? V : C;
     DecodeParams& p = out->p;
@@ -453,8 +456,20 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
 template <int PROG>
 static int launch_decode(const DecodePlan& pl, cudaStream_t st) {
     void (*k)(const DecodeParams);
-    if (pl.threads > 512) k = pl.eb == 2 ? decode_kernel<PROG, 1024, 2> : decode_kernel<PROG, 1024, 4>;
-    else k = pl.eb == 2 ? decode_kernel<PROG, 512, 2> : decode_kernel<PROG, 512, 4>;
+    if constexpr (PROG == GD_PROG_V2_4) {
+        // NPOLY: how many of every 4 hidden-unit pairs take the FMA-pipe polynomial lg2 (-1 = scalar MUFU loop).
+        // Measured on B200 (profiles/r01_npoly_sweep.txt): 2 is best (8.70 vs 6.84 M syndromes/s for -1).
+        const char* en = getenv("GD_NPOLY");
+        const int np = en ? atoi(en) : 2;
+#define GD_PICK(MT, EBV)                                                                               \
+        (np < 0 ? decode_kernel<PROG, MT, EBV, -1> : np == 3 ? decode_kernel<PROG, MT, EBV, 3> : decode_kernel<PROG, MT, EBV, 2>)
+        if (pl.threads > 512) k = pl.eb == 2 ? GD_PICK(1024, 2) : GD_PICK(1024, 4);
+        else k = pl.eb == 2 ? GD_PICK(512, 2) : GD_PICK(512, 4);
+#undef GD_PICK
+    } else {
+        if (pl.threads > 512) k = pl.eb == 2 ? decode_kernel<PROG, 1024, 2, -1> : decode_kernel<PROG, 1024, 4, -1>;
+        else k = pl.eb == 2 ? decode_kernel<PROG, 512, 2, -1> : decode_kernel<PROG, 512, 4, -1>;
+    }
     GD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     k<<<pl.grid, pl.threads, pl.smem, st>>>(pl.p);
     GD_CUDA(cudaGetLastError());
