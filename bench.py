@@ -328,8 +328,8 @@ def main():
                 "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:
             rng = np.random.RandomState(1234)
-            n_s = 2048
-            rate, n_done, secs = cpu_reference_rate(program, pcm, T, weights, x[:n_s].cpu().double(), 128, 20.0, cores)
+            n_s = min(B, 32768)      # bounded sample: stop after ~15 s of CPU work (sustained, not a burst)
+            rate, n_done, secs = cpu_reference_rate(program, pcm, T, weights, x[:n_s].cpu().double(), 128, 15.0, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "syndromes/s", "cores": cores, "kind": "port",
                                     "sample": "%d syndromes of this workload in chunks of 128 (the reference's BATCH_SIZE), "
                                               "fp64, %.1f s, oracle/restate.py on %d torch threads" % (n_done, secs, cores)}

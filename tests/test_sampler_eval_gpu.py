@@ -79,3 +79,32 @@ def test_failure_counters_exact():
     assert tuple(got.tolist()) == want and want[1] > 0 and want[0] > 0
     got2 = count_failures(g, err, err.clone(), logical)
     assert got2.tolist() == [0, 0, 0]
+
+
+def test_logical_error_rate_matches_reference_statistics(codes_npz):
+    """End-to-end sampler -> fused decoder -> failure counters, against (a) the oracle decoder on the
+    SAME samples (failure counts must be equal: hard decisions are bit-exact) and (b) the loose
+    known answer of the shimmed reference quantum/BP.py (L=4, Nc=10, p=0.01): 99/4096 = 2.4 %
+    failures -- statistically indistinguishable within a binomial CI."""
+    from gnn_decode_b200.quantum import BP
+    from oracle import restate
+    L = 4
+    pcm = codes.toric_pcm(L)
+    logical = codes_npz["toric_logical_L4"]                      # the reference's own `logical`
+    g = TannerGraph.from_pcm(pcm, DEV)
+    dec = BP.GNNI(10).to(DEV).eval().bind_graph(g)
+    B = 40960
+    x, err = sample_syndromes(g, B, [0.01], noise=0, seed=2024)
+    prob, hard = dec.decode(x, return_hard=True)
+    got = count_failures(g, err, hard, logical).tolist()
+    rate = got[2] / B
+    p_ref = 99 / 4096
+    sigma = np.sqrt(p_ref * (1 - p_ref) * (1 / B + 1 / 4096))
+    assert abs(rate - p_ref) < 4 * sigma, (rate, p_ref)
+    # same samples through the fp64 oracle decoder
+    n = 4096
+    ei = torch.from_numpy(codes.edge_index_of(pcm))
+    ref = restate.decode("bp_quantum", ei, g.V, g.C, x[:n].cpu().double(), {}, T=10)
+    want = philox.count_failures(pcm, logical, err[:n].cpu().numpy(), (ref["prob"] > 0.5).numpy().astype(np.uint8))
+    got_n = count_failures(g, err[:n], hard[:n], logical).tolist()
+    assert abs(got_n[2] - want[2]) <= 1, (got_n, want)            # a tie-break flip at most
