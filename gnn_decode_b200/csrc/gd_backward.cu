@@ -1,0 +1,378 @@
+// Backward of the fused decoder_v2_4 decoder (training, BASELINE config 4): gradient of a loss
+// w.r.t. the 10h+3 MLP weights, given dL/dlogit [B, V].  Replaces autograd through the reference's
+// T x 2 x ~12 eager ops (quantum/decoder_v2_4.py:280-292, loss.backward() at :335).
+//
+// Structure per tile of syndromes (edge arrays [E][tile] fp32 in shared memory), iterations in
+// reverse, activations (m_it, a_it) re-read from the stash the training forward wrote:
+//   * "sum over siblings minus self" is self-adjoint, so the gather-of-gradients is the same
+//     deterministic segmented sum as the forward reduce;
+//   * the per-edge MLP backward is the expensive part and is mapped DIFFERENTLY from the forward:
+//     a warp takes one (syndrome, edge) item at a time and its LANES ARE HIDDEN UNITS (4 per
+//     lane for h = 128).  Each lane keeps its units' weights and its weight-gradient accumulators
+//     in registers for the whole kernel -- no atomics and no per-item cross-lane reduction for the
+//     weight gradients; only the scalar input gradient dx needs one 5-step shuffle sum per item;
+//   * weight gradients leave the kernel as per-warp partial vectors and are summed by a second
+//     kernel in a fixed order in double precision: bit-reproducible ("deterministic two-stage
+//     wgrad reduction"), ready for one NCCL all-reduce of 10h+3 floats.
+#include "gd_common.cuh"
+#include "gd_math.cuh"
+#include <string.h>
+
+namespace gd {
+
+constexpr int kBwdThreads = 512;
+constexpr int kUPL = 4;          // hidden units per lane (h <= 128)
+constexpr int kItems = 4;        // items processed together per warp (ILP across the MUFU / shuffle chains)
+
+struct BwdParams {
+    const float* x;           // [B, N]
+    const float* stash;       // [(T+1)][2][E][B]
+    const float* grad_logit;  // [B, V]
+    const float* weights;     // packed raw weights
+    float* partials;          // [grid * warps][np_pad]
+    GraphTables tb;
+    long long B;
+    int T, V, C, E, N, hid;
+    int tile, R, n_tiles, maxvc, np_pad;
+    int off_tab, off_x, off_node, off_dm, off_a, off_xin, off_g, off_dx;
+};
+
+struct LaneMlp {           // this lane's kUPL hidden units of one MLP (pre-scaled to base 2 like the forward)
+    float w1a[kUPL], w1b[kUPL], b1[kUPL], w2[kUPL];
+};
+struct LaneAcc {
+    float w1a[kUPL], w1b[kUPL], b1[kUPL], w2[kUPL];
+    float b2;
+};
+
+__device__ __forceinline__ void load_lane_mlp(LaneMlp& L, const float* w, int h, bool two_in, int lane) {
+#pragma unroll
+    for (int u = 0; u < kUPL; ++u) {
+        const int k = lane * kUPL + u;
+        const bool in = k < h;
+        L.w1a[u] = in ? w[two_in ? 2 * k : k] * kLog2e : 0.f;
+        L.w1b[u] = (in && two_in) ? w[2 * k + 1] * kLog2e : 0.f;
+        L.b1[u] = in ? w[(two_in ? 2 : 1) * h + k] * kLog2e : 0.f;
+        L.w2[u] = in ? w[(two_in ? 3 : 2) * h + k] : 0.f;          // natural units
+    }
+}
+__device__ __forceinline__ void zero_acc(LaneAcc& A) {
+#pragma unroll
+    for (int u = 0; u < kUPL; ++u) A.w1a[u] = A.w1b[u] = A.b1[u] = A.w2[u] = 0.f;
+    A.b2 = 0.f;
+}
+
+// One MLP backward over all items of the tile.  xin/g/dx are [E][tile] shared arrays (item index
+// i = e*tile + s is linear).  For the two-input MLP the second input is prior[var(e)] from the x slab.
+template <bool TWO_IN>
+__device__ __forceinline__ void mlp_backward_items(const LaneMlp& L, LaneAcc& A, const float* xin, const float* g,
+                                                   float* dx, int n_items, int tile, const uint16_t* edge_var,
+                                                   const float* xs, int N, int warp, int n_warps, int lane) {
+    for (int i0 = warp * kItems; i0 < n_items; i0 += n_warps * kItems) {
+        float x0[kItems], x1[kItems], gg[kItems], dxl[kItems];
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            const int i = i0 + j < n_items ? i0 + j : n_items - 1;
+            x0[j] = xin[i];
+            gg[j] = i0 + j < n_items ? g[i] : 0.f;
+            x1[j] = 0.f;
+            if (TWO_IN) {
+                const int e = i / tile, s = i - e * tile;
+                x1[j] = xs[s * N + edge_var[e]];
+            }
+            dxl[j] = 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kUPL; ++u) {
+#pragma unroll
+            for (int j = 0; j < kItems; ++j) {
+                float h = fmaf(L.w1a[u], x0[j], L.b1[u]);
+                if (TWO_IN) h = fmaf(L.w1b[u], x1[j], h);
+                const float t = ex2_approx(-fabsf(h));
+                const float one_t = 1.0f + t;
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(one_t));
+                const float sp2 = fmaxf(h, 0.f) + lg2_approx(one_t);       // softplus / ln2
+                const float sig = h >= 0.f ? r : t * r;                    // sigmoid(h)
+                const float dh = gg[j] * L.w2[u] * sig;                    // dL/d(pre-activation), natural units
+                A.w2[u] = fmaf(gg[j], sp2, A.w2[u]);                       // x ln2 when written out
+                A.w1a[u] = fmaf(dh, x0[j], A.w1a[u]);
+                if (TWO_IN) A.w1b[u] = fmaf(dh, x1[j], A.w1b[u]);
+                A.b1[u] += dh;
+                dxl[j] = fmaf(dh, L.w1a[u], dxl[j]);                       // / log2e when written out
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            A.b2 += gg[j];
+            float v = dxl[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && i0 + j < n_items) dx[i0 + j] = v * kLn2;      // 1/log2e == ln2
+        }
+    }
+}
+
+__device__ __forceinline__ void store_acc(float* dst, const LaneAcc& A, int h, bool two_in, int lane) {
+    // packed order of one MLP: W1 [h, k_in] row-major | b1 [h] | W2 [h] | b2
+#pragma unroll
+    for (int u = 0; u < kUPL; ++u) {
+        const int k = lane * kUPL + u;
+        if (k < h) {
+            if (two_in) { dst[2 * k] = A.w1a[u]; dst[2 * k + 1] = A.w1b[u]; }
+            else dst[k] = A.w1a[u];
+            dst[(two_in ? 2 : 1) * h + k] = A.b1[u];
+            dst[(two_in ? 3 : 2) * h + k] = A.w2[u] * kLn2;
+        }
+    }
+    if (lane == 0) dst[(two_in ? 4 : 3) * h] = A.b2;
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tile = p.tile, R = p.R, E = p.E, V = p.V, C = p.C, N = p.N, h = p.hid, T = p.T;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
+    const int s = tid % tile, r = tid / tile;
+    const bool ew = r < R;                      // threads beyond R*tile only take part in the MLP phases
+    float* xs = reinterpret_cast<float*>(smem + p.off_x);
+    float* node = reinterpret_cast<float*>(smem + p.off_node);
+    float* DM = reinterpret_cast<float*>(smem + p.off_dm);
+    float* A_ = reinterpret_cast<float*>(smem + p.off_a);
+    float* XI = reinterpret_cast<float*>(smem + p.off_xin);
+    float* G_ = reinterpret_cast<float*>(smem + p.off_g);
+    float* DX = reinterpret_cast<float*>(smem + p.off_dx);
+    uint16_t* tab = reinterpret_cast<uint16_t*>(smem + p.off_tab);
+    uint16_t* edge_var = tab;
+    uint16_t* edge_chk = edge_var + E;
+    uint16_t* var_ptr = edge_chk + E;
+    uint16_t* var_edges = var_ptr + (V + 1);
+    uint16_t* chk_ptr = var_edges + E;
+    uint16_t* chk_edges = chk_ptr + (C + 1);
+    for (int i = tid; i < E; i += nthr) {
+        edge_var[i] = (uint16_t)p.tb.edge_var[i];
+        edge_chk[i] = (uint16_t)p.tb.edge_chk[i];
+        var_edges[i] = (uint16_t)p.tb.var_edges[i];
+        chk_edges[i] = (uint16_t)p.tb.chk_edges[i];
+    }
+    for (int i = tid; i <= V; i += nthr) var_ptr[i] = (uint16_t)p.tb.var_ptr[i];
+    for (int i = tid; i <= C; i += nthr) chk_ptr[i] = (uint16_t)p.tb.chk_ptr[i];
+
+    LaneAcc acc1, acc2, acc3;
+    zero_acc(acc1); zero_acc(acc2); zero_acc(acc3);
+    const float* w1p = p.weights;
+    const float* w2p = w1p + 4 * h + 1;
+    const float* w3p = w2p + 3 * h + 1;
+    const int n_items = E * tile;
+    const size_t EB_ = (size_t)E * p.B;
+    __syncthreads();
+
+    auto seg_sum = [&](const uint16_t* ptr, const uint16_t* ids, int n_nodes, const float* src) {
+        if (ew)
+            for (int n = r; n < n_nodes; n += R) {
+                float a = 0.f;
+                for (int i = ptr[n]; i < ptr[n + 1]; ++i) a += src[ids[i] * tile + s];
+                node[n * tile + s] = a;
+            }
+    };
+
+    for (int tix = blockIdx.x; tix < p.n_tiles; tix += gridDim.x) {
+        const long long s0 = (long long)tix * tile;
+        const int nvalid = (int)min((long long)tile, p.B - s0);
+        const bool valid = s < nvalid;
+        for (int i = tid; i < tile * N; i += nthr) xs[i] = i < nvalid * N ? __ldg(p.x + s0 * N + i) : 0.f;
+        // ---- read-out backward: logit[v] = sum_{e in v} mlp3(m_T[e]) + prior[v] ----
+        if (ew)
+            for (int e = r; e < E; e += R) {
+                const int at = e * tile + s;
+                XI[at] = valid ? __ldg(p.stash + (size_t)T * 2 * EB_ + (size_t)e * p.B + s0 + s) : 0.f;
+                G_[at] = valid ? __ldg(p.grad_logit + (s0 + s) * V + edge_var[e]) : 0.f;
+            }
+        __syncthreads();
+        {
+            LaneMlp L;
+            load_lane_mlp(L, w3p, h, false, lane);
+            mlp_backward_items<false>(L, acc3, XI, G_, DM, n_items, tile, edge_var, xs, N, warp, n_warps, lane);
+        }
+        __syncthreads();
+        for (int it = T - 1; it >= 0; --it) {
+            const float* st_m = p.stash + (size_t)it * 2 * EB_;
+            const float* st_a = st_m + EB_;
+            // t = tanh(a_it / 2)
+            if (ew)
+                for (int e = r; e < E; e += R) {
+                    const int at = e * tile + s;
+                    A_[at] = valid ? tanh_half(__ldg(st_a + (size_t)e * p.B + s0 + s)) : 0.f;
+                }
+            __syncthreads();
+            seg_sum(chk_ptr, chk_edges, C, A_);
+            __syncthreads();
+            // m_{it+1} = mlp2(ext_c) * sign + m_it :  dg = dm' * sign, ext_c = Sc[chk] - t
+            if (ew)
+                for (int e = r; e < E; e += R) {
+                    const int at = e * tile + s, c = edge_chk[e];
+                    XI[at] = node[c * tile + s] - A_[at];
+                    G_[at] = DM[at] * xs[s * N + V + c];
+                }
+            __syncthreads();
+            {
+                LaneMlp L;
+                load_lane_mlp(L, w2p, h, false, lane);
+                mlp_backward_items<false>(L, acc2, XI, G_, DX, n_items, tile, edge_var, xs, N, warp, n_warps, lane);
+            }
+            __syncthreads();
+            seg_sum(chk_ptr, chk_edges, C, DX);                   // gather of gradients over the check
+            __syncthreads();
+            // dt = S[chk] - dext_c ; da = dt (1 - t^2) / 2 ; then reuse A_ for m_it
+            if (ew)
+                for (int e = r; e < E; e += R) {
+                    const int at = e * tile + s;
+                    const float t = A_[at];
+                    const float dt = node[edge_chk[e] * tile + s] - DX[at];
+                    G_[at] = dt * (1.0f - t * t) * 0.5f;
+                    A_[at] = valid ? __ldg(st_m + (size_t)e * p.B + s0 + s) : 0.f;
+                }
+            __syncthreads();
+            seg_sum(var_ptr, var_edges, V, A_);
+            __syncthreads();
+            if (ew)
+                for (int e = r; e < E; e += R) {
+                    const int at = e * tile + s;
+                    XI[at] = node[edge_var[e] * tile + s] - A_[at];   // ext_v
+                }
+            __syncthreads();
+            {
+                LaneMlp L;
+                load_lane_mlp(L, w1p, h, true, lane);
+                mlp_backward_items<true>(L, acc1, XI, G_, DX, n_items, tile, edge_var, xs, N, warp, n_warps, lane);
+            }
+            __syncthreads();
+            seg_sum(var_ptr, var_edges, V, DX);                   // gather of gradients over the variable
+            __syncthreads();
+            if (ew)
+                for (int e = r; e < E; e += R) {
+                    const int at = e * tile + s;
+                    DM[at] += node[edge_var[e] * tile + s] - DX[at];
+                }
+            __syncthreads();
+        }
+    }
+    // ---- per-warp partial weight gradients, packed order ----
+    float* dst = p.partials + ((size_t)blockIdx.x * n_warps + warp) * p.np_pad;
+    store_acc(dst, acc1, h, true, lane);
+    store_acc(dst + 4 * h + 1, acc2, h, false, lane);
+    store_acc(dst + 7 * h + 2, acc3, h, false, lane);
+}
+
+// stage 2: fixed-order sum over the per-warp partials (double accumulation) -> grad[n_params]
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_rows, int np_pad, int n_params,
+                                       float* __restrict__ grad, int accumulate) {
+    const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pidx >= n_params) return;
+    double a = 0.0;
+    for (int rw = 0; rw < n_rows; ++rw) a += (double)partials[(size_t)rw * np_pad + pidx];
+    grad[pidx] = accumulate ? grad[pidx] + (float)a : (float)a;
+}
+
+static int align_up_b(int x, int a) { return (x + a - 1) / a * a; }
+
+struct BwdPlan {
+    BwdParams p;
+    int threads, grid, smem, n_rows;
+};
+
+static int plan_bwd(const gd_graph* g, const gd_model* m, int64_t B, BwdPlan* out) {
+    BwdParams& p = out->p;
+    memset(&p, 0, sizeof(p));
+    const int V = g->V, C = g->C, N = g->N, E = (int)g->E;
+    const int maxvc = V > C ? V : C;
+    p.B = B; p.T = m->iters; p.V = V; p.C = C; p.E = E; p.N = N; p.hid = m->hidden; p.maxvc = maxvc;
+    p.tb = g->t;
+    p.np_pad = align_up_b((int)gd_weights_size(m), 32);
+    const int tab_bytes = (4 * E + V + C + 2) * 2;
+    const int fixed = align_up_b(tab_bytes, 128);
+    const int64_t per_syn = ((int64_t)N + maxvc + 5LL * E) * 4;
+    const int64_t tmax = (g->max_smem_optin - fixed) / per_syn;
+    if (g->E >= 65536 || tmax < 8) {
+        set_error("gd_decode_bwd: code too large for the shared-memory backward kernel (E=%lld)", (long long)g->E);
+        return GD_ERR_UNSUPPORTED;
+    }
+    // tile: multiple of 8 dividing the work evenly over the SMs (same criterion as the forward)
+    int tile = 8;
+    double best = -1.0;
+    for (int t = 8; t <= tmax && t <= 128; t += 8) {
+        const int64_t n_t = (B + t - 1) / t;
+        const int64_t rounds = (n_t + g->sm_count - 1) / g->sm_count;
+        const double eff = (double)B / ((double)rounds * g->sm_count * t);
+        if (eff > best + 1e-9) { best = eff; tile = t; }
+    }
+    p.tile = tile;
+    p.R = kBwdThreads / tile;
+    if (p.R > E) p.R = E;
+    if (p.R < 1) p.R = 1;
+    int o = 0;
+    p.off_tab = o; o = fixed;
+    p.off_x = o; o += tile * N * 4; o = align_up_b(o, 16);
+    p.off_node = o; o += maxvc * tile * 4;
+    p.off_dm = o; o += E * tile * 4;
+    p.off_a = o; o += E * tile * 4;
+    p.off_xin = o; o += E * tile * 4;
+    p.off_g = o; o += E * tile * 4;
+    p.off_dx = o; o += E * tile * 4;
+    out->smem = o;
+    out->threads = kBwdThreads;
+    p.n_tiles = (int)((B + tile - 1) / tile);
+    out->grid = p.n_tiles < g->sm_count ? p.n_tiles : g->sm_count;
+    out->n_rows = out->grid * (kBwdThreads / 32);
+    return GD_OK;
+}
+
+}  // namespace gd
+
+extern "C" int64_t gd_bwd_workspace_floats(const gd_graph* g, const gd_model* model, int64_t B) {
+    if (!g || !gd_model_valid(model) || model->program != GD_PROG_V2_4 || model->hidden > 32 * gd::kUPL || B <= 0) {
+        gd::set_error("gd_bwd_workspace_floats: unsupported model (need GD_PROG_V2_4, hidden <= %d)", 32 * gd::kUPL);
+        return -1;
+    }
+    gd::BwdPlan pl;
+    if (gd::plan_bwd(g, model, B, &pl) != GD_OK) return -1;
+    return (int64_t)pl.n_rows * pl.p.np_pad;
+}
+
+extern "C" int gd_decode_bwd(const gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev,
+                             const float* stash_dev, const float* grad_logit_dev, float* grad_weights_dev,
+                             float* workspace_dev, int32_t accumulate, int64_t B, void* stream) {
+    GD_CHECK_ARG(g != nullptr, "gd_decode_bwd: graph is NULL");
+    GD_CHECK_ARG(gd_model_valid(model) && model->program == GD_PROG_V2_4,
+                 "gd_decode_bwd: only GD_PROG_V2_4 has a backward kernel");
+    GD_CHECK_ARG(model->hidden <= 32 * gd::kUPL, "gd_decode_bwd: hidden=%d > %d unsupported", model->hidden, 32 * gd::kUPL);
+    GD_CHECK_ARG(B >= 0, "gd_decode_bwd: negative B");
+    GD_CHECK_ARG(grad_weights_dev != nullptr, "gd_decode_bwd: grad_weights is NULL");
+    const int n_params = (int)gd_weights_size(model);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) {
+        if (!accumulate) GD_CUDA(cudaMemsetAsync(grad_weights_dev, 0, sizeof(float) * n_params, st));
+        return GD_OK;
+    }
+    GD_CHECK_ARG(weights_dev && x_dev && stash_dev && grad_logit_dev && workspace_dev, "gd_decode_bwd: NULL buffer");
+    gd::BwdPlan pl;
+    int rc = gd::plan_bwd(g, model, B, &pl);
+    if (rc != GD_OK) return rc;
+    pl.p.x = x_dev; pl.p.stash = stash_dev; pl.p.grad_logit = grad_logit_dev; pl.p.weights = weights_dev;
+    pl.p.partials = workspace_dev;
+    int prev = 0;
+    GD_CUDA(cudaGetDevice(&prev));
+    if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
+    cudaError_t e = cudaFuncSetAttribute(gd::decode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
+    if (e == cudaSuccess) {
+        gd::decode_bwd_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(pl.p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        gd::reduce_partials_kernel<<<(n_params + 127) / 128, 128, 0, st>>>(workspace_dev, pl.n_rows, pl.p.np_pad, n_params,
+                                                                           grad_weights_dev, accumulate ? 1 : 0);
+        e = cudaGetLastError();
+    }
+    if (prev != g->device) cudaSetDevice(prev);
+    GD_CUDA(e);
+    return GD_OK;
+}

@@ -30,6 +30,7 @@ struct DecodeParams {
     float* logit;
     uint8_t* hard;
     const float* weights;
+    float* stash;           // training only: [(T+1)][2][E][B] = per-iteration (m_it, a_it), final m in slot T
     GraphTables tb;
     long long B;
     int T, V, C, E, N;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             // ---- V2: variable-phase message + the `pre` of the check phase, per edge ----
             if constexpr (PROG == GD_PROG_V2_4) {
                 for (int i0 = 0; i0 < n_iter; i0 += kEB) {
-                    float x0[kEB], x1[kEB], o[kEB];
+                    float x0[kEB], x1[kEB], o[kEB], mo[kEB];
                     int ee[kEB];
 #pragma unroll
                     for (int j = 0; j < kEB; ++j) {
@@ -204,14 +205,22 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         ee[j] = e;
                         const int ec = e < E ? e : E - 1;
                         const int v = tb.ld(tb.edge_var, ec);
-                        x0[j] = node[v * tile + s] - m_st[(size_t)ec * tile + s];
+                        mo[j] = m_st[(size_t)ec * tile + s];
+                        x0[j] = node[v * tile + s] - mo[j];
                         x1[j] = xrow[v];
                     }
                     if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, true, (NPOLY > 0 ? NPOLY : 0)>(W1, hp, x0, x1, o);
                     else mlp_softplus<kEB, true>(W1, hp, x0, x1, o);
 #pragma unroll
                     for (int j = 0; j < kEB; ++j)
-                        if (ee[j] < E) t_st[(size_t)ee[j] * tile + s] = tanh_half(o[j]);
+                        if (ee[j] < E) {
+                            t_st[(size_t)ee[j] * tile + s] = tanh_half(o[j]);
+                            if (p.stash && s < nvalid) {   // training: keep (m_it, a_it) for the backward kernel
+                                float* st = p.stash + ((size_t)it * 2 * E + ee[j]) * (size_t)p.B + s0 + s;
+                                st[0] = mo[j];
+                                st[(size_t)E * p.B] = o[j];
+                            }
+                        }
                 }
             } else {
                 for (int i = 0; i < n_iter; ++i) {
@@ -293,6 +302,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                     const int e = r + (i0 + j) * R;
                     ee[j] = e;
                     x0[j] = m_st[(size_t)(e < E ? e : E - 1) * tile + s];
+                    if (p.stash && e < E && s < nvalid) p.stash[((size_t)p.T * 2 * E + e) * (size_t)p.B + s0 + s] = x0[j];
                 }
                 if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W3, hp, x0, x0, o);
                 else mlp_softplus<kEB, false>(W3, hp, x0, x0, o);
@@ -491,9 +501,44 @@ extern "C" int gd_decode_launch_info(const gd_graph* g, const gd_model* model, i
     return GD_OK;
 }
 
+static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
+                           float* prob_dev, float* logit_dev, uint8_t* hard_dev, float* stash_dev, int64_t B,
+                           void* stream);
+
 extern "C" int gd_decode_fwd(const gd_graph* gc, const gd_model* model, const float* weights_dev,
                              const float* x_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, int64_t B,
                              void* stream) {
+    return decode_fwd_impl(gc, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, nullptr, B, stream);
+}
+
+extern "C" int64_t gd_stash_floats(const gd_graph* g, const gd_model* model, int64_t B) {
+    if (!g || !gd_model_valid(model) || B < 0) {
+        gd::set_error("gd_stash_floats: invalid argument");
+        return -1;
+    }
+    return (int64_t)(model->iters + 1) * 2 * g->E * B;
+}
+
+extern "C" int gd_decode_fwd_train(const gd_graph* gc, const gd_model* model, const float* weights_dev,
+                                   const float* x_dev, float* prob_dev, float* logit_dev, float* stash_dev, int64_t B,
+                                   void* stream) {
+    GD_CHECK_ARG(model && model->program == GD_PROG_V2_4, "gd_decode_fwd_train: only GD_PROG_V2_4 has a backward kernel");
+    GD_CHECK_ARG(stash_dev != nullptr || B == 0, "gd_decode_fwd_train: stash is NULL");
+    gd_launch_info li;
+    if (B > 0) {
+        int rc = gd_decode_launch_info(gc, model, B, &li);
+        if (rc != GD_OK) return rc;
+        if (!li.resident) {
+            gd::set_error("gd_decode_fwd_train: code too large for the resident kernel (training needs it)");
+            return GD_ERR_UNSUPPORTED;
+        }
+    }
+    return decode_fwd_impl(gc, model, weights_dev, x_dev, prob_dev, logit_dev, nullptr, stash_dev, B, stream);
+}
+
+static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
+                           float* prob_dev, float* logit_dev, uint8_t* hard_dev, float* stash_dev, int64_t B,
+                           void* stream) {
     gd_graph* g = const_cast<gd_graph*>(gc);
     GD_CHECK_ARG(g != nullptr, "gd_decode_fwd: graph is NULL");
     GD_CHECK_ARG(gd_model_valid(model), "gd_decode_fwd: invalid model (program=%d hidden=%d iters=%d)",
@@ -509,6 +554,7 @@ extern "C" int gd_decode_fwd(const gd_graph* gc, const gd_model* model, const fl
     int rc = gd::plan_decode(g, model, B, &pl);
     if (rc != GD_OK) return rc;
     pl.p.x = x_dev; pl.p.prob = prob_dev; pl.p.logit = logit_dev; pl.p.hard = hard_dev; pl.p.weights = weights_dev;
+    pl.p.stash = stash_dev;
     cudaStream_t st = (cudaStream_t)stream;
     int prev = 0;
     GD_CUDA(cudaGetDevice(&prev));

@@ -138,6 +138,23 @@ int gd_decode_fwd(const gd_graph* g, const gd_model* model, const float* weights
 int gd_decode_host(const gd_graph* g, const gd_model* model, const float* weights_host,
                    const float* x_host, float* prob_host, uint8_t* hard_host, int64_t B);
 
+/* ---- training (BASELINE config 4): forward that also stashes the per-iteration activations, and
+ *      the hand-written backward (replaces autograd through the loop, decoder_v2_4.py:334-340).
+ *      GD_PROG_V2_4 only.  stash_dev holds gd_stash_floats() floats: [(iters+1)][2][E][B].
+ *      gd_decode_bwd takes dL/dlogit [B,V] (prob = sigmoid(-logit), so dL/dlogit = -dL/dprob *
+ *      prob * (1 - prob)) and writes (accumulate == 0) or adds (accumulate != 0) dL/dweights in the
+ *      packed order of gd_model.  workspace_dev: gd_bwd_workspace_floats() floats of per-warp
+ *      partial sums, reduced in a fixed order -> bit-reproducible gradients. ---- */
+int64_t gd_stash_floats(const gd_graph* g, const gd_model* model, int64_t B);
+int gd_decode_fwd_train(const gd_graph* g, const gd_model* model, const float* weights_dev,
+                        const float* x_dev, float* prob_dev, float* logit_dev, float* stash_dev,
+                        int64_t B, void* stream);
+int64_t gd_bwd_workspace_floats(const gd_graph* g, const gd_model* model, int64_t B);
+int gd_decode_bwd(const gd_graph* g, const gd_model* model, const float* weights_dev,
+                  const float* x_dev, const float* stash_dev, const float* grad_logit_dev,
+                  float* grad_weights_dev, float* workspace_dev, int32_t accumulate, int64_t B,
+                  void* stream);
+
 /* Launch geometry the library picked for (graph, model, B): for benchmarks / roofline. */
 typedef struct gd_launch_info {
     int32_t tile;            /* syndromes per CTA tile                          */

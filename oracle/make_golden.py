@@ -76,6 +76,34 @@ def _run_case(name, script, program, consts, raw_subs=(), ckpt=None, loader="tes
               (path, rows, cols, E, B, Nc, pred.min().item(), pred.max().item()))
 
 
+def _grad_case(name, consts, ckpt, T, seed=1234):
+    """One train-step gradient of the reference: loss = criterion(decoder(datas), datas);
+    loss.backward()  (decoder_v2_4.py:331-335) -> per-parameter gradients."""
+    with ref_loader.reference_session("quantum"):
+        ns = ref_loader.load_reference("quantum/decoder_v2_4.py", consts=consts, seed=seed)
+        rows, cols, B = int(ns.rows), int(ns.cols), int(ns.BATCH_SIZE)
+        dec = ns.GNNI(T)
+        dec.load_state_dict(torch.load(ckpt))
+        dec.train()
+        batch = next(iter(ns.train_loader))
+        crit = ns.LossFunc(ns.H, ns.H_prep)
+        pred = dec(batch)
+        loss = crit(pred, batch)
+        loss.backward()
+        E = batch.edge_index.size(1) // B
+        out = dict(program="v2_4", V=rows, C=cols, E=E, B=B, T=T, dtype="float64",
+                   edge_index=_np(batch.edge_index[:, :E]).astype(np.int64), H=_np(ns.H).astype(np.uint8),
+                   x=_np(batch.x.reshape(B, rows + cols)), y=_np(batch.y.reshape(B, rows)),
+                   prob=_np(pred.reshape(B, rows)), logical=_np(ns.logical).astype(np.uint8), loss=float(loss.item()))
+        for k, v in dec.state_dict().items():
+            out["w:" + k] = _np(v)
+        for k, v in dec.named_parameters():
+            out["g:" + k] = _np(v.grad)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote %s  loss %.6f  |grad| max %.3g" % (path, loss.item(), max(v.grad.abs().max().item() for v in dec.parameters())))
+
+
 def _codes():
     """Code-construction fixtures: toric H / H_prep / logical from error_generate.py."""
     eg = ref_loader.load_error_generate()
@@ -128,6 +156,10 @@ def main():
     _run_case("cgnni_bch_seeded", "classical/CGNNI.py", "cgnni", c_small, loader="train_loader", seed=4321)
     _run_case("bp_classical_bch", "classical/BP.py", "bp_classical",
               {"num": "4", "BATCH_SIZE": "24", "SNR2": "[1, 2, 3, 4, 5, 6]"})
+    _grad_case("grad_v2_4_toricL4_epoch1", dict(q_small, L="4", BATCH_SIZE="8", run1="8", run2="8"),
+               R + "/quantum/new_model/decoder_parameters_epoch1.pkl", T=15)
+    _grad_case("grad_v2_4_toricL5_epoch3_T6", dict(q_small, L="5", BATCH_SIZE="12", run1="12", run2="12"),
+               R + "/quantum/new_model/decoder_parameters_epoch3.pkl", T=6, seed=77)
     _codes()
 
 

@@ -1,0 +1,106 @@
+"""GPU suite: the training path (forward-with-stash + hand-written backward) against the gradients
+of the REFERENCE's own train step (loss = criterion(decoder(datas), datas); loss.backward(),
+quantum/decoder_v2_4.py:331-335) stored in tests/golden/grad_*.npz, and against the oracle.
+
+Bar: fp32 kernels vs the fp64 reference, per parameter tensor
+     max |g_cuda - g_ref| <= GRAD_RTOL * max |g_ref|  (GRAD_RTOL = 2e-3), loss within 1e-5 relative;
+     gradients bit-reproducible run to run (fixed-order two-stage reduction, no atomics)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+GRAD_RTOL = 2e-3
+DEV = "cuda:0"
+
+
+class _Case(object):
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.V, self.C, self.E, self.B, self.T = (int(z[k]) for k in ("V", "C", "E", "B", "T"))
+        self.edge_index = torch.from_numpy(z["edge_index"])
+        self.x, self.y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+        self.H, self.logical = torch.from_numpy(z["H"]).double(), torch.from_numpy(z["logical"]).double()
+        self.weights = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+        self.grads = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("g:")}
+        self.loss, self.prob = float(z["loss"]), torch.from_numpy(z["prob"])
+
+
+class _Data(object):
+    pass
+
+
+def _train_step(case, dec, reps=1):
+    from gnn_decode_b200.quantum import decoder_v2_4  # noqa: F401
+    N = case.V + case.C
+    d = _Data()
+    d.x = case.x.repeat(reps, 1).reshape(-1, 1).to(DEV)
+    B = case.B * reps
+    off = (torch.arange(B) * N).repeat_interleave(case.E)
+    d.edge_index = (case.edge_index.repeat(1, B) + off).to(DEV)
+    y = case.y.repeat(reps, 1).to(DEV)
+    dec.zero_grad()
+    pred = dec(d)                                                        # [B*V, 1], requires grad
+    assert pred.requires_grad
+    loss = restate.loss_v2_4(pred.reshape(B, case.V), y, case.H.to(DEV), case.logical.to(DEV))
+    loss.backward()
+    return loss.item(), {k: p.grad.detach().clone() for k, p in dec.named_parameters()}, pred.detach()
+
+
+@pytest.mark.parametrize("name", ["grad_v2_4_toricL4_epoch1", "grad_v2_4_toricL5_epoch3_T6"])
+def test_gradients_match_reference_train_step(name):
+    from gnn_decode_b200.quantum import decoder_v2_4
+    case = _Case(name)
+    dec = decoder_v2_4.GNNI(case.T)
+    dec.load_state_dict(case.weights)
+    dec = dec.to(DEV).train()
+    loss, grads, pred = _train_step(case, dec)
+    assert abs(loss - case.loss) <= 1e-5 * abs(case.loss), (loss, case.loss)
+    assert (pred.reshape(case.B, case.V).cpu() - case.prob).abs().max().item() < 1e-5
+    assert set(grads) == set(case.grads)
+    for k, gref in case.grads.items():
+        g = grads[k].double().cpu()
+        assert g.shape == gref.shape
+        err = (g - gref).abs().max().item()
+        scale = gref.abs().max().item()
+        assert err <= GRAD_RTOL * scale + 1e-9, "%s: max err %.3g vs max |g| %.3g" % (k, err, scale)
+    # bit-reproducible, and linear in the batch (3 copies of the batch -> 3x the gradient)
+    loss2, grads2, _ = _train_step(case, dec)
+    assert loss2 == loss and all(torch.equal(grads[k], grads2[k]) for k in grads)
+    loss3, grads3, _ = _train_step(case, dec, reps=3)
+    for k in grads:
+        assert (grads3[k] - 3 * grads[k]).abs().max().item() <= 2e-4 * (3 * grads[k]).abs().max().item() + 1e-9
+
+
+def test_adam_step_and_eval_mode():
+    """One optimizer step changes the weights the next forward uses (packed-weight cache is
+    invalidated), eval()/no_grad() take the inference kernel, and other programs refuse to train."""
+    from gnn_decode_b200 import _cabi
+    from gnn_decode_b200.quantum import QGNNI, decoder_v2_4
+    case = _Case("grad_v2_4_toricL4_epoch1")
+    dec = decoder_v2_4.GNNI(3)
+    dec.load_state_dict(case.weights)
+    dec = dec.to(DEV).train()
+    opt = torch.optim.Adam(dec.parameters(), 3e-4, weight_decay=1e-9)       # decoder_v2_4.py:323
+    l0, _, p0 = _train_step(case, dec)
+    opt.step()
+    l1, _, p1 = _train_step(case, dec)
+    assert not torch.equal(p0, p1)
+    dec.eval()
+    with torch.no_grad():
+        d = _Data()
+        d.x = case.x.reshape(-1, 1).to(DEV)
+        N = case.V + case.C
+        d.edge_index = (case.edge_index.repeat(1, case.B) + (torch.arange(case.B) * N).repeat_interleave(case.E)).to(DEV)
+        pe = dec(d)
+    assert not pe.requires_grad
+    assert (pe - p1).abs().max().item() < 1e-6
+    q = QGNNI.GNNI(2, rows=case.V, cols=case.C).to(DEV).train()
+    with pytest.raises(_cabi.GdError):
+        q(d)
