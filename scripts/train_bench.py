@@ -1,0 +1,71 @@
+"""Training-step timing (BASELINE config 4): decoder_v2_4 program on the rotated surface code d=7,
+B syndromes per GPU, fp32: forward(+stash) + LossFunc + hand-written backward + gradient all-reduce
+(NCCL when launched under torchrun) + Adam.  Developer script, not the driver's bench.py."""
+import math, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch.distributed as dist
+from gnn_decode_b200 import codes
+from gnn_decode_b200.dist import allreduce_flat_grads
+from gnn_decode_b200.graph import TannerGraph
+from gnn_decode_b200.quantum import decoder_v2_4
+from gnn_decode_b200.sampler import sample_syndromes
+
+rank, world, lr_ = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lr_)
+dev = torch.device("cuda", lr_)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+d = int(sys.argv[1]) if len(sys.argv) > 1 else 7
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+T = 15
+Hz, Hx = codes.rotated_surface_checks(d)
+pcm = codes.css_pcm(Hz, Hx)
+logical = torch.from_numpy(codes.css_logicals(Hz, Hx)).float().to(dev)
+Ht = torch.from_numpy(pcm.T.copy()).float().to(dev)          # the reference's H [V, C]
+g = TannerGraph.from_pcm(pcm, dev)
+torch.manual_seed(0)
+dec = decoder_v2_4.GNNI(T).to(dev).train().bind_graph(g)
+opt = torch.optim.Adam(dec.parameters(), 3e-4, weight_decay=1e-9)
+x, err = sample_syndromes(g, B, [0.01, 0.03, 0.05, 0.08], noise=1, seed=1, first_sample=rank * B)
+y = err.float()
+
+def loss_fn(prob):
+    z = (y + prob).t()
+    return torch.sin(Ht.t() @ z * (math.pi / 2)).abs().sum() + torch.sin(logical @ z * (math.pi / 2)).abs().sum()
+
+def step(timers=None):
+    opt.zero_grad(set_to_none=False)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+    prob = dec.decode(x)
+    ev[1].record()
+    loss = loss_fn(prob)
+    ev[2].record()
+    loss.backward()
+    ev[3].record()
+    allreduce_flat_grads(dec.parameters())
+    opt.step()
+    ev[4].record()
+    if timers is not None:
+        torch.cuda.synchronize()
+        for i, k in enumerate(("fwd", "loss", "bwd", "allreduce+adam")):
+            timers[k] = timers.get(k, 0.0) + ev[i].elapsed_time(ev[i + 1])
+    return loss
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+n = 10
+timers = {}
+t0 = time.perf_counter()
+for _ in range(n):
+    l = step(timers)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / n
+if rank == 0:
+    print("rotated d=%d V=%d C=%d E=%d  B/GPU=%d x %d GPU  T=%d: %.3f ms/step  %.1f steps/s  %.3f M syndromes/s  loss %.2f" %
+          (d, g.V, g.C, g.E, B, world, T, dt * 1e3, 1 / dt, world * B / dt / 1e6, l.item()))
+    print("  per-step ms:", {k: round(v / n, 3) for k, v in timers.items()})
+if world > 1:
+    dist.destroy_process_group()
