@@ -22,7 +22,7 @@ namespace gd {
 
 constexpr int kBwdThreads = 512;
 constexpr int kUPL = 4;          // hidden units per lane (h <= 128)
-constexpr int kItems = 4;        // items processed together per warp (ILP across the MUFU / shuffle chains)
+constexpr int kItems = 4;        // items processed together per warp (ILP across the MUFU chains; the dx reduction assumes 4)
 
 struct BwdParams {
     const float* x;           // [B, N]
@@ -34,95 +34,150 @@ struct BwdParams {
     long long B;
     int T, V, C, E, N, hid;
     int tile, R, n_tiles, maxvc, np_pad;
-    int off_tab, off_x, off_node, off_dm, off_a, off_xin, off_g, off_dx;
+    int off_tab, off_x, off_node, off_node2, off_dm, off_a, off_xin, off_x1, off_g, off_dx, off_mb, off_ab;
 };
 
-struct LaneMlp {           // this lane's kUPL hidden units of one MLP (pre-scaled to base 2 like the forward)
-    float w1a[kUPL], w1b[kUPL], b1[kUPL], w2[kUPL];
+constexpr int kPairs = kUPL / 2;
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src_gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float sign_one(float h) {   // copysign(1, h)
+    return __uint_as_float((__float_as_uint(h) & 0x80000000u) | 0x3f800000u);
+}
+
+// This lane's kUPL hidden units of one MLP as kPairs packed (f32x2) pairs; w1a/w1b/b1 pre-scaled to
+// base 2 like the forward, w2 in natural units.
+struct LaneMlp {
+    u64 w1a[kPairs], w1b[kPairs], b1[kPairs], w2[kPairs];
 };
 struct LaneAcc {
-    float w1a[kUPL], w1b[kUPL], b1[kUPL], w2[kUPL];
+    u64 w1a[kPairs], w1b[kPairs], b1[kPairs], w2[kPairs];
     float b2;
 };
 
 __device__ __forceinline__ void load_lane_mlp(LaneMlp& L, const float* w, int h, bool two_in, int lane) {
 #pragma unroll
-    for (int u = 0; u < kUPL; ++u) {
-        const int k = lane * kUPL + u;
-        const bool in = k < h;
-        L.w1a[u] = in ? w[two_in ? 2 * k : k] * kLog2e : 0.f;
-        L.w1b[u] = (in && two_in) ? w[2 * k + 1] * kLog2e : 0.f;
-        L.b1[u] = in ? w[(two_in ? 2 : 1) * h + k] * kLog2e : 0.f;
-        L.w2[u] = in ? w[(two_in ? 3 : 2) * h + k] : 0.f;          // natural units
+    for (int q = 0; q < kPairs; ++q) {
+        float a[2], b[2], c[2], d[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane * kUPL + q * 2 + u;
+            const bool in = k < h;
+            a[u] = in ? w[two_in ? 2 * k : k] * kLog2e : 0.f;
+            d[u] = (in && two_in) ? w[2 * k + 1] * kLog2e : 0.f;
+            b[u] = in ? w[(two_in ? 2 : 1) * h + k] * kLog2e : 0.f;
+            c[u] = in ? w[(two_in ? 3 : 2) * h + k] : 0.f;
+        }
+        L.w1a[q] = pack2(a[0], a[1]); L.w1b[q] = pack2(d[0], d[1]);
+        L.b1[q] = pack2(b[0], b[1]); L.w2[q] = pack2(c[0], c[1]);
     }
 }
 __device__ __forceinline__ void zero_acc(LaneAcc& A) {
 #pragma unroll
-    for (int u = 0; u < kUPL; ++u) A.w1a[u] = A.w1b[u] = A.b1[u] = A.w2[u] = 0.f;
+    for (int q = 0; q < kPairs; ++q) A.w1a[q] = A.w1b[q] = A.b1[q] = A.w2[q] = 0ull;
     A.b2 = 0.f;
 }
 
 // One MLP backward over all items of the tile.  xin/g/dx are [E][tile] shared arrays (item index
 // i = e*tile + s is linear).  For the two-input MLP the second input is prior[var(e)] from the x slab.
+// Per hidden unit: h' -> t = 2^-|h'| -> r = 1/(1+t), l = lg2(1+t) (3 MUFU); softplus/ln2 = max(h',0)+l;
+// sigmoid(h) = 1/2 + sign(h)(r - 1/2); dh = g w2 sigmoid.  All FMA-type work is packed f32x2 over a
+// pair of hidden units (half the issue slots), so the loop is bound by the MUFU pipe.
 template <bool TWO_IN>
-__device__ __forceinline__ void mlp_backward_items(const LaneMlp& L, LaneAcc& A, const float* xin, const float* g,
-                                                   float* dx, int n_items, int tile, const uint16_t* edge_var,
-                                                   const float* xs, int N, int warp, int n_warps, int lane) {
+__device__ __forceinline__ void mlp_backward_items(const LaneMlp& L, LaneAcc& A, const float* xin, const float* xin1,
+                                                   const float* g, float* dx, int n_items, int warp, int n_warps,
+                                                   int lane) {
+    const u64 one2 = pack2(1.0f, 1.0f), half2 = pack2(0.5f, 0.5f), mhalf2 = pack2(-0.5f, -0.5f);
     for (int i0 = warp * kItems; i0 < n_items; i0 += n_warps * kItems) {
-        float x0[kItems], x1[kItems], gg[kItems], dxl[kItems];
+        u64 xx[kItems], yy[kItems], gg[kItems], dx2[kItems];
 #pragma unroll
         for (int j = 0; j < kItems; ++j) {
             const int i = i0 + j < n_items ? i0 + j : n_items - 1;
-            x0[j] = xin[i];
-            gg[j] = i0 + j < n_items ? g[i] : 0.f;
-            x1[j] = 0.f;
-            if (TWO_IN) {
-                const int e = i / tile, s = i - e * tile;
-                x1[j] = xs[s * N + edge_var[e]];
-            }
-            dxl[j] = 0.f;
+            const float x0 = xin[i];
+            const float gv = i0 + j < n_items ? g[i] : 0.f;
+            const float x1 = TWO_IN ? xin1[i] : 0.f;
+            xx[j] = pack2(x0, x0); yy[j] = pack2(x1, x1); gg[j] = pack2(gv, gv);
+            dx2[j] = 0ull;
+            A.b2 += gv;
         }
 #pragma unroll
-        for (int u = 0; u < kUPL; ++u) {
+        for (int q = 0; q < kPairs; ++q) {
 #pragma unroll
             for (int j = 0; j < kItems; ++j) {
-                float h = fmaf(L.w1a[u], x0[j], L.b1[u]);
-                if (TWO_IN) h = fmaf(L.w1b[u], x1[j], h);
-                const float t = ex2_approx(-fabsf(h));
-                const float one_t = 1.0f + t;
-                float r;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(one_t));
-                const float sp2 = fmaxf(h, 0.f) + lg2_approx(one_t);       // softplus / ln2
-                const float sig = h >= 0.f ? r : t * r;                    // sigmoid(h)
-                const float dh = gg[j] * L.w2[u] * sig;                    // dL/d(pre-activation), natural units
-                A.w2[u] = fmaf(gg[j], sp2, A.w2[u]);                       // x ln2 when written out
-                A.w1a[u] = fmaf(dh, x0[j], A.w1a[u]);
-                if (TWO_IN) A.w1b[u] = fmaf(dh, x1[j], A.w1b[u]);
-                A.b1[u] += dh;
-                dxl[j] = fmaf(dh, L.w1a[u], dxl[j]);                       // / log2e when written out
+                u64 h2 = fma2(L.w1a[q], xx[j], L.b1[q]);
+                if (TWO_IN) h2 = fma2(L.w1b[q], yy[j], h2);
+                float hl, hh;
+                unpack2(h2, hl, hh);
+                const float tl = ex2_approx(-fabsf(hl)), th = ex2_approx(-fabsf(hh));
+                float ol, oh;
+                unpack2(add2(pack2(tl, th), one2), ol, oh);
+                const u64 r2 = pack2(rcp_approx(ol), rcp_approx(oh));
+                const u64 l2 = pack2(lg2_approx(ol), lg2_approx(oh));
+                const u64 sp2 = add2(l2, pack2(fmaxf(hl, 0.f), fmaxf(hh, 0.f)));        // softplus / ln2
+                const u64 sig2 = fma2(pack2(sign_one(hl), sign_one(hh)), add2(r2, mhalf2), half2);
+                const u64 dh2 = mul2(mul2(gg[j], L.w2[q]), sig2);                        // dL/d(pre-activation)
+                A.w2[q] = fma2(gg[j], sp2, A.w2[q]);                                     // x ln2 when written out
+                A.w1a[q] = fma2(dh2, xx[j], A.w1a[q]);
+                if (TWO_IN) A.w1b[q] = fma2(dh2, yy[j], A.w1b[q]);
+                A.b1[q] = add2(A.b1[q], dh2);
+                dx2[j] = fma2(dh2, L.w1a[q], dx2[j]);                                    // / log2e when written out
             }
         }
+        // transposed warp reduction of the kItems (= 4) per-lane partial dx: 6 shuffles instead of 20;
+        // lanes 0, 8, 16, 24 end up holding the sums of items 0, 1, 2, 3
+        float v[kItems];
 #pragma unroll
         for (int j = 0; j < kItems; ++j) {
-            A.b2 += gg[j];
-            float v = dxl[j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && i0 + j < n_items) dx[i0 + j] = v * kLn2;      // 1/log2e == ln2
+            float lo, hi;
+            unpack2(dx2[j], lo, hi);
+            v[j] = lo + hi;
         }
+        const bool b4 = lane & 16, b3 = lane & 8;
+        const float ra = __shfl_xor_sync(0xffffffffu, b4 ? v[0] : v[2], 16);
+        const float rb = __shfl_xor_sync(0xffffffffu, b4 ? v[1] : v[3], 16);
+        const float k0 = (b4 ? v[2] : v[0]) + ra, k1 = (b4 ? v[3] : v[1]) + rb;
+        const float rc = __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
+        float k = (b3 ? k1 : k0) + rc;
+        k += __shfl_xor_sync(0xffffffffu, k, 4);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        const int item = i0 + (b4 ? 2 : 0) + (b3 ? 1 : 0);
+        if ((lane & 7) == 0 && item < n_items) dx[item] = k * kLn2;        // 1/log2e == ln2
     }
 }
 
 __device__ __forceinline__ void store_acc(float* dst, const LaneAcc& A, int h, bool two_in, int lane) {
     // packed order of one MLP: W1 [h, k_in] row-major | b1 [h] | W2 [h] | b2
 #pragma unroll
-    for (int u = 0; u < kUPL; ++u) {
-        const int k = lane * kUPL + u;
-        if (k < h) {
-            if (two_in) { dst[2 * k] = A.w1a[u]; dst[2 * k + 1] = A.w1b[u]; }
-            else dst[k] = A.w1a[u];
-            dst[(two_in ? 2 : 1) * h + k] = A.b1[u];
-            dst[(two_in ? 3 : 2) * h + k] = A.w2[u] * kLn2;
+    for (int q = 0; q < kPairs; ++q) {
+        float a[2], d[2], b[2], c[2];
+        unpack2(A.w1a[q], a[0], a[1]); unpack2(A.w1b[q], d[0], d[1]);
+        unpack2(A.b1[q], b[0], b[1]); unpack2(A.w2[q], c[0], c[1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane * kUPL + q * 2 + u;
+            if (k < h) {
+                if (two_in) { dst[2 * k] = a[u]; dst[2 * k + 1] = d[u]; }
+                else dst[k] = a[u];
+                dst[(two_in ? 2 : 1) * h + k] = b[u];
+                dst[(two_in ? 3 : 2) * h + k] = c[u] * kLn2;
+            }
         }
     }
     if (lane == 0) dst[(two_in ? 4 : 3) * h] = A.b2;
@@ -139,6 +194,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
     float* DM = reinterpret_cast<float*>(smem + p.off_dm);
     float* A_ = reinterpret_cast<float*>(smem + p.off_a);
     float* XI = reinterpret_cast<float*>(smem + p.off_xin);
+    float* X1 = reinterpret_cast<float*>(smem + p.off_x1);
+    float* MB = reinterpret_cast<float*>(smem + p.off_mb);
+    float* AB = reinterpret_cast<float*>(smem + p.off_ab);
+    float* node2 = reinterpret_cast<float*>(smem + p.off_node2);
     float* G_ = reinterpret_cast<float*>(smem + p.off_g);
     float* DX = reinterpret_cast<float*>(smem + p.off_dx);
     uint16_t* tab = reinterpret_cast<uint16_t*>(smem + p.off_tab);
@@ -166,13 +225,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
     const size_t EB_ = (size_t)E * p.B;
     __syncthreads();
 
-    auto seg_sum = [&](const uint16_t* ptr, const uint16_t* ids, int n_nodes, const float* src) {
+    auto seg_sum = [&](const uint16_t* ptr, const uint16_t* ids, int n_nodes, const float* src, float* dstn) {
         if (ew)
             for (int n = r; n < n_nodes; n += R) {
                 float a = 0.f;
                 for (int i = ptr[n]; i < ptr[n + 1]; ++i) a += src[ids[i] * tile + s];
-                node[n * tile + s] = a;
+                dstn[n * tile + s] = a;
             }
+    };
+    // asynchronous prefetch of one iteration's stash (a_it -> AB, m_it -> MB) by the thread that will
+    // consume the same elements; latency is hidden behind the MLP phases
+    auto prefetch_stash = [&](int it, long long s0, bool valid) {
+        if (ew && valid && it >= 0) {
+            const float* st_m = p.stash + (size_t)it * 2 * EB_ + s0 + s;
+            const float* st_a = st_m + EB_;
+            for (int e = r; e < E; e += R) {
+                cp_async4(MB + e * tile + s, st_m + (size_t)e * p.B);
+                cp_async4(AB + e * tile + s, st_a + (size_t)e * p.B);
+            }
+        }
+        cp_async_commit();
     };
 
     for (int tix = blockIdx.x; tix < p.n_tiles; tix += gridDim.x) {
@@ -180,6 +252,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
         const int nvalid = (int)min((long long)tile, p.B - s0);
         const bool valid = s < nvalid;
         for (int i = tid; i < tile * N; i += nthr) xs[i] = i < nvalid * N ? __ldg(p.x + s0 * N + i) : 0.f;
+        if (ew && !valid)
+            for (int e = r; e < E; e += R) MB[e * tile + s] = AB[e * tile + s] = 0.f;   // padded syndromes stay 0
+        prefetch_stash(T - 1, s0, valid);
         // ---- read-out backward: logit[v] = sum_{e in v} mlp3(m_T[e]) + prior[v] ----
         if (ew)
             for (int e = r; e < E; e += R) {
@@ -188,23 +263,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
                 G_[at] = valid ? __ldg(p.grad_logit + (s0 + s) * V + edge_var[e]) : 0.f;
             }
         __syncthreads();
+        if (ew)
+            for (int e = r; e < E; e += R) X1[e * tile + s] = xs[s * N + edge_var[e]];   // prior of the edge's variable
         {
             LaneMlp L;
             load_lane_mlp(L, w3p, h, false, lane);
-            mlp_backward_items<false>(L, acc3, XI, G_, DM, n_items, tile, edge_var, xs, N, warp, n_warps, lane);
+            mlp_backward_items<false>(L, acc3, XI, XI, G_, DM, n_items, warp, n_warps, lane);
         }
+        cp_async_wait_all();
+        if (ew)
+            for (int e = r; e < E; e += R) A_[e * tile + s] = tanh_half(AB[e * tile + s]);   // t of iteration T-1
         __syncthreads();
         for (int it = T - 1; it >= 0; --it) {
-            const float* st_m = p.stash + (size_t)it * 2 * EB_;
-            const float* st_a = st_m + EB_;
-            // t = tanh(a_it / 2)
-            if (ew)
-                for (int e = r; e < E; e += R) {
-                    const int at = e * tile + s;
-                    A_[at] = valid ? tanh_half(__ldg(st_a + (size_t)e * p.B + s0 + s)) : 0.f;
-                }
-            __syncthreads();
-            seg_sum(chk_ptr, chk_edges, C, A_);
+            // entry: A_ = t_it = tanh(a_it/2), MB = m_it, DM = dL/dm_{it+1}
+            seg_sum(chk_ptr, chk_edges, C, A_, node);             // Sc(t)
+            seg_sum(var_ptr, var_edges, V, MB, node2);            // Sv(m_it)
             __syncthreads();
             // m_{it+1} = mlp2(ext_c) * sign + m_it :  dg = dm' * sign, ext_c = Sc[chk] - t
             if (ew)
@@ -217,41 +290,36 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
             {
                 LaneMlp L;
                 load_lane_mlp(L, w2p, h, false, lane);
-                mlp_backward_items<false>(L, acc2, XI, G_, DX, n_items, tile, edge_var, xs, N, warp, n_warps, lane);
+                mlp_backward_items<false>(L, acc2, XI, XI, G_, DX, n_items, warp, n_warps, lane);
             }
             __syncthreads();
-            seg_sum(chk_ptr, chk_edges, C, DX);                   // gather of gradients over the check
+            seg_sum(chk_ptr, chk_edges, C, DX, node);             // gather of gradients over the check
             __syncthreads();
-            // dt = S[chk] - dext_c ; da = dt (1 - t^2) / 2 ; then reuse A_ for m_it
+            // dt = S[chk] - dext_c ; da = dt (1 - t^2) / 2 ; ext_v = Sv[var] - m_it
             if (ew)
                 for (int e = r; e < E; e += R) {
                     const int at = e * tile + s;
                     const float t = A_[at];
                     const float dt = node[edge_chk[e] * tile + s] - DX[at];
                     G_[at] = dt * (1.0f - t * t) * 0.5f;
-                    A_[at] = valid ? __ldg(st_m + (size_t)e * p.B + s0 + s) : 0.f;
+                    XI[at] = node2[edge_var[e] * tile + s] - MB[at];
                 }
-            __syncthreads();
-            seg_sum(var_ptr, var_edges, V, A_);
-            __syncthreads();
-            if (ew)
-                for (int e = r; e < E; e += R) {
-                    const int at = e * tile + s;
-                    XI[at] = node[edge_var[e] * tile + s] - A_[at];   // ext_v
-                }
+            prefetch_stash(it - 1, s0, valid);                    // MB / AB are free now
             __syncthreads();
             {
                 LaneMlp L;
                 load_lane_mlp(L, w1p, h, true, lane);
-                mlp_backward_items<true>(L, acc1, XI, G_, DX, n_items, tile, edge_var, xs, N, warp, n_warps, lane);
+                mlp_backward_items<true>(L, acc1, XI, X1, G_, DX, n_items, warp, n_warps, lane);
             }
             __syncthreads();
-            seg_sum(var_ptr, var_edges, V, DX);                   // gather of gradients over the variable
+            seg_sum(var_ptr, var_edges, V, DX, node);             // gather of gradients over the variable
             __syncthreads();
+            cp_async_wait_all();
             if (ew)
                 for (int e = r; e < E; e += R) {
                     const int at = e * tile + s;
                     DM[at] += node[edge_var[e] * tile + s] - DX[at];
+                    A_[at] = tanh_half(AB[at]);                   // t of the next (earlier) iteration
                 }
             __syncthreads();
         }
@@ -290,16 +358,16 @@ static int plan_bwd(const gd_graph* g, const gd_model* m, int64_t B, BwdPlan* ou
     p.np_pad = align_up_b((int)gd_weights_size(m), 32);
     const int tab_bytes = (4 * E + V + C + 2) * 2;
     const int fixed = align_up_b(tab_bytes, 128);
-    const int64_t per_syn = ((int64_t)N + maxvc + 5LL * E) * 4;
+    const int64_t per_syn = ((int64_t)N + 2LL * maxvc + 8LL * E) * 4;
     const int64_t tmax = (g->max_smem_optin - fixed) / per_syn;
-    if (g->E >= 65536 || tmax < 8) {
+    if (g->E >= 65536 || tmax < 4) {
         set_error("gd_decode_bwd: code too large for the shared-memory backward kernel (E=%lld)", (long long)g->E);
         return GD_ERR_UNSUPPORTED;
     }
     // tile: multiple of 8 dividing the work evenly over the SMs (same criterion as the forward)
-    int tile = 8;
+    int tile = 4;
     double best = -1.0;
-    for (int t = 8; t <= tmax && t <= 128; t += 8) {
+    for (int t = 4; t <= tmax && t <= 128; t += 4) {
         const int64_t n_t = (B + t - 1) / t;
         const int64_t rounds = (n_t + g->sm_count - 1) / g->sm_count;
         const double eff = (double)B / ((double)rounds * g->sm_count * t);
@@ -313,11 +381,15 @@ static int plan_bwd(const gd_graph* g, const gd_model* m, int64_t B, BwdPlan* ou
     p.off_tab = o; o = fixed;
     p.off_x = o; o += tile * N * 4; o = align_up_b(o, 16);
     p.off_node = o; o += maxvc * tile * 4;
+    p.off_node2 = o; o += maxvc * tile * 4;
     p.off_dm = o; o += E * tile * 4;
     p.off_a = o; o += E * tile * 4;
     p.off_xin = o; o += E * tile * 4;
+    p.off_x1 = o; o += E * tile * 4;
     p.off_g = o; o += E * tile * 4;
     p.off_dx = o; o += E * tile * 4;
+    p.off_mb = o; o += E * tile * 4;
+    p.off_ab = o; o += E * tile * 4;
     out->smem = o;
     out->threads = kBwdThreads;
     p.n_tiles = (int)((B + tile - 1) / tile);

@@ -18,6 +18,12 @@ __global__ void __launch_bounds__(512) ubench_kernel(float* out, int iters) {
             if (KIND == 0) a[j] = ex2_approx(-fabsf(a[j]));                       // 1 MUFU
             else if (KIND == 1) a[j] = lg2_approx(1.0f + ex2_approx(-fabsf(a[j])));  // 2 MUFU + 1 FADD
             else if (KIND == 2) a[j] = fmaf(a[j], b, c);                          // 1 FFMA
+            else if (KIND == 5) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a[j] + 1.5f)); a[j] = y; }   // 1 MUFU.RCP + FADD
+            else if (KIND == 6) {                                               // backward unit: ex2 + rcp + lg2
+                const float t = ex2_approx(-fabsf(a[j])), o = 1.0f + t;
+                float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(o));
+                a[j] = y + lg2_approx(o);
+            }
             else if (KIND == 3) {                                                // softplus unit: the v2_4 inner step
                 const float z = fmaf(a[j], b, c);
                 const float s = fmaxf(z, 0.f) + lg2_approx(1.0f + ex2_approx(-fabsf(z)));
@@ -47,7 +53,7 @@ __global__ void __launch_bounds__(512) ubench_kernel(float* out, int iters) {
 // result[0] = "units" per second (kind 0/2: instructions x lanes; kind 1/3: units; kind 4: FMAs),
 // result[1] = milliseconds of the timed launch.
 extern "C" int gd_microbench(int32_t kind, int32_t iters, int device, double* result) {
-    GD_CHECK_ARG(result && kind >= 0 && kind <= 4 && iters > 0, "gd_microbench: bad argument");
+    GD_CHECK_ARG(result && kind >= 0 && kind <= 6 && iters > 0, "gd_microbench: bad argument");
     int prev = 0;
     GD_CUDA(cudaGetDevice(&prev));
     GD_CUDA(cudaSetDevice(device));
@@ -67,7 +73,9 @@ extern "C" int gd_microbench(int32_t kind, int32_t iters, int device, double* re
             case 1: gd::ubench_kernel<1><<<grid, threads>>>(out, iters); break;
             case 2: gd::ubench_kernel<2><<<grid, threads>>>(out, iters); break;
             case 3: gd::ubench_kernel<3><<<grid, threads>>>(out, iters); break;
-            default: gd::ubench_kernel<4><<<grid, threads>>>(out, iters); break;
+            case 4: gd::ubench_kernel<4><<<grid, threads>>>(out, iters); break;
+            case 5: gd::ubench_kernel<5><<<grid, threads>>>(out, iters); break;
+            default: gd::ubench_kernel<6><<<grid, threads>>>(out, iters); break;
         }
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);

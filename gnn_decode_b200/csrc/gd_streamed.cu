@@ -56,7 +56,7 @@ __device__ __forceinline__ void mlp_softplus_blocks(const MlpSmem& W, int hp, in
         if (blk == 0 || d > blk) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { a[j] = x0[blk + j]; b[j] = x1[blk + j]; }
-            mlp_softplus<4, TWO_IN>(W, hp, a, b, o);
+            mlp_softplus_x2<4, TWO_IN, 2>(W, hp, a, b, o);   // packed f32x2 + FMA-pipe polynomial lg2 (see gd_math.cuh)
 #pragma unroll
             for (int j = 0; j < 4; ++j) out[blk + j] = o[j];
         }
@@ -263,7 +263,7 @@ static int plan_streamed(const gd_graph* g, const gd_model* m, int64_t B, Stream
     StreamParams& p = out->p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.T = m->iters; p.V = g->V; p.C = g->C; p.E = (int)g->E; p.N = g->N;
-    p.hid = bp ? 0 : m->hidden; p.hp = (p.hid + 3) / 4 * 4; p.tb = g->t;
+    p.hid = bp ? 0 : m->hidden; p.hp = (p.hid + 7) / 8 * 8; p.tb = g->t;
     const int n_slots = bp ? 0 : (m->program == GD_PROG_V2_4 ? 3 : 2);
     out->smem = n_slots * 4 * p.hp * 4 + 16;
     // tile: multiple of 8 (32-byte sectors stay whole) that wastes the fewest tile slots over the rounds

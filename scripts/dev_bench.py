@@ -17,7 +17,7 @@ from gnn_decode_b200.classical import CGNNI
 def microbench():
     lib = _cabi.lib()
     out = {}
-    for kind, name in enumerate(["ex2", "ex2+lg2", "ffma", "softplus_unit", "ffma2"]):
+    for kind, name in enumerate(["ex2", "ex2+lg2", "ffma", "softplus_unit", "ffma2", "rcp", "ex2+rcp+lg2"]):
         r = (C.c_double * 2)()
         _cabi.check(lib.gd_microbench(kind, 4096, 0, r))
         out[name] = r[0]
