@@ -44,15 +44,14 @@ __device__ __forceinline__ void stage_mlp_s(float* dst, int hp, int hid, const f
     }
 }
 
-constexpr int kDMax = 8;   // node degrees up to this are processed with register-batched loads
 
-// Softplus MLP on up to kDMax edges of one node, 4 at a time (second block only when d > 4).
-template <bool TWO_IN>
-__device__ __forceinline__ void mlp_softplus_blocks(const MlpSmem& W, int hp, int d, const float (&x0)[kDMax],
-                                                    const float (&x1)[kDMax], float (&out)[kDMax]) {
+// Softplus MLP on up to D edges of one node, 4 at a time (second block only when d > 4).
+template <bool TWO_IN, int D>
+__device__ __forceinline__ void mlp_softplus_blocks(const MlpSmem& W, int hp, int d, const float (&x0)[D],
+                                                    const float (&x1)[D], float (&out)[D]) {
     float a[4], b[4], o[4];
 #pragma unroll
-    for (int blk = 0; blk < kDMax; blk += 4) {
+    for (int blk = 0; blk < D; blk += 4) {
         if (blk == 0 || d > blk) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { a[j] = x0[blk + j]; b[j] = x1[blk + j]; }
@@ -63,7 +62,10 @@ __device__ __forceinline__ void mlp_softplus_blocks(const MlpSmem& W, int hp, in
     }
 }
 
-template <int PROG>
+// VD / CD: register batch sizes (4 or 8) for variable / check nodes = the graph's max degrees rounded
+// up; larger degrees take the generic loops.  VSORT: edges are sorted by variable (the canonical
+// H.to_sparse() order), so a variable's edges are the contiguous rows var_ptr[v] .. var_ptr[v+1]-1.
+template <int PROG, int VD, int CD, bool VSORT>
 __global__ void __launch_bounds__(1024, 1) decode_streamed_kernel(const StreamParams p) {
     extern __shared__ __align__(16) float wsm[];
     constexpr bool kIsBP = (PROG == GD_PROG_BP_QUANTUM || PROG == GD_PROG_BP_CLASSICAL);
@@ -113,32 +115,35 @@ __global__ void __launch_bounds__(1024, 1) decode_streamed_kernel(const StreamPa
             for (int v = r; v < V; v += R) {
                 const int b = __ldg(tb.var_ptr + v), d = __ldg(tb.var_ptr + v + 1) - b;
                 const float prior = xT[(size_t)v * tile + s];
-                if (d <= kDMax) {
+                if (d <= VD) {
                     // batched: issue all loads of the node first (memory-level parallelism), then compute
-                    uint32_t at[kDMax];
-                    float val[kDMax], res[kDMax], pr[kDMax];
+                    uint32_t at[VD];
+                    float val[VD], res[VD], pr[VD];
 #pragma unroll
-                    for (int k = 0; k < kDMax; ++k) at[k] = (uint32_t)__ldg(tb.var_edges + b + (k < d ? k : 0)) * tile + s;
+                    for (int k = 0; k < VD; ++k) {
+                        const int kk = k < d ? k : 0;
+                        at[k] = (uint32_t)(VSORT ? b + kk : __ldg(tb.var_edges + b + kk)) * tile + s;
+                    }
 #pragma unroll
-                    for (int k = 0; k < kDMax; ++k) val[k] = k < d ? m_st[at[k]] : 0.f;
+                    for (int k = 0; k < VD; ++k) val[k] = k < d ? m_st[at[k]] : 0.f;
                     float acc = 0.f;
 #pragma unroll
-                    for (int k = 0; k < kDMax; ++k) acc += val[k];        // ascending edge id; padded slots add 0
+                    for (int k = 0; k < VD; ++k) acc += val[k];        // ascending edge id; padded slots add 0
 #pragma unroll
-                    for (int k = 0; k < kDMax; ++k) { val[k] = acc - val[k]; pr[k] = prior; }
+                    for (int k = 0; k < VD; ++k) { val[k] = acc - val[k]; pr[k] = prior; }
                     if constexpr (PROG == GD_PROG_V2_4) {
-                        mlp_softplus_blocks<true>(W1, hp, d, val, pr, res);
+                        mlp_softplus_blocks<true, VD>(W1, hp, d, val, pr, res);
 #pragma unroll
-                        for (int k = 0; k < kDMax; ++k) if (k < d) t_st[at[k]] = tanh_half(res[k]);
+                        for (int k = 0; k < VD; ++k) if (k < d) t_st[at[k]] = tanh_half_fast(res[k]);
                     } else {
 #pragma unroll
-                        for (int k = 0; k < kDMax; ++k) if (k < d) {
+                        for (int k = 0; k < VD; ++k) if (k < d) {
                             const float a = val[k] + prior;
                             if constexpr (kIsBP) {
                                 t_st[at[k]] = bp_log_abs_tanh_half(a, PROG == GD_PROG_BP_QUANTUM ? -46.0517019f : -16.1180957f);
                                 m_st[at[k]] = a < 0.f ? 1.f : 0.f;
                             } else {
-                                t_st[at[k]] = tanh_half(a);
+                                t_st[at[k]] = tanh_half_fast(a);
                             }
                         }
                     }
@@ -152,13 +157,13 @@ __global__ void __launch_bounds__(1024, 1) decode_streamed_kernel(const StreamPa
                         if constexpr (PROG == GD_PROG_V2_4) {
                             float a0[1] = {ext}, a1[1] = {prior}, o[1];
                             mlp_softplus<1, true>(W1, hp, a0, a1, o);
-                            t_st[at1] = tanh_half(o[0]);
+                            t_st[at1] = tanh_half_fast(o[0]);
                         } else if constexpr (kIsBP) {
                             const float a = ext + prior;
                             t_st[at1] = bp_log_abs_tanh_half(a, PROG == GD_PROG_BP_QUANTUM ? -46.0517019f : -16.1180957f);
                             m_st[at1] = a < 0.f ? 1.f : 0.f;   // sign flag; this variable's sum is already taken
                         } else {
-                            t_st[at1] = tanh_half(ext + prior);
+                            t_st[at1] = tanh_half_fast(ext + prior);
                         }
                     }
                 }
@@ -168,30 +173,30 @@ __global__ void __launch_bounds__(1024, 1) decode_streamed_kernel(const StreamPa
             for (int c = r; c < C; c += R) {
                 const int b = __ldg(tb.chk_ptr + c), d = __ldg(tb.chk_ptr + c + 1) - b;
                 const float sg = PROG == GD_PROG_CGNNI || PROG == GD_PROG_BP_CLASSICAL ? 1.f : xT[(size_t)(V + c) * tile + s];
-                if (d <= kDMax) {
-                    uint32_t at[kDMax];
-                    float val[kDMax], old[kDMax], res[kDMax];
+                if (d <= CD) {
+                    uint32_t at[CD];
+                    float val[CD], old[CD], res[CD];
 #pragma unroll
-                    for (int k = 0; k < kDMax; ++k) at[k] = (uint32_t)__ldg(tb.chk_edges + b + (k < d ? k : 0)) * tile + s;
+                    for (int k = 0; k < CD; ++k) at[k] = (uint32_t)__ldg(tb.chk_edges + b + (k < d ? k : 0)) * tile + s;
 #pragma unroll
-                    for (int k = 0; k < kDMax; ++k) { val[k] = k < d ? t_st[at[k]] : 0.f; old[k] = k < d ? m_st[at[k]] : 0.f; }
+                    for (int k = 0; k < CD; ++k) { val[k] = k < d ? t_st[at[k]] : 0.f; old[k] = k < d ? m_st[at[k]] : 0.f; }
                     float acc = 0.f, cnt = 0.f;
 #pragma unroll
-                    for (int k = 0; k < kDMax; ++k) { acc += val[k]; if constexpr (kIsBP) cnt += old[k]; }
+                    for (int k = 0; k < CD; ++k) { acc += val[k]; if constexpr (kIsBP) cnt += old[k]; }
 #pragma unroll
-                    for (int k = 0; k < kDMax; ++k) val[k] = acc - val[k];
+                    for (int k = 0; k < CD; ++k) val[k] = acc - val[k];
                     if constexpr (kIsBP) {
 #pragma unroll
-                        for (int k = 0; k < kDMax; ++k) if (k < d) {
+                        for (int k = 0; k < CD; ++k) if (k < d) {
                             int q = (int)(cnt - old[k]);
                             if constexpr (PROG == GD_PROG_BP_QUANTUM) q += sg < 0.f ? 1 : 0;
                             m_st[at[k]] = bp_check_out(val[k], q & 1, PROG == GD_PROG_BP_QUANTUM ? 1e-12f : 1e-7f);
                         }
                     } else {
-                        if constexpr (kSoftplus) mlp_softplus_blocks<false>(W2, hp, d, val, val, res);
-                        else mlp_relu<kDMax>(W2, hp, val, res);
+                        if constexpr (kSoftplus) mlp_softplus_blocks<false, CD>(W2, hp, d, val, val, res);
+                        else mlp_relu<CD>(W2, hp, val, res);
 #pragma unroll
-                        for (int k = 0; k < kDMax; ++k) if (k < d) m_st[at[k]] = res[k] * sg + old[k];
+                        for (int k = 0; k < CD; ++k) if (k < d) m_st[at[k]] = res[k] * sg + old[k];
                     }
                 } else {
                     const int e_end = b + d;
@@ -332,13 +337,21 @@ int streamed_decode(gd_graph* g, const gd_model* model, const float* weights_dev
         pl.p.slab = g->gstate;
     }
     void (*k)(const StreamParams);
+    const bool v8 = g->max_var_deg > 4, c8 = g->max_chk_deg > 4;
+    bool vsort = true;
+    for (size_t i = 0; i < g->h_var_edges.size() && vsort; ++i) vsort = g->h_var_edges[i] == (int32_t)i;
+#define GD_SK(P)                                                                                         \
+    (vsort ? (v8 ? (c8 ? decode_streamed_kernel<P, 8, 8, true> : decode_streamed_kernel<P, 8, 4, true>)  \
+                 : (c8 ? decode_streamed_kernel<P, 4, 8, true> : decode_streamed_kernel<P, 4, 4, true>)) \
+           : (c8 ? decode_streamed_kernel<P, 8, 8, false> : decode_streamed_kernel<P, 8, 4, false>))
     switch (model->program) {
-        case GD_PROG_CGNNI: k = decode_streamed_kernel<GD_PROG_CGNNI>; break;
-        case GD_PROG_QGNNI: k = decode_streamed_kernel<GD_PROG_QGNNI>; break;
-        case GD_PROG_V2_4: k = decode_streamed_kernel<GD_PROG_V2_4>; break;
-        case GD_PROG_BP_QUANTUM: k = decode_streamed_kernel<GD_PROG_BP_QUANTUM>; break;
-        default: k = decode_streamed_kernel<GD_PROG_BP_CLASSICAL>; break;
+        case GD_PROG_CGNNI: k = GD_SK(GD_PROG_CGNNI); break;
+        case GD_PROG_QGNNI: k = GD_SK(GD_PROG_QGNNI); break;
+        case GD_PROG_V2_4: k = GD_SK(GD_PROG_V2_4); break;
+        case GD_PROG_BP_QUANTUM: k = GD_SK(GD_PROG_BP_QUANTUM); break;
+        default: k = GD_SK(GD_PROG_BP_CLASSICAL); break;
     }
+#undef GD_SK
     k<<<pl.grid, pl.threads, pl.smem, st>>>(pl.p);
     GD_CUDA(cudaGetLastError());
     return GD_OK;
