@@ -7,7 +7,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgnn_decode_b200.so")
-SOURCES = ["gd_graph.cu", "gd_decode.cu", "gd_streamed.cu", "gd_propagate.cu", "gd_host.cu", "gd_sampler.cu", "gd_eval.cu",
+SOURCES = ["gd_graph.cu", "gd_decode.cu", "gd_streamed.cu", "gd_streamed_tma.cu", "gd_propagate.cu", "gd_host.cu", "gd_sampler.cu", "gd_eval.cu",
            "gd_backward.cu", "gd_bench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -34,16 +34,36 @@ def is_stale():
 
 
 def build_library(force=False, verbose=False):
-    """Compile every CUDA source into one shared library.  Returns the library path."""
+    """Compile every CUDA source (one object each, in parallel, rebuilt only when stale) and link
+    them into one shared library.  Returns the library path."""
     if not force and not is_stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    headers.append(os.path.join(os.path.dirname(_PKG), "include", "gnn_decode.h"))
+    t_hdr = max(os.path.getmtime(h) for h in headers)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), t_hdr):
+            return obj, ""
+        cmd = [_nvcc()] + flags + ["-c", src, "-o", obj]
+        res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stdout + res.stderr))
+        return obj, res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + [o for o, _ in results]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stdout + res.stderr))
+        raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), res.stdout + res.stderr))
     if verbose:
-        print(res.stdout + res.stderr)
+        print("".join(log for _, log in results))
     return LIB_PATH
 
 

@@ -199,6 +199,59 @@ __device__ __forceinline__ void mlp_relu(const MlpSmem& W, int hp, const float (
     for (int j = 0; j < EB; ++j) out[j] = acc[j] + W.b2;
 }
 
+// ---- 1 -> h -> 1 ReLU MLP as the piecewise-linear function it is --------------------------------
+// f(x) = b2 + sum_u c_u relu(a_u x + b_u) has at most h breakpoints t_u = -b_u / a_u; between two
+// consecutive breakpoints it is one line S_j x + I_j.  One warp builds the sorted breakpoints and
+// the (S_j, I_j) table once per CTA in double precision (exactly the reference's sum, rounded once),
+// then every evaluation is a branch-free binary search (log2 NPAD shared-memory loads; the tables
+// have <= 32 words, so two lanes on the same bank read the same word: conflict-free) + ONE FMA
+// instead of 3h instructions.  f is continuous, so landing in the neighbouring segment within an
+// ulp of a breakpoint changes nothing beyond rounding.  Used when h < NPAD <= 32 (the reference's
+// CGNNI / QGNNI have h = 10: classical/CGNNI.py:217-222, quantum/QGNNI.py:190-194).
+struct PwlSmem {
+    const float* bp;    // [NPAD] ascending breakpoints, +inf padded (entries 0 .. NPAD-2 are searched)
+    const float2* seg;  // [NPAD] (slope, intercept) of segment j = #{breakpoints < x}
+};
+__host__ __device__ constexpr int pwl_smem_floats(int npad) { return 3 * npad; }
+
+// Called by ONE full warp.  w1[h], b1[h], w2[h] are the reference's Linear(1,h).weight/bias and
+// Linear(h,1).weight (global memory), h < npad <= 32.
+__device__ __forceinline__ void pwl_build(float* bp, float2* seg, int npad, const float* w1, const float* b1,
+                                          const float* w2, float b2, int h, int lane) {
+    const double a = lane < h ? (double)w1[lane] : 0.0, b = lane < h ? (double)b1[lane] : 0.0;
+    const double c = lane < h ? (double)w2[lane] : 0.0;
+    const float t = (lane < h && a != 0.0) ? (float)(-b / a) : __int_as_float(0x7f800000);
+    int rank = 0;
+    for (int v = 0; v < h; ++v) {
+        const float tv = __shfl_sync(0xffffffffu, t, v);
+        rank += (tv < t || (tv == t && v < lane)) ? 1 : 0;
+    }
+    if (lane < h) bp[rank] = t;
+    else if (lane < npad) bp[lane] = __int_as_float(0x7f800000);
+    double S = 0.0, I = (double)b2;
+    for (int v = 0; v < h; ++v) {
+        const double av = __shfl_sync(0xffffffffu, a, v), bv = __shfl_sync(0xffffffffu, b, v);
+        const double cv = __shfl_sync(0xffffffffu, c, v);
+        const int rv = __shfl_sync(0xffffffffu, rank, v);
+        if (av == 0.0) {
+            I += cv * (bv > 0.0 ? bv : 0.0);
+        } else if (av > 0.0 ? (rv < lane) : (rv >= lane)) {   // unit v is active on segment `lane`
+            S += cv * av;
+            I += cv * bv;
+        }
+    }
+    if (lane < npad) seg[lane] = make_float2((float)S, (float)I);
+}
+
+template <int NPAD>
+__device__ __forceinline__ float pwl_eval(const PwlSmem& P, float x) {
+    int i = 0;
+#pragma unroll
+    for (int s = NPAD / 2; s >= 1; s >>= 1) i += (P.bp[i + s - 1] < x) ? s : 0;
+    const float2 sg = P.seg[i];
+    return fmaf(sg.x, x, sg.y);
+}
+
 // tanh(a/2): one per edge-iteration, so the full-accuracy libm version is affordable.
 // (tanh.approx.f32 has ~5e-4 relative error: too coarse for the 1e-4 logit bar)
 __device__ __forceinline__ float tanh_half(float a) { return tanhf(0.5f * a); }

@@ -304,6 +304,7 @@ static int plan_streamed(const gd_graph* g, const gd_model* m, int64_t B, Stream
 }
 
 int streamed_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out) {
+    if (streamed_tma_launch_info(g, model, B, out)) return GD_OK;   // the TMA-staged kernel (gd_streamed_tma.cu)
     StreamPlan pl;
     int rc = plan_streamed(g, model, B, &pl);
     if (rc != GD_OK) return rc;
@@ -314,6 +315,12 @@ int streamed_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd
 
 int streamed_decode(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, float* prob_dev,
                     float* logit_dev, uint8_t* hard_dev, int64_t B, cudaStream_t st) {
+    {
+        // default: the TMA-staged kernel; it declines (rc < 0) graphs whose edges are not in the
+        // canonical variable-sorted order or whose largest node does not fit a pipeline stage
+        const int rc = streamed_tma_decode(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, B, st);
+        if (rc >= 0) return rc;
+    }
     StreamPlan pl;
     int rc = plan_streamed(g, model, B, &pl);
     if (rc != GD_OK) return rc;
