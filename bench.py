@@ -38,26 +38,72 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_P10 = [0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.1]
+_P5 = [0.01, 0.02, 0.03, 0.04, 0.05]
+_SNR = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0]
 WORKLOADS = {
-    # name: (program, code builder, T, per-GPU batch, noise, p list)
-    "v2_4_rotated_d5_depol_B65536": ("v2_4", ("rotated", 5), 15, 65536, 1, [0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.1]),
-    "v2_4_toric_L5_iidxz_B65536": ("v2_4", ("toric", 5), 15, 65536, 0, [0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.1]),
-    "v2_4_toric_L11_iidxz_B65536": ("v2_4", ("toric", 11), 15, 65536, 0, [0.01, 0.02, 0.03, 0.04, 0.05]),
-    "v2_4_rotated_d11_depol_B65536": ("v2_4", ("rotated", 11), 15, 65536, 1, [0.01, 0.02, 0.03, 0.04, 0.05]),
+    # name: (program, code builder, T, per-GPU batch, noise, p list / SNR list)
+    # BASELINE.json configs[1] -- the N = 1 default:
+    "v2_4_rotated_d5_depol_B65536": ("v2_4", ("rotated", 5), 15, 65536, 1, _P10),
+    "v2_4_toric_L5_iidxz_B65536": ("v2_4", ("toric", 5), 15, 65536, 0, _P10),
+    # configs[2]: d = 11, batch sharded over the GPUs
+    "v2_4_toric_L11_iidxz_B65536": ("v2_4", ("toric", 11), 15, 65536, 0, _P5),
+    "v2_4_rotated_d11_depol_B65536": ("v2_4", ("rotated", 11), 15, 65536, 1, _P5),
+    # configs[0]: classical decoder on the smallest bundled code (and BCH(63,45)), B = 1024
+    "cgnni_ldpc_awgn_B1024": ("cgnni", ("ldpc", 8), 25, 1024, 2, _SNR),
+    "cgnni_bch_awgn_B1024": ("cgnni", ("bch", 63), 25, 1024, 3, _SNR),
+    "cgnni_bch_awgn_B65536": ("cgnni", ("bch", 63), 25, 65536, 3, _SNR),
+    # configs[4]: hypergraph-product [[1600,64]], many iterations, streamed global-memory path
+    "qgnni_hgp1600_depol_B16384_T50": ("qgnni", ("hgp", 1600), 50, 16384, 1, _P5),
+    "bp_hgp1600_depol_B16384_T50": ("bp_quantum", ("hgp", 1600), 50, 16384, 1, _P5),
+    "v2_4_hgp1600_depol_B8192": ("v2_4", ("hgp", 1600), 15, 8192, 1, _P5),
 }
 DEFAULT_WORKLOAD = "v2_4_rotated_d5_depol_B65536"
+PROGRAM_NAMES = {"v2_4": "quantum/decoder_v2_4.GNNI (h=128 Softplus)", "qgnni": "quantum/QGNNI.GNNI (h=10 ReLU)",
+                 "bp_quantum": "quantum/BP.GNNI (sum-product)", "cgnni": "classical/CGNNI.GNNI (h=10 ReLU)"}
 
 
 def build_pcm(spec):
     from gnn_decode_b200 import codes
     kind, size = spec
-    return codes.rotated_surface_pcm(size) if kind == "rotated" else codes.toric_pcm(size)
+    if kind == "rotated":
+        return codes.rotated_surface_pcm(size)
+    if kind == "toric":
+        return codes.toric_pcm(size)
+    if kind == "hgp":
+        return codes.hgp_pcm()
+    if kind == "ldpc":
+        return codes.ldpc_toy_pcm()
+    return codes.bch_63_45_pcm()
 
 
-def load_v2_4_weights():
-    """The shipped trained checkpoint (quantum/new_model/epoch3), carried in the golden fixture."""
-    z = np.load(os.path.join(ROOT, "tests", "golden", "v2_4_toricL5_epoch3.npz"))
+def _golden_weights(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name))
     return {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+
+
+def load_weights(program):
+    """Weights as a reference state_dict: the shipped checkpoints (carried in the golden fixtures) for
+    decoder_v2_4 (quantum/new_model/epoch3) and CGNNI (classical/model/epoch18); the reference ships no
+    QGNNI checkpoint, so that program runs its own seeded default initialisation; BP has none."""
+    if program == "v2_4":
+        return _golden_weights("v2_4_toricL5_epoch3.npz"), "reference checkpoint quantum/new_model epoch3"
+    if program == "cgnni":
+        return _golden_weights("cgnni_ldpc_epoch18.npz"), "reference checkpoint classical/model epoch18"
+    if program == "qgnni":
+        from gnn_decode_b200.quantum import QGNNI
+        torch.manual_seed(1234)
+        return {k: v.detach().clone() for k, v in QGNNI.GNNI(1).state_dict().items()}, "seeded default init (no shipped checkpoint)"
+    return {}, "none (parameter-free)"
+
+
+def make_decoder(program, T, weights):
+    from gnn_decode_b200.quantum import decoder_v2_4, QGNNI, BP
+    from gnn_decode_b200.classical import CGNNI
+    dec = {"v2_4": decoder_v2_4.GNNI, "qgnni": QGNNI.GNNI, "bp_quantum": BP.GNNI, "cgnni": CGNNI.GNNI}[program](T)
+    if weights:
+        dec.load_state_dict(weights)
+    return dec
 
 
 class ClockSampler(object):
@@ -165,11 +211,12 @@ def main():
     Cn, V = pcm.shape
     N = V + Cn
     E = int(pcm.sum())
-    weights = load_v2_4_weights()
+    weights, weights_src = load_weights(program)
     cores = os.cpu_count() or 1
-    config = {"workload": args.workload, "program": "quantum/decoder_v2_4.GNNI (h=128 Softplus)", "code": "%s-%d" % code_spec,
-              "V": V, "C": Cn, "E": E, "T": T, "batch_per_gpu": B, "noise": "depolarizing" if noise else "iid-xz",
-              "l2": "L2 flushed (256 MiB write) between timed steps", "weights": "reference checkpoint epoch3"}
+    config = {"workload": args.workload, "program": PROGRAM_NAMES[program], "code": "%s-%d" % code_spec,
+              "V": V, "C": Cn, "E": E, "T": T, "batch_per_gpu": B,
+              "noise": ["iid-xz", "depolarizing", "awgn (all-zero codeword)", "awgn (all-one codeword)"][noise],
+              "l2": "L2 flushed (256 MiB write) between timed steps", "weights": weights_src}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -191,10 +238,11 @@ def main():
         value = per_step * args.steps / dt
         line = {"impl": "reference", "metric": "decoded syndromes/sec", "value": value, "unit": "syndromes/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if program == "cgnni" else "f64", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": value, "unit": "syndromes/s", "cores": cores, "kind": "port",
-                                 "sample": "%d syndromes per step in chunks of 128 (the reference's BATCH_SIZE), fp64, "
+                                 "sample": "%d syndromes per step in chunks of 128 (the reference's BATCH_SIZE), reference dtype, "
                                            "torch CPU %d threads, oracle/restate.py" % (per_step, cores)},
                 "e2e": {"value": value, "unit": "syndromes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -204,7 +252,6 @@ def main():
     import torch.distributed as dist
     from gnn_decode_b200 import _cabi
     from gnn_decode_b200.graph import TannerGraph
-    from gnn_decode_b200.quantum import decoder_v2_4
     from gnn_decode_b200.sampler import sample_syndromes
 
     torch.cuda.set_device(local_rank)
@@ -212,9 +259,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     g = TannerGraph.from_pcm(pcm, dev)
-    dec = decoder_v2_4.GNNI(T)
-    dec.load_state_dict(weights)
-    dec = dec.to(dev).eval()
+    dec = make_decoder(program, T, weights).to(dev).eval()
     dec.bind_graph(g)
     model = dec.gd_model()
     info = g.launch_info(model, B)
@@ -224,12 +269,13 @@ def main():
     prob = torch.empty((B, V), dtype=torch.float32, device=dev)
     hard = torch.empty((B, V), dtype=torch.uint8, device=dev)
     wdev = dec.packed_weights(dev)
+    wptr = C.c_void_p(wdev.data_ptr()) if wdev is not None else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lib = _cabi.lib()
     stream = torch.cuda.current_stream(dev)
 
     def step():
-        _cabi.check(lib.gd_decode_fwd(g.handle, C.byref(model), C.c_void_p(wdev.data_ptr()), C.c_void_p(x.data_ptr()),
+        _cabi.check(lib.gd_decode_fwd(g.handle, C.byref(model), wptr, C.c_void_p(x.data_ptr()),
                                       C.c_void_p(prob.data_ptr()), None, C.c_void_p(hard.data_ptr()), B,
                                       C.c_void_p(stream.cuda_stream)))
 
@@ -292,29 +338,41 @@ def main():
             hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
         else:
             hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        alg_bytes = B * (4 * N + 4 * V + V)                      # x in, prob + hard out, per launch
+        io_bytes = B * (4 * N + 4 * V + V)                       # x in, prob + hard out, per launch
         med_ms = statistics.median(kernel_ms)
-        achieved = alg_bytes / (med_ms * 1e-3) / 1e9
-        r = (C.c_double * 2)()
-        _cabi.check(lib.gd_microbench(1, 4096, local_rank, r))   # ex2+lg2 pairs / s: the Softplus unit rate
-        unit_peak = r[0]
-        units = B * E * (T * 256 + 128)                          # Softplus hidden-unit evaluations per launch
-        unit_rate = units / (med_ms * 1e-3)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_decode_kernel_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload)
+        if info["resident"]:
+            alg_bytes = io_bytes
+            kname = "gd::decode_kernel<%s, resident>" % program
+            note = ("fused resident kernel: ~%d B/syndrome, so HBM is not the binding resource; see pipe" % (alg_bytes // B)
+                    if program == "v2_4" else "fused resident kernel: ~%d B/syndrome; FP32-issue bound, not HBM" % (alg_bytes // B))
+        else:
+            # streamed path: per edge and iteration m: R,R,W  t: W,R = 20 B for the learned
+            # programs, 16 B for sum-product (sign rides in t); the first iteration reads no m (m == 0).
+            per_edge = (16 * T - 4) if program.startswith("bp") else (20 * T - 8)
+            alg_bytes = io_bytes + B * E * max(per_edge, 0)
+            kname = "gd::decode_streamed_tma_kernel<%s>" % program
+            note = "streamed global-memory path: %.2f MB of edge-state traffic per syndrome" % (E * per_edge / 1e6)
+        achieved = alg_bytes / (med_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": "gd::decode_kernel<V2_4, resident>",
-                    "kernel_ms": med_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                    "note": "fused resident kernel: ~%d B/syndrome, so HBM is not the binding resource; see pipe" % (alg_bytes // B),
-                    "pipe": {"name": "xu (MUFU): Softplus hidden-unit evaluations; peak = the 2-MUFU-per-unit (ex2+lg2) "
-                                     "rate; the kernel needs 1.5 MUFU/unit (half of the lg2 run as an FMA-pipe polynomial), "
-                                     "so frac can exceed 1", "achieved": unit_rate / 1e12,
-                             "peak": unit_peak / 1e12, "unit": "T Softplus units/s", "frac": unit_rate / unit_peak,
-                             "frac_of_1p5_mufu_bound": unit_rate / (unit_peak * 2.0 / 1.5),
-                             "peak_source": "gd_microbench kind=1 (ex2+lg2 pairs/s), measured live on this GPU",
-                             "units_per_launch": units}}
+                    "traffic": traffic, "peak_source": peak_src, "kernel": kname,
+                    "kernel_ms": med_ms, "algorithmic_bytes_per_launch": alg_bytes, "note": note}
+        if program == "v2_4":
+            r = (C.c_double * 2)()
+            _cabi.check(lib.gd_microbench(1, 4096, local_rank, r))   # ex2+lg2 pairs / s: the Softplus unit rate
+            unit_peak = r[0]
+            units = B * E * (T * 256 + 128)                          # Softplus hidden-unit evaluations per launch
+            unit_rate = units / (med_ms * 1e-3)
+            roofline["pipe"] = {"name": "xu (MUFU): Softplus hidden-unit evaluations; peak = the 2-MUFU-per-unit (ex2+lg2) "
+                                        "rate; the kernel needs 1.5 MUFU/unit (half of the lg2 run as an FMA-pipe polynomial), "
+                                        "so frac can exceed 1", "achieved": unit_rate / 1e12,
+                                "peak": unit_peak / 1e12, "unit": "T Softplus units/s", "frac": unit_rate / unit_peak,
+                                "frac_of_1p5_mufu_bound": unit_rate / (unit_peak * 2.0 / 1.5),
+                                "peak_source": "gd_microbench kind=1 (ex2+lg2 pairs/s), measured live on this GPU",
+                                "units_per_launch": units}
         line = {"metric": "decoded syndromes/sec", "value": value, "unit": "syndromes/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -324,7 +382,7 @@ def main():
                         "d2h_bytes_per_step": B * V * 5, "api": "GNNI.decode_host -> gd_decode_host (pinned host buffers)",
                         "matches_device_path": same},
                 "gpu_launches": args.steps * 1,     # timed `value` region: one gd::decode_kernel launch per step
-                "gpu_launches_e2e": args.steps * min(4, max(1, B // 8192)),
+                "gpu_launches_e2e": args.steps * (min(4, max(1, B // 8192)) if info["resident"] else 1),
                 "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:
             rng = np.random.RandomState(1234)
@@ -340,8 +398,14 @@ def main():
 
 
 def _host_sample(pcm, noise, p_list, n, rng):
-    """Host-side synthetic syndromes with gen_syn's layout (quantum/error_generate.py:252-278)."""
+    """Host-side synthetic syndromes with gen_syn's layout (quantum/error_generate.py:252-278), or the
+    classical AWGN LLRs of classical/CGNNI.py:125-147,159 for noise 2 / 3."""
     Cn, V = pcm.shape
+    if noise >= 2:
+        snr = np.asarray(p_list)[rng.randint(0, len(p_list), n)]
+        sigma = np.sqrt(1.0 / 10.0 ** (snr / 10.0))[:, None]
+        y = (1.0 if noise == 2 else -1.0) + sigma * rng.standard_normal((n, V))
+        return torch.from_numpy(np.concatenate([2.0 * y / sigma ** 2, np.zeros((n, Cn))], 1))
     p = np.asarray(p_list)[rng.randint(0, len(p_list), n)]
     if noise == 0:
         err = (rng.random_sample((n, V)) < p[:, None]).astype(np.uint8)

@@ -4,6 +4,9 @@
 // independent X and Z flips, x = [prior | (-1)^(H^T e mod 2)], y = e) -- the reference itself
 // uses the unseeded Mersenne Twister of Python/NumPy, so only the distribution can match.
 // noise == 1 adds the depolarizing channel BASELINE.json names (not present in the reference).
+// noise == 2 / 3 is the classical input of classical/CGNNI.py:125-147,159: BPSK of the all-zero (2) or
+// all-one (3) codeword over AWGN, sigma = 10^(-SNR/20) with the SNR (dB) drawn from the list per
+// sample, x = [2 y / sigma^2 | 0 ... 0]; the "err" output is the transmitted codeword (data.y).
 #include "gd_common.cuh"
 
 namespace gd {
@@ -49,6 +52,30 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
         const uint4 sel = philox4x32_10(make_uint4(s_lo, s_hi, 0u, 0u), key);   // stream 0: p choice
         const int pi = (int)(sel.x % (uint32_t)p.n_p);
         const float pr = p.p[pi], prior = p.prior[pi];
+        if (p.noise >= 2) {
+            // AWGN: Box-Muller on the four uniforms of a Philox block -> four N(0,1) draws
+            const float sigma = pr, inv_var2 = prior;      // p[] holds sigma, prior[] holds 2 / sigma^2
+            const float tx = p.noise == 2 ? 1.0f : -1.0f;
+            float* xr = p.x + b * p.N;
+            for (int j0 = lane * 4; j0 < V; j0 += 128) {
+                const uint4 r = philox4x32_10(make_uint4(s_lo, s_hi, (uint32_t)(j0 >> 2), 1u), key);
+                const float u0 = ((float)(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = u01(r.y);
+                const float u2 = ((float)(r.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = u01(r.w);
+                const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+                float s0, c0, s1, c1;
+                sincospif(2.0f * u1, &s0, &c0);
+                sincospif(2.0f * u3, &s1, &c1);
+                const float nz[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (j0 + q < V) {
+                        xr[j0 + q] = (tx + sigma * nz[q]) * inv_var2;
+                        if (p.err) p.err[b * V + j0 + q] = p.noise == 3 ? 1 : 0;
+                    }
+            }
+            for (int c = lane; c < p.C; c += 32) xr[V + c] = 0.0f;
+            continue;
+        }
         if (p.noise == 0) {
             for (int j0 = lane * 4; j0 < V; j0 += 128) {
                 const uint4 r = philox4x32_10(make_uint4(s_lo, s_hi, (uint32_t)(j0 >> 2), 1u), key);
@@ -92,14 +119,19 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
 extern "C" int gd_sample(const gd_graph* g, int32_t noise, const float* p_list, int32_t n_p, uint64_t seed,
                          uint64_t first_sample, float* x_dev, uint8_t* err_dev, int64_t B, void* stream) {
     GD_CHECK_ARG(g != nullptr, "gd_sample: graph is NULL");
-    GD_CHECK_ARG(noise == 0 || noise == 1, "gd_sample: noise must be 0 (iid X/Z) or 1 (depolarizing)");
+    GD_CHECK_ARG(noise >= 0 && noise <= 3, "gd_sample: noise must be 0 (iid X/Z), 1 (depolarizing), 2/3 (AWGN, codeword 0/1)");
     GD_CHECK_ARG(p_list && n_p >= 1 && n_p <= gd::kMaxP, "gd_sample: need 1..%d error rates", gd::kMaxP);
-    GD_CHECK_ARG(noise == 0 || (g->V % 2) == 0, "gd_sample: depolarizing noise needs V = 2n slots");
+    GD_CHECK_ARG(noise != 1 || (g->V % 2) == 0, "gd_sample: depolarizing noise needs V = 2n slots");
     GD_CHECK_ARG(B >= 0, "gd_sample: negative B");
     if (B == 0) return GD_OK;
     GD_CHECK_ARG(x_dev != nullptr, "gd_sample: x is NULL");
     gd::SampleParams p;
-    for (int i = 0; i < n_p; ++i) {
+    for (int i = 0; i < n_p && noise >= 2; ++i) {   // p_list = SNR in dB (CGNNI.py:129: sigma = (1 / 10^(SNR/10))^0.5)
+        const double sigma = sqrt(1.0 / pow(10.0, (double)p_list[i] / 10.0));
+        p.p[i] = (float)sigma;
+        p.prior[i] = (float)(2.0 / (sigma * sigma));
+    }
+    for (int i = 0; i < n_p && noise < 2; ++i) {
         GD_CHECK_ARG(p_list[i] > 0.f && p_list[i] < 1.f, "gd_sample: error rate %g outside (0,1)", (double)p_list[i]);
         const double pd = (double)p_list[i];
         const double pm = noise == 0 ? pd : 2.0 * pd / 3.0;   // marginal flip probability of one slot

@@ -7,11 +7,12 @@ import torch
 
 from . import _cabi
 
-NOISE_IID_XZ, NOISE_DEPOLARIZING = 0, 1
+NOISE_IID_XZ, NOISE_DEPOLARIZING, NOISE_AWGN_ZERO, NOISE_AWGN_ONE = 0, 1, 2, 3
 
 
 def sample_syndromes(graph, B, p_list, noise=NOISE_IID_XZ, seed=1234, first_sample=0, x_out=None, err_out=None):
     """Returns (x [B, V+C] fp32 = [prior | (-1)^syndrome], err [B, V] uint8) on graph.device.
+    noise 2 / 3 (classical, CGNNI.py:125-159): p_list = SNR in dB, x = [channel LLR | 0], err = codeword.
     Sample s depends only on (seed, first_sample + s): shards of a batch can be drawn on
     different ranks and are bit-identical to the single-GPU draw."""
     dev = graph.device

@@ -171,7 +171,11 @@ int gd_decode_launch_info(const gd_graph* g, const gd_model* model, int64_t B, g
  *      x = [log((1-p)/p)]*V | (-1)^(H^T e mod 2);  y = e.
  *      noise: 0 = reference iid X/Z flips (each of the V slots flips w.p. p);
  *             1 = depolarizing on V/2 qubits (X,Y,Z each p/3; slot j = X part, j+V/2 = Z part,
- *                 prior = log((1-2p/3)/(2p/3))). */
+ *                 prior = log((1-2p/3)/(2p/3)));
+ *             2 / 3 = the classical input of Gen_Data.AWGN + CustomDataset (classical/CGNNI.py:
+ *                 125-147,159): BPSK of the all-zero (2) / all-one (3) codeword over AWGN,
+ *                 p_list = SNR in dB (one drawn per sample), sigma = 10^(-SNR/20),
+ *                 x = [2 y / sigma^2]*V | 0*C (Box-Muller on the Philox words); err = the codeword. */
 int gd_sample(const gd_graph* g, int32_t noise, const float* p_list_host, int32_t n_p,
               uint64_t seed, uint64_t first_sample, float* x_dev, uint8_t* err_dev, int64_t B,
               void* stream);

@@ -64,6 +64,32 @@ def sample(pcm, B, p_list, noise=0, seed=1234, first_sample=0):
     return x, err
 
 
+def sample_awgn(V, Cn, B, snr_db_list, codeword_bit=0, seed=1234, first_sample=0):
+    """The classical input (classical/CGNNI.py:125-147,159) as csrc/gd_sampler.cu draws it (noise 2/3):
+    sigma = (1/10^(SNR/10))^0.5, y = (1 - 2c) + sigma * N(0,1) (Box-Muller on Philox words),
+    x = [2 y / sigma^2 | 0].  float64 arithmetic: pins the CUDA kernel to ~1e-5 relative, not bitwise."""
+    snr = np.asarray(snr_db_list, dtype=np.float32)
+    sid = np.uint64(first_sample) + np.arange(B, dtype=np.uint64)
+    s_lo, s_hi = (sid & MASK).astype(np.uint32), (sid >> np.uint64(32)).astype(np.uint32)
+    k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    sel = philox4x32_10(s_lo, s_hi, np.uint32(0), np.uint32(0), k0, k1)[0]
+    pi = (sel % np.uint32(len(snr))).astype(np.int64)
+    sigma = np.sqrt(1.0 / 10.0 ** (snr.astype(np.float64) / 10.0)).astype(np.float32).astype(np.float64)[pi]
+    inv2 = (2.0 / np.sqrt(1.0 / 10.0 ** (snr.astype(np.float64) / 10.0)) ** 2).astype(np.float32).astype(np.float64)[pi]
+    nblk = (V + 3) // 4
+    blk = np.arange(nblk, dtype=np.uint32)
+    r = philox4x32_10(s_lo[:, None], s_hi[:, None], blk[None, :], np.uint32(1), k0, k1)
+    ua = lambda w: ((w >> np.uint32(8)).astype(np.float64) + 1.0) / 16777216.0
+    ub = lambda w: (w >> np.uint32(8)).astype(np.float64) / 16777216.0
+    r0, r1 = np.sqrt(-2.0 * np.log(ua(r[0]))), np.sqrt(-2.0 * np.log(ua(r[2])))
+    a0, a1 = 2.0 * np.pi * ub(r[1]), 2.0 * np.pi * ub(r[3])
+    nz = np.stack([r0 * np.cos(a0), r0 * np.sin(a0), r1 * np.cos(a1), r1 * np.sin(a1)], axis=-1).reshape(B, nblk * 4)[:, :V]
+    tx = 1.0 - 2.0 * codeword_bit
+    llr = (tx + sigma[:, None] * nz) * inv2[:, None]
+    x = np.concatenate([llr, np.zeros((B, Cn))], 1).astype(np.float32)
+    return x, np.full((B, V), codeword_bit, dtype=np.uint8)
+
+
 def count_failures(pcm, logical, err, hard):
     """LossFunc.forward(train=0) of quantum/neural_BP.py:338-348 on 0/1 arrays:
     (syndrome failures, logical failures among syndrome-ok, total)."""

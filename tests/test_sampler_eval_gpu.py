@@ -31,6 +31,31 @@ def test_sampler_bit_exact_vs_oracle(code, noise):
     assert torch.equal(e2, err[300:400]) and torch.equal(x2, x[300:400])
 
 
+@pytest.mark.parametrize("bit", [0, 1])
+def test_awgn_sampler_matches_oracle_and_reference_statistics(bit):
+    """Classical input (classical/CGNNI.py:125-147,159): x = [2y/sigma^2 | 0], y = BPSK + AWGN.  The Box-Muller
+    draw is pinned to the float64 oracle; mean / variance of the LLR match the channel the reference builds."""
+    pcm = codes.bch_63_45_pcm()
+    g = TannerGraph.from_pcm(pcm, DEV)
+    snr = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0]
+    B = 4096
+    x, cw = sample_syndromes(g, B, snr, noise=2 + bit, seed=77, first_sample=123)
+    xo, cwo = philox.sample_awgn(g.V, g.C, B, snr, codeword_bit=bit, seed=77, first_sample=123)
+    x = x.cpu().numpy()
+    assert np.array_equal(cw.cpu().numpy(), cwo)
+    assert np.array_equal(x[:, g.V:], np.zeros((B, g.C), np.float32))               # check slots zero-filled (:159)
+    assert np.allclose(x[:, :g.V], xo[:, :g.V], rtol=2e-5, atol=2e-4)
+    x1, _ = sample_syndromes(g, B, [4.0], noise=2 + bit, seed=5)                     # one SNR: LLR ~ N(2 tx / s^2, 4 / s^2)
+    s2 = 1.0 / 10 ** 0.4
+    llr = x1.cpu().numpy()[:, :g.V].astype(np.float64)
+    tx = 1.0 - 2.0 * bit
+    n = llr.size
+    assert abs(llr.mean() - 2 * tx / s2) < 5 * (2 / np.sqrt(s2)) / np.sqrt(n)
+    assert abs(llr.var() - 4 / s2) < 0.02 * 4 / s2
+    x2, _ = sample_syndromes(g, 100, snr, noise=2 + bit, seed=77, first_sample=123 + 300)
+    assert np.array_equal(x2.cpu().numpy(), x[300:400])                               # shards are slices
+
+
 def test_sampler_distribution_matches_gen_syn_layout(codes_npz):
     """Layout of the reference's gen_syn output (fixture produced by the reference, seeded) and its
     flip statistics: every slot flips independently w.p. p, prior = log((1-p)/p), syndrome signs."""
