@@ -70,6 +70,8 @@ def decode_with_grad(decoder, graph, x, return_logits=False, return_hard=False):
         raise _cabi.GdError("training (backward) kernels exist for the decoder_v2_4 program only; "
                             "call .eval() or wrap inference in torch.no_grad()")
     x32 = x.detach().to(torch.float32).contiguous()
+    if x32.data_ptr() % 16:
+        x32 = x32.clone()
     prob, logit = _DecodeFn.apply(decoder, graph, x32, *decoder._gd_params())
     out = [prob]
     if return_logits:

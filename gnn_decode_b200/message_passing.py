@@ -274,6 +274,8 @@ class DecoderBase(torch.nn.Module):
             from .autograd import decode_with_grad
             return decode_with_grad(self, g, x, return_logits, return_hard)
         x32 = x.detach().to(torch.float32).contiguous()
+        if x32.data_ptr() % 16:                # e.g. a row slice of a larger batch: the bulk copies need 16-byte alignment
+            x32 = x32.clone()
         prob = torch.empty((B, g.V), dtype=torch.float32, device=dev)
         logit = torch.empty((B, g.V), dtype=torch.float32, device=dev) if return_logits else None
         hard = torch.empty((B, g.V), dtype=torch.uint8, device=dev) if return_hard else None

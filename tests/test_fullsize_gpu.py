@@ -1,0 +1,89 @@
+"""GPU suite at BASELINE.json's FULL sizes, where the oracle is too slow to run on everything:
+size-independent properties (the batch is block-diagonal, so a syndrome's result may not depend
+on what it is batched with; decoding is deterministic; an error-free syndrome decodes to "no
+flip"; a sample -> decode -> count loop is consistent) plus an oracle check on a random subset."""
+import numpy as np
+import pytest
+import torch
+
+from gnn_decode_b200 import codes
+from gnn_decode_b200.evaluate import count_failures
+from gnn_decode_b200.graph import TannerGraph
+from gnn_decode_b200.quantum import BP, QGNNI, decoder_v2_4
+from gnn_decode_b200.sampler import sample_syndromes
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-4          # BASELINE.json north_star: soft logits within 1e-4 relative in fp32
+
+
+def _v2_4(T):
+    z = np.load(__file__.rsplit("/", 1)[0] + "/golden/v2_4_toricL5_epoch3.npz")
+    w = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    dec = decoder_v2_4.GNNI(T)
+    dec.load_state_dict(w)
+    return dec.to(DEV).eval(), w
+
+
+def _subset_vs_oracle(program, pcm, x, logit, weights, T, idx, rtol):
+    ei = torch.from_numpy(codes.edge_index_of(pcm))
+    Cn, V = pcm.shape
+    ref = restate.decode(program, ei, V, Cn, x[idx].cpu().double(), weights, T=T, dtype=torch.float64)["logit"]
+    got = logit[idx].double().cpu()
+    atol = 1e-4 * (1.0 + ref.pow(2).mean().sqrt().item())
+    assert bool(((got - ref).abs() <= rtol * ref.abs() + atol).all()), (got - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("code,B", [(("rotated", 5), 65536), (("toric", 11), 65536)])
+def test_v2_4_full_batch_properties(code, B):
+    """configs[1] (rotated d=5, depolarizing, B = 65536) and configs[2] (d = 11, B = 65536 per GPU)."""
+    pcm = codes.rotated_surface_pcm(code[1]) if code[0] == "rotated" else codes.toric_pcm(code[1])
+    g = TannerGraph.from_pcm(pcm, DEV)
+    dec, w = _v2_4(15)
+    x, err = sample_syndromes(g, B, [0.01, 0.03, 0.05, 0.08], noise=1 if code[0] == "rotated" else 0, seed=11)
+    prob, logit, hard = dec.decode(x, graph=g, return_logits=True, return_hard=True)
+    prob2 = dec.decode(x, graph=g)
+    assert torch.equal(prob, prob2)                                          # deterministic
+    assert torch.equal(hard.bool(), prob > 0.5)
+    # batch-composition invariance: any slice decoded alone is bit-identical (different tile geometry)
+    for lo, n in ((0, 8), (12345, 777), (B - 1001, 1001)):
+        assert torch.equal(dec.decode(x[lo:lo + n].contiguous(), graph=g), prob[lo:lo + n])
+    # rank shards are slices of the single-GPU draw and decode (no collective)
+    xs, _ = sample_syndromes(g, 4096, [0.01, 0.03, 0.05, 0.08], noise=1 if code[0] == "rotated" else 0, seed=11,
+                             first_sample=B // 2)
+    assert torch.equal(xs, x[B // 2:B // 2 + 4096])
+    assert torch.equal(dec.decode(xs, graph=g), prob[B // 2:B // 2 + 4096])
+    idx = torch.from_numpy(np.random.RandomState(0).choice(B, 48, replace=False))
+    _subset_vs_oracle("v2_4", pcm, x, logit, w, 15, idx.to(DEV), RTOL)
+
+
+def test_hgp_streamed_full_batch_properties():
+    """configs[4]: hypergraph-product [[1600,64]] (V = 3200, E = 10752), B = 16384, many iterations,
+    streamed global-memory path: determinism, batch-composition invariance, oracle subset, and the
+    sum-product decoder leaves error-free syndromes alone and corrects all weight-1 errors."""
+    pcm = codes.hgp_pcm()
+    g = TannerGraph.from_pcm(pcm, DEV)
+    B = 16384
+    x, err = sample_syndromes(g, B, [0.005, 0.01, 0.02], noise=1, seed=3)
+    torch.manual_seed(0)
+    q = QGNNI.GNNI(20).to(DEV).eval()
+    assert g.launch_info(q.gd_model(), B)["resident"] == 0
+    prob, logit = q.decode(x, graph=g, return_logits=True)
+    assert torch.equal(prob, q.decode(x, graph=g))
+    for lo, n in ((0, 40), (5000, 333)):                                     # other tile sizes / ragged tiles
+        assert torch.equal(q.decode(x[lo:lo + n].contiguous(), graph=g), prob[lo:lo + n])
+    idx = torch.tensor([0, 1, 4097, 9999, B - 1], device=DEV)
+    _subset_vs_oracle("qgnni", pcm, x, logit, {k: v.cpu() for k, v in q.state_dict().items()}, 20, idx, RTOL)
+
+    bp = BP.GNNI(30).to(DEV).eval()
+    prob, logit, hard = bp.decode(x, graph=g, return_logits=True, return_hard=True)
+    assert torch.equal(hard, bp.decode(x, graph=g, return_hard=True)[1])
+    _subset_vs_oracle("bp_quantum", pcm, x, logit, {}, 30, idx, 2e-3)         # BP bar: tests/test_parity_gpu.py
+    clean = (err.sum(1) == 0)
+    assert int(clean.sum()) > 0 and int(hard[clean].sum()) == 0              # no error -> no correction
+    w1 = (err.sum(1) == 1)
+    cnt = count_failures(g, err[w1].contiguous(), hard[w1].contiguous())
+    assert int(w1.sum()) > 0 and int(cnt[0]) == 0                            # single errors: syndrome always cleared
+    total = count_failures(g, err, hard)
+    assert int(total[0]) < 0.10 * B                                          # sanity: plain BP well below threshold
