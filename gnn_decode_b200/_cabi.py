@@ -9,6 +9,8 @@ from .build import LIB_PATH
 
 GD_OK, GD_ERR_INVALID, GD_ERR_CUDA, GD_ERR_UNSUPPORTED = 0, 1, 2, 3
 PROG_CGNNI, PROG_QGNNI, PROG_V2_4, PROG_BP_QUANTUM, PROG_BP_CLASSICAL = 0, 1, 2, 3, 4
+PROG_NEURAL_BP, PROG_GRU_CA = 5, 6
+FLAG_ALL_ITERS = 1
 PHASE_VAR, PHASE_CHK = 0, 1
 ABI_VERSION = 1
 

@@ -64,8 +64,13 @@ struct gd_graph {
 
 static inline bool gd_model_valid(const gd_model* m) {
     if (!m) return false;
-    if (m->flags != 0 || m->iters < 0) return false;
+    if (m->iters < 0) return false;
+    if (m->flags != 0 && !(m->flags == GD_FLAG_ALL_ITERS && m->program == GD_PROG_GRU_CA)) return false;
     switch (m->program) {
+        case GD_PROG_GRU_CA:
+            return m->hidden >= 1 && m->hidden <= 256;
+        case GD_PROG_NEURAL_BP:
+            return m->hidden >= 1;          // = E, checked against the graph at launch
         case GD_PROG_CGNNI:
         case GD_PROG_QGNNI:
         case GD_PROG_V2_4:

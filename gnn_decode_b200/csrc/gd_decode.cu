@@ -34,7 +34,7 @@ struct DecodeParams {
     GraphTables tb;
     long long B;
     int T, V, C, E, N;
-    int tile, R, hid, hp, n_tiles, maxvc;
+    int tile, R, hid, hp, n_tiles, maxvc, all_iters;
     int off_w, off_tab, off_x, off_node, off_m, off_t;
 };
 
@@ -102,13 +102,15 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool kIsBP = (PROG == GD_PROG_BP_QUANTUM || PROG == GD_PROG_BP_CLASSICAL);
     constexpr bool kSoftplus = (PROG == GD_PROG_V2_4);
+    constexpr bool kNBP = (PROG == GD_PROG_NEURAL_BP);   // sum-product + per-edge weights (quantum/neural_BP.py)
+    constexpr bool kGRU = (PROG == GD_PROG_GRU_CA);      // MLP + GRUCell updates (quantum/QGNNNI_ca.py)
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     float* wsm = reinterpret_cast<float*>(smem + p.off_w);
     float* xs = reinterpret_cast<float*>(smem + p.off_x);
     float* node = reinterpret_cast<float*>(smem + p.off_node);
     const int tile = p.tile, R = p.R, E = p.E, V = p.V, C = p.C, N = p.N, hp = p.hp;
-    float* node2 = node + (size_t)p.maxvc * tile;  // BP only (allocated only then)
+    float* node2 = node + (size_t)p.maxvc * tile;  // sum-product programs only (allocated only then)
     float* m_st = reinterpret_cast<float*>(smem + p.off_m);
     float* t_st = reinterpret_cast<float*>(smem + p.off_t);
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -136,7 +138,25 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         tb.var_edges = d_ve; tb.chk_ptr = d_cp; tb.chk_edges = d_ce;
     }
     MlpSmem W1{}, W2{}, W3{};
-    if constexpr (!kIsBP) {
+    const float* gru = nullptr;   // GRU_CA: the two GRUCell(1,1) parameter sets, [2][12] in shared memory
+    if constexpr (kGRU) {
+        const float* w = p.weights;
+        const int h = p.hid;
+        float* slot = wsm;
+        float* gs = wsm + 3 * 4 * hp;
+        for (int k = 0; k < 3; ++k) {       // ggc1.mlp1 | ggc1.rnn | ggc2.mlp2 | ggc2.rnn | mlp
+            stage_mlp(slot, hp, h, w, 1, false, w + h, w + 2 * h, 1.f, 1.f, tid, nthr);
+            const MlpSmem Wk{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
+            if (k == 0) W1 = Wk; else if (k == 1) W2 = Wk; else W3 = Wk;
+            w += 3 * h + 1;
+            slot += 4 * hp;
+            if (k < 2) {
+                if (tid < 12) gs[k * 12 + tid] = w[tid];
+                w += 12;
+            }
+        }
+        gru = gs;
+    } else if constexpr (!kIsBP && !kNBP) {
         const float* w = p.weights;
         const int h = p.hid;
         const float s1 = kSoftplus ? kLog2e : 1.f, s2 = kSoftplus ? kLn2 : 1.f;
@@ -185,12 +205,102 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         __syncthreads();
         const float* xrow = xs + (size_t)s * N;  // prior = xrow[0..V), check input = xrow[V..V+C)
 
+        // read-out as a callable: GRU_CA with GD_FLAG_ALL_ITERS emits one prediction per iteration
+        auto emit = [&](const long long out_off) {
+            // ---- read-out: logits staged as [tile][V] in the node region ----
+            if constexpr (PROG == GD_PROG_V2_4) {  // per-EDGE MLP, then sum at the variable
+                for (int i0 = 0; i0 < n_iter; i0 += kEB) {
+                    float x0[kEB], o[kEB];
+                    int ee[kEB];
+    #pragma unroll
+                    for (int j = 0; j < kEB; ++j) {
+                        const int e = r + (i0 + j) * R;
+                        ee[j] = e;
+                        x0[j] = m_st[(size_t)(e < E ? e : E - 1) * tile + s];
+                        if (p.stash && e < E && s < nvalid) p.stash[((size_t)p.T * 2 * E + e) * (size_t)p.B + s0 + s] = x0[j];
+                    }
+                    if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W3, hp, x0, x0, o);
+                    else mlp_softplus<kEB, false>(W3, hp, x0, x0, o);
+    #pragma unroll
+                    for (int j = 0; j < kEB; ++j)
+                        if (ee[j] < E) t_st[(size_t)ee[j] * tile + s] = o[j];
+                }
+                __syncthreads();
+            }
+            float* stage = node;  // [tile][V]
+            for (int v = r; v < V; v += R) {
+                const int b = tb.ld(tb.var_ptr, v), e_end = tb.ld(tb.var_ptr, v + 1);
+                const float* src = PROG == GD_PROG_V2_4 ? t_st : m_st;
+                float acc = 0.f, acc_p = 0.f;
+                for (int i = b; i < e_end; ++i) {
+                    const int e = tb.ld(tb.var_edges, i);
+                    if constexpr (kNBP) {   // neural_BP.py:308-312: scatter(m W) + scatter(prior W_p), no bare prior
+                        const float* wo = p.weights + (size_t)p.T * 2 * E;
+                        acc += src[(size_t)e * tile + s] * __ldg(wo + e);
+                        acc_p += xrow[v] * __ldg(wo + E + e);
+                    } else {
+                        acc += src[(size_t)e * tile + s];
+                    }
+                }
+                float lg = kNBP ? acc + acc_p : (kGRU ? acc : acc + xrow[v]);   // QGNNNI_ca.py:241-245: mlp(sum), no prior
+                if constexpr (kGRU) {
+                    float xi[1] = {lg}, oo[1];
+                    mlp_relu<1>(W3, hp, xi, oo);
+                    lg = oo[0];
+                }
+                if constexpr (PROG == GD_PROG_CGNNI || PROG == GD_PROG_QGNNI) {
+                    float xi[1] = {lg}, oo[1];
+                    mlp_relu<1>(W3, hp, xi, oo);
+                    lg = oo[0];
+                }
+                stage[(size_t)s * V + v] = lg;
+            }
+            __syncthreads();
+            // ---- outputs: coalesced 128-bit stores of prob / logit, 32-bit stores of hard bytes ----
+            {
+                const int total = nvalid * V;
+                const long long g0 = out_off + s0 * V;  // s0 * V is a multiple of 8 elements: tile % 8 == 0
+                const bool vec_ok = (g0 & 3) == 0;
+                constexpr bool kClamp = (PROG == GD_PROG_CGNNI || PROG == GD_PROG_BP_CLASSICAL || PROG == GD_PROG_GRU_CA);
+                for (int i = tid * 4; i < total; i += nthr * 4) {
+                    float l[4], pr[4];
+                    const int n = min(4, total - i);
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        l[j] = j < n ? stage[i + j] : 0.f;
+                        pr[j] = sigmoid_neg(l[j]);
+                        if (kClamp) pr[j] = fminf(fmaxf(pr[j], 1e-7f), 1.0f - 1e-7f);
+                    }
+                    if (n == 4 && vec_ok) {
+                        if (p.prob) *reinterpret_cast<float4*>(p.prob + g0 + i) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+                        if (p.logit) *reinterpret_cast<float4*>(p.logit + g0 + i) = make_float4(l[0], l[1], l[2], l[3]);
+                        if (p.hard)
+                            *reinterpret_cast<uchar4*>(p.hard + g0 + i) =
+                                make_uchar4(pr[0] > 0.5f, pr[1] > 0.5f, pr[2] > 0.5f, pr[3] > 0.5f);
+                    } else {
+                        for (int j = 0; j < n; ++j) {
+                            if (p.prob) p.prob[g0 + i + j] = pr[j];
+                            if (p.logit) p.logit[g0 + i + j] = l[j];
+                            if (p.hard) p.hard[g0 + i + j] = pr[j] > 0.5f;
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // xs / node / state are rewritten by the next tile
+        };
         for (int it = 0; it < p.T; ++it) {
+            // NEURAL_BP: this layer's per-edge weights W_l[E] | W_p,l[E] (warp-uniform reads)
+            const float* wl = kNBP ? p.weights + (size_t)it * 2 * E : nullptr;
             // ---- V1: per-variable sums of m (ascending edge id) ----
             for (int v = r; v < V; v += R) {
                 const int b = tb.ld(tb.var_ptr, v), e_end = tb.ld(tb.var_ptr, v + 1);
                 float acc = 0.f;
-                for (int i = b; i < e_end; ++i) acc += m_st[(size_t)tb.ld(tb.var_edges, i) * tile + s];
+                for (int i = b; i < e_end; ++i) {
+                    const int e = tb.ld(tb.var_edges, i);
+                    float mv = m_st[(size_t)e * tile + s];
+                    if constexpr (kNBP) mv *= __ldg(wl + e);
+                    acc += mv;
+                }
                 node[v * tile + s] = acc;
             }
             __syncthreads();
@@ -227,6 +337,20 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                     const int e = r + i * R;
                     if (e < E) {
                         const int v = tb.ld(tb.edge_var, e);
+                        if constexpr (kNBP) {          // neural_BP.py:244-258: (m W) summed, + prior W_p; m itself stays = m_p
+                            const float mw = m_st[(size_t)e * tile + s] * __ldg(wl + e);
+                            const float a = node[v * tile + s] - mw + xrow[v] * __ldg(wl + E + e);
+                            const float tv = bp_log_abs_tanh_half<false>(a, -46.0517019f);    // < 0 always
+                            t_st[(size_t)e * tile + s] = a < 0.f ? -tv : tv;                 // sign flag rides in the sign bit
+                            continue;
+                        }
+                        if constexpr (kGRU) {          // QGNNNI_ca.py:103-106,197-198,208-209
+                            const float mo = m_st[(size_t)e * tile + s];
+                            float ai[1] = {node[v * tile + s] - mo + xrow[v]}, oo[1];
+                            mlp_relu<1>(W1, hp, ai, oo);
+                            m_st[(size_t)e * tile + s] = gru_cell(gru, mo, oo[0]);
+                            continue;
+                        }
                         const float a = node[v * tile + s] - m_st[(size_t)e * tile + s] + xrow[v];
                         if constexpr (kIsBP) {
                             const float le1 = PROG == GD_PROG_BP_QUANTUM ? -46.0517019f : -16.1180957f;
@@ -245,15 +369,48 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                 float acc = 0.f, cnt = 0.f;
                 for (int i = b; i < e_end; ++i) {
                     const int e = tb.ld(tb.chk_edges, i);
-                    acc += t_st[(size_t)e * tile + s];
-                    if constexpr (kIsBP) cnt += m_st[(size_t)e * tile + s];
+                    if constexpr (kNBP) {
+                        const float tv = t_st[(size_t)e * tile + s];
+                        acc -= fabsf(tv);
+                        cnt += tv > 0.f ? 1.f : 0.f;
+                    } else if constexpr (kGRU) {
+                        acc += m_st[(size_t)e * tile + s];          // no tanh in this script's check phase
+                    } else {
+                        acc += t_st[(size_t)e * tile + s];
+                        if constexpr (kIsBP) cnt += m_st[(size_t)e * tile + s];
+                    }
                 }
                 node[c * tile + s] = acc;
-                if constexpr (kIsBP) node2[c * tile + s] = cnt;
+                if constexpr (kIsBP || kNBP) node2[c * tile + s] = cnt;
             }
             __syncthreads();
             // ---- C2: check-phase message, residual ----
-            if constexpr (kIsBP) {
+            if constexpr (kNBP) {          // neural_BP.py:108-122 (eps2 = 1e-15) and :304 (+ alpha * m_p)
+                const float alpha = __ldg(p.weights + (size_t)(2 * p.T + 2) * E);
+                for (int i = 0; i < n_iter; ++i) {
+                    const int e = r + i * R;
+                    if (e < E) {
+                        const int c = tb.ld(tb.edge_chk, e);
+                        const float tv = t_st[(size_t)e * tile + s];
+                        int cnt = (int)(node2[c * tile + s] - (tv > 0.f ? 1.f : 0.f));
+                        cnt += xrow[V + c] < 0.f ? 1 : 0;
+                        float* mp = m_st + (size_t)e * tile + s;
+                        *mp = fmaf(alpha, *mp, bp_check_out(node[c * tile + s] + fabsf(tv), cnt & 1, 1e-15f));
+                    }
+                }
+            } else if constexpr (kGRU) {   // QGNNNI_ca.py:109,197-198,206-207
+                for (int i = 0; i < n_iter; ++i) {
+                    const int e = r + i * R;
+                    if (e < E) {
+                        const int c = tb.ld(tb.edge_chk, e);
+                        float* mp = m_st + (size_t)e * tile + s;
+                        const float mo = *mp;
+                        float ai[1] = {(node[c * tile + s] - mo) * xrow[V + c]}, oo[1];
+                        mlp_relu<1>(W2, hp, ai, oo);
+                        *mp = gru_cell(gru + 12, mo, oo[0]);
+                    }
+                }
+            } else if constexpr (kIsBP) {
                 for (int i = 0; i < n_iter; ++i) {
                     const int e = r + i * R;
                     if (e < E) {
@@ -290,73 +447,11 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                 }
             }
             __syncthreads();
-        }
-
-        // ---- read-out: logits staged as [tile][V] in the node region ----
-        if constexpr (PROG == GD_PROG_V2_4) {  // per-EDGE MLP, then sum at the variable
-            for (int i0 = 0; i0 < n_iter; i0 += kEB) {
-                float x0[kEB], o[kEB];
-                int ee[kEB];
-#pragma unroll
-                for (int j = 0; j < kEB; ++j) {
-                    const int e = r + (i0 + j) * R;
-                    ee[j] = e;
-                    x0[j] = m_st[(size_t)(e < E ? e : E - 1) * tile + s];
-                    if (p.stash && e < E && s < nvalid) p.stash[((size_t)p.T * 2 * E + e) * (size_t)p.B + s0 + s] = x0[j];
-                }
-                if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W3, hp, x0, x0, o);
-                else mlp_softplus<kEB, false>(W3, hp, x0, x0, o);
-#pragma unroll
-                for (int j = 0; j < kEB; ++j)
-                    if (ee[j] < E) t_st[(size_t)ee[j] * tile + s] = o[j];
-            }
-            __syncthreads();
-        }
-        float* stage = node;  // [tile][V]
-        for (int v = r; v < V; v += R) {
-            const int b = tb.ld(tb.var_ptr, v), e_end = tb.ld(tb.var_ptr, v + 1);
-            const float* src = PROG == GD_PROG_V2_4 ? t_st : m_st;
-            float acc = 0.f;
-            for (int i = b; i < e_end; ++i) acc += src[(size_t)tb.ld(tb.var_edges, i) * tile + s];
-            float lg = acc + xrow[v];
-            if constexpr (PROG == GD_PROG_CGNNI || PROG == GD_PROG_QGNNI) {
-                float xi[1] = {lg}, oo[1];
-                mlp_relu<1>(W3, hp, xi, oo);
-                lg = oo[0];
-            }
-            stage[(size_t)s * V + v] = lg;
-        }
-        __syncthreads();
-        // ---- outputs: coalesced 128-bit stores of prob / logit, 32-bit stores of hard bytes ----
-        {
-            const int total = nvalid * V;
-            const long long g0 = s0 * V;  // multiple of 8 elements: tile % 8 == 0
-            constexpr bool kClamp = (PROG == GD_PROG_CGNNI || PROG == GD_PROG_BP_CLASSICAL);
-            for (int i = tid * 4; i < total; i += nthr * 4) {
-                float l[4], pr[4];
-                const int n = min(4, total - i);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    l[j] = j < n ? stage[i + j] : 0.f;
-                    pr[j] = sigmoid_neg(l[j]);
-                    if (kClamp) pr[j] = fminf(fmaxf(pr[j], 1e-7f), 1.0f - 1e-7f);
-                }
-                if (n == 4) {
-                    if (p.prob) *reinterpret_cast<float4*>(p.prob + g0 + i) = make_float4(pr[0], pr[1], pr[2], pr[3]);
-                    if (p.logit) *reinterpret_cast<float4*>(p.logit + g0 + i) = make_float4(l[0], l[1], l[2], l[3]);
-                    if (p.hard)
-                        *reinterpret_cast<uchar4*>(p.hard + g0 + i) =
-                            make_uchar4(pr[0] > 0.5f, pr[1] > 0.5f, pr[2] > 0.5f, pr[3] > 0.5f);
-                } else {
-                    for (int j = 0; j < n; ++j) {
-                        if (p.prob) p.prob[g0 + i + j] = pr[j];
-                        if (p.logit) p.logit[g0 + i + j] = l[j];
-                        if (p.hard) p.hard[g0 + i + j] = pr[j] > 0.5f;
-                    }
-                }
+            if constexpr (kGRU) {
+                if (p.all_iters) emit((long long)it * p.B * V);
             }
         }
-        __syncthreads();  // xs / node / state are rewritten by the next tile
+        if (!(kGRU && p.all_iters)) emit(0);
     }
 }
 
@@ -371,10 +466,12 @@ static int align_up(int x, int a) { return (x + a - 1) / a * a; }
 static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePlan* out) {
     const int V = g->V, C = g->C, N = g->N, Cn = g->C;
     const int64_t E64 = g->E;
-    const bool bp = m->program == GD_PROG_BP_QUANTUM || m->program == GD_PROG_BP_CLASSICAL;
+    // "bp" here = the sum-product family: no MLP slots, a second node array for the sign counts
+    const bool bp = m->program == GD_PROG_BP_QUANTUM || m->program == GD_PROG_BP_CLASSICAL || m->program == GD_PROG_NEURAL_BP;
     const int hid = bp ? 0 : m->hidden;
     const int hp = align_up(hid, 8);
-    const int n_slots = bp ? 0 : (m->program == GD_PROG_V2_4 ? 3 : 2);
+    const bool gru = m->program == GD_PROG_GRU_CA;
+    const int n_slots = bp ? 0 : ((m->program == GD_PROG_V2_4 || gru) ? 3 : 2);
     const int maxvc = V > C ? V : C;
     DecodeParams& p = out->p;
     memset(&p, 0, sizeof(p));
@@ -385,7 +482,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
 
     const int smem_max = g->max_smem_optin;
     int off = 16;                                  // mbarrier
-    p.off_w = off; off += n_slots * 4 * hp * 4; off = align_up(off, 16);
+    p.off_w = off; off += n_slots * 4 * hp * 4 + (gru ? 24 * 4 : 0); off = align_up(off, 16);
     const bool fits16 = E64 < 65536 && V < 65535 && C < 65535;
     const int tab_bytes = (int)(4 * E64 + V + C + 2) * 2;
     // resident layout first
@@ -555,6 +652,15 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     if (rc != GD_OK) return rc;
     pl.p.x = x_dev; pl.p.prob = prob_dev; pl.p.logit = logit_dev; pl.p.hard = hard_dev; pl.p.weights = weights_dev;
     pl.p.stash = stash_dev;
+    pl.p.all_iters = (model->flags & GD_FLAG_ALL_ITERS) ? 1 : 0;
+    GD_CHECK_ARG(model->program != GD_PROG_NEURAL_BP || model->hidden == g->E,
+                 "gd_decode_fwd: GD_PROG_NEURAL_BP needs model.hidden == E (%lld per-edge weights), got %d",
+                 (long long)g->E, model->hidden);
+    if (!pl.resident && (model->program == GD_PROG_NEURAL_BP || model->program == GD_PROG_GRU_CA)) {
+        gd::set_error("gd_decode_fwd: program %d has a resident kernel only and this code's edge state does not fit "
+                      "shared memory", model->program);
+        return GD_ERR_UNSUPPORTED;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int prev = 0;
     GD_CUDA(cudaGetDevice(&prev));
@@ -569,6 +675,8 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
         case GD_PROG_QGNNI: rc = gd::launch_decode<GD_PROG_QGNNI>(pl, st); break;
         case GD_PROG_V2_4: rc = gd::launch_decode<GD_PROG_V2_4>(pl, st); break;
         case GD_PROG_BP_QUANTUM: rc = gd::launch_decode<GD_PROG_BP_QUANTUM>(pl, st); break;
+        case GD_PROG_NEURAL_BP: rc = gd::launch_decode<GD_PROG_NEURAL_BP>(pl, st); break;
+        case GD_PROG_GRU_CA: rc = gd::launch_decode<GD_PROG_GRU_CA>(pl, st); break;
         default: rc = gd::launch_decode<GD_PROG_BP_CLASSICAL>(pl, st); break;
     }
     if (prev != g->device) cudaSetDevice(prev);

@@ -62,6 +62,7 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
     GD_CHECK_ARG(g != nullptr, "gd_decode_host: graph is NULL");
     GD_CHECK_ARG(gd_model_valid(model), "gd_decode_host: invalid model");
     GD_CHECK_ARG(B >= 0 && B < ((int64_t)1 << 31), "gd_decode_host: B out of range");
+    GD_CHECK_ARG(model->flags == 0, "gd_decode_host: per-iteration outputs (GD_FLAG_ALL_ITERS) are device-path only");
     if (B == 0) return GD_OK;
     GD_CHECK_ARG(x_host != nullptr, "gd_decode_host: x is NULL");
     GD_CHECK_ARG(prob_host || hard_host, "gd_decode_host: no output requested");

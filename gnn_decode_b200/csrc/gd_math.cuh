@@ -278,8 +278,9 @@ __device__ __forceinline__ float tanh_half_fast(float a) {
 //   |a| <  1.4 : ln2 * lg2((1 - q) / (1 + q))                    (value <= -0.5: lg2.approx is accurate)
 //   |a| >= 1.4 : -2 atanh(q) = -2 q (1 + q^2/3 + q^4/5 + q^6/7 + q^8/9)   (q <= 0.25; no cancellation
 //                near saturation, where log|tanh| ~ -2q is tiny and feeds log(1 - prod) downstream)
+template <bool CLAMP_IN = true>   // false: quantum/neural_BP.py:108 takes tanh(m/2) without the +-10 clamp
 __device__ __forceinline__ float bp_log_abs_tanh_half(float a, float log_eps1) {
-    const float aa = fminf(fabsf(a), 10.0f);
+    const float aa = CLAMP_IN ? fminf(fabsf(a), 10.0f) : fabsf(a);
     const float q = ex2_approx(-aa * kLog2e);
     const float q2 = q * q;
     float ser = fmaf(q2, 1.0f / 9.0f, 1.0f / 7.0f);
@@ -302,6 +303,18 @@ __device__ __forceinline__ float bp_check_out(float ext, bool odd, float eps2) {
     const float one_minus = fmaxf(u < 0.1f ? u * ser : 1.0f - p, eps2);
     const float mag = kLn2 * (lg2_approx(1.0f + fminf(p, 1.0f - eps2)) - lg2_approx(one_minus));
     return odd ? -mag : mag;
+}
+
+// torch.nn.GRUCell(1, 1) (quantum/QGNNNI_ca.py:188,198; gate order r, z, n):
+//   r = s(w_ir x + b_ir + w_hr h + b_hr), z = s(w_iz x + b_iz + w_hz h + b_hz),
+//   n = tanh(w_in x + b_in + r (w_hn h + b_hn)),  h' = (1 - z) n + z h
+// g = weight_ih[3] | weight_hh[3] | bias_ih[3] | bias_hh[3].  sigmoid / tanh via ex2 + rcp (abs. error ~2e-7).
+__device__ __forceinline__ float sigmoid_fast(float a) { return rcp_fast(1.0f + ex2_approx(-a * kLog2e)); }
+__device__ __forceinline__ float gru_cell(const float* g, float x, float h) {
+    const float r = sigmoid_fast(fmaf(g[0], x, g[6]) + fmaf(g[3], h, g[9]));
+    const float z = sigmoid_fast(fmaf(g[1], x, g[7]) + fmaf(g[4], h, g[10]));
+    const float n = tanh_half_fast(2.0f * (fmaf(g[2], x, g[8]) + r * fmaf(g[5], h, g[11])));
+    return fmaf(z, h - n, n);
 }
 
 }  // namespace gd

@@ -25,7 +25,9 @@ template <int PROG, int PHASE>
 __global__ void __launch_bounds__(128) propagate_kernel(const PropParams p) {
     extern __shared__ __align__(16) float wsm[];
     constexpr bool kIsBP = (PROG == GD_PROG_BP_QUANTUM || PROG == GD_PROG_BP_CLASSICAL);
-    constexpr bool kHasMlp = (PROG == GD_PROG_V2_4) || (!kIsBP && PHASE == GD_PHASE_CHK);
+    constexpr bool kNBP = (PROG == GD_PROG_NEURAL_BP);
+    constexpr bool kGRU = (PROG == GD_PROG_GRU_CA);
+    constexpr bool kHasMlp = (PROG == GD_PROG_V2_4) || kGRU || (!kIsBP && !kNBP && PHASE == GD_PHASE_CHK);
     const int hp = p.hp, h = p.hid;
     MlpSmem W{};
     if (kHasMlp && p.fuse) {
@@ -57,8 +59,11 @@ __global__ void __launch_bounds__(128) propagate_kernel(const PropParams p) {
         float acc = 0.f, cnt = 0.f;
         for (int i = e0; i < e1; ++i) {
             const float v = mb[ids[i]];
-            if constexpr (PHASE == GD_PHASE_VAR) {
-                acc += v;
+            if constexpr (PHASE == GD_PHASE_VAR || kGRU) {
+                acc += v;                                      // QGNNNI_ca.py:101: no tanh in either phase
+            } else if constexpr (kNBP) {
+                acc += bp_log_abs_tanh_half<false>(v, -46.0517019f);
+                cnt += v < 0.f ? 1.f : 0.f;
             } else if constexpr (kIsBP) {
                 acc += bp_log_abs_tanh_half(v, PROG == GD_PROG_BP_QUANTUM ? -46.0517019f : -16.1180957f);
                 cnt += v < 0.f ? 1.f : 0.f;
@@ -80,9 +85,31 @@ __global__ void __launch_bounds__(128) propagate_kernel(const PropParams p) {
                         mlp_softplus<1, true>(W, hp, a0, a1, o);
                         res0 = o[0];
                     } else { res0 = ext; two_out = true; }
+                } else if constexpr (kNBP) {                  // neural_BP.py:122-124,253-255: cat[ext, prior]; update = ext + prior * W_p
+                    if (p.fuse) res0 = ext + extra * p.w[e];
+                    else { res0 = ext; two_out = true; }
+                } else if constexpr (kGRU) {                  // QGNNNI_ca.py:103-106,208-209: mlp1(ext + prior)
+                    res0 = ext + extra;
+                    if (p.fuse) {
+                        float a0[1] = {res0}, o[1];
+                        mlp_relu<1>(W, hp, a0, o);
+                        res0 = o[0];
+                    }
                 } else {
                     res0 = ext + extra;                        // + post / extra; update = identity
                 }
+            } else if constexpr (kGRU) {                      // QGNNNI_ca.py:109,206-207: mlp2((sum - self) * s)
+                res0 = (acc - v) * extra;
+                if (p.fuse) {
+                    float a0[1] = {res0}, o[1];
+                    mlp_relu<1>(W, hp, a0, o);
+                    res0 = o[0];
+                }
+            } else if constexpr (kNBP) {                      // neural_BP.py:108-122
+                const float lg = bp_log_abs_tanh_half<false>(v, -46.0517019f);
+                int k = (int)(cnt - (v < 0.f ? 1.f : 0.f));
+                k += extra < 0.f ? 1 : 0;
+                res0 = bp_check_out(acc - lg, k & 1, 1e-15f);
             } else if constexpr (kIsBP) {
                 const float lg = bp_log_abs_tanh_half(v, PROG == GD_PROG_BP_QUANTUM ? -46.0517019f : -16.1180957f);
                 int k = (int)(cnt - (v < 0.f ? 1.f : 0.f));
@@ -122,7 +149,7 @@ static int launch_prop(const PropParams& p, int phase, int grid, int smem, cudaS
 }  // namespace gd
 
 extern "C" int gd_propagate_features(int32_t program, int32_t phase) {
-    if (phase == GD_PHASE_VAR) return program == GD_PROG_V2_4 ? 2 : 1;
+    if (phase == GD_PHASE_VAR) return (program == GD_PROG_V2_4 || program == GD_PROG_NEURAL_BP) ? 2 : 1;
     if (phase == GD_PHASE_CHK) return (program == GD_PROG_V2_4 || program == GD_PROG_QGNNI) ? 2 : 1;
     return -1;
 }
@@ -139,8 +166,9 @@ extern "C" int gd_propagate_fwd(const gd_graph* g, const gd_model* model, int32_
     const int prog = model->program;
     const bool x_optional = (prog == GD_PROG_CGNNI || prog == GD_PROG_BP_CLASSICAL) && phase == GD_PHASE_CHK;
     GD_CHECK_ARG(x_dev || x_optional, "gd_propagate_fwd: x (extra/post) is NULL");
-    const bool bp = prog == GD_PROG_BP_QUANTUM || prog == GD_PROG_BP_CLASSICAL;
-    const bool has_mlp = fuse_update && !bp && (prog == GD_PROG_V2_4 || phase == GD_PHASE_CHK);
+    const bool bp = prog == GD_PROG_BP_QUANTUM || prog == GD_PROG_BP_CLASSICAL || prog == GD_PROG_NEURAL_BP;
+    const bool has_mlp = fuse_update && ((!bp && (prog == GD_PROG_V2_4 || prog == GD_PROG_GRU_CA || phase == GD_PHASE_CHK)) ||
+                                         (prog == GD_PROG_NEURAL_BP && phase == GD_PHASE_VAR));   // W_p[E] there
     GD_CHECK_ARG(!has_mlp || weights_dev, "gd_propagate_fwd: weights is NULL");
     gd::PropParams p;
     p.m = m_dev; p.x = x_optional && (prog == GD_PROG_CGNNI || prog == GD_PROG_BP_CLASSICAL) ? nullptr : x_dev;
@@ -161,6 +189,8 @@ extern "C" int gd_propagate_fwd(const gd_graph* g, const gd_model* model, int32_
         case GD_PROG_QGNNI: rc = gd::launch_prop<GD_PROG_QGNNI>(p, phase, (int)blocks, smem, st); break;
         case GD_PROG_V2_4: rc = gd::launch_prop<GD_PROG_V2_4>(p, phase, (int)blocks, smem, st); break;
         case GD_PROG_BP_QUANTUM: rc = gd::launch_prop<GD_PROG_BP_QUANTUM>(p, phase, (int)blocks, smem, st); break;
+        case GD_PROG_NEURAL_BP: rc = gd::launch_prop<GD_PROG_NEURAL_BP>(p, phase, (int)blocks, smem, st); break;
+        case GD_PROG_GRU_CA: rc = gd::launch_prop<GD_PROG_GRU_CA>(p, phase, (int)blocks, smem, st); break;
         default: rc = gd::launch_prop<GD_PROG_BP_CLASSICAL>(p, phase, (int)blocks, smem, st); break;
     }
     if (prev != g->device) cudaSetDevice(prev);

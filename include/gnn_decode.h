@@ -46,8 +46,18 @@ enum gd_program {
     GD_PROG_QGNNI = 1,        /* quantum/QGNNI.py:186-252        hidden 10 ReLU, x syndrome  */
     GD_PROG_V2_4 = 2,         /* quantum/decoder_v2_4.py:230-294 hidden 128 Softplus         */
     GD_PROG_BP_QUANTUM = 3,   /* quantum/BP.py:101-124,191-219   sum-product, syndrome sign  */
-    GD_PROG_BP_CLASSICAL = 4  /* classical/BP.py:99-123,231-259  sum-product                 */
+    GD_PROG_BP_CLASSICAL = 4, /* classical/BP.py:99-123,231-259  sum-product                 */
+    /* the "next" update programs; resident kernel only: */
+    GD_PROG_NEURAL_BP = 5,    /* quantum/neural_BP.py:236-314    sum-product + per-edge learned weights,
+                                 2*Nc un-tied layers, gated residual alpha * m_p, weighted read-out */
+    GD_PROG_GRU_CA = 6        /* quantum/QGNNNI_ca.py:177-251    hidden 20 ReLU MLPs + GRUCell(1,1) updates,
+                                 sign-multiplied check phase, one read-out per iteration              */
 };
+
+/* gd_model.flags */
+#define GD_FLAG_ALL_ITERS 1   /* GD_PROG_GRU_CA only: the reference returns a LIST of Nc predictions
+                                 (deep supervision, QGNNNI_ca.py:239-249); prob / logit / hard are then
+                                 [iters, B, V] instead of [B, V] (the last iteration otherwise) */
 
 /* flow of one propagate(): which node type the reduce runs over. */
 enum gd_phase {
@@ -67,12 +77,16 @@ typedef struct gd_graph gd_graph;
  *   CGNNI      : ggc2.mlp2.{...}, mlp.{...}                                                (6h+2)
  *   QGNNI      : ggc2.mlp.{...},  mlp.{...}                                                (6h+2)
  *   BP_*       : none (weights may be NULL)
+ *   NEURAL_BP  : for l in 0..iters-1: layers.{2l}.W[E], layers.{2l}.W_p[E]; then W[E], W_p[E], alpha
+ *                ((2 iters + 2) E + 1 floats; `hidden` carries E, checked against the graph)
+ *   GRU_CA     : ggc1.mlp1{0.weight[h,1],0.bias[h],2.weight[1,h],2.bias[1]}, ggc1.rnn{weight_ih[3],
+ *                weight_hh[3],bias_ih[3],bias_hh[3]}, ggc2.mlp2{...}, ggc2.rnn{...}, mlp{...}   (9h+27)
  */
 typedef struct gd_model {
     int32_t program;   /* enum gd_program                                   */
-    int32_t hidden;    /* h: 128 for V2_4, 10 for CGNNI/QGNNI, 0 for BP     */
+    int32_t hidden;    /* h: 128 for V2_4, 10 for CGNNI/QGNNI, 0 for BP, 20 for GRU_CA; E for NEURAL_BP */
     int32_t iters;     /* Nc (T) message-passing iterations                  */
-    int32_t flags;     /* reserved, must be 0                                */
+    int32_t flags;     /* 0, or GD_FLAG_ALL_ITERS (GRU_CA)                   */
 } gd_model;
 
 const char* gd_last_error(void);

@@ -76,6 +76,61 @@ def _run_case(name, script, program, consts, raw_subs=(), ckpt=None, loader="tes
               (path, rows, cols, E, B, Nc, pred.min().item(), pred.max().item()))
 
 
+def _ext_case(name, script, program, consts, T, seed=1234):
+    """The "next" update programs of SURVEY.md 8(f)-3: quantum/neural_BP.py (per-edge learned weights,
+    un-tied layers) and quantum/QGNNNI_ca.py (GRUCell(1,1) updates, one prediction per iteration).
+    No shipped checkpoint matches either script, so the weights are a seeded
+    perturbation of the script's own initialisation (all-ones weights would not exercise them).
+    QGNNNI_ca.py builds an fp32 model but the shipped gen_syn returns fp64 samples (internal drift):
+    the INPUT is cast to the model's dtype at the call site, the class bodies are untouched."""
+    with ref_loader.reference_session("quantum"):
+        ns = ref_loader.load_reference(script, consts=consts, seed=seed)
+        rows, cols, B = int(ns.rows), int(ns.cols), int(ns.BATCH_SIZE)
+        torch.manual_seed(seed + 1)
+        dec = ns.GNNI(T)
+        with torch.no_grad():
+            for n_, p_ in dec.named_parameters():
+                if program == "neural_bp":
+                    p_.copy_(torch.full_like(p_, 0.3) if n_ == "alpha" else torch.rand_like(p_) * 0.8 + 0.5)
+                else:
+                    p_.mul_(2.5)
+        dec.eval()
+        batch = next(iter(ns.train_loader))
+        dtype = next(dec.parameters()).dtype
+        batch.x = batch.x.to(dtype)
+        ei_b = torch.cat([batch.edge_index[0].unsqueeze(0), batch.edge_index[1].unsqueeze(0).add(rows)], 0)
+        g = torch.Generator().manual_seed(seed + 2)
+        m0 = (torch.randn(ei_b.size(1), 1, generator=g, dtype=torch.float64) * 1.5).to(dtype)
+        with torch.no_grad():
+            pred = dec(batch)
+            if program == "neural_bp":
+                ph_var = dec.layers[0](m0, ei_b, batch.x)
+                ph_chk = dec.layers[1](m0, ei_b, batch.x)
+            else:
+                ph_var = dec.ggc1(m0, ei_b, batch.x, [])[0]
+                ph_chk = dec.ggc2(m0, ei_b, batch.x, [])[0]
+        E = ei_b.size(1) // B
+        ei = batch.edge_index[:, :E].clone()
+        H = ns.H
+        assert torch.equal(ei, H.to_sparse()._indices())
+        out = dict(program=program, script=script, V=rows, C=cols, E=E, B=B, T=T,
+                   dtype=str(dtype).replace("torch.", ""), edge_index=_np(ei).astype(np.int64),
+                   H=_np(H).astype(np.uint8), x=_np(batch.x.reshape(B, rows + cols)),
+                   y=_np(batch.y.reshape(B, -1)), m0=_np(m0.reshape(B, E)),
+                   phase_var=_np(ph_var.reshape(B, E)), phase_chk=_np(ph_chk.reshape(B, E)))
+        if isinstance(pred, list):
+            out["all_prob"] = np.stack([_np(p_.reshape(B, rows)) for p_ in pred], 0)
+            out["prob"] = out["all_prob"][-1]
+        else:
+            out["prob"] = _np(pred.reshape(B, rows))
+        for k, v in dec.state_dict().items():
+            out["w:" + k] = _np(v)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote %s  (V=%d C=%d E=%d B=%d T=%d, prob range %.3g..%.3g)" %
+              (path, rows, cols, E, B, T, out["prob"].min(), out["prob"].max()))
+
+
 def _grad_case(name, consts, ckpt, T, seed=1234):
     """One train-step gradient of the reference: loss = criterion(decoder(datas), datas);
     loss.backward()  (decoder_v2_4.py:331-335) -> per-parameter gradients."""
@@ -160,6 +215,8 @@ def main():
                R + "/quantum/new_model/decoder_parameters_epoch1.pkl", T=15)
     _grad_case("grad_v2_4_toricL5_epoch3_T6", dict(q_small, L="5", BATCH_SIZE="12", run1="12", run2="12"),
                R + "/quantum/new_model/decoder_parameters_epoch3.pkl", T=6, seed=77)
+    _ext_case("ext_neural_bp_toricL4", "quantum/neural_BP.py", "neural_bp", dict(q_small, L="4"), T=5)
+    _ext_case("ext_gru_ca_toricL4", "quantum/QGNNNI_ca.py", "gru_ca", dict(q_small, L="4"), T=6)
     _codes()
 
 

@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gnn_decode_b200 import _cabi, codes
 from gnn_decode_b200.graph import TannerGraph
-from gnn_decode_b200.quantum import decoder_v2_4, QGNNI, BP
+from gnn_decode_b200.quantum import decoder_v2_4, QGNNI, BP, neural_BP, QGNNNI_ca
 from gnn_decode_b200.classical import CGNNI
 
 
@@ -55,7 +55,9 @@ if __name__ == "__main__":
              ("bp_q toric-L5", BP.GNNI(10), codes.toric_pcm(5), 65536),
              ("bp_q hgp1600", BP.GNNI(20), codes.hgp_pcm(), 16384),
              ("qgnni hgp1600", QGNNI.GNNI(20), codes.hgp_pcm(), 16384),
-             ("v2_4 hgp1600", decoder_v2_4.GNNI(3), codes.hgp_pcm(), 8192)]
+             ("v2_4 hgp1600", decoder_v2_4.GNNI(3), codes.hgp_pcm(), 8192),
+             ("neural_bp toric-L5", neural_BP.GNNI(15, n_edges=192), codes.toric_pcm(5), 65536),
+             ("gru_ca toric-L5", QGNNNI_ca.GNNI(25), codes.toric_pcm(5), 65536)]
     only = sys.argv[1:] 
     for name, dec, pcm, B in cases:
         if only and not any(o in name for o in only):

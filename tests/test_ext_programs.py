@@ -1,0 +1,161 @@
+"""The "next" update programs of SURVEY.md 8(f)-3 -- quantum/neural_BP.py (per-edge learned weights,
+un-tied layers, gated residual) and quantum/QGNNNI_ca.py (GRUCell(1,1) updates, one prediction per
+iteration).  CPU part: the oracle restatement against the fixtures written by the reference's own
+classes (bit-exact) and against the reference run live; GPU part: the CUDA kernels against both."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden
+from oracle import ref_loader, restate
+
+CASES = {"ext_neural_bp_toricL4": "quantum.neural_BP", "ext_gru_ca_toricL4": "quantum.QGNNNI_ca"}
+RTOL, LOGIT_TIE = 1e-4, 1e-3
+
+
+def _all_prob(name):
+    z = np.load(__file__.rsplit("/", 1)[0] + "/golden/" + name + ".npz")
+    return torch.from_numpy(z["all_prob"]) if "all_prob" in z.files else None
+
+
+def _make(g, name):
+    import importlib
+    mod = importlib.import_module("gnn_decode_b200." + CASES[name])
+    dec = mod.GNNI(g.T, n_edges=g.E) if g.program == "neural_bp" else mod.GNNI(g.T)
+    dec.load_state_dict(g.weights, strict=True)
+    return mod, dec
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_restatement_matches_golden_bit_exact(name):
+    g = Golden(name)
+    out = restate.decode(g.program, g.edge_index, g.V, g.C, g.x, g.weights, T=g.T, dtype=g.dtype)
+    assert out["prob"].dtype == g.dtype and torch.equal(out["prob"], g.prob)
+    if g.program == "gru_ca":
+        assert torch.equal(out["all_prob"], _all_prob(name))          # every iteration's prediction
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_state_dict_and_weight_count(name):
+    import ctypes as C
+    from gnn_decode_b200 import _cabi
+    g = Golden(name)
+    mod, dec = _make(g, name)
+    assert list(dec.state_dict().keys()) == list(g.weights.keys())
+    assert sum(p.numel() for p in dec._gd_params()) == _cabi.lib().gd_weights_size(C.byref(dec.gd_model()))
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("script,program", [("quantum/neural_BP.py", "neural_bp"), ("quantum/QGNNNI_ca.py", "gru_ca")])
+def test_restatement_matches_live_reference(script, program):
+    with ref_loader.reference_session("quantum"):
+        ns = ref_loader.load_reference(script, consts={"BATCH_SIZE": "6", "run1": "6", "run2": "6", "L": "4"}, seed=7)
+        torch.manual_seed(3)
+        dec = ns.GNNI(3)
+        with torch.no_grad():
+            for n_, p_ in dec.named_parameters():
+                p_.copy_(torch.rand_like(p_) + 0.25 if program == "neural_bp" else p_ * 2)
+        batch = next(iter(ns.train_loader))
+        batch.x = batch.x.to(next(dec.parameters()).dtype)     # QGNNNI_ca is fp32, gen_syn emits fp64 (input cast only)
+        with torch.no_grad():
+            want = dec(batch)
+        rows, cols = int(ns.rows), int(ns.cols)
+        ei = batch.edge_index[:, : batch.edge_index.size(1) // 6]
+        got = restate.decode(program, ei, rows, cols, batch.x.reshape(6, rows + cols), dec.state_dict(), T=3)
+    if program == "gru_ca":
+        assert len(want) == 3
+        for i in range(3):
+            assert torch.equal(got["all_prob"][i].reshape(-1, 1), want[i])
+    else:
+        assert torch.equal(got["prob"].reshape(-1, 1), want)
+
+
+# ------------------------------------------------------------------------------------------ GPU
+def _close(got, want, rtol):
+    want = want.double()
+    got = got.double().cpu()
+    atol = 1e-4 * (1.0 + want.pow(2).mean().sqrt().item())
+    err = (got - want).abs()
+    return (err / (rtol * want.abs() + atol)).max().item(), err.max().item()
+
+
+class _Data(object):
+    def __init__(self, g, dev):
+        self.x = g.x.reshape(-1, 1).to(dev, g.dtype)
+        self.edge_index = g.batched_edge_index().to(dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fused_decoder_matches_reference(name):
+    from gnn_decode_b200.graph import TannerGraph
+    g = Golden(name)
+    dev = torch.device("cuda", 0)
+    mod, dec = _make(g, name)
+    dec = dec.to(dev).eval()
+    ref = restate.decode(g.program, g.edge_index, g.V, g.C, g.x, g.weights, T=g.T, dtype=torch.float64)
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    prob, logit, hard = dec.decode(g.x.to(dev), graph=tg, return_logits=True, return_hard=True)
+    bp = g.program == "neural_bp"
+    worst, max_err = _close(logit, ref["logit"], 2e-3 if bp else RTOL)      # sum-product bar: tests/test_parity_gpu.py
+    assert worst <= 1.0, "logit mismatch: %.3g x bound (max abs err %.3g)" % (worst, max_err)
+    assert (prob.double().cpu() - g.prob.double()).abs().max().item() <= (2e-3 if bp else 1e-5)
+    decided = ref["logit"].abs() > LOGIT_TIE
+    assert torch.equal(hard.cpu().bool()[decided], (g.prob > 0.5)[decided])
+    with torch.no_grad():
+        pred = dec(_Data(g, dev))                                          # the reference's entry point
+    if g.program == "gru_ca":
+        assert isinstance(pred, list) and len(pred) == g.T
+        allp, alll = dec.decode_all(g.x.to(dev), graph=tg, return_logits=True)
+        assert torch.equal(allp[-1], prob) and torch.equal(pred[-1].reshape(g.B, g.V), prob)
+        worst, max_err = _close(alll, ref["all_logit"], RTOL)
+        assert worst <= 1.0, "per-iteration logits: %.3g x bound (max abs %.3g)" % (worst, max_err)
+        assert (allp.double().cpu() - _all_prob(name).double()).abs().max().item() <= 1e-5
+    else:
+        assert pred.shape == (g.B * g.V, 1) and pred.dtype == g.dtype
+        assert torch.equal(pred.reshape(g.B, g.V).float(), prob)
+    # deterministic, independent of the tiling
+    x5 = g.x.repeat(5, 1).to(dev)
+    p5 = dec.decode(x5, graph=tg)
+    assert torch.equal(p5, dec.decode(x5, graph=tg)) and torch.equal(p5[:g.B], prob) and torch.equal(p5[-g.B:], prob)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_single_layer_matches_reference(name):
+    """GraphConv.forward / GatedGraphConv.forward == propagate + update (+ GRUCell) through gd_propagate_fwd."""
+    g = Golden(name)
+    dev = torch.device("cuda", 0)
+    mod, dec = _make(g, name)
+    dec = dec.to(dev).eval()
+    dec.bind_code(g.V, g.C)
+    ei = g.batched_edge_index().to(dev)
+    ei[1] += g.V
+    x = g.x.reshape(-1, 1).to(dev, g.dtype)
+    m0 = g.m0.reshape(-1, 1).to(dev, g.dtype)
+    with torch.no_grad():
+        if g.program == "neural_bp":
+            got_var, got_chk = dec.layers[0](m0, ei, x), dec.layers[1](m0, ei, x)
+        else:
+            got_var, got_chk = dec.ggc1(m0, ei, x, [])[0], dec.ggc2(m0, ei, x, [])[0]
+    for got, want, rtol in ((got_var, g.phase_var, RTOL), (got_chk, g.phase_chk, 2e-3 if g.program == "neural_bp" else RTOL)):
+        assert got.shape == (g.B * g.E, 1) and got.dtype == g.dtype
+        worst, max_err = _close(got.reshape(g.B, g.E), want, rtol)
+        assert worst <= 1.0, "phase mismatch %.3g x bound (max abs %.3g)" % (worst, max_err)
+
+
+@pytest.mark.gpu
+def test_ext_programs_reject_what_they_do_not_support():
+    from gnn_decode_b200 import _cabi, codes
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.quantum import neural_BP, QGNNNI_ca
+    dev = torch.device("cuda", 0)
+    g = Golden("ext_neural_bp_toricL4")
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    bad = neural_BP.GNNI(2, n_edges=g.E + 1).to(dev).eval()
+    with pytest.raises(ValueError):
+        bad.decode(g.x.to(dev), graph=tg)                                  # per-edge weight count != E
+    big = TannerGraph.from_pcm(codes.hgp_pcm(), dev)                       # too large for the resident kernel
+    dec = QGNNNI_ca.GNNI(2).to(dev).eval()
+    with pytest.raises(_cabi.GdError):
+        dec.decode(torch.zeros(8, big.N, device=dev), graph=big)
