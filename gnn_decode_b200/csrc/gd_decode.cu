@@ -34,7 +34,7 @@ struct DecodeParams {
     GraphTables tb;
     long long B;
     int T, V, C, E, N;
-    int tile, R, hid, hp, n_tiles, maxvc, all_iters;
+    int tile, R, hid, hp, n_tiles, maxvc, all_iters, wslot;
     int off_w, off_tab, off_x, off_node, off_m, off_t;
 };
 
@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     constexpr bool kSoftplus = (PROG == GD_PROG_V2_4);
     constexpr bool kNBP = (PROG == GD_PROG_NEURAL_BP);   // sum-product + per-edge weights (quantum/neural_BP.py)
     constexpr bool kGRU = (PROG == GD_PROG_GRU_CA);      // MLP + GRUCell updates (quantum/QGNNNI_ca.py)
+    // ReLU programs: NPOLY carries NPAD -- > 0 evaluates their 1->h->1 MLPs as piecewise-linear tables (gd_math.cuh)
+    constexpr int kNPAD = (PROG == GD_PROG_CGNNI || PROG == GD_PROG_QGNNI || kGRU) ? (NPOLY > 0 ? NPOLY : 0) : 0;
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     float* wsm = reinterpret_cast<float*>(smem + p.off_w);
@@ -139,17 +141,38 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     }
     MlpSmem W1{}, W2{}, W3{};
     const float* gru = nullptr;   // GRU_CA: the two GRUCell(1,1) parameter sets, [2][12] in shared memory
-    if constexpr (kGRU) {
+    PwlSmem P1{}, P2{}, P3{};
+    if constexpr (kNPAD > 0) {
+        // MLP k of the packed weights: CGNNI/QGNNI  k = 0 check phase, 1 read-out;  GRU_CA  k = 0 ggc1.mlp1, 1 ggc2.mlp2, 2 mlp
+        constexpr int kM = kGRU ? 3 : 2;
+        const int h = p.hid, warp = tid >> 5, nwarp = nthr >> 5;
+        for (int k = warp; k < kM; k += nwarp) {
+            const float* w = p.weights + k * (3 * h + 1) + (kGRU ? k * 12 : 0);
+            float* t = wsm + k * p.wslot;
+            pwl_build(t, reinterpret_cast<float2*>(t + kNPAD), kNPAD, w, w + h, w + 2 * h, w[3 * h], h, tid & 31);
+        }
+        const PwlSmem Pa{wsm, reinterpret_cast<const float2*>(wsm + kNPAD)};
+        const PwlSmem Pb{wsm + p.wslot, reinterpret_cast<const float2*>(wsm + p.wslot + kNPAD)};
+        const PwlSmem Pc{wsm + 2 * p.wslot, reinterpret_cast<const float2*>(wsm + 2 * p.wslot + kNPAD)};
+        if constexpr (kGRU) {
+            P1 = Pa; P2 = Pb; P3 = Pc;
+            float* gs = wsm + 3 * p.wslot;
+            if (tid < 24) gs[tid] = p.weights[(tid < 12 ? 3 * h + 1 : 2 * (3 * h + 1)) + tid];
+            gru = gs;
+        } else {
+            P2 = Pa; P3 = Pb;
+        }
+    } else if constexpr (kGRU) {
         const float* w = p.weights;
         const int h = p.hid;
         float* slot = wsm;
-        float* gs = wsm + 3 * 4 * hp;
+        float* gs = wsm + 3 * p.wslot;
         for (int k = 0; k < 3; ++k) {       // ggc1.mlp1 | ggc1.rnn | ggc2.mlp2 | ggc2.rnn | mlp
             stage_mlp(slot, hp, h, w, 1, false, w + h, w + 2 * h, 1.f, 1.f, tid, nthr);
             const MlpSmem Wk{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
             if (k == 0) W1 = Wk; else if (k == 1) W2 = Wk; else W3 = Wk;
             w += 3 * h + 1;
-            slot += 4 * hp;
+            slot += p.wslot;
             if (k < 2) {
                 if (tid < 12) gs[k * 12 + tid] = w[tid];
                 w += 12;
@@ -245,12 +268,14 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                 float lg = kNBP ? acc + acc_p : (kGRU ? acc : acc + xrow[v]);   // QGNNNI_ca.py:241-245: mlp(sum), no prior
                 if constexpr (kGRU) {
                     float xi[1] = {lg}, oo[1];
-                    mlp_relu<1>(W3, hp, xi, oo);
+                    if constexpr (kNPAD > 0) oo[0] = pwl_eval<kNPAD>(P3, xi[0]);
+                    else mlp_relu<1>(W3, hp, xi, oo);
                     lg = oo[0];
                 }
                 if constexpr (PROG == GD_PROG_CGNNI || PROG == GD_PROG_QGNNI) {
                     float xi[1] = {lg}, oo[1];
-                    mlp_relu<1>(W3, hp, xi, oo);
+                    if constexpr (kNPAD > 0) oo[0] = pwl_eval<kNPAD>(P3, xi[0]);
+                    else mlp_relu<1>(W3, hp, xi, oo);
                     lg = oo[0];
                 }
                 stage[(size_t)s * V + v] = lg;
@@ -347,7 +372,8 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         if constexpr (kGRU) {          // QGNNNI_ca.py:103-106,197-198,208-209
                             const float mo = m_st[(size_t)e * tile + s];
                             float ai[1] = {node[v * tile + s] - mo + xrow[v]}, oo[1];
-                            mlp_relu<1>(W1, hp, ai, oo);
+                            if constexpr (kNPAD > 0) oo[0] = pwl_eval<kNPAD>(P1, ai[0]);
+                            else mlp_relu<1>(W1, hp, ai, oo);
                             m_st[(size_t)e * tile + s] = gru_cell(gru, mo, oo[0]);
                             continue;
                         }
@@ -406,7 +432,8 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         float* mp = m_st + (size_t)e * tile + s;
                         const float mo = *mp;
                         float ai[1] = {(node[c * tile + s] - mo) * xrow[V + c]}, oo[1];
-                        mlp_relu<1>(W2, hp, ai, oo);
+                        if constexpr (kNPAD > 0) oo[0] = pwl_eval<kNPAD>(P2, ai[0]);
+                        else mlp_relu<1>(W2, hp, ai, oo);
                         *mp = gru_cell(gru + 12, mo, oo[0]);
                     }
                 }
@@ -437,7 +464,10 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                     }
                     if constexpr (kSoftplus && NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W2, hp, x0, x0, o);
                     else if constexpr (kSoftplus) mlp_softplus<kEB, false>(W2, hp, x0, x0, o);
-                    else mlp_relu<kEB>(W2, hp, x0, o);
+                    else if constexpr (kNPAD > 0) {
+#pragma unroll
+                        for (int j = 0; j < kEB; ++j) o[j] = pwl_eval<kNPAD>(P2, x0[j]);
+                    } else mlp_relu<kEB>(W2, hp, x0, o);
 #pragma unroll
                     for (int j = 0; j < kEB; ++j)
                         if (ee[j] < E) {
@@ -458,7 +488,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
 // ---------------------------------------------------------------------------------------------
 struct DecodePlan {
     DecodeParams p;
-    int threads, grid, smem, resident, cps, eb;
+    int threads, grid, smem, resident, cps, eb, npad;
 };
 
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -482,7 +512,11 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
 
     const int smem_max = g->max_smem_optin;
     int off = 16;                                  // mbarrier
-    p.off_w = off; off += n_slots * 4 * hp * 4 + (gru ? 24 * 4 : 0); off = align_up(off, 16);
+    // ReLU programs with h < 32: piecewise-linear tables (3 * NPAD floats per MLP) instead of the SoA weight rows
+    const bool relu_prog = m->program == GD_PROG_CGNNI || m->program == GD_PROG_QGNNI || gru;
+    out->npad = (relu_prog && hid < 32 && !getenv("GD_NO_PWL")) ? (hid < 16 ? 16 : 32) : 0;
+    p.wslot = 4 * hp > 3 * out->npad ? 4 * hp : 3 * out->npad;
+    p.off_w = off; off += n_slots * p.wslot * 4 + (gru ? 24 * 4 : 0); off = align_up(off, 16);
     const bool fits16 = E64 < 65536 && V < 65535 && C < 65535;
     const int tab_bytes = (int)(4 * E64 + V + C + 2) * 2;
     // resident layout first
@@ -573,6 +607,11 @@ static int launch_decode(const DecodePlan& pl, cudaStream_t st) {
         if (pl.threads > 512) k = pl.eb == 2 ? GD_PICK(1024, 2) : GD_PICK(1024, 4);
         else k = pl.eb == 2 ? GD_PICK(512, 2) : GD_PICK(512, 4);
 #undef GD_PICK
+    } else if constexpr (PROG == GD_PROG_CGNNI || PROG == GD_PROG_QGNNI || PROG == GD_PROG_GRU_CA) {
+        if (pl.npad == 16) k = pl.threads > 512 ? decode_kernel<PROG, 1024, 2, 16> : decode_kernel<PROG, 512, 2, 16>;
+        else if (pl.npad == 32) k = pl.threads > 512 ? decode_kernel<PROG, 1024, 2, 32> : decode_kernel<PROG, 512, 2, 32>;
+        else if (pl.threads > 512) k = pl.eb == 2 ? decode_kernel<PROG, 1024, 2, -1> : decode_kernel<PROG, 1024, 4, -1>;
+        else k = pl.eb == 2 ? decode_kernel<PROG, 512, 2, -1> : decode_kernel<PROG, 512, 4, -1>;
     } else {
         if (pl.threads > 512) k = pl.eb == 2 ? decode_kernel<PROG, 1024, 2, -1> : decode_kernel<PROG, 1024, 4, -1>;
         else k = pl.eb == 2 ? decode_kernel<PROG, 512, 2, -1> : decode_kernel<PROG, 512, 4, -1>;

@@ -19,7 +19,7 @@ def pytest_configure(config):
 
 def golden_cases():
     return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not f.endswith("codes.npz") and not os.path.basename(f).startswith("grad_"))
+                  if not f.endswith("codes.npz") and not os.path.basename(f).startswith(("grad_", "ext_")))
 
 
 class Golden(object):
