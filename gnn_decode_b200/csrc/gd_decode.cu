@@ -35,6 +35,8 @@ struct DecodeParams {
     long long B;
     int T, V, C, E, N;
     int tile, R, hid, hp, n_tiles, maxvc, all_iters, wslot;
+    int ctab_n, off_ctab;   // V2_4: intervals of the check-phase cubic table (0 = direct evaluation) and its smem offset
+    float ctab_R;           // half-width of its domain: max check degree - 1
     int off_w, off_tab, off_x, off_node, off_m, off_t;
 };
 
@@ -196,6 +198,35 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         slot += 4 * hp;
         stage_mlp(slot, hp, h, w, 1, false, w + h, w + 2 * h, s1, s2, tid, nthr);  // read-out MLP
         W3 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
+    }
+    // V2_4: tabulate the 1 -> h -> 1 check-phase MLP on its compact domain (gd_math.cuh, CubicTab)
+    CubicTab ctab{};
+    bool use_ctab = false;
+    if constexpr (PROG == GD_PROG_V2_4) {
+        if (p.ctab_n > 0) {
+            const float* w = p.weights + 4 * p.hid + 1;       // ggc2.mlp: w1[h] | b1[h] | w2[h] | b2 (raw)
+            const int h = p.hid, n = p.ctab_n;
+            const float step = 2.0f * p.ctab_R / (float)n;
+            float m4 = 0.f;                                   // same arithmetic in every thread: a uniform decision
+            for (int k = 0; k < h; ++k) {
+                float a = __ldg(w + k);
+                a *= a;
+                m4 = fmaf(fabsf(__ldg(w + 2 * h + k)), a * a, m4);
+            }
+            const float s2 = step * step;
+            use_ctab = s2 * s2 * (0.125f / 384.0f) * m4 <= 1e-7f;
+            if (use_ctab) {
+                float4* dst = reinterpret_cast<float4*>(smem + p.off_ctab);
+                for (int i = tid; i < n; i += nthr) {
+                    double f0, d0, f1, d1;
+                    softplus_mlp_node(w, h, -p.ctab_R + step * (float)i, step, f0, d0);
+                    softplus_mlp_node(w, h, -p.ctab_R + step * (float)(i + 1), step, f1, d1);
+                    dst[i] = make_float4((float)f0, (float)d0, (float)(3.0 * (f1 - f0) - 2.0 * d0 - d1),
+                                         (float)(2.0 * (f0 - f1) + d0 + d1));
+                }
+                ctab = CubicTab{dst, 1.0f / step, p.ctab_R / step, (float)n - 0.001f};
+            }
+        }
     }
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -383,7 +414,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                             t_st[(size_t)e * tile + s] = bp_log_abs_tanh_half(a, le1);
                             m_st[(size_t)e * tile + s] = a < 0.f ? 1.f : 0.f;  // sign flag (m is dead here)
                         } else {
-                            t_st[(size_t)e * tile + s] = tanh_half(a);
+                            t_st[(size_t)e * tile + s] = tanh_half_fast(a);   // ex2 + rcp, abs. error ~2e-7 (libm tanhf: ~25 instructions)
                         }
                     }
                 }
@@ -462,7 +493,10 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         x0[j] = node[c * tile + s] - t_st[(size_t)ec * tile + s];
                         sg[j] = PROG == GD_PROG_CGNNI ? 1.f : xrow[V + c];
                     }
-                    if constexpr (kSoftplus && NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W2, hp, x0, x0, o);
+                    if (kSoftplus && use_ctab) {
+#pragma unroll
+                        for (int j = 0; j < kEB; ++j) o[j] = cubic_tab_eval(ctab, x0[j]);
+                    } else if constexpr (kSoftplus && NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W2, hp, x0, x0, o);
                     else if constexpr (kSoftplus) mlp_softplus<kEB, false>(W2, hp, x0, x0, o);
                     else if constexpr (kNPAD > 0) {
 #pragma unroll
@@ -517,6 +551,14 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     out->npad = (relu_prog && hid < 32 && !getenv("GD_NO_PWL")) ? (hid < 16 ? 16 : 32) : 0;
     p.wslot = 4 * hp > 3 * out->npad ? 4 * hp : 3 * out->npad;
     p.off_w = off; off += n_slots * p.wslot * 4 + (gru ? 24 * 4 : 0); off = align_up(off, 16);
+    if (m->program == GD_PROG_V2_4 && !getenv("GD_NO_CTAB")) {
+        const char* en = getenv("GD_CTAB_N");
+        p.ctab_n = en ? atoi(en) : 512;
+        if (p.ctab_n < 16 || p.ctab_n > 4096) p.ctab_n = 512;
+        p.ctab_R = (float)(g->max_chk_deg > 1 ? g->max_chk_deg - 1 : 1);
+        p.off_ctab = off;
+        off += p.ctab_n * 16;
+    }
     const bool fits16 = E64 < 65536 && V < 65535 && C < 65535;
     const int tab_bytes = (int)(4 * E64 + V + C + 2) * 2;
     // resident layout first

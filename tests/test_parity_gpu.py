@@ -201,7 +201,8 @@ def test_fp32_and_fp64_inputs_agree():
     assert torch.equal(p64.float(), p32)
 
 
-@pytest.mark.parametrize("name", ["v2_4_toricL4_epoch1", "qgnni_toricL4_seeded", "cgnni_bch_seeded", "bp_quantum_toricL4"])
+@pytest.mark.parametrize("name", ["v2_4_toricL4_epoch1", "qgnni_toricL4_seeded", "cgnni_bch_seeded", "cgnni_ldpc_epoch18",
+                                  "bp_quantum_toricL4", "bp_classical_bch"])
 def test_streamed_kernel_matches_resident_and_reference(name, monkeypatch):
     """The global-memory (streamed) kernel used for codes too large for shared memory, forced on
     a small code: same logits as the oracle (same bar) and hard decisions identical to the
