@@ -39,6 +39,7 @@ struct GraphTables {
     const int32_t* var_edges;  // [E]   edge ids of each variable, ascending
     const int32_t* chk_ptr;    // [C+1]
     const int32_t* chk_edges;  // [E]
+    const int32_t* vlist;      // [E]   edge ids: first the n_vact edges whose variable has degree >= 2, then the rest
 };
 
 }  // namespace gd
@@ -47,13 +48,14 @@ struct gd_graph {
     int32_t V, C, N;
     int64_t E;
     int32_t max_var_deg, max_chk_deg;
+    int32_t n_vact;             // edges on variables of degree >= 2 (a degree-1 variable's message never changes)
     int device;
     int sm_count;
     int max_smem_optin;
     int max_smem_sm;
     int32_t* blob_dev;          // single allocation holding all tables
     gd::GraphTables t;          // device pointers into blob_dev
-    std::vector<int32_t> h_edge_var, h_edge_chk, h_var_ptr, h_var_edges, h_chk_ptr, h_chk_edges;
+    std::vector<int32_t> h_edge_var, h_edge_chk, h_var_ptr, h_var_edges, h_chk_ptr, h_chk_edges, h_vlist;
     // lazily grown scratch (guarded by mu): global edge-state workspace for codes too large
     // for shared memory, and pinned/device staging for gd_decode_host.
     std::mutex mu;

@@ -35,6 +35,7 @@ struct DecodeParams {
     long long B;
     int T, V, C, E, N;
     int tile, R, hid, hp, n_tiles, maxvc, all_iters, wslot;
+    int n_vact;             // edges on variables of degree >= 2 (GraphTables::vlist)
     int ctab_n, off_ctab;   // V2_4: intervals of the check-phase cubic table (0 = direct evaluation) and its smem offset
     float ctab_R;           // half-width of its domain: max check degree - 1
     int off_w, off_tab, off_x, off_node, off_m, off_t;
@@ -80,7 +81,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // Graph tables: 16-bit copies in shared memory (warp-uniform reads: broadcast, conflict-free).
 struct Tables {
-    const uint16_t *edge_var, *edge_chk, *var_ptr, *var_edges, *chk_ptr, *chk_edges;
+    const uint16_t *edge_var, *edge_chk, *var_ptr, *var_edges, *chk_ptr, *chk_edges, *vlist;
     __device__ __forceinline__ static int ld(const uint16_t* p, int i) { return p[i]; }
 };
 
@@ -130,7 +131,9 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         uint16_t* d_ve = d_vp + (V + 1);
         uint16_t* d_cp = d_ve + E;
         uint16_t* d_ce = d_cp + (C + 1);
+        uint16_t* d_vl = d_ce + E;
         for (int i = tid; i < E; i += nthr) {
+            d_vl[i] = (uint16_t)p.tb.vlist[i];
             d_ev[i] = (uint16_t)p.tb.edge_var[i];
             d_ec[i] = (uint16_t)p.tb.edge_chk[i];
             d_ve[i] = (uint16_t)p.tb.var_edges[i];
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         for (int i = tid; i <= V; i += nthr) d_vp[i] = (uint16_t)p.tb.var_ptr[i];
         for (int i = tid; i <= C; i += nthr) d_cp[i] = (uint16_t)p.tb.chk_ptr[i];
         tb.edge_var = d_ev; tb.edge_chk = d_ec; tb.var_ptr = d_vp;
-        tb.var_edges = d_ve; tb.chk_ptr = d_cp; tb.chk_edges = d_ce;
+        tb.var_edges = d_ve; tb.chk_ptr = d_cp; tb.chk_edges = d_ce; tb.vlist = d_vl;
     }
     MlpSmem W1{}, W2{}, W3{};
     const float* gru = nullptr;   // GRU_CA: the two GRUCell(1,1) parameter sets, [2][12] in shared memory
@@ -362,12 +365,18 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             __syncthreads();
             // ---- V2: variable-phase message + the `pre` of the check phase, per edge ----
             if constexpr (PROG == GD_PROG_V2_4) {
-                for (int i0 = 0; i0 < n_iter; i0 += kEB) {
+                // A degree-1 variable has no sibling edge: ext == 0 in every iteration, so its message
+                // mlp([0, prior]) is computed in the first iteration only (vlist puts those edges last).
+                // Training keeps all edges: the backward kernel wants every iteration's stash.
+                const int n_act = (it == 0 || p.stash) ? E : p.n_vact;
+                const int n_it_act = (n_act + R - 1) / R;
+                for (int i0 = 0; i0 < n_it_act; i0 += kEB) {
                     float x0[kEB], x1[kEB], o[kEB], mo[kEB];
                     int ee[kEB];
 #pragma unroll
                     for (int j = 0; j < kEB; ++j) {
-                        const int e = r + (i0 + j) * R;
+                        const int li = r + (i0 + j) * R;
+                        const int e = li < n_act ? tb.ld(tb.vlist, li) : E;
                         ee[j] = e;
                         const int ec = e < E ? e : E - 1;
                         const int v = tb.ld(tb.edge_var, ec);
@@ -560,7 +569,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
         off += p.ctab_n * 16;
     }
     const bool fits16 = E64 < 65536 && V < 65535 && C < 65535;
-    const int tab_bytes = (int)(4 * E64 + V + C + 2) * 2;
+    const int tab_bytes = (int)(5 * E64 + V + C + 2) * 2;
     // resident layout first
     int tile = 0, resident = 0, R = 0;
     if (fits16 && off + tab_bytes < smem_max) {
@@ -734,6 +743,7 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     pl.p.x = x_dev; pl.p.prob = prob_dev; pl.p.logit = logit_dev; pl.p.hard = hard_dev; pl.p.weights = weights_dev;
     pl.p.stash = stash_dev;
     pl.p.all_iters = (model->flags & GD_FLAG_ALL_ITERS) ? 1 : 0;
+    pl.p.n_vact = getenv("GD_NO_VSKIP") ? (int)g->E : g->n_vact;
     GD_CHECK_ARG(model->program != GD_PROG_NEURAL_BP || model->hidden == g->E,
                  "gd_decode_fwd: GD_PROG_NEURAL_BP needs model.hidden == E (%lld per-edge weights), got %d",
                  (long long)g->E, model->hidden);

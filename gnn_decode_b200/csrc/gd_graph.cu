@@ -85,17 +85,30 @@ extern "C" int gd_graph_create(const int64_t* ei, int64_t E, int32_t V, int32_t 
     build_segments(g->h_edge_var, V, g->h_var_ptr, g->h_var_edges, g->max_var_deg);
     build_segments(g->h_edge_chk, C, g->h_chk_ptr, g->h_chk_edges, g->max_chk_deg);
 
-    // one blob: edge_var | edge_chk | var_ptr | var_edges | chk_ptr | chk_edges
-    const size_t words = (size_t)E * 4 + (size_t)V + 1 + (size_t)C + 1;
+    // edges of variables with degree >= 2 first: only their variable-phase message depends on the iteration
+    g->h_vlist.clear();
+    for (int pass = 0; pass < 2; ++pass)
+        for (int64_t e = 0; e < E; ++e) {
+            const int32_t v = g->h_edge_var[(size_t)e];
+            const bool act = g->h_var_ptr[(size_t)v + 1] - g->h_var_ptr[(size_t)v] >= 2;
+            if (act == (pass == 0)) g->h_vlist.push_back((int32_t)e);
+        }
+    g->n_vact = 0;
+    for (int32_t v = 0; v < V; ++v) {
+        const int32_t d = g->h_var_ptr[(size_t)v + 1] - g->h_var_ptr[(size_t)v];
+        if (d >= 2) g->n_vact += d;
+    }
+    // one blob: edge_var | edge_chk | var_ptr | var_edges | chk_ptr | chk_edges | vlist
+    const size_t words = (size_t)E * 5 + (size_t)V + 1 + (size_t)C + 1;
     std::vector<int32_t> blob(words);
-    size_t o = 0, o_ev, o_ec, o_vp, o_ve, o_cp, o_ce;
+    size_t o = 0, o_ev, o_ec, o_vp, o_ve, o_cp, o_ce, o_vl;
     auto put = [&](const std::vector<int32_t>& v, size_t& where) {
         where = o;
         memcpy(blob.data() + o, v.data(), v.size() * sizeof(int32_t));
         o += v.size();
     };
     put(g->h_edge_var, o_ev); put(g->h_edge_chk, o_ec); put(g->h_var_ptr, o_vp);
-    put(g->h_var_edges, o_ve); put(g->h_chk_ptr, o_cp); put(g->h_chk_edges, o_ce);
+    put(g->h_var_edges, o_ve); put(g->h_chk_ptr, o_cp); put(g->h_chk_edges, o_ce); put(g->h_vlist, o_vl);
 
     int prev = 0;
     cudaError_t e1 = cudaGetDevice(&prev);
@@ -123,6 +136,7 @@ extern "C" int gd_graph_create(const int64_t* ei, int64_t E, int32_t V, int32_t 
     g->t.var_edges = g->blob_dev + o_ve;
     g->t.chk_ptr = g->blob_dev + o_cp;
     g->t.chk_edges = g->blob_dev + o_ce;
+    g->t.vlist = g->blob_dev + o_vl;
     *out = g;
     return GD_OK;
 }
