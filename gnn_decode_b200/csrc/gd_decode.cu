@@ -36,6 +36,8 @@ struct DecodeParams {
     int T, V, C, E, N;
     int tile, R, hid, hp, n_tiles, maxvc, all_iters, wslot;
     int n_vact;             // edges on variables of degree >= 2 (GraphTables::vlist)
+    int scratch_bytes;      // bytes of shared memory from off_x to the end (prologue scratch)
+    int rtab_n, off_rtab;   // V2_4: intervals of the read-out MLP's cubic table (0 = direct) and its smem offset
     int ctab_n, off_ctab;   // V2_4: intervals of the check-phase cubic table (0 = direct evaluation) and its smem offset
     float ctab_R;           // half-width of its domain: max check degree - 1
     int off_w, off_tab, off_x, off_node, off_m, off_t;
@@ -203,31 +205,75 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         W3 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
     }
     // V2_4: tabulate the 1 -> h -> 1 check-phase MLP on its compact domain (gd_math.cuh, CubicTab)
-    CubicTab ctab{};
-    bool use_ctab = false;
+    // V2_4: the two 1 -> h -> 1 Softplus MLPs as cubic tables on their compact domains (gd_math.cuh, CubicTab).
+    //   check phase (decoder_v2_4.py:257): |ext| <= max check degree - 1 (a sum of tanh values minus one of them);
+    //   read-out (decoder_v2_4.py:291, per edge on m): m starts at 0 and every iteration adds mlp2(ext) * (+-1), so
+    //     |m| <= T * max|mlp2| -- known once the check table exists; lanes outside it (possible only when the
+    //     caller's check inputs are not +-1) take the direct path.
+    // Node values come from the same packed MUFU/FMA evaluation the direct path uses, node derivatives from 4th-order
+    // central differences of them; the interpolation-error bound h^4/384 * 0.125 * sum|w2| w1^4 is checked from the
+    // raw weights (identical arithmetic in every thread -> a uniform decision), else the direct evaluation stays.
+    CubicTab ctab{}, rtab{};
+    bool use_ctab = false, use_rtab = false;
+    float rtab_R = 0.f;
     if constexpr (PROG == GD_PROG_V2_4) {
-        if (p.ctab_n > 0) {
-            const float* w = p.weights + 4 * p.hid + 1;       // ggc2.mlp: w1[h] | b1[h] | w2[h] | b2 (raw)
-            const int h = p.hid, n = p.ctab_n;
-            const float step = 2.0f * p.ctab_R / (float)n;
-            float m4 = 0.f;                                   // same arithmetic in every thread: a uniform decision
-            for (int k = 0; k < h; ++k) {
+        float* const F = reinterpret_cast<float*>(smem + p.off_x);        // scratch: the state regions are idle here
+        auto bound = [&](const float* w, float step) {                    // w: raw w1[h] | b1[h] | w2[h]
+            float m4 = 0.f;
+            for (int k = 0; k < p.hid; ++k) {
                 float a = __ldg(w + k);
                 a *= a;
-                m4 = fmaf(fabsf(__ldg(w + 2 * h + k)), a * a, m4);
+                m4 = fmaf(fabsf(__ldg(w + 2 * p.hid + k)), a * a, m4);
             }
             const float s2 = step * step;
-            use_ctab = s2 * s2 * (0.125f / 384.0f) * m4 <= 1e-7f;
+            return s2 * s2 * (0.125f / 384.0f) * m4;
+        };
+        auto build = [&](const MlpSmem& W, float Rdom, int n, float4* dst) {
+            const float step = 2.0f * Rdom / (float)n;
+            for (int j0 = tid * 2; j0 < n + 5; j0 += nthr * 2) {          // nodes -2 .. n+2, two per thread per pass
+                const float xa[2] = {-Rdom + step * (float)(j0 - 2), -Rdom + step * (float)(j0 - 1)};
+                float oa[2];
+                mlp_softplus_x2<2, false, 2>(W, hp, xa, xa, oa);
+                F[j0] = oa[0];
+                F[j0 + 1] = oa[1];
+            }
+            __syncthreads();
+            float fm = 0.f;
+            for (int i = tid; i < n; i += nthr) {
+                const float a = F[i], b = F[i + 1], f0 = F[i + 2], f1 = F[i + 3], c = F[i + 4], d = F[i + 5];
+                const float d0 = (8.f * (f1 - b) - (c - a)) * (1.f / 12.f);      // h f'(x_i), 4th-order central difference
+                const float d1 = (8.f * (c - f0) - (d - b)) * (1.f / 12.f);
+                dst[i] = make_float4(f0, d0, 3.f * (f1 - f0) - 2.f * d0 - d1, 2.f * (f0 - f1) + d0 + d1);
+                fm = fmaxf(fm, fmaxf(fabsf(f0), fabsf(f1)));
+            }
+            __syncthreads();
+            return fm;
+        };
+        const int scratch_floats = p.scratch_bytes >> 2;
+        if (p.ctab_n > 0 && p.ctab_n + 8 <= scratch_floats) {
+            __syncthreads();                                              // the staged (pre-scaled) weights are visible
+            const float step = 2.0f * p.ctab_R / (float)p.ctab_n;
+            use_ctab = bound(p.weights + 4 * p.hid + 1, step) <= 1e-7f;
             if (use_ctab) {
                 float4* dst = reinterpret_cast<float4*>(smem + p.off_ctab);
-                for (int i = tid; i < n; i += nthr) {
-                    double f0, d0, f1, d1;
-                    softplus_mlp_node(w, h, -p.ctab_R + step * (float)i, step, f0, d0);
-                    softplus_mlp_node(w, h, -p.ctab_R + step * (float)(i + 1), step, f1, d1);
-                    dst[i] = make_float4((float)f0, (float)d0, (float)(3.0 * (f1 - f0) - 2.0 * d0 - d1),
-                                         (float)(2.0 * (f0 - f1) + d0 + d1));
+                const float fm = build(W2, p.ctab_R, p.ctab_n, dst);
+                ctab = CubicTab{dst, 1.0f / step, p.ctab_R / step, (float)p.ctab_n - 0.001f};
+                if (p.rtab_n > 0 && p.T > 0 && p.rtab_n + 8 <= scratch_floats) {
+                    unsigned int* fmax_bits = reinterpret_cast<unsigned int*>(smem + 8);     // after the 8-byte mbarrier
+                    if (tid == 0) *fmax_bits = 0u;
+                    __syncthreads();
+                    atomicMax(fmax_bits, __float_as_uint(fm));            // non-negative floats order like uints
+                    __syncthreads();
+                    // 1.02: a cubic piece may overshoot its end values slightly inside an interval
+                    rtab_R = (float)p.T * (__uint_as_float(*fmax_bits) * 1.02f + 1e-6f);
+                    const float rstep = 2.0f * rtab_R / (float)p.rtab_n;
+                    use_rtab = bound(p.weights + 7 * p.hid + 2, rstep) <= 5e-7f;   // feeds the logit directly, not the iteration
+                    if (use_rtab) {
+                        float4* rdst = reinterpret_cast<float4*>(smem + p.off_rtab);
+                        build(W3, rtab_R, p.rtab_n, rdst);
+                        rtab = CubicTab{rdst, 1.0f / rstep, rtab_R / rstep, (float)p.rtab_n - 0.001f};
+                    }
                 }
-                ctab = CubicTab{dst, 1.0f / step, p.ctab_R / step, (float)n - 0.001f};
             }
         }
     }
@@ -276,7 +322,13 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         x0[j] = m_st[(size_t)(e < E ? e : E - 1) * tile + s];
                         if (p.stash && e < E && s < nvalid) p.stash[((size_t)p.T * 2 * E + e) * (size_t)p.B + s0 + s] = x0[j];
                     }
-                    if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W3, hp, x0, x0, o);
+                    bool in_range = use_rtab;
+    #pragma unroll
+                    for (int j = 0; j < kEB; ++j) in_range = in_range && fabsf(x0[j]) <= rtab_R;
+                    if (in_range) {
+    #pragma unroll
+                        for (int j = 0; j < kEB; ++j) o[j] = cubic_tab_eval(rtab, x0[j]);
+                    } else if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, false, (NPOLY > 0 ? NPOLY : 0)>(W3, hp, x0, x0, o);
                     else mlp_softplus<kEB, false>(W3, hp, x0, x0, o);
     #pragma unroll
                     for (int j = 0; j < kEB; ++j)
@@ -389,7 +441,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
 #pragma unroll
                     for (int j = 0; j < kEB; ++j)
                         if (ee[j] < E) {
-                            t_st[(size_t)ee[j] * tile + s] = tanh_half(o[j]);
+                            t_st[(size_t)ee[j] * tile + s] = tanh_half_fast(o[j]);
                             if (p.stash && s < nvalid) {   // training: keep (m_it, a_it) for the backward kernel
                                 float* st = p.stash + ((size_t)it * 2 * E + ee[j]) * (size_t)p.B + s0 + s;
                                 st[0] = mo[j];
@@ -560,6 +612,13 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     out->npad = (relu_prog && hid < 32 && !getenv("GD_NO_PWL")) ? (hid < 16 ? 16 : 32) : 0;
     p.wslot = 4 * hp > 3 * out->npad ? 4 * hp : 3 * out->npad;
     p.off_w = off; off += n_slots * p.wslot * 4 + (gru ? 24 * 4 : 0); off = align_up(off, 16);
+    if (m->program == GD_PROG_V2_4 && !getenv("GD_NO_CTAB") && !getenv("GD_NO_RTAB")) {
+        const char* en = getenv("GD_RTAB_N");
+        p.rtab_n = en ? atoi(en) : 2048;
+        if (p.rtab_n < 16 || p.rtab_n > 8192) p.rtab_n = 2048;
+        p.off_rtab = off;
+        off += p.rtab_n * 16;
+    }
     if (m->program == GD_PROG_V2_4 && !getenv("GD_NO_CTAB")) {
         const char* en = getenv("GD_CTAB_N");
         p.ctab_n = en ? atoi(en) : 512;
@@ -630,6 +689,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
             p.off_m = o2; o2 += (int)E64 * tile * 4;
             p.off_t = o2; o2 += (int)E64 * tile * 4;
             out->smem = o2;
+            p.scratch_bytes = o2 - p.off_x;
         }
     }
     if (!resident || getenv("GD_FORCE_STREAMED")) {

@@ -256,13 +256,13 @@ __device__ __forceinline__ float pwl_eval(const PwlSmem& P, float x) {
 // The check-phase MLP of decoder_v2_4 (quantum/decoder_v2_4.py:257, `self.mlp(aggr_out[:, 0])`) is a
 // smooth scalar function f(x) = b2 + sum_k w2_k softplus(w1_k x + b1_k) of ONE variable whose argument
 // is a sum of tanh values minus one of them: |x| <= (max check degree - 1), a domain known from the
-// graph.  Each CTA tabulates it once per launch: N uniform intervals, per interval the cubic Hermite
-// interpolant through (f, f') at both ends (node values from accurate expf / log1pf, accumulated in
-// double, coefficients rounded once to fp32).  The interpolation error is bounded by
-// h^4 / 384 * max|d4f/dx4| <= h^4 / 384 * 0.125 * sum_k |w2_k| w1_k^4, evaluated from the weights in
-// the prologue; if the bound exceeds 1e-7 the kernel keeps the direct evaluation.  One evaluation is
-// then ~12 instructions + one 16-byte shared load instead of h x (1.5 MUFU + ~7 FMA), and it is MORE
-// accurate than the direct fp32 sum (measured 5e-7 max abs error at |f| ~ 2.7 for N >= 256).
+// graph (the read-out MLP's argument m is bounded by T * max|f|).  Each CTA tabulates it once per
+// launch: N uniform intervals, per interval the cubic Hermite interpolant through (f, f') at both
+// ends -- node values from the packed direct evaluation, node derivatives from 4th-order central
+// differences.  The interpolation error is bounded by h^4 / 384 * max|d4f/dx4| <= h^4 / 384 * 0.125 *
+// sum_k |w2_k| w1_k^4, evaluated from the weights in the prologue; if the bound exceeds the budget
+// (1e-7 check phase, 5e-7 read-out) the kernel keeps the direct evaluation.  One evaluation is then
+// ~12 instructions + one 16-byte shared load instead of h x (1.5 MUFU + ~7 FMA).
 struct CubicTab {
     const float4* c;   // [N] (a0, a1, a2, a3): f(x_i + t h) ~= a0 + t (a1 + t (a2 + t a3)), t in [0, 1]
     float inv_h, off, umax;
@@ -276,22 +276,6 @@ __device__ __forceinline__ float cubic_tab_eval(const CubicTab& T, float x) {
     const float4 c = T.c[i];
     return fmaf(fmaf(fmaf(c.w, t, c.z), t, c.y), t, c.x);
 }
-// f and h * f' at x, from the RAW (unscaled) weights w1[h] | b1[h] | w2[h] | b2 in global memory
-__device__ __forceinline__ void softplus_mlp_node(const float* w, int h, float x, float step, double& F, double& D) {
-    double f = (double)w[3 * h], d = 0.0;
-    for (int k = 0; k < h; ++k) {
-        const float z = fmaf(__ldg(w + k), x, __ldg(w + h + k));
-        const float e = expf(-fabsf(z));
-        const float sp = fmaxf(z, 0.f) + log1pf(e);
-        const float sg = (z >= 0.f ? 1.0f : e) / (1.0f + e);
-        const double w2 = (double)__ldg(w + 2 * h + k);
-        f += w2 * (double)sp;
-        d += w2 * (double)__ldg(w + k) * (double)sg;
-    }
-    F = f;
-    D = d * (double)step;
-}
-
 // tanh(a/2): one per edge-iteration, so the full-accuracy libm version is affordable.
 // (tanh.approx.f32 has ~5e-4 relative error: too coarse for the 1e-4 logit bar)
 __device__ __forceinline__ float tanh_half(float a) { return tanhf(0.5f * a); }
