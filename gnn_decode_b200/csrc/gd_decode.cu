@@ -605,7 +605,15 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     p.B = B; p.T = m->iters; p.V = V; p.C = C; p.E = (int)E64; p.N = N; p.hid = hid; p.hp = hp; p.maxvc = maxvc;
     p.tb = g->t;
 
-    const int smem_max = g->max_smem_optin;
+    // CTAs per SM: two half-size CTAs let one CTA's light phases (node sums, table look-ups, barriers) overlap the
+    // other's MUFU-bound variable phase
+    {
+        const char* ec = getenv("GD_CPS");
+        out->cps = ec ? atoi(ec) : 1;
+        if (out->cps < 1 || out->cps > 4) out->cps = 1;
+    }
+    const int smem_max = out->cps == 1 ? g->max_smem_optin : (g->max_smem_sm - 1024 * out->cps) / out->cps;
+    const int thr_max = out->cps == 1 ? kMaxThreads : (kMaxThreads / out->cps) / 32 * 32;
     int off = 16;                                  // mbarrier
     // ReLU programs with h < 32: piecewise-linear tables (3 * NPAD floats per MLP) instead of the SoA weight rows
     const bool relu_prog = m->program == GD_PROG_CGNNI || m->program == GD_PROG_QGNNI || gru;
@@ -642,20 +650,20 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
             // x w(threads): measured sensitivity of the MUFU-bound inner loop to resident warps
             //   and to the register blocking (profiles/r01_geometry_sweep.txt).
             const int E = (int)E64;
-            const int64_t slots = g->sm_count;
+            const int64_t slots = (int64_t)g->sm_count * out->cps;
             static const int wx[] = {32, 128, 256, 384, 512, 640, 896, 1024};
             static const double wy[] = {0.20, 0.62, 0.80, 0.90, 0.96, 0.985, 1.0, 1.0};
             double best = -1.0;
             const char* et = getenv("GD_TILE");
             const char* er = getenv("GD_R");
             const char* eb = getenv("GD_EB");
-            for (int t = 8; t <= tmax && t <= kMaxThreads; t += 8) {
+            for (int t = 8; t <= tmax && t <= thr_max; t += 8) {
                 if (et && atoi(et) != t) continue;
                 if (t < 32 && (32 % t)) continue;
                 const int64_t n_t = (B + t - 1) / t;
                 const int64_t rounds = (n_t + slots - 1) / slots;
                 const double eff_round = (double)B / ((double)rounds * (double)slots * t);
-                for (int r = 1; r * t <= kMaxThreads && r <= E; ++r) {
+                for (int r = 1; r * t <= thr_max && r <= E; ++r) {
                     if (er && atoi(er) != r) continue;
                     const int thr = r * t;
                     if (thr % 32) continue;
@@ -700,7 +708,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     p.R = R;
     out->threads = R * tile;
     p.n_tiles = (int)((B + tile - 1) / tile);
-    out->grid = p.n_tiles < g->sm_count ? p.n_tiles : g->sm_count;
+    out->grid = p.n_tiles < g->sm_count * out->cps ? p.n_tiles : g->sm_count * out->cps;
     out->resident = resident;
     return GD_OK;
 }
@@ -715,7 +723,7 @@ static int launch_decode(const DecodePlan& pl, cudaStream_t st) {
         const int np = en ? atoi(en) : 2;
 #define GD_PICK(MT, EBV)                                                                               \
         (np < 0 ? decode_kernel<PROG, MT, EBV, -1> : np == 3 ? decode_kernel<PROG, MT, EBV, 3> : decode_kernel<PROG, MT, EBV, 2>)
-        if (pl.threads > 512) k = pl.eb == 2 ? GD_PICK(1024, 2) : GD_PICK(1024, 4);
+        if (pl.threads > 512 || pl.cps > 1) k = pl.eb == 2 ? GD_PICK(1024, 2) : GD_PICK(1024, 4);   // the <= 64-register build
         else k = pl.eb == 2 ? GD_PICK(512, 2) : GD_PICK(512, 4);
 #undef GD_PICK
     } else if constexpr (PROG == GD_PROG_CGNNI || PROG == GD_PROG_QGNNI || PROG == GD_PROG_GRU_CA) {
