@@ -254,3 +254,35 @@ def test_hgp_1600_streamed_matches_oracle():
     assert worst <= 1.0, "HGP bp: %.3g x bound (max abs %.3g)" % (worst, max_err)
     decided = ref["logit"].abs() > LOGIT_TIE
     assert torch.equal(hard.cpu().bool()[decided], (ref["prob"] > 0.5)[decided])
+
+
+@pytest.mark.parametrize("scale,T", [(1.0, 15), (6.0, 4), (1.0, 60)])
+def test_v2_4_tabulated_mlps_match_direct_evaluation_and_oracle(scale, T, monkeypatch):
+    """decoder_v2_4's 1->128->1 check-phase and read-out MLPs run from per-launch cubic tables when the
+    in-kernel error bound allows.  (a) tabulated == direct evaluation (GD_NO_CTAB) far inside
+    the logit tolerance; (b) with first-layer weights scaled up the bound fails and the kernel must fall back
+    by itself -- results still match the oracle; (c) a long run (T = 60) widens the read-out domain."""
+    from gnn_decode_b200.graph import TannerGraph
+    g = Golden("v2_4_toricL5_epoch3")
+    dev = _dev()
+    w = {k: v.clone() for k, v in g.weights.items()}
+    for k in ("ggc2.mlp.0.weight", "mlp.0.weight"):
+        w[k] = w[k] * scale
+    mod, dec = make_decoder(g)
+    dec.Nc = T
+    dec.load_state_dict(w)
+    dec = dec.to(dev).eval()
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    x = g.x.repeat(9, 1).to(dev)
+    _, l_tab, h_tab = dec.decode(x, graph=tg, return_logits=True, return_hard=True)
+    monkeypatch.setenv("GD_NO_CTAB", "1")
+    _, l_dir, h_dir = dec.decode(x, graph=tg, return_logits=True, return_hard=True)
+    monkeypatch.delenv("GD_NO_CTAB")
+    ref = restate.decode("v2_4", g.edge_index, g.V, g.C, g.x, w, T=T, dtype=torch.float64)
+    for l in (l_tab, l_dir):
+        worst, max_err = _logit_close(l[:g.B], ref["logit"], RTOL)
+        assert worst <= 1.0, "logit mismatch: %.3g x bound (max abs err %.3g)" % (worst, max_err)
+    rms = ref["logit"].pow(2).mean().sqrt().item()
+    assert (l_tab - l_dir).abs().max().item() <= 2e-5 * (1.0 + rms)
+    decided = (ref["logit"].abs() > LOGIT_TIE).repeat(9, 1)
+    assert torch.equal(h_tab.cpu()[decided], h_dir.cpu()[decided])
