@@ -218,45 +218,14 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     float rtab_R = 0.f;
     if constexpr (PROG == GD_PROG_V2_4) {
         float* const F = reinterpret_cast<float*>(smem + p.off_x);        // scratch: the state regions are idle here
-        auto bound = [&](const float* w, float step) {                    // w: raw w1[h] | b1[h] | w2[h]
-            float m4 = 0.f;
-            for (int k = 0; k < p.hid; ++k) {
-                float a = __ldg(w + k);
-                a *= a;
-                m4 = fmaf(fabsf(__ldg(w + 2 * p.hid + k)), a * a, m4);
-            }
-            const float s2 = step * step;
-            return s2 * s2 * (0.125f / 384.0f) * m4;
-        };
-        auto build = [&](const MlpSmem& W, float Rdom, int n, float4* dst) {
-            const float step = 2.0f * Rdom / (float)n;
-            for (int j0 = tid * 2; j0 < n + 5; j0 += nthr * 2) {          // nodes -2 .. n+2, two per thread per pass
-                const float xa[2] = {-Rdom + step * (float)(j0 - 2), -Rdom + step * (float)(j0 - 1)};
-                float oa[2];
-                mlp_softplus_x2<2, false, 2>(W, hp, xa, xa, oa);
-                F[j0] = oa[0];
-                F[j0 + 1] = oa[1];
-            }
-            __syncthreads();
-            float fm = 0.f;
-            for (int i = tid; i < n; i += nthr) {
-                const float a = F[i], b = F[i + 1], f0 = F[i + 2], f1 = F[i + 3], c = F[i + 4], d = F[i + 5];
-                const float d0 = (8.f * (f1 - b) - (c - a)) * (1.f / 12.f);      // h f'(x_i), 4th-order central difference
-                const float d1 = (8.f * (c - f0) - (d - b)) * (1.f / 12.f);
-                dst[i] = make_float4(f0, d0, 3.f * (f1 - f0) - 2.f * d0 - d1, 2.f * (f0 - f1) + d0 + d1);
-                fm = fmaxf(fm, fmaxf(fabsf(f0), fabsf(f1)));
-            }
-            __syncthreads();
-            return fm;
-        };
         const int scratch_floats = p.scratch_bytes >> 2;
         if (p.ctab_n > 0 && p.ctab_n + 8 <= scratch_floats) {
             __syncthreads();                                              // the staged (pre-scaled) weights are visible
             const float step = 2.0f * p.ctab_R / (float)p.ctab_n;
-            use_ctab = bound(p.weights + 4 * p.hid + 1, step) <= 1e-7f;
+            use_ctab = cubic_tab_bound(p.weights + 4 * p.hid + 1, p.hid, step) <= 1e-7f;
             if (use_ctab) {
                 float4* dst = reinterpret_cast<float4*>(smem + p.off_ctab);
-                const float fm = build(W2, p.ctab_R, p.ctab_n, dst);
+                const float fm = cubic_tab_build(W2, hp, p.ctab_R, p.ctab_n, dst, F, tid, nthr);
                 ctab = CubicTab{dst, 1.0f / step, p.ctab_R / step, (float)p.ctab_n - 0.001f};
                 if (p.rtab_n > 0 && p.T > 0 && p.rtab_n + 8 <= scratch_floats) {
                     unsigned int* fmax_bits = reinterpret_cast<unsigned int*>(smem + 8);     // after the 8-byte mbarrier
@@ -267,10 +236,10 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                     // 1.02: a cubic piece may overshoot its end values slightly inside an interval
                     rtab_R = (float)p.T * (__uint_as_float(*fmax_bits) * 1.02f + 1e-6f);
                     const float rstep = 2.0f * rtab_R / (float)p.rtab_n;
-                    use_rtab = bound(p.weights + 7 * p.hid + 2, rstep) <= 5e-7f;   // feeds the logit directly, not the iteration
+                    use_rtab = cubic_tab_bound(p.weights + 7 * p.hid + 2, p.hid, rstep) <= 5e-7f;   // feeds the logit directly, not the iteration
                     if (use_rtab) {
                         float4* rdst = reinterpret_cast<float4*>(smem + p.off_rtab);
-                        build(W3, rtab_R, p.rtab_n, rdst);
+                        cubic_tab_build(W3, hp, rtab_R, p.rtab_n, rdst, F, tid, nthr);
                         rtab = CubicTab{rdst, 1.0f / rstep, rtab_R / rstep, (float)p.rtab_n - 0.001f};
                     }
                 }

@@ -276,6 +276,43 @@ __device__ __forceinline__ float cubic_tab_eval(const CubicTab& T, float x) {
     const float4 c = T.c[i];
     return fmaf(fmaf(fmaf(c.w, t, c.z), t, c.y), t, c.x);
 }
+// Interpolation-error bound of an n-interval table on [-R, R] from the RAW weights w1[h] | b1[h] | w2[h]
+// (identical arithmetic in every thread -> a CTA-uniform decision).
+__device__ __forceinline__ float cubic_tab_bound(const float* w, int h, float step) {
+    float m4 = 0.f;
+    for (int k = 0; k < h; ++k) {
+        float a = __ldg(w + k);
+        a *= a;
+        m4 = fmaf(fabsf(__ldg(w + 2 * h + k)), a * a, m4);
+    }
+    const float s2 = step * step;
+    return s2 * s2 * (0.125f / 384.0f) * m4;
+}
+// Build the table with the whole CTA (contains __syncthreads()).  W: the MLP staged (pre-scaled) in shared
+// memory; F: n + 6 floats of shared scratch.  Returns this thread's max |f| over the nodes it touched.
+__device__ __forceinline__ float cubic_tab_build(const MlpSmem& W, int hp, float Rdom, int n, float4* dst, float* F,
+                                                 int tid, int nthr) {
+    const float step = 2.0f * Rdom / (float)n;
+    for (int j0 = tid * 2; j0 < n + 5; j0 += nthr * 2) {          // nodes -2 .. n+2, two per thread per pass
+        const float xa[2] = {-Rdom + step * (float)(j0 - 2), -Rdom + step * (float)(j0 - 1)};
+        float oa[2];
+        mlp_softplus_x2<2, false, 2>(W, hp, xa, xa, oa);
+        F[j0] = oa[0];
+        F[j0 + 1] = oa[1];
+    }
+    __syncthreads();
+    float fm = 0.f;
+    for (int i = tid; i < n; i += nthr) {
+        const float a = F[i], b = F[i + 1], f0 = F[i + 2], f1 = F[i + 3], c = F[i + 4], d = F[i + 5];
+        const float d0 = (8.f * (f1 - b) - (c - a)) * (1.f / 12.f);      // h f'(x_i), 4th-order central difference
+        const float d1 = (8.f * (c - f0) - (d - b)) * (1.f / 12.f);
+        dst[i] = make_float4(f0, d0, 3.f * (f1 - f0) - 2.f * d0 - d1, 2.f * (f0 - f1) + d0 + d1);
+        fm = fmaxf(fm, fmaxf(fabsf(f0), fabsf(f1)));
+    }
+    __syncthreads();
+    return fm;
+}
+
 // tanh(a/2): one per edge-iteration, so the full-accuracy libm version is affordable.
 // (tanh.approx.f32 has ~5e-4 relative error: too coarse for the 1e-4 logit bar)
 __device__ __forceinline__ float tanh_half(float a) { return tanhf(0.5f * a); }

@@ -31,6 +31,8 @@ struct StreamParams {
     long long slab_floats;   // per CTA
     int T, V, C, E, N;
     int tile, R, hid, hp, n_tiles;
+    int ctab_n, rtab_n;      // V2_4: intervals of the check-phase / read-out cubic tables (0 = direct evaluation)
+    float ctab_R;
 };
 
 __device__ __forceinline__ void stage_mlp_s(float* dst, int hp, int hid, const float* w1, int w1_stride, bool two_in,
@@ -98,6 +100,39 @@ __global__ void __launch_bounds__(1024, 1) decode_streamed_kernel(const StreamPa
         W3 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
     }
     __syncthreads();
+    // V2_4: the two 1 -> h -> 1 MLPs as cubic tables on their compact domains (gd_math.cuh CubicTab; same scheme
+    // as the resident kernel)
+    CubicTab ctab{}, rtab{};
+    bool use_ctab = false, use_rtab = false;
+    float rtab_R = 0.f;
+    if constexpr (PROG == GD_PROG_V2_4) {
+        if (p.ctab_n > 0) {
+            float* tabs = wsm + 3 * 4 * hp;
+            float4* cdst = reinterpret_cast<float4*>(tabs);
+            float4* rdst = cdst + p.ctab_n;
+            float* F = reinterpret_cast<float*>(rdst + p.rtab_n);
+            unsigned int* fmax_bits = reinterpret_cast<unsigned int*>(F + (p.ctab_n > p.rtab_n ? p.ctab_n : p.rtab_n) + 8);
+            const float step = 2.0f * p.ctab_R / (float)p.ctab_n;
+            use_ctab = cubic_tab_bound(p.weights + 4 * p.hid + 1, p.hid, step) <= 1e-7f;
+            if (use_ctab) {
+                const float fm = cubic_tab_build(W2, hp, p.ctab_R, p.ctab_n, cdst, F, tid, nthr);
+                ctab = CubicTab{cdst, 1.0f / step, p.ctab_R / step, (float)p.ctab_n - 0.001f};
+                if (p.rtab_n > 0 && p.T > 0) {
+                    if (tid == 0) *fmax_bits = 0u;
+                    __syncthreads();
+                    atomicMax(fmax_bits, __float_as_uint(fm));
+                    __syncthreads();
+                    rtab_R = (float)p.T * (__uint_as_float(*fmax_bits) * 1.02f + 1e-6f);
+                    const float rstep = 2.0f * rtab_R / (float)p.rtab_n;
+                    use_rtab = cubic_tab_bound(p.weights + 7 * p.hid + 2, p.hid, rstep) <= 5e-7f;
+                    if (use_rtab) {
+                        cubic_tab_build(W3, hp, rtab_R, p.rtab_n, rdst, F, tid, nthr);
+                        rtab = CubicTab{rdst, 1.0f / rstep, rtab_R / rstep, (float)p.rtab_n - 0.001f};
+                    }
+                }
+            }
+        }
+    }
 
     for (int tix = blockIdx.x; tix < p.n_tiles; tix += gridDim.x) {
         const long long s0 = (long long)tix * tile;
@@ -193,7 +228,10 @@ __global__ void __launch_bounds__(1024, 1) decode_streamed_kernel(const StreamPa
                             m_st[at[k]] = bp_check_out(val[k], q & 1, PROG == GD_PROG_BP_QUANTUM ? 1e-12f : 1e-7f);
                         }
                     } else {
-                        if constexpr (kSoftplus) mlp_softplus_blocks<false, CD>(W2, hp, d, val, val, res);
+                        if (kSoftplus && use_ctab) {
+#pragma unroll
+                            for (int k = 0; k < CD; ++k) res[k] = cubic_tab_eval(ctab, val[k]);
+                        } else if constexpr (kSoftplus) mlp_softplus_blocks<false, CD>(W2, hp, d, val, val, res);
                         else mlp_relu<CD>(W2, hp, val, res);
 #pragma unroll
                         for (int k = 0; k < CD; ++k) if (k < d) m_st[at[k]] = res[k] * sg + old[k];
@@ -215,7 +253,8 @@ __global__ void __launch_bounds__(1024, 1) decode_streamed_kernel(const StreamPa
                             m_st[at1] = bp_check_out(ext, q & 1, PROG == GD_PROG_BP_QUANTUM ? 1e-12f : 1e-7f);
                         } else {
                             float a0[1] = {ext}, o[1];
-                            if constexpr (kSoftplus) mlp_softplus<1, false>(W2, hp, a0, a0, o);
+                            if (kSoftplus && use_ctab) o[0] = cubic_tab_eval(ctab, ext);
+                            else if constexpr (kSoftplus) mlp_softplus<1, false>(W2, hp, a0, a0, o);
                             else mlp_relu<1>(W2, hp, a0, o);
                             m_st[at1] = o[0] * sg + m_st[at1];
                         }
@@ -233,7 +272,8 @@ __global__ void __launch_bounds__(1024, 1) decode_streamed_kernel(const StreamPa
                 const float mv = m_st[(size_t)__ldg(tb.var_edges + i) * tile + s];
                 if constexpr (PROG == GD_PROG_V2_4) {
                     float a0[1] = {mv}, o[1];
-                    mlp_softplus<1, false>(W3, hp, a0, a0, o);
+                    if (use_rtab && fabsf(mv) <= rtab_R) o[0] = cubic_tab_eval(rtab, mv);
+                    else mlp_softplus<1, false>(W3, hp, a0, a0, o);
                     acc += o[0];
                 } else {
                     acc += mv;
@@ -271,6 +311,13 @@ static int plan_streamed(const gd_graph* g, const gd_model* m, int64_t B, Stream
     p.hid = bp ? 0 : m->hidden; p.hp = (p.hid + 7) / 8 * 8; p.tb = g->t;
     const int n_slots = bp ? 0 : (m->program == GD_PROG_V2_4 ? 3 : 2);
     out->smem = n_slots * 4 * p.hp * 4 + 16;
+    if (m->program == GD_PROG_V2_4 && !getenv("GD_NO_CTAB")) {
+        p.ctab_n = 512;
+        p.rtab_n = getenv("GD_NO_RTAB") ? 0 : 2048;
+        p.ctab_R = (float)(g->max_chk_deg > 1 ? g->max_chk_deg - 1 : 1);
+        const int big = p.ctab_n > p.rtab_n ? p.ctab_n : p.rtab_n;
+        out->smem += (p.ctab_n + p.rtab_n) * 16 + (big + 8) * 4 + 16;
+    }
     // tile: multiple of 8 (32-byte sectors stay whole) that wastes the fewest tile slots over the rounds
     int tile = 32;
     {
@@ -359,6 +406,7 @@ int streamed_decode(gd_graph* g, const gd_model* model, const float* weights_dev
         default: k = GD_SK(GD_PROG_BP_CLASSICAL); break;
     }
 #undef GD_SK
+    if (pl.smem > 48 * 1024) GD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     k<<<pl.grid, pl.threads, pl.smem, st>>>(pl.p);
     GD_CUDA(cudaGetLastError());
     return GD_OK;
