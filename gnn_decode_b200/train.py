@@ -1,0 +1,120 @@
+"""Fused training step for the decoder_v2_4 program (BASELINE config 4): forward-with-stash kernel ->
+fused sparse loss + gradient kernel (LossFunc of quantum/decoder_v2_4.py:304-317) -> hand-written backward
+kernel -> parameter .grad, with no autograd graph and no dense H matmul.  The optimizer step (Adam on
+1 283 parameters) and the data-parallel all-reduce (dist.allreduce_flat_grads) stay in PyTorch."""
+import ctypes as ct
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _ptr(t):
+    return ct.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _logical_dev(graph, logical):
+    if logical is None:
+        return None, 0
+    key = np.ascontiguousarray(np.asarray(logical.detach().cpu() if torch.is_tensor(logical) else logical, dtype=np.uint8))
+    if key.shape[1] != graph.V:
+        raise ValueError("logical must be [K, V=%d]" % graph.V)
+    ldev = graph._logical_dev.get(key.tobytes())
+    if ldev is None:
+        ldev = torch.from_numpy(key).to(graph.device)
+        graph._logical_dev[key.tobytes()] = ldev
+    return ldev, key.shape[0]
+
+
+def sin_loss(graph, prob, y, logical=None, want_grad_prob=False, want_grad_logit=True):
+    """LossFunc.forward(pred, datas) of decoder_v2_4.py:304-317 on prob [B, V] fp32 CUDA and y [B, V] uint8
+    (0/1 errors), fused with its gradient.  Returns (loss [scalar tensor], grad_prob or None, grad_logit or None)."""
+    if not prob.is_cuda:
+        raise _cabi.GdError("prob is on %s: gnn_decode_b200 has no CPU fallback" % prob.device)
+    B, V = prob.shape
+    if V != graph.V:
+        raise ValueError("prob must be [B, V=%d]" % graph.V)
+    dev = prob.device
+    prob = prob.detach().to(torch.float32).contiguous()
+    y8 = y.detach().reshape(B, V).to(device=dev, dtype=torch.uint8).contiguous()
+    ldev, K = _logical_dev(graph, logical)
+    per = torch.empty(B, dtype=torch.float32, device=dev)
+    gp = torch.empty((B, V), dtype=torch.float32, device=dev) if want_grad_prob else None
+    gl = torch.empty((B, V), dtype=torch.float32, device=dev) if want_grad_logit else None
+    st = ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().gd_loss_v2_4(graph.handle, _ptr(ldev), K, _ptr(prob), _ptr(y8), _ptr(per), _ptr(gp), _ptr(gl),
+                                             B, st), "gd_loss_v2_4")
+    return per.double().sum(), gp, gl
+
+
+class _SinLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prob, graph, y, logical):
+        loss, gp, _ = sin_loss(graph, prob, y, logical, want_grad_prob=True, want_grad_logit=False)
+        ctx.save_for_backward(gp)
+        ctx.dtype = prob.dtype
+        return loss.to(prob.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (gp,) = ctx.saved_tensors
+        return (gp * grad_out).to(ctx.dtype), None, None, None
+
+
+class LossFunc(torch.nn.Module):
+    """Drop-in for `LossFunc(H, H_prep)` of decoder_v2_4.py:297-317.  The reference reads the dense `H` and the
+    module global `logical`; here the sparse tables of `graph` and the `logical` argument are used.
+    forward(pred, datas): pred [B*V, 1] as returned by GNNI.forward, datas.y [B*V, 1] -> scalar loss (autograd ok)."""
+
+    def __init__(self, H=None, H_prep=None, *, graph, logical=None):
+        super(LossFunc, self).__init__()
+        self.graph, self.logical = graph, logical
+
+    def forward(self, pred, datas):
+        V = self.graph.V
+        return _SinLossFn.apply(pred.reshape(-1, V), self.graph, datas.y.reshape(-1, V), self.logical)
+
+
+def train_step_grads(decoder, graph, x, y, logical=None, accumulate=False):
+    """One forward + loss + backward of decoder_v2_4.GNNI on a batch: x [B, V+C] CUDA, y [B, V] 0/1.
+    Sets / accumulates p.grad of the decoder's MLP parameters and returns (loss, prob)."""
+    if decoder._gd_program != _cabi.PROG_V2_4:
+        raise _cabi.GdError("the training kernels exist for the decoder_v2_4 program only")
+    lib = _cabi.lib()
+    dev = x.device
+    B = x.size(0)
+    params = decoder._gd_params()
+    model = decoder.gd_model()
+    x32 = x.detach().to(torch.float32).contiguous()
+    if x32.data_ptr() % 16:
+        x32 = x32.clone()
+    w = decoder.packed_weights(dev)
+    n_stash = lib.gd_stash_floats(graph.handle, ct.byref(model), B)
+    n_ws = lib.gd_bwd_workspace_floats(graph.handle, ct.byref(model), B)
+    if n_stash < 0 or n_ws < 0:
+        _cabi.check(_cabi.GD_ERR_INVALID, "gd_stash_floats / gd_bwd_workspace_floats")
+    stash = torch.empty(max(n_stash, 1), dtype=torch.float32, device=dev)
+    ws = torch.empty(max(n_ws, 1), dtype=torch.float32, device=dev)
+    prob = torch.empty((B, graph.V), dtype=torch.float32, device=dev)
+    logit = torch.empty((B, graph.V), dtype=torch.float32, device=dev)
+    gw = torch.empty(w.numel(), dtype=torch.float32, device=dev)
+    st = ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.gd_decode_fwd_train(graph.handle, ct.byref(model), _ptr(w), _ptr(x32), _ptr(prob), _ptr(logit),
+                                            _ptr(stash), B, st), "gd_decode_fwd_train")
+    loss, _, grad_logit = sin_loss(graph, prob, y, logical)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.gd_decode_bwd(graph.handle, ct.byref(model), _ptr(w), _ptr(x32), _ptr(stash), _ptr(grad_logit),
+                                      _ptr(gw), _ptr(ws), 0, B, st), "gd_decode_bwd")
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = gw[off:off + n].view(p.shape).to(p.dtype)
+        if accumulate and p.grad is not None:
+            p.grad += g
+        else:
+            p.grad = g.clone()
+        off += n
+    return loss, prob

@@ -169,6 +169,17 @@ int gd_decode_bwd(const gd_graph* g, const gd_model* model, const float* weights
                   float* grad_weights_dev, float* workspace_dev, int32_t accumulate, int64_t B,
                   void* stream);
 
+/* ---- training loss, fused with its gradient (replaces LossFunc.forward(train=1) + the autograd of it,
+ *      quantum/decoder_v2_4.py:304-317; sparse check lists instead of the dense H^T matmul and the O(B)
+ *      cat loops):  z = y + prob;  loss_b = sum_c |sin(pi/2 sum_{v in c} z_v)| + sum_k |sin(pi/2 logical_k . z)|.
+ *      prob_dev [B,V] fp32, y_dev [B,V] uint8 (the sampled error, data.y), logical_dev [K,V] uint8.
+ *      Outputs: loss_per_syndrome_dev [B] (the caller sums it: a fixed order, deterministic),
+ *      grad_prob_dev [B,V] = dL/dprob and grad_logit_dev [B,V] = -dL/dprob * prob * (1 - prob), the
+ *      tensor gd_decode_bwd takes (either gradient pointer may be NULL). ---- */
+int gd_loss_v2_4(const gd_graph* g, const uint8_t* logical_dev, int32_t K, const float* prob_dev,
+                 const uint8_t* y_dev, float* loss_per_syndrome_dev, float* grad_prob_dev,
+                 float* grad_logit_dev, int64_t B, void* stream);
+
 /* Launch geometry the library picked for (graph, model, B): for benchmarks / roofline. */
 typedef struct gd_launch_info {
     int32_t tile;            /* syndromes per CTA tile                          */

@@ -10,6 +10,7 @@ from gnn_decode_b200.dist import allreduce_flat_grads
 from gnn_decode_b200.graph import TannerGraph
 from gnn_decode_b200.quantum import decoder_v2_4
 from gnn_decode_b200.sampler import sample_syndromes
+from gnn_decode_b200.train import train_step_grads
 
 rank, world, lr_ = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr_)
@@ -34,7 +35,28 @@ def loss_fn(prob):
     z = (y + prob).t()
     return torch.sin(Ht.t() @ z * (math.pi / 2)).abs().sum() + torch.sin(logical @ z * (math.pi / 2)).abs().sum()
 
+FUSED = os.environ.get("GD_TRAIN_AUTOGRAD") is None     # default: fused forward -> sparse loss kernel -> backward
+logical_u8 = codes.css_logicals(Hz, Hx)
+
+
+def step_fused(timers=None):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    loss, _ = train_step_grads(dec, g, x, err, logical_u8)
+    ev[1].record()
+    allreduce_flat_grads(dec.parameters())
+    opt.step()
+    ev[2].record()
+    if timers is not None:
+        torch.cuda.synchronize()
+        for i, k in enumerate(("fwd+loss+bwd", "allreduce+adam")):
+            timers[k] = timers.get(k, 0.0) + ev[i].elapsed_time(ev[i + 1])
+    return loss
+
+
 def step(timers=None):
+    if FUSED:
+        return step_fused(timers)
     opt.zero_grad(set_to_none=False)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()

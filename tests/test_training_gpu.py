@@ -104,3 +104,61 @@ def test_adam_step_and_eval_mode():
     q = QGNNI.GNNI(2, rows=case.V, cols=case.C).to(DEV).train()
     with pytest.raises(_cabi.GdError):
         q(d)
+
+
+@pytest.mark.parametrize("name", ["grad_v2_4_toricL4_epoch1", "grad_v2_4_toricL5_epoch3_T6"])
+def test_fused_loss_and_train_step_match_reference(name):
+    """gd_loss_v2_4 (sparse fused LossFunc + gradient, decoder_v2_4.py:304-317) against the oracle's dense fp64
+    restatement and its autograd; train_step_grads (forward -> fused loss -> backward, no autograd graph) against
+    the gradients of the reference's own train step; the drop-in LossFunc module through autograd."""
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.quantum import decoder_v2_4
+    from gnn_decode_b200.train import LossFunc, sin_loss, train_step_grads
+    case = _Case(name)
+    g = TannerGraph(case.edge_index, case.V, case.C, DEV)
+    # (1) the loss kernel alone, on the reference's own prediction
+    prob = case.prob.float().to(DEV)
+    loss, gp, gl = sin_loss(g, prob, case.y.to(DEV), case.logical, want_grad_prob=True)
+    assert abs(loss.item() - case.loss) <= 1e-5 * abs(case.loss)
+    p64 = case.prob.double().clone().requires_grad_(True)
+    ref = restate.loss_v2_4(p64, case.y.double(), case.H, case.logical)
+    ref.backward()
+    # |sin| has kinks where a residual parity is exactly even: there the reference's own gradient sign is decided by
+    # fp64 rounding noise (sin(pi) = +1.2e-16), so dL/dprob is compared away from the kinks only; dL/dlogit below is
+    # compared everywhere (at a kink prob is saturated and prob * (1 - prob) kills the ambiguous term).
+    z = (case.y.double() + case.prob.double())
+    near_kink = ((torch.sin(z @ case.H * math.pi / 2).abs() < 1e-6).double() @ case.H.t() > 0) | \
+                ((torch.sin(z @ case.logical.t() * math.pi / 2).abs() < 1e-6).double() @ case.logical > 0)
+    ok = ~near_kink
+    assert int(ok.sum()) > 0
+    assert (gp.double().cpu() - p64.grad)[ok].abs().max().item() <= 1e-4 * p64.grad.abs().max().item()
+    want_gl = -p64.grad * case.prob.double() * (1 - case.prob.double())
+    assert (gl.double().cpu() - want_gl).abs().max().item() <= 1e-4 * want_gl.abs().max().item() + 1e-9
+    # (2) fused train step == the reference's gradients
+    dec = decoder_v2_4.GNNI(case.T)
+    dec.load_state_dict(case.weights)
+    dec = dec.to(DEV).train()
+    loss2, pred = train_step_grads(dec, g, case.x.to(DEV), case.y.to(DEV), case.logical)
+    assert abs(loss2.item() - case.loss) <= 1e-5 * abs(case.loss)
+    for k, p in dec.named_parameters():
+        gref = case.grads[k]
+        err = (p.grad.double().cpu() - gref).abs().max().item()
+        assert err <= GRAD_RTOL * gref.abs().max().item() + 1e-9, "%s: %.3g" % (k, err)
+    first = {k: p.grad.clone() for k, p in dec.named_parameters()}
+    train_step_grads(dec, g, case.x.to(DEV), case.y.to(DEV), case.logical)
+    assert all(torch.equal(first[k], p.grad) for k, p in dec.named_parameters())      # bit-reproducible
+    train_step_grads(dec, g, case.x.to(DEV), case.y.to(DEV), case.logical, accumulate=True)
+    assert all(torch.equal(2 * first[k], p.grad) for k, p in dec.named_parameters())
+    # (3) the drop-in LossFunc through autograd gives the same gradients as the fused step
+    crit = LossFunc(None, None, graph=g, logical=case.logical)
+    N = case.V + case.C
+    d = _Data()
+    d.x = case.x.reshape(-1, 1).to(DEV)
+    d.edge_index = (case.edge_index.repeat(1, case.B) + (torch.arange(case.B) * N).repeat_interleave(case.E)).to(DEV)
+    d.y = case.y.reshape(-1, 1).to(DEV)
+    dec.zero_grad()
+    l3 = crit(dec(d), d)
+    l3.backward()
+    assert abs(l3.item() - case.loss) <= 1e-5 * abs(case.loss)
+    for k, p in dec.named_parameters():
+        assert (p.grad - first[k]).abs().max().item() <= 1e-5 * first[k].abs().max().item() + 1e-12
