@@ -16,6 +16,7 @@
 //     wgrad reduction"), ready for one NCCL all-reduce of 10h+3 floats.
 #include "gd_common.cuh"
 #include "gd_math.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace gd {
@@ -35,6 +36,9 @@ struct BwdParams {
     int T, V, C, E, N, hid;
     int tile, R, n_tiles, maxvc, np_pad;
     int off_tab, off_x, off_node, off_node2, off_dm, off_a, off_xin, off_x1, off_g, off_dx, off_mb, off_ab;
+    // check-phase MLP through its cubic table and the table's ADJOINT (see decode_bwd_kernel)
+    int ctab_n, off_ctab, off_w2s, off_bins, off_mbins;
+    float ctab_R;
 };
 
 constexpr int kPairs = kUPL / 2;
@@ -223,6 +227,42 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
     const float* w3p = w2p + 3 * h + 1;
     const int n_items = E * tile;
     const size_t EB_ = (size_t)E * p.B;
+    // ---- the 1 -> h -> 1 check-phase MLP (decoder_v2_4.py:257) without per-unit work ----
+    // Forward it is a cubic table f on |x| <= d_c - 1 (gd_math.cuh CubicTab).  Backward:
+    //   dL/dx      = g f'(x)                      -- the derivative of the table's cubic piece;
+    //   dL/dtheta  = sum_i g_i phi_theta(x_i)     -- phi_theta = df/dtheta is again a smooth scalar function of x, so
+    //                its Hermite interpolant gives  sum_j [ A_j phi(x_j) + D_j h phi'(x_j) ]  with the ADJOINT bins
+    //                A_j = sum_i g_i h00/h01(t_i), D_j = sum_i g_i h10/h11(t_i): four scatter-adds per item now, and one
+    //                pass over (nodes x hidden units) at the very end, instead of h x 3 MUFU per item.
+    // The bins are accumulated as 32-bit FIXED-POINT integers (scale from the phase's max |g|: integer adds commute,
+    // so shared-memory atomics stay bit-reproducible) and flushed into double master bins after every phase.
+    CubicTab ctab{};
+    bool use_ctab = false;
+    unsigned int* bins = reinterpret_cast<unsigned int*>(smem + p.off_bins);      // [2][n+1]
+    double* mbins = reinterpret_cast<double*>(smem + p.off_mbins);                // [2][n+1]
+    unsigned int* gmax_bits = bins + 2 * (p.ctab_n + 1);
+    if (p.ctab_n > 0 && E * tile >= p.ctab_n + 8) {
+        float* w2s = reinterpret_cast<float*>(smem + p.off_w2s);
+        const int hp = (h + 7) / 8 * 8;
+        for (int k = tid; k < hp; k += nthr) {
+            const bool in = k < h;
+            w2s[k] = in ? w2p[k] * kLog2e : 0.f;
+            w2s[hp + k] = 0.f;
+            w2s[2 * hp + k] = in ? w2p[h + k] * kLog2e : 0.f;
+            w2s[3 * hp + k] = in ? w2p[2 * h + k] * kLn2 : 0.f;
+        }
+        __syncthreads();
+        const float step = 2.0f * p.ctab_R / (float)p.ctab_n;
+        use_ctab = cubic_tab_bound(w2p, h, step) <= 1e-7f;
+        if (use_ctab) {
+            const MlpSmem W2s{w2s, w2s + hp, w2s + 2 * hp, w2s + 3 * hp, w2p[3 * h]};
+            float4* cdst = reinterpret_cast<float4*>(smem + p.off_ctab);
+            cubic_tab_build(W2s, hp, p.ctab_R, p.ctab_n, cdst, DM, tid, nthr);    // DM is idle scratch here
+            ctab = CubicTab{cdst, 1.0f / step, p.ctab_R / step, (float)p.ctab_n - 0.001f};
+            for (int j = tid; j < 2 * (p.ctab_n + 1); j += nthr) { bins[j] = 0u; mbins[j] = 0.0; }
+            if (tid == 0) *gmax_bits = 0u;
+        }
+    }
     __syncthreads();
 
     auto seg_sum = [&](const uint16_t* ptr, const uint16_t* ids, int n_nodes, const float* src, float* dstn) {
@@ -287,7 +327,44 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
                     G_[at] = DM[at] * xs[s * N + V + c];
                 }
             __syncthreads();
-            {
+            if (use_ctab) {
+                const int nb = p.ctab_n + 1;
+                float gm = 0.f;
+                for (int i = tid; i < n_items; i += nthr) gm = fmaxf(gm, fabsf(G_[i]));
+                for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+                if (lane == 0) atomicMax(gmax_bits, __float_as_uint(gm));
+                __syncthreads();
+                const float gmax = __uint_as_float(*gmax_bits);
+                // |sum over a bin| <= n_items * gmax: keep it below 2^30
+                const float scale = gmax > 0.f ? 1073741824.0f / (gmax * (float)n_items) : 0.f;
+                for (int i = tid; i < n_items; i += nthr) {
+                    const float xv = XI[i], gv = G_[i];
+                    float u = fmaf(xv, ctab.inv_h, ctab.off);
+                    u = fminf(fmaxf(u, 0.f), ctab.umax);
+                    const float vv = (u - 0.5f) + 12582912.0f;
+                    const int j = __float_as_int(vv) - 0x4B400000;
+                    const float t = u - (vv - 12582912.0f);
+                    const float4 c = ctab.c[j];
+                    DX[i] = gv * fmaf(fmaf(3.0f * c.w, t, 2.0f * c.z), t, c.y) * ctab.inv_h;
+                    if (gv != 0.f) {
+                        const float t2 = t * t, t3 = t2 * t, gs = gv * scale;
+                        const float h01 = 3.0f * t2 - 2.0f * t3;
+                        atomicAdd(bins + j, (unsigned int)__float2int_rn(gs * (1.0f - h01)));
+                        atomicAdd(bins + j + 1, (unsigned int)__float2int_rn(gs * h01));
+                        atomicAdd(bins + nb + j, (unsigned int)__float2int_rn(gs * (t3 - 2.0f * t2 + t)));
+                        atomicAdd(bins + nb + j + 1, (unsigned int)__float2int_rn(gs * (t3 - t2)));
+                    }
+                }
+                __syncthreads();
+                if (scale > 0.f) {
+                    const double inv = 1.0 / (double)scale;
+                    for (int j = tid; j < 2 * nb; j += nthr) {
+                        mbins[j] += (double)(int)bins[j] * inv;
+                        bins[j] = 0u;
+                    }
+                }
+                if (tid == 0) *gmax_bits = 0u;
+            } else {
                 LaneMlp L;
                 load_lane_mlp(L, w2p, h, false, lane);
                 mlp_backward_items<false>(L, acc2, XI, XI, G_, DX, n_items, warp, n_warps, lane);
@@ -329,6 +406,37 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
     store_acc(dst, acc1, h, true, lane);
     store_acc(dst + 4 * h + 1, acc2, h, false, lane);
     store_acc(dst + 7 * h + 2, acc3, h, false, lane);
+    if (use_ctab) {
+        // weight gradients of the check-phase MLP from the adjoint bins: one pass over (nodes x hidden units)
+        __syncthreads();
+        float* d0 = p.partials + (size_t)blockIdx.x * n_warps * p.np_pad + 4 * h + 1;     // warp 0's row, MLP 2
+        const int nb = p.ctab_n + 1;
+        const float step = 2.0f * p.ctab_R / (float)p.ctab_n;
+        for (int k = tid; k < h; k += nthr) {
+            const float w1 = w2p[k], b1 = w2p[h + k], w2 = w2p[2 * h + k];
+            double gw1 = 0.0, gb1 = 0.0, gw2 = 0.0;
+            for (int j = 0; j < nb; ++j) {
+                const float xj = -p.ctab_R + step * (float)j;
+                const float z = fmaf(w1, xj, b1);
+                const float e = expf(-fabsf(z));
+                const float sp = fmaxf(z, 0.f) + log1pf(e);
+                const float sg = (z >= 0.f ? 1.0f : e) / (1.0f + e);
+                const float dsg = sg * (1.0f - sg);
+                const double A = mbins[j], D = mbins[nb + j] * (double)step;
+                gw2 += A * (double)sp + D * (double)(sg * w1);
+                gb1 += A * (double)(w2 * sg) + D * (double)(w2 * dsg * w1);
+                gw1 += A * (double)(w2 * sg * xj) + D * (double)(w2 * (dsg * w1 * xj + sg));
+            }
+            d0[k] += (float)gw1;
+            d0[h + k] += (float)gb1;
+            d0[2 * h + k] += (float)gw2;
+        }
+        if (tid == 0) {
+            double gb2 = 0.0;
+            for (int j = 0; j < nb; ++j) gb2 += mbins[j];
+            d0[3 * h] += (float)gb2;
+        }
+    }
 }
 
 // stage 2: fixed-order sum over the per-warp partials (double accumulation) -> grad[n_params]
@@ -357,7 +465,17 @@ static int plan_bwd(const gd_graph* g, const gd_model* m, int64_t B, BwdPlan* ou
     p.tb = g->t;
     p.np_pad = align_up_b((int)gd_weights_size(m), 32);
     const int tab_bytes = (4 * E + V + C + 2) * 2;
-    const int fixed = align_up_b(tab_bytes, 128);
+    int fixed = align_up_b(tab_bytes, 128);
+    if (!getenv("GD_NO_CTAB") && !getenv("GD_NO_BWD_CTAB")) {
+        p.ctab_n = 512;
+        p.ctab_R = (float)(g->max_chk_deg > 1 ? g->max_chk_deg - 1 : 1);
+        const int hp = (m->hidden + 7) / 8 * 8;
+        p.off_ctab = fixed; fixed += p.ctab_n * 16;
+        p.off_w2s = fixed; fixed += 4 * hp * 4;
+        p.off_mbins = fixed; fixed += 2 * (p.ctab_n + 1) * 8;
+        p.off_bins = fixed; fixed += (2 * (p.ctab_n + 1) + 4) * 4;
+        fixed = align_up_b(fixed, 128);
+    }
     const int64_t per_syn = ((int64_t)N + 2LL * maxvc + 8LL * E) * 4;
     const int64_t tmax = (g->max_smem_optin - fixed) / per_syn;
     if (g->E >= 65536 || tmax < 4) {
