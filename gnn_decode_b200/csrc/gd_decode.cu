@@ -13,7 +13,13 @@
 //     computed in ascending edge order (deterministic, same order as the CPU index_add_ of
 //     the reference), the per-edge MLPs are evaluated for EB edges at a time in registers;
 //   * the tile's input slab x[tile][V+C] is fetched with one bulk async copy (TMA, UBLKCP)
-//     completing on an mbarrier; outputs go out as 128-bit coalesced stores.
+//     completing on an mbarrier; outputs go out as 128-bit coalesced stores;
+//   * the scalar (1 -> h -> 1) MLPs are not summed per hidden unit: the ReLU ones are evaluated
+//     as the piecewise-linear functions they are (exact), decoder_v2_4's two Softplus ones from
+//     per-launch cubic tables on their compact domains with an in-kernel error bound and automatic
+//     fall-back (gd_math.cuh: PwlSmem, CubicTab); what remains MUFU-bound is the 2-input
+//     variable-phase MLP (1 ex2 + half an lg2 per hidden unit, the other half on the FMA pipe);
+//   * messages of degree-1 variables are iteration-invariant and are computed once.
 #include "gd_common.cuh"
 #include "gd_math.cuh"
 #include "gd_decode.cuh"

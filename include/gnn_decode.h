@@ -138,6 +138,11 @@ int gd_propagate_fwd(const gd_graph* g, const gd_model* model, int32_t phase, in
  * iterations.  Outputs (any may be NULL): prob_dev [B,V] fp32 = sigmoid(-logit) (clamped to
  * [1e-7,1-1e-7] for the classical programs as the reference does), logit_dev [B,V] fp32,
  * hard_dev [B,V] uint8 = (prob > 0.5) (neural_BP.py:338 semantics).
+ * Arithmetic: fp32.  The scalar 1 -> h -> 1 MLPs are evaluated as tables built per launch from the weights
+ * (ReLU: exact piecewise-linear segments; Softplus: cubic Hermite on the compact argument domain, used only
+ * when an error bound computed from the weights is below 1e-7 / 5e-7, else the direct sum) -- logits stay
+ * within 1e-4 relative of the fp64 reference (tests/test_parity_gpu.py).  Results are deterministic and do
+ * not depend on how the batch is tiled or sharded.
  * Codes whose edge state does not fit shared memory run the streamed global-memory kernel, whose
  * per-graph state slab is allocated lazily and is NOT re-entrant: serialise streamed decodes of
  * one gd_graph across streams (gd_decode_launch_info().resident == 0 tells which path is taken). */
