@@ -39,6 +39,10 @@ struct BwdParams {
     // check-phase MLP through its cubic table and the table's ADJOINT (see decode_bwd_kernel)
     int ctab_n, off_ctab, off_w2s, off_bins, off_mbins;
     float ctab_R;
+    // variable-phase MLP items are laid out in vlist order (edges of variables with degree >= 2 first); the
+    // n_static = E - n_vact edges of degree-1 variables see ext == 0 in every iteration, so their upstream
+    // gradients are summed over the iterations (off_gacc) and pushed through the MLP once per tile
+    int n_vact, off_gacc;
 };
 
 constexpr int kPairs = kUPL / 2;
@@ -211,6 +215,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
     uint16_t* var_edges = var_ptr + (V + 1);
     uint16_t* chk_ptr = var_edges + E;
     uint16_t* chk_edges = chk_ptr + (C + 1);
+    uint16_t* vpos = chk_edges + E;                      // position of edge e in vlist order
+    for (int i = tid; i < E; i += nthr) vpos[p.tb.vlist[i]] = (uint16_t)i;
+    const int n_act = p.n_vact, n_static = E - n_act;
+    float* GA = reinterpret_cast<float*>(smem + p.off_gacc);
     for (int i = tid; i < E; i += nthr) {
         edge_var[i] = (uint16_t)p.tb.edge_var[i];
         edge_chk[i] = (uint16_t)p.tb.edge_chk[i];
@@ -304,7 +312,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
             }
         __syncthreads();
         if (ew)
-            for (int e = r; e < E; e += R) X1[e * tile + s] = xs[s * N + edge_var[e]];   // prior of the edge's variable
+            for (int e = r; e < E; e += R) X1[vpos[e] * tile + s] = xs[s * N + edge_var[e]];   // prior of the edge's variable (vlist order)
+        for (int i = tid; i < n_static * tile; i += nthr) GA[i] = 0.f;
         {
             LaneMlp L;
             load_lane_mlp(L, w3p, h, false, lane);
@@ -378,26 +387,50 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
                     const int at = e * tile + s;
                     const float t = A_[at];
                     const float dt = node[edge_chk[e] * tile + s] - DX[at];
-                    G_[at] = dt * (1.0f - t * t) * 0.5f;
-                    XI[at] = node2[edge_var[e] * tile + s] - MB[at];
+                    const float gq = dt * (1.0f - t * t) * 0.5f;
+                    const int pos = vpos[e];
+                    if (pos < n_act) {
+                        G_[pos * tile + s] = gq;
+                        XI[pos * tile + s] = node2[edge_var[e] * tile + s] - MB[at];
+                    } else {
+                        GA[(pos - n_act) * tile + s] += gq;      // degree-1 variable: ext == 0, same input every iteration
+                    }
                 }
             prefetch_stash(it - 1, s0, valid);                    // MB / AB are free now
             __syncthreads();
             {
                 LaneMlp L;
                 load_lane_mlp(L, w1p, h, true, lane);
-                mlp_backward_items<true>(L, acc1, XI, X1, G_, DX, n_items, warp, n_warps, lane);
+                mlp_backward_items<true>(L, acc1, XI, X1, G_, DX, n_act * tile, warp, n_warps, lane);
             }
             __syncthreads();
-            seg_sum(var_ptr, var_edges, V, DX, node);             // gather of gradients over the variable
+            // gather of gradients over the variable (DX is in vlist order; a degree-1 variable has no sibling: 0)
+            if (ew)
+                for (int n = r; n < V; n += R) {
+                    float a = 0.f;
+                    for (int i = var_ptr[n]; i < var_ptr[n + 1]; ++i) {
+                        const int pos = vpos[var_edges[i]];
+                        a += pos < n_act ? DX[pos * tile + s] : 0.f;
+                    }
+                    node[n * tile + s] = a;
+                }
             __syncthreads();
             cp_async_wait_all();
             if (ew)
                 for (int e = r; e < E; e += R) {
-                    const int at = e * tile + s;
-                    DM[at] += node[edge_var[e] * tile + s] - DX[at];
+                    const int at = e * tile + s, pos = vpos[e];
+                    DM[at] += node[edge_var[e] * tile + s] - (pos < n_act ? DX[pos * tile + s] : 0.f);
                     A_[at] = tanh_half(AB[at]);                   // t of the next (earlier) iteration
                 }
+            __syncthreads();
+        }
+        if (n_static > 0) {
+            // the degree-1 variables' edges: one MLP backward with the iteration-summed gradient, input (0, prior)
+            for (int i = tid; i < n_static * tile; i += nthr) XI[i] = 0.f;
+            __syncthreads();
+            LaneMlp L;
+            load_lane_mlp(L, w1p, h, true, lane);
+            mlp_backward_items<true>(L, acc1, XI, X1 + n_act * tile, GA, DX, n_static * tile, warp, n_warps, lane);
             __syncthreads();
         }
     }
@@ -464,8 +497,9 @@ static int plan_bwd(const gd_graph* g, const gd_model* m, int64_t B, BwdPlan* ou
     p.B = B; p.T = m->iters; p.V = V; p.C = C; p.E = E; p.N = N; p.hid = m->hidden; p.maxvc = maxvc;
     p.tb = g->t;
     p.np_pad = align_up_b((int)gd_weights_size(m), 32);
-    const int tab_bytes = (4 * E + V + C + 2) * 2;
+    const int tab_bytes = (5 * E + V + C + 2) * 2;
     int fixed = align_up_b(tab_bytes, 128);
+    p.n_vact = getenv("GD_NO_VSKIP") ? E : g->n_vact;
     if (!getenv("GD_NO_CTAB") && !getenv("GD_NO_BWD_CTAB")) {
         p.ctab_n = 512;
         p.ctab_R = (float)(g->max_chk_deg > 1 ? g->max_chk_deg - 1 : 1);
@@ -476,7 +510,7 @@ static int plan_bwd(const gd_graph* g, const gd_model* m, int64_t B, BwdPlan* ou
         p.off_bins = fixed; fixed += (2 * (p.ctab_n + 1) + 4) * 4;
         fixed = align_up_b(fixed, 128);
     }
-    const int64_t per_syn = ((int64_t)N + 2LL * maxvc + 8LL * E) * 4;
+    const int64_t per_syn = ((int64_t)N + 2LL * maxvc + 8LL * E + (E - p.n_vact)) * 4;
     const int64_t tmax = (g->max_smem_optin - fixed) / per_syn;
     if (g->E >= 65536 || tmax < 4) {
         set_error("gd_decode_bwd: code too large for the shared-memory backward kernel (E=%lld)", (long long)g->E);
@@ -508,6 +542,7 @@ static int plan_bwd(const gd_graph* g, const gd_model* m, int64_t B, BwdPlan* ou
     p.off_dx = o; o += E * tile * 4;
     p.off_mb = o; o += E * tile * 4;
     p.off_ab = o; o += E * tile * 4;
+    p.off_gacc = o; o += (E - p.n_vact) * tile * 4;
     out->smem = o;
     out->threads = kBwdThreads;
     p.n_tiles = (int)((B + tile - 1) / tile);

@@ -162,3 +162,35 @@ def test_fused_loss_and_train_step_match_reference(name):
     assert abs(l3.item() - case.loss) <= 1e-5 * abs(case.loss)
     for k, p in dec.named_parameters():
         assert (p.grad - first[k]).abs().max().item() <= 1e-5 * first[k].abs().max().item() + 1e-12
+
+
+def test_degree_one_variables_and_table_adjoint_do_not_change_gradients(monkeypatch):
+    """Rotated surface codes have degree-1 variables (the toric gradient fixtures do not): their variable-phase
+    messages are iteration-invariant, so the backward sums their upstream gradient over the iterations and runs
+    the MLP once; the check-phase MLP goes through its cubic table and the table's adjoint.  Both are pure
+    re-associations of the same sums: gradients must agree with the plain per-item path."""
+    from gnn_decode_b200 import codes
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.quantum import decoder_v2_4
+    from gnn_decode_b200.sampler import sample_syndromes
+    from gnn_decode_b200.train import train_step_grads
+    case = _Case("grad_v2_4_toricL5_epoch3_T6")
+    Hz, Hx = codes.rotated_surface_checks(5)
+    pcm = codes.css_pcm(Hz, Hx)
+    logical = codes.css_logicals(Hz, Hx)
+    g = TannerGraph.from_pcm(pcm, DEV)
+    assert int((pcm.sum(0) == 1).sum()) > 0                                   # the code does have degree-1 variables
+    dec = decoder_v2_4.GNNI(7)
+    dec.load_state_dict(case.weights)
+    dec = dec.to(DEV).train()
+    x, err = sample_syndromes(g, 333, [0.03, 0.08, 0.12], noise=1, seed=5)
+    loss_a, _ = train_step_grads(dec, g, x, err, logical)
+    ga = {k: p.grad.clone() for k, p in dec.named_parameters()}
+    monkeypatch.setenv("GD_NO_VSKIP", "1")
+    monkeypatch.setenv("GD_NO_CTAB", "1")
+    loss_b, _ = train_step_grads(dec, g, x, err, logical)
+    gb = {k: p.grad.clone() for k, p in dec.named_parameters()}
+    assert abs(loss_a.item() - loss_b.item()) <= 1e-5 * abs(loss_b.item())
+    for k in ga:
+        scale = gb[k].abs().max().item()
+        assert (ga[k] - gb[k]).abs().max().item() <= 2e-4 * scale + 1e-9, k
