@@ -230,6 +230,19 @@ def bch_63_45_pcm():
     return np.stack([np.roll(first, i) for i in range(18)])
 
 
+def read_pcm_txt(path, transpose=False):
+    """Read a parity-check matrix in the reference's text format (`classical/BCH(63,45).txt`: whitespace-separated
+    0/1 rows, loaded there with np.loadtxt, CGNNI.py:181).  Returns uint8 [C, V] (transpose=True for files stored [V, C])."""
+    H = np.loadtxt(path).astype(np.uint8)
+    H = H.reshape(1, -1) if H.ndim == 1 else H
+    return np.ascontiguousarray(H.T if transpose else H)
+
+
+def write_pcm_txt(path, pcm):
+    """Write a [C, V] 0/1 matrix in the same text format (one row per line, single spaces)."""
+    np.savetxt(path, np.asarray(pcm, dtype=np.uint8), fmt="%d")
+
+
 def edge_index_of(pcm):
     """Per-graph edge_index [2, E] int64 of H = pcm.T in `H.to_sparse()._indices()` order."""
     H = np.ascontiguousarray(np.array(pcm).T)

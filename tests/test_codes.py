@@ -59,3 +59,13 @@ def test_ldpc_toy_and_edge_index():
     ei = codes.edge_index_of(pcm)
     assert ei.shape == (2, 16)
     assert np.all(np.diff(ei[0]) >= 0)       # sorted by variable
+
+
+def test_pcm_text_round_trip(tmp_path, codes_npz):
+    """The reference's .txt matrix format (classical/BCH(63,45).txt, np.loadtxt at CGNNI.py:181)."""
+    pcm = codes.bch_63_45_pcm()
+    f = tmp_path / "H.txt"
+    codes.write_pcm_txt(str(f), pcm)
+    assert np.array_equal(codes.read_pcm_txt(str(f)), pcm)
+    assert np.array_equal(codes.read_pcm_txt(str(f)), codes_npz["bch_63_45_H"])
+    assert np.array_equal(codes.read_pcm_txt(str(f), transpose=True), pcm.T)
