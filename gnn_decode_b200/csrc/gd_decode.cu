@@ -726,6 +726,7 @@ extern "C" int gd_decode_launch_info(const gd_graph* g, const gd_model* model, i
     int rc = gd::plan_decode(g, model, B, &pl);
     if (rc != GD_OK) return rc;
     if (!pl.resident) return gd::streamed_launch_info(g, model, B, out);
+    if (gd::light_launch_info(g, model, B, out)) return GD_OK;      // node-owner kernel for the light programs
     out->tile = pl.p.tile; out->threads = pl.threads; out->grid = pl.grid; out->smem_bytes = pl.smem;
     out->resident = pl.resident; out->n_tiles = pl.p.n_tiles;
     return GD_OK;
@@ -803,6 +804,14 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
         rc = gd::streamed_decode(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, B, st);
         if (prev != g->device) cudaSetDevice(prev);
         return rc;
+    }
+    if (!stash_dev) {
+        // light programs (CGNNI, QGNNI, sum-product): the node-owner kernel of gd_decode_light.cu
+        const int lrc = gd::light_decode(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, B, st);
+        if (lrc >= 0) {
+            if (prev != g->device) cudaSetDevice(prev);
+            return lrc;
+        }
     }
     switch (model->program) {
         case GD_PROG_CGNNI: rc = gd::launch_decode<GD_PROG_CGNNI>(pl, st); break;
