@@ -42,6 +42,7 @@ struct DecodeParams {
     int T, V, C, E, N;
     int tile, R, hid, hp, n_tiles, maxvc, all_iters, wslot;
     int n_vact;             // edges on variables of degree >= 2 (GraphTables::vlist)
+    int vdirect, cdirect;   // V2_4: max variable degree <= 2 / max check degree <= 4 -> sibling messages are read directly
     int scratch_bytes;      // bytes of shared memory from off_x to the end (prologue scratch)
     int rtab_n, off_rtab;   // V2_4: intervals of the read-out MLP's cubic table (0 = direct) and its smem offset
     int ctab_n, off_ctab;   // V2_4: intervals of the check-phase cubic table (0 = direct evaluation) and its smem offset
@@ -90,6 +91,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Graph tables: 16-bit copies in shared memory (warp-uniform reads: broadcast, conflict-free).
 struct Tables {
     const uint16_t *edge_var, *edge_chk, *var_ptr, *var_edges, *chk_ptr, *chk_edges, *vlist;
+    const uint16_t *vsib, *csib;     // [E] sibling edge on the same variable, [E][3] sibling edges on the same check (0xFFFF = none)
     __device__ __forceinline__ static int ld(const uint16_t* p, int i) { return p[i]; }
 };
 
@@ -151,6 +153,25 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         for (int i = tid; i <= C; i += nthr) d_cp[i] = (uint16_t)p.tb.chk_ptr[i];
         tb.edge_var = d_ev; tb.edge_chk = d_ec; tb.var_ptr = d_vp;
         tb.var_edges = d_ve; tb.chk_ptr = d_cp; tb.chk_edges = d_ce; tb.vlist = d_vl;
+        tb.vsib = d_vl + E; tb.csib = d_vl + 2 * E;
+    }
+    // decoder_v2_4 on low-degree graphs (every surface / toric code: variable degree <= 2, check degree <= 4): the
+    // "sum over siblings minus self" is just the one sibling message (variables) or the sum of <= 3 of them (checks), read
+    // directly -- no node-sum passes, no node arrays, two barriers per iteration instead of four.
+    const bool vdir = PROG == GD_PROG_V2_4 && p.vdirect, cdir = PROG == GD_PROG_V2_4 && p.cdirect;
+    if (vdir || cdir) {
+        __syncthreads();                                   // the 16-bit graph tables are complete
+        uint16_t* vs = const_cast<uint16_t*>(tb.vsib);
+        uint16_t* cs = const_cast<uint16_t*>(tb.csib);
+        for (int e = tid; e < E; e += nthr) {
+            const int v = tb.edge_var[e], vb = tb.var_ptr[v], vd = tb.var_ptr[v + 1] - vb;
+            vs[e] = vd == 2 ? (tb.var_edges[vb] == e ? tb.var_edges[vb + 1] : tb.var_edges[vb]) : (uint16_t)0xFFFF;
+            const int c = tb.edge_chk[e], cb = tb.chk_ptr[c], ce = tb.chk_ptr[c + 1];
+            int n = 0;
+            for (int i = cb; i < ce && n < 3; ++i)
+                if (tb.chk_edges[i] != e) cs[3 * e + n++] = tb.chk_edges[i];       // ascending edge id
+            for (; n < 3; ++n) cs[3 * e + n] = (uint16_t)0xFFFF;
+        }
     }
     MlpSmem W1{}, W2{}, W3{};
     const float* gru = nullptr;   // GRU_CA: the two GRUCell(1,1) parameter sets, [2][12] in shared memory
@@ -378,6 +399,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             // NEURAL_BP: this layer's per-edge weights W_l[E] | W_p,l[E] (warp-uniform reads)
             const float* wl = kNBP ? p.weights + (size_t)it * 2 * E : nullptr;
             // ---- V1: per-variable sums of m (ascending edge id) ----
+            if (!vdir) {
             for (int v = r; v < V; v += R) {
                 const int b = tb.ld(tb.var_ptr, v), e_end = tb.ld(tb.var_ptr, v + 1);
                 float acc = 0.f;
@@ -390,6 +412,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                 node[v * tile + s] = acc;
             }
             __syncthreads();
+            }
             // ---- V2: variable-phase message + the `pre` of the check phase, per edge ----
             if constexpr (PROG == GD_PROG_V2_4) {
                 // A degree-1 variable has no sibling edge: ext == 0 in every iteration, so its message
@@ -408,7 +431,12 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         const int ec = e < E ? e : E - 1;
                         const int v = tb.ld(tb.edge_var, ec);
                         mo[j] = m_st[(size_t)ec * tile + s];
-                        x0[j] = node[v * tile + s] - mo[j];
+                        if (vdir) {
+                            const int sb = tb.ld(tb.vsib, ec);
+                            x0[j] = sb != 0xFFFF ? m_st[(size_t)sb * tile + s] : 0.f;
+                        } else {
+                            x0[j] = node[v * tile + s] - mo[j];
+                        }
                         x1[j] = xrow[v];
                     }
                     if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, true, (NPOLY > 0 ? NPOLY : 0)>(W1, hp, x0, x1, o);
@@ -457,6 +485,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             }
             __syncthreads();
             // ---- C1: per-check sums ----
+            if (!cdir) {
             for (int c = r; c < C; c += R) {
                 const int b = tb.ld(tb.chk_ptr, c), e_end = tb.ld(tb.chk_ptr, c + 1);
                 float acc = 0.f, cnt = 0.f;
@@ -477,6 +506,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                 if constexpr (kIsBP || kNBP) node2[c * tile + s] = cnt;
             }
             __syncthreads();
+            }
             // ---- C2: check-phase message, residual ----
             if constexpr (kNBP) {          // neural_BP.py:108-122 (eps2 = 1e-15) and :304 (+ alpha * m_p)
                 const float alpha = __ldg(p.weights + (size_t)(2 * p.T + 2) * E);
@@ -526,7 +556,17 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         ee[j] = e;
                         const int ec = e < E ? e : E - 1;
                         const int c = tb.ld(tb.edge_chk, ec);
-                        x0[j] = node[c * tile + s] - t_st[(size_t)ec * tile + s];
+                        if (cdir) {
+                            float a3 = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const int sb = tb.ld(tb.csib, 3 * ec + q);
+                                a3 += sb != 0xFFFF ? t_st[(size_t)sb * tile + s] : 0.f;
+                            }
+                            x0[j] = a3;
+                        } else {
+                            x0[j] = node[c * tile + s] - t_st[(size_t)ec * tile + s];
+                        }
                         sg[j] = PROG == GD_PROG_CGNNI ? 1.f : xrow[V + c];
                     }
                     if (kSoftplus && use_ctab) {
@@ -611,7 +651,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
         off += p.ctab_n * 16;
     }
     const bool fits16 = E64 < 65536 && V < 65535 && C < 65535;
-    const int tab_bytes = (int)(5 * E64 + V + C + 2) * 2;
+    const int tab_bytes = (int)(9 * E64 + V + C + 2) * 2;
     // resident layout first
     int tile = 0, resident = 0, R = 0;
     if (fits16 && off + tab_bytes < smem_max) {
@@ -788,6 +828,8 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     pl.p.stash = stash_dev;
     pl.p.all_iters = (model->flags & GD_FLAG_ALL_ITERS) ? 1 : 0;
     pl.p.n_vact = getenv("GD_NO_VSKIP") ? (int)g->E : g->n_vact;
+    pl.p.vdirect = (g->max_var_deg <= 2 && !getenv("GD_NO_DIRECT")) ? 1 : 0;
+    pl.p.cdirect = (g->max_chk_deg <= 4 && !getenv("GD_NO_DIRECT")) ? 1 : 0;
     GD_CHECK_ARG(model->program != GD_PROG_NEURAL_BP || model->hidden == g->E,
                  "gd_decode_fwd: GD_PROG_NEURAL_BP needs model.hidden == E (%lld per-edge weights), got %d",
                  (long long)g->E, model->hidden);
