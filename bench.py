@@ -393,8 +393,10 @@ def main():
                         "2-MUFU-per-unit (ex2+lg2) rate; the kernel needs 1.5 MUFU/unit (half of the lg2 run as an FMA-pipe "
                         "polynomial), so frac can exceed 1")
             else:
-                units = B * E * (T * 256 + 128)
-                what = "xu (MUFU): Softplus hidden-unit evaluations (streamed path evaluates all three MLPs directly)"
+                units = B * dec.mlp[0].out_features * T * E
+                what = ("xu (MUFU): Softplus hidden units evaluated on the direct path = the 2-input variable-phase MLP, every "
+                        "edge and iteration (streamed path; check-phase + read-out MLPs are cubic tables); peak = the "
+                        "2-MUFU-per-unit (ex2+lg2) rate")
             unit_rate = units / (med_ms * 1e-3)
             roofline["pipe"] = {"name": what, "achieved": unit_rate / 1e12,
                                 "peak": unit_peak / 1e12, "unit": "T Softplus units/s", "frac": unit_rate / unit_peak,
