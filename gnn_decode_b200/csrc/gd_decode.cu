@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             }
         }
     }
+    fence_proxy_async();   // the prologue used the slab region as generic-proxy scratch; the bulk copies (async proxy) come next
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
