@@ -72,3 +72,35 @@ def test_random_graph_matches_oracle(program, seed, monkeypatch):
         assert bool(ok.all()), "%s %s: max abs err %.3g" % (program, mode, (got - ref).abs().max().item())
         decided = ref.abs() > 1e-3
         assert torch.equal(hard.cpu().bool()[decided], (ref < 0)[decided])
+
+
+@pytest.mark.parametrize("mode", ["v2_4-resident", "qgnni-light", "bp-light", "qgnni-streamed", "bp-streamed", "v2_4-streamed"])
+def test_repeated_launches_are_bit_identical(mode, monkeypatch):
+    """compute-sanitizer is not available on the GPU pool, so data races are hunted the blunt way: 25 launches of
+    every kernel family on a ragged batch, concurrently on two streams, must all be bit-identical."""
+    from gnn_decode_b200.quantum import decoder_v2_4, QGNNI, BP
+    from gnn_decode_b200.sampler import sample_syndromes
+    prog, kern = mode.split("-")
+    pcm = codes.rotated_surface_pcm(5) if prog == "v2_4" else codes.toric_pcm(4)
+    g = TannerGraph.from_pcm(pcm, DEV)
+    torch.manual_seed(3)
+    dec = {"v2_4": decoder_v2_4.GNNI(6), "qgnni": QGNNI.GNNI(7), "bp": BP.GNNI(7)}[prog].to(DEV).eval()
+    B = 5003 if kern != "streamed" else 1203
+    x, _ = sample_syndromes(g, B, [0.03, 0.08], noise=1 if prog == "v2_4" else 0, seed=4)
+    if kern == "light":
+        monkeypatch.setenv("GD_FORCE_LIGHT", "1")
+    if kern == "streamed":
+        monkeypatch.setenv("GD_FORCE_STREAMED", "1")
+    first = dec.decode(x, graph=g, return_logits=True)[1].clone()
+    streams = [torch.cuda.Stream(DEV), torch.cuda.Stream(DEV)]
+    torch.cuda.synchronize()
+    outs = []
+    for i in range(25):
+        if kern == "streamed":                      # the streamed slab is per graph: one stream at a time (include/gnn_decode.h)
+            outs.append(dec.decode(x, graph=g, return_logits=True)[1])
+        else:
+            with torch.cuda.stream(streams[i & 1]):
+                outs.append(dec.decode(x, graph=g, return_logits=True)[1])
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o, first)
