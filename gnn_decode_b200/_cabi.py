@@ -49,6 +49,8 @@ _SIGNATURES = {
     "gd_bwd_workspace_floats": (C.c_int64, [_p, C.POINTER(GdModel), C.c_int64]),
     "gd_decode_bwd": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, _p, _p, C.c_int32, C.c_int64, _p]),
     "gd_loss_v2_4": (C.c_int, [_p, _p, C.c_int32, _p, _p, _p, _p, _p, C.c_int64, _p]),
+    "gd_p2p_buffer_floats": (C.c_int64, [C.c_int32]),
+    "gd_p2p_allreduce": (C.c_int, [_p, C.c_int32, C.c_int32, _p, _p, C.c_int32, C.c_uint32, C.c_float, _p, _p]),
 }
 # entry points added after ABI v1 froze; bound when present (tests assert the header/.so agree)
 _OPTIONAL = {}

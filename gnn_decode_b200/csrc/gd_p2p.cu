@@ -1,0 +1,79 @@
+// One-shot all-reduce of the flat gradient vector over NVLink / NVSwitch PEER MEMORY, fused into a single
+// kernel (the training path's only exchange step is 10h+3 = 1 283 floats -- latency-bound, so a
+// ring or tree is pointless: every rank publishes its vector in its own symmetric buffer, raises an epoch flag, waits
+// for the peers' flags and sums all vectors in RANK ORDER straight from peer memory: the same fixed order on every
+// rank -> bit-identical results everywhere).  The symmetric buffers and their peer mappings come from
+// torch.distributed._symmetric_memory (plumbing); the data path is this kernel.
+//   buffer of rank r (floats):  [ slot 0: n_pad ][ slot 1: n_pad ][ flag (uint32, as one float slot) ]
+// Double-buffered by epoch parity: a rank overwrites slot p at step k+2 only after passing the flag wait of step
+// k+1, by which time every peer has finished reading slot p of step k.
+#include "gd_common.cuh"
+
+namespace gd {
+
+constexpr int kMaxWorld = 16;
+struct P2PParams {
+    float* peer[kMaxWorld];       // peer[r] = rank r's symmetric buffer mapped into this process
+    const float* src;
+    float* dst;
+    int* err;                     // set to 1 when a peer never showed up (bounded spin)
+    int world, rank, n, n_pad;
+    unsigned int epoch;
+    float scale;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(const P2PParams p) {
+    const int tid = threadIdx.x;
+    float* mine = p.peer[p.rank] + (size_t)(p.epoch & 1u) * p.n_pad;
+    for (int i = tid; i < p.n; i += blockDim.x) mine[i] = p.src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) st_release_sys(reinterpret_cast<unsigned int*>(p.peer[p.rank] + 2 * (size_t)p.n_pad), p.epoch);
+    if (tid < p.world && tid != p.rank) {
+        const unsigned int* flag = reinterpret_cast<const unsigned int*>(p.peer[tid] + 2 * (size_t)p.n_pad);
+        long long spins = 0;
+        // epochs only grow; (int) difference tolerates wrap-around
+        while ((int)(ld_acquire_sys(flag) - p.epoch) < 0) {
+            if (++spins > (1ll << 27)) { *p.err = 1; break; }        // ~ seconds: a peer is gone, do not hang the GPU
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < p.n; i += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < p.world; ++r)                             // fixed rank order on every rank
+            acc += __ldcg(p.peer[r] + (size_t)(p.epoch & 1u) * p.n_pad + i);
+        p.dst[i] = acc * p.scale;
+    }
+}
+
+}  // namespace gd
+
+extern "C" int64_t gd_p2p_buffer_floats(int32_t n) {
+    if (n <= 0) return -1;
+    return 2 * (int64_t)((n + 31) / 32 * 32) + 32;
+}
+
+extern "C" int gd_p2p_allreduce(const uint64_t* peer_ptrs_host, int32_t world, int32_t rank, const float* src_dev,
+                                float* dst_dev, int32_t n, uint32_t epoch, float scale, int32_t* err_dev, void* stream) {
+    GD_CHECK_ARG(peer_ptrs_host && src_dev && dst_dev && err_dev, "gd_p2p_allreduce: NULL argument");
+    GD_CHECK_ARG(world >= 1 && world <= gd::kMaxWorld && rank >= 0 && rank < world, "gd_p2p_allreduce: bad rank %d / world %d",
+                 rank, world);
+    GD_CHECK_ARG(n > 0 && epoch > 0, "gd_p2p_allreduce: n and epoch must be positive");
+    gd::P2PParams p;
+    for (int r = 0; r < world; ++r) p.peer[r] = reinterpret_cast<float*>((uintptr_t)peer_ptrs_host[r]);
+    p.src = src_dev; p.dst = dst_dev; p.err = err_dev; p.world = world; p.rank = rank; p.n = n; p.n_pad = (n + 31) / 32 * 32;
+    p.epoch = epoch; p.scale = scale;
+    gd::p2p_allreduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}

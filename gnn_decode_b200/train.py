@@ -77,9 +77,11 @@ class LossFunc(torch.nn.Module):
         return _SinLossFn.apply(pred.reshape(-1, V), self.graph, datas.y.reshape(-1, V), self.logical)
 
 
-def train_step_grads(decoder, graph, x, y, logical=None, accumulate=False):
+def train_step_grads(decoder, graph, x, y, logical=None, accumulate=False, p2p=None):
     """One forward + loss + backward of decoder_v2_4.GNNI on a batch: x [B, V+C] CUDA, y [B, V] 0/1.
-    Sets / accumulates p.grad of the decoder's MLP parameters and returns (loss, prob)."""
+    Sets / accumulates p.grad of the decoder's MLP parameters and returns (loss, prob).
+    p2p: a dist.P2PAllReduce -- data-parallel training: the flat gradient is averaged over the ranks by the
+    peer-memory kernel before it is scattered into p.grad (no NCCL call, no flatten / unflatten round trip)."""
     if decoder._gd_program != _cabi.PROG_V2_4:
         raise _cabi.GdError("the training kernels exist for the decoder_v2_4 program only")
     lib = _cabi.lib()
@@ -108,6 +110,8 @@ def train_step_grads(decoder, graph, x, y, logical=None, accumulate=False):
     with torch.cuda.device(dev):
         _cabi.check(lib.gd_decode_bwd(graph.handle, ct.byref(model), _ptr(w), _ptr(x32), _ptr(stash), _ptr(grad_logit),
                                       _ptr(gw), _ptr(ws), 0, B, st), "gd_decode_bwd")
+    if p2p is not None:
+        p2p(gw, average=True)
     off = 0
     for p in params:
         n = p.numel()

@@ -185,6 +185,17 @@ int gd_loss_v2_4(const gd_graph* g, const uint8_t* logical_dev, int32_t K, const
                  const uint8_t* y_dev, float* loss_per_syndrome_dev, float* grad_prob_dev,
                  float* grad_logit_dev, int64_t B, void* stream);
 
+/* ---- data-parallel training: one-shot all-reduce of the flat gradient (10h+3 floats) over NVLink / NVSwitch peer
+ *      memory in ONE kernel (replaces nothing in the reference, which is single-GPU; BASELINE config 4).
+ *      Every rank owns a symmetric buffer of gd_p2p_buffer_floats(n) floats (zero-initialised once) that all ranks
+ *      have mapped; peer_ptrs_host[r] is rank r's buffer as seen from THIS process.  The kernel publishes src in the
+ *      caller's buffer, raises its epoch flag, waits (bounded) for the peers and writes dst[i] = scale * sum over ranks
+ *      in rank order -- bit-identical on every rank.  epoch must be 1, 2, 3, ... on successive calls, the same on all
+ *      ranks; *err_dev is set to 1 if a peer never arrived. ---- */
+int64_t gd_p2p_buffer_floats(int32_t n);
+int gd_p2p_allreduce(const uint64_t* peer_ptrs_host, int32_t world, int32_t rank, const float* src_dev,
+                     float* dst_dev, int32_t n, uint32_t epoch, float scale, int32_t* err_dev, void* stream);
+
 /* Launch geometry the library picked for (graph, model, B): for benchmarks / roofline. */
 typedef struct gd_launch_info {
     int32_t tile;            /* syndromes per CTA tile                          */

@@ -1,0 +1,52 @@
+"""Multi-GPU check of the peer-memory all-reduce (run under torchrun, >= 2 GPUs):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 scripts/p2p_check.py
+Compares gd_p2p_allreduce with NCCL's all_reduce on random vectors over many epochs (incl. the double-buffer reuse),
+checks that all ranks hold bit-identical results, and times both."""
+import os, sys, time
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gnn_decode_b200.dist import P2PAllReduce
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dev = torch.device("cuda", lr)
+dist.init_process_group("nccl", device_id=dev)
+n = 1283
+p2p = P2PAllReduce(n, dev)
+gen = torch.Generator(device=dev).manual_seed(100 + rank)
+worst = 0.0
+for step in range(200):
+    v = torch.randn(n, device=dev, generator=gen) * (1.0 + step % 7)
+    ref = v.clone()
+    dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+    ref /= world
+    out = torch.empty_like(v)
+    p2p(v, out)
+    worst = max(worst, (out - ref).abs().max().item() / (ref.abs().max().item() + 1e-30))
+    gathered = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out)
+    assert all(torch.equal(gathered[0], gq) for gq in gathered), "ranks disagree at step %d" % step
+p2p.check()
+assert worst < 1e-6, worst
+# timing: device time per call, max over ranks
+def timed(fn, iters=200):
+    for _ in range(20):
+        fn()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item() * 1e3
+v = torch.randn(n, device=dev)
+t_p2p = timed(lambda: p2p(v))
+t_nccl = timed(lambda: dist.all_reduce(v))
+p2p.check()
+if rank == 0:
+    print("p2p all-reduce ok on %d GPUs: max rel diff vs NCCL %.2e, bit-identical across ranks; %.1f us/call vs NCCL %.1f us/call"
+          % (world, worst, t_p2p, t_nccl))
+dist.destroy_process_group()

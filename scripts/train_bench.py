@@ -39,12 +39,23 @@ FUSED = os.environ.get("GD_TRAIN_AUTOGRAD") is None     # default: fused forward
 logical_u8 = codes.css_logicals(Hz, Hx)
 
 
+P2P = None
+if world > 1 and os.environ.get("GD_NCCL_ALLREDUCE") is None:
+    try:
+        from gnn_decode_b200.dist import P2PAllReduce
+        P2P = P2PAllReduce(sum(p.numel() for p in dec._gd_params()), dev)   # peer-memory kernel (csrc/gd_p2p.cu)
+    except Exception as e:                                                    # no symmetric memory: NCCL
+        if rank == 0:
+            print("P2PAllReduce unavailable (%s): using NCCL" % e)
+
+
 def step_fused(timers=None):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
-    loss, _ = train_step_grads(dec, g, x, err, logical_u8)
+    loss, _ = train_step_grads(dec, g, x, err, logical_u8, p2p=P2P)
     ev[1].record()
-    allreduce_flat_grads(dec.parameters())
+    if P2P is None:
+        allreduce_flat_grads(dec.parameters())
     opt.step()
     ev[2].record()
     if timers is not None:
@@ -85,7 +96,10 @@ for _ in range(n):
     l = step(timers)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
+if P2P is not None:
+    P2P.check()
 if rank == 0:
+    print("gradient all-reduce:", "peer-memory kernel (gd_p2p_allreduce)" if P2P is not None else ("NCCL" if world > 1 else "none (1 GPU)"))
     print("rotated d=%d V=%d C=%d E=%d  B/GPU=%d x %d GPU  T=%d: %.3f ms/step  %.1f steps/s  %.3f M syndromes/s  loss %.2f" %
           (d, g.V, g.C, g.E, B, world, T, dt * 1e3, 1 / dt, world * B / dt / 1e6, l.item()))
     print("  per-step ms:", {k: round(v / n, 3) for k, v in timers.items()})

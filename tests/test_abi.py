@@ -96,3 +96,12 @@ def test_product_does_not_import_oracle():
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
     for f in glob.glob(os.path.join(ROOT, "gnn_decode_b200", "**", "*.py"), recursive=True):
         assert "oracle" not in re.sub(r"#.*", "", open(f).read()).replace("no CPU fallback", ""), f
+
+
+def test_p2p_allreduce_argument_checks():
+    import ctypes as C
+    lib = _cabi.lib()
+    assert lib.gd_p2p_buffer_floats(1283) == 2 * 1312 + 32 and lib.gd_p2p_buffer_floats(0) == -1
+    ptrs = (C.c_uint64 * 2)(0, 0)
+    assert lib.gd_p2p_allreduce(ptrs, 2, 5, None, None, 10, 1, C.c_float(1.0), None, None) == _cabi.GD_ERR_INVALID
+    assert b"gd_p2p_allreduce" in lib.gd_last_error()
