@@ -131,6 +131,41 @@ def _ext_case(name, script, program, consts, T, seed=1234):
               (path, rows, cols, E, B, T, out["prob"].min(), out["prob"].max()))
 
 
+def _v1_1_case(name, consts, T, seed=1234):
+    """quantum/decoder_v1_1.py: neural BP with weights shared per edge type (one-hot `feat_onehot` from H_one).  The script
+    loads './model2_2/decoder_parameters_epoch714.pkl' at import, a directory the repository does not ship: that one
+    module-level call is neutralised (the class bodies are untouched) and seeded random type tables are used."""
+    script = "quantum/decoder_v1_1.py"
+    with open(os.path.join(ref_loader.REF_ROOT, script)) as f:
+        load_line = [l for l in f.read().split("\n") if "load_state_dict" in l and not l.strip().startswith("#")][0]
+    with ref_loader.reference_session("quantum"):
+        ns = ref_loader.load_reference(script, consts=consts, seed=seed, raw_subs=[(load_line, "pass")])
+        rows, cols, B = int(ns.rows), int(ns.cols), int(ns.BATCH_SIZE)
+        torch.manual_seed(seed + 1)
+        dec = ns.GNNI(T)
+        with torch.no_grad():
+            for n_, p_ in dec.named_parameters():
+                p_.copy_(torch.full_like(p_, 0.3) if n_ == "alpha" else torch.rand_like(p_) * 0.8 + 0.5)
+        dec.eval()
+        batch = next(iter(ns.train_loader))
+        with torch.no_grad():
+            pred = dec(batch)
+        E = batch.edge_index.size(1) // B
+        ei = batch.edge_index[:, :E].clone()
+        oh = ns.feat_onehot[:E]
+        assert bool((oh.sum(1) == 1).all())
+        out = dict(program="neural_bp", script=script, V=rows, C=cols, E=E, B=B, T=T, dtype="float64",
+                   edge_index=_np(ei).astype(np.int64), H=_np(ns.H).astype(np.uint8), x=_np(batch.x.reshape(B, rows + cols)),
+                   y=_np(batch.y.reshape(B, -1)), prob=_np(pred.reshape(B, rows)), edge_types=_np(oh.argmax(1)).astype(np.int64),
+                   nb_digits=int(ns.nb_digits), m0=np.zeros((B, E)), phase_var=np.zeros((B, E)), phase_chk=np.zeros((B, E)))
+        for k, v in dec.state_dict().items():
+            out["w:" + k] = _np(v)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote %s  (V=%d C=%d E=%d B=%d T=%d, %d edge types, prob range %.3g..%.3g)" %
+              (path, rows, cols, E, B, T, int(ns.nb_digits), out["prob"].min(), out["prob"].max()))
+
+
 def _grad_case(name, consts, ckpt, T, seed=1234):
     """One train-step gradient of the reference: loss = criterion(decoder(datas), datas);
     loss.backward()  (decoder_v2_4.py:331-335) -> per-parameter gradients."""
@@ -217,6 +252,7 @@ def main():
                R + "/quantum/new_model/decoder_parameters_epoch3.pkl", T=6, seed=77)
     _ext_case("ext_neural_bp_toricL4", "quantum/neural_BP.py", "neural_bp", dict(q_small, L="4"), T=5)
     _ext_case("ext_gru_ca_toricL4", "quantum/QGNNNI_ca.py", "gru_ca", dict(q_small, L="4"), T=6)
+    _v1_1_case("ext_v1_1_onehot_toricL4", dict(q_small, L="4"), T=5)
     _codes()
 
 

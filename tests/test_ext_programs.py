@@ -159,3 +159,62 @@ def test_ext_programs_reject_what_they_do_not_support():
     dec = QGNNNI_ca.GNNI(2).to(dev).eval()
     with pytest.raises(_cabi.GdError):
         dec.decode(torch.zeros(8, big.N, device=dev), graph=big)
+
+
+# ---- quantum/decoder_v1_1.py: neural BP with weights shared per edge type (one-hot feat_onehot) ----------------------
+def _v1_1_fixture():
+    z = np.load(__file__.rsplit("/", 1)[0] + "/golden/ext_v1_1_onehot_toricL4.npz")
+    g = Golden("ext_v1_1_onehot_toricL4")
+    types = torch.from_numpy(z["edge_types"])
+    return g, types, int(z["nb_digits"])
+
+
+def _expand_v1_1(w, types, T):
+    """Per-edge weight vectors of the neural_bp program from decoder_v1_1's type tables: matmul(m * onehot, W) == m * W[type]."""
+    out = {}
+    for l in range(T):
+        out["layers.%d.W" % (2 * l)] = w["layers.%d.W" % (2 * l)][types]
+        out["layers.%d.W_p" % (2 * l)] = w["layers.%d.W_p" % (2 * l)][types]
+    out["W"], out["W_p"], out["alpha"] = w["W"][types], w["W_p"][types], w["alpha"]
+    return out
+
+
+def test_v1_1_onehot_restatement_matches_golden_bit_exact():
+    g, types, nb = _v1_1_fixture()
+    out = restate.decode("neural_bp", g.edge_index, g.V, g.C, g.x, _expand_v1_1(g.weights, types, g.T), T=g.T, dtype=g.dtype)
+    assert torch.equal(out["prob"], g.prob)
+
+
+def test_v1_1_state_dict_keys():
+    from gnn_decode_b200.quantum import decoder_v1_1
+    g, types, nb = _v1_1_fixture()
+    dec = decoder_v1_1.GNNI(g.T, edge_types=types, nb_digits=nb)
+    assert list(dec.state_dict().keys()) == list(g.weights.keys())          # target_to_source layers own no parameters
+    dec.load_state_dict(g.weights, strict=True)
+    assert sum(p.numel() for p in dec._gd_params()) == (2 * g.T + 2) * g.E + 1
+
+
+@pytest.mark.gpu
+def test_v1_1_onehot_decoder_matches_reference():
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.quantum import decoder_v1_1
+    g, types, nb = _v1_1_fixture()
+    dev = torch.device("cuda", 0)
+    dec = decoder_v1_1.GNNI(g.T, edge_types=types, nb_digits=nb)
+    dec.load_state_dict(g.weights, strict=True)
+    dec = dec.to(dev).eval()
+    ref = restate.decode("neural_bp", g.edge_index, g.V, g.C, g.x, _expand_v1_1(g.weights, types, g.T), T=g.T, dtype=torch.float64)
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    prob, logit, hard = dec.decode(g.x.to(dev), graph=tg, return_logits=True, return_hard=True)
+    worst, max_err = _close(logit, ref["logit"], 2e-3)
+    assert worst <= 1.0, "logit mismatch: %.3g x bound (max abs err %.3g)" % (worst, max_err)
+    assert (prob.double().cpu() - g.prob.double()).abs().max().item() <= 2e-3
+    decided = ref["logit"].abs() > LOGIT_TIE
+    assert torch.equal(hard.cpu().bool()[decided], (g.prob > 0.5)[decided])
+    with torch.no_grad():
+        pred = dec(_Data(g, dev))
+    assert pred.shape == (g.B * g.V, 1) and torch.equal(pred.reshape(g.B, g.V).float(), prob)
+    # a weight update is picked up by the next call (type tables are re-gathered)
+    with torch.no_grad():
+        dec.W.mul_(1.5)
+    assert not torch.equal(dec.decode(g.x.to(dev), graph=tg), prob)
