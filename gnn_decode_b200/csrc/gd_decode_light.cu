@@ -308,6 +308,221 @@ __global__ void __launch_bounds__(512, 2) decode_light_kernel(const LightParams 
     }
 }
 
+// ---- the "next" programs on the same mapping: neural BP (quantum/neural_BP.py, quantum/decoder_v1_1.py: per-edge weights,
+// un-tied layers, + alpha * m_p) and the GRU decoder (quantum/QGNNNI_ca.py: MLP + GRUCell(1,1) per phase, m updated in place).
+// Same layout, phases and barriers as decode_light_kernel; node loops over the runtime degree (registers for d <= 4).
+template <int PROG, int NPAD>
+__global__ void __launch_bounds__(512, 2) decode_light_ext_kernel(const LightParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr bool kNBP = PROG == GD_PROG_NEURAL_BP;
+    const int tile = p.tile, E = p.E, V = p.V, C = p.C, N = p.N, R = p.R;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int l4 = (tid % p.lanes) * 4, r = tid / p.lanes;
+    const bool worker = r < R;
+    float* const xT = reinterpret_cast<float*>(smem + p.off_x);
+    float* const m_st = reinterpret_cast<float*>(smem + p.off_m);
+    float* const t_st = reinterpret_cast<float*>(smem + p.off_t);
+    uint16_t* const var_ptr = reinterpret_cast<uint16_t*>(smem + p.off_tab);
+    uint16_t* const chk_ptr = var_ptr + (V + 1);
+    uint16_t* const chk_edges = chk_ptr + (C + 1);
+    for (int i = tid; i <= V; i += nthr) var_ptr[i] = (uint16_t)p.tb.var_ptr[i];
+    for (int i = tid; i <= C; i += nthr) chk_ptr[i] = (uint16_t)p.tb.chk_ptr[i];
+    for (int i = tid; i < E; i += nthr) chk_edges[i] = (uint16_t)p.tb.chk_edges[i];
+    PwlSmem P1{}, P2{}, P3{};
+    const float* gru = nullptr;
+    if constexpr (!kNBP) {      // GRU_CA: ggc1.mlp1 | ggc1.rnn | ggc2.mlp2 | ggc2.rnn | mlp  (packed order)
+        float* wsm = reinterpret_cast<float*>(smem + p.off_w);
+        const int h = p.hid, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
+        for (int k = warp; k < 3; k += nwarp) {
+            const float* w = p.weights + k * (3 * h + 1) + k * 12;
+            float* t = wsm + k * pwl_smem_floats(NPAD);
+            pwl_build(t, reinterpret_cast<float2*>(t + NPAD), NPAD, w, w + h, w + 2 * h, w[3 * h], h, tid & 31);
+        }
+        float* gs = wsm + 3 * pwl_smem_floats(NPAD);
+        if (tid < 24) gs[tid] = p.weights[(tid < 12 ? 3 * h + 1 : 2 * (3 * h + 1)) + tid];
+        gru = gs;
+        P1 = PwlSmem{wsm, reinterpret_cast<const float2*>(wsm + NPAD)};
+        P2 = PwlSmem{wsm + pwl_smem_floats(NPAD), reinterpret_cast<const float2*>(wsm + pwl_smem_floats(NPAD) + NPAD)};
+        P3 = PwlSmem{wsm + 2 * pwl_smem_floats(NPAD), reinterpret_cast<const float2*>(wsm + 2 * pwl_smem_floats(NPAD) + NPAD)};
+    }
+    __syncthreads();
+
+    for (int tix = blockIdx.x; tix < p.n_tiles; tix += gridDim.x) {
+        const long long s0 = (long long)tix * tile;
+        const int nvalid = (int)min((long long)tile, p.B - s0);
+        {
+            const float* xg = p.x + s0 * N;
+            const int pitch = N | 1;
+            if (p.trows >= pitch) {
+                for (int i = tid; i < tile * N; i += nthr) {
+                    const int si = i / N, n = i - si * N;
+                    t_st[si * pitch + n] = si < nvalid ? __ldg(xg + i) : 0.f;
+                }
+                __syncthreads();
+                for (int i = tid; i < tile * N; i += nthr) {
+                    const int n = i / tile, si = i - n * tile;
+                    xT[i] = t_st[si * pitch + n];
+                }
+            } else {
+                for (int i = tid; i < tile * N; i += nthr) {
+                    const int si = i / N, n = i - si * N;
+                    xT[n * tile + si] = si < nvalid ? __ldg(xg + i) : 0.f;
+                }
+            }
+            for (int i = tid; i < E * tile; i += nthr) m_st[i] = 0.f;
+        }
+        __syncthreads();
+
+        for (int it = 0; it < p.T; ++it) {
+            const float* wl = kNBP ? p.weights + (size_t)it * 2 * E : nullptr;      // this layer's W[E] | W_p[E]
+            // ---- variable phase ----
+            if (worker)
+                for (int v = r; v < V; v += R) {
+                    const int b = var_ptr[v], d = var_ptr[v + 1] - b;
+                    const float4 pr4 = lds4(xT + v * tile + l4);
+                    const float pr[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int k = 0; k < d; ++k) {                  // ascending edge id
+                        const float4 mv = lds4(m_st + (b + k) * tile + l4);
+                        const float wk = kNBP ? __ldg(wl + b + k) : 1.f;
+                        acc[0] = fmaf(mv.x, wk, acc[0]); acc[1] = fmaf(mv.y, wk, acc[1]);
+                        acc[2] = fmaf(mv.z, wk, acc[2]); acc[3] = fmaf(mv.w, wk, acc[3]);
+                    }
+                    for (int k = 0; k < d; ++k) {
+                        float* mp = m_st + (b + k) * tile + l4;
+                        const float4 mv = lds4(mp);
+                        const float m4[4] = {mv.x, mv.y, mv.z, mv.w};
+                        float out[4];
+                        if constexpr (kNBP) {       // neural_BP.py:244-258: t from (sum of m W) - m W + prior W_p; m itself stays = m_p
+                            const float wk = __ldg(wl + b + k), wpk = __ldg(wl + E + b + k);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float a = acc[j] - m4[j] * wk + pr[j] * wpk;
+                                const float tv = bp_log_abs_tanh_half<false>(a, -46.0517019f);
+                                out[j] = a < 0.f ? -tv : tv;
+                            }
+                            stg4(t_st + (b + k) * tile + l4, out);
+                        } else {                    // QGNNNI_ca.py:103-106,197-198,208-209
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                out[j] = gru_cell(gru, m4[j], pwl_eval<NPAD>(P1, acc[j] - m4[j] + pr[j]));
+                            stg4(t_st + (b + k) * tile + l4, out);      // staged in t: siblings still need the old m
+                        }
+                    }
+                    if constexpr (!kNBP)
+                        for (int k = 0; k < d; ++k) {
+                            const float4 nv = lds4(t_st + (b + k) * tile + l4);
+                            *reinterpret_cast<float4*>(m_st + (b + k) * tile + l4) = nv;
+                        }
+                }
+            __syncthreads();
+            // ---- check phase ----
+            if (worker)
+                for (int c = r; c < C; c += R) {
+                    const int b = chk_ptr[c], d = chk_ptr[c + 1] - b;
+                    const float4 s4 = lds4(xT + (V + c) * tile + l4);
+                    const float sg[4] = {s4.x, s4.y, s4.z, s4.w};
+                    const uint16_t* edges = chk_edges + b;
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    int cnt[4] = {0, 0, 0, 0};
+                    for (int k = 0; k < d; ++k) {
+                        const float4 tv = lds4((kNBP ? t_st : m_st) + edges[k] * tile + l4);
+                        const float t4[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if constexpr (kNBP) {
+                                acc[j] -= fabsf(t4[j]);
+                                cnt[j] += t4[j] > 0.f ? 1 : 0;
+                            } else {
+                                acc[j] += t4[j];
+                            }
+                        }
+                    }
+                    if constexpr (kNBP) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) cnt[j] += sg[j] < 0.f ? 1 : 0;
+                        const float alpha = __ldg(p.weights + (size_t)(2 * p.T + 2) * E);
+                        for (int k = 0; k < d; ++k) {
+                            const int eo = edges[k] * tile + l4;
+                            const float4 tv = lds4(t_st + eo), mo = lds4(m_st + eo);
+                            const float t4[4] = {tv.x, tv.y, tv.z, tv.w}, m4[4] = {mo.x, mo.y, mo.z, mo.w};
+                            float out[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int q = cnt[j] - (t4[j] > 0.f ? 1 : 0);
+                                out[j] = fmaf(alpha, m4[j], bp_check_out(acc[j] + fabsf(t4[j]), q & 1, 1e-15f));
+                            }
+                            stg4(m_st + eo, out);
+                        }
+                    } else {                        // QGNNNI_ca.py:109,197-198,206-207: new values staged in t, then copied
+                        for (int k = 0; k < d; ++k) {
+                            const int eo = edges[k] * tile + l4;
+                            const float4 mo = lds4(m_st + eo);
+                            const float m4[4] = {mo.x, mo.y, mo.z, mo.w};
+                            float out[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                out[j] = gru_cell(gru + 12, m4[j], pwl_eval<NPAD>(P2, (acc[j] - m4[j]) * sg[j]));
+                            stg4(t_st + eo, out);
+                        }
+                        for (int k = 0; k < d; ++k) {
+                            const int eo = edges[k] * tile + l4;
+                            *reinterpret_cast<float4*>(m_st + eo) = lds4(t_st + eo);
+                        }
+                    }
+                }
+            __syncthreads();
+        }
+
+        // ---- read-out ----
+        if (worker)
+            for (int v = r; v < V; v += R) {
+                const int b = var_ptr[v], d = var_ptr[v + 1] - b;
+                const float4 pr4 = lds4(xT + v * tile + l4);
+                const float pr[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
+                float acc[4] = {0.f, 0.f, 0.f, 0.f}, accp[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* wo = kNBP ? p.weights + (size_t)p.T * 2 * E : nullptr;
+                for (int k = 0; k < d; ++k) {
+                    const float4 mv = lds4(m_st + (b + k) * tile + l4);
+                    const float m4[4] = {mv.x, mv.y, mv.z, mv.w};
+                    const float wk = kNBP ? __ldg(wo + b + k) : 1.f, wpk = kNBP ? __ldg(wo + E + b + k) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[j] = fmaf(m4[j], wk, acc[j]);
+                        accp[j] = fmaf(pr[j], wpk, accp[j]);
+                    }
+                }
+                float lg[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) lg[j] = kNBP ? acc[j] + accp[j] : pwl_eval<(NPAD > 0 ? NPAD : 16)>(P3, acc[j]);
+                stg4(t_st + v * tile + l4, lg);
+            }
+        __syncthreads();
+        {
+            const long long g0 = s0 * V;
+            const int pitch = V | 1;
+            const bool via_m = E >= pitch;
+            if (via_m) {
+                for (int i = tid; i < V * tile; i += nthr) {
+                    const int v = i / tile, si = i - v * tile;
+                    m_st[si * pitch + v] = t_st[i];
+                }
+                __syncthreads();
+            }
+            for (int i = tid; i < nvalid * V; i += nthr) {
+                const int si = i / V, v = i - si * V;
+                const float lg = via_m ? m_st[si * pitch + v] : t_st[v * tile + si];
+                float pr = sigmoid_neg(lg);
+                if (!kNBP) pr = fminf(fmaxf(pr, 1e-7f), 1.0f - 1e-7f);      // QGNNNI_ca.py:247
+                if (p.prob) p.prob[g0 + i] = pr;
+                if (p.logit) p.logit[g0 + i] = lg;
+                if (p.hard) p.hard[g0 + i] = pr > 0.5f;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 struct LightPlan {
     LightParams p;
     int threads, grid, smem, npad, cps;
@@ -321,19 +536,24 @@ static void plan_light(const gd_graph* g, const gd_model* m, int64_t B, LightPla
     memset(&p, 0, sizeof(p));
     out->ok = false;
     const int prog = m->program;
-    if (prog != GD_PROG_CGNNI && prog != GD_PROG_QGNNI && prog != GD_PROG_BP_QUANTUM && prog != GD_PROG_BP_CLASSICAL) return;
+    const bool ext = prog == GD_PROG_NEURAL_BP || prog == GD_PROG_GRU_CA;
+    if (prog != GD_PROG_CGNNI && prog != GD_PROG_QGNNI && prog != GD_PROG_BP_QUANTUM && prog != GD_PROG_BP_CLASSICAL && !ext) return;
+    if (prog == GD_PROG_GRU_CA && (m->hidden >= 32 || (m->flags & GD_FLAG_ALL_ITERS) || getenv("GD_NO_PWL"))) return;
+    if (prog == GD_PROG_NEURAL_BP && m->hidden != g->E) return;      // the caller's argument check reports it
     if (getenv("GD_NO_LIGHT") || getenv("GD_FORCE_STREAMED")) return;
     if (g->E >= 65536 || g->V >= 65535 || g->C >= 65535) return;
     for (size_t i = 0; i < g->h_var_edges.size(); ++i)
         if (g->h_var_edges[i] != (int32_t)i) return;           // needs the canonical variable-sorted edge order
-    const bool bp = prog == GD_PROG_BP_QUANTUM || prog == GD_PROG_BP_CLASSICAL;
+    const bool bp = prog == GD_PROG_BP_QUANTUM || prog == GD_PROG_BP_CLASSICAL || prog == GD_PROG_NEURAL_BP;
     p.B = B; p.T = m->iters; p.V = g->V; p.C = g->C; p.E = (int)g->E; p.N = g->N; p.tb = g->t;
     p.hid = bp ? 0 : m->hidden;
     p.hp = align_up_l(p.hid, 4);
     out->npad = (!bp && m->hidden < 32 && !getenv("GD_NO_PWL")) ? (m->hidden < 16 ? 16 : 32) : 0;
     p.trows = g->E > g->V ? (int)g->E : g->V;                  // the t region doubles as the logit rows lg[V][tile]
     int off = 0;
-    p.off_w = off; off += bp ? 0 : (out->npad ? 2 * pwl_smem_floats(out->npad) * 4 : 2 * 4 * p.hp * 4);
+    p.off_w = off;
+    off += bp ? 0 : (prog == GD_PROG_GRU_CA ? (3 * pwl_smem_floats(32) + 24) * 4
+                                             : (out->npad ? 2 * pwl_smem_floats(out->npad) * 4 : 2 * 4 * p.hp * 4));
     off = align_up_l(off, 16);
     p.off_tab = off; off += (g->V + 1 + g->C + 1 + (int)g->E) * 2;
     off = align_up_l(off, 128);
@@ -434,6 +654,8 @@ int light_decode(const gd_graph* g, const gd_model* model, const float* weights_
                 : pl.npad == 32 ? decode_light_kernel<GD_PROG_QGNNI, 32> : decode_light_kernel<GD_PROG_QGNNI, 0>;
             break;
         case GD_PROG_BP_QUANTUM: k = decode_light_kernel<GD_PROG_BP_QUANTUM, 0>; break;
+        case GD_PROG_NEURAL_BP: k = decode_light_ext_kernel<GD_PROG_NEURAL_BP, 0>; break;
+        case GD_PROG_GRU_CA: k = decode_light_ext_kernel<GD_PROG_GRU_CA, 32>; break;
         default: k = decode_light_kernel<GD_PROG_BP_CLASSICAL, 0>; break;
     }
     GD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
