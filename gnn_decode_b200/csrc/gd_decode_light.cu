@@ -541,6 +541,7 @@ static void plan_light(const gd_graph* g, const gd_model* m, int64_t B, LightPla
     if (prog == GD_PROG_GRU_CA && (m->hidden >= 32 || (m->flags & GD_FLAG_ALL_ITERS) || getenv("GD_NO_PWL"))) return;
     if (prog == GD_PROG_NEURAL_BP && m->hidden != g->E) return;      // the caller's argument check reports it
     if (getenv("GD_NO_LIGHT") || getenv("GD_FORCE_STREAMED")) return;
+    if ((B + 15) / 16 < g->sm_count && !getenv("GD_FORCE_LIGHT")) return;   // cannot fill the GPU at any tile size: skip the search
     if (g->E >= 65536 || g->V >= 65535 || g->C >= 65535) return;
     for (size_t i = 0; i < g->h_var_edges.size(); ++i)
         if (g->h_var_edges[i] != (int32_t)i) return;           // needs the canonical variable-sorted edge order
