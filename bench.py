@@ -417,8 +417,10 @@ def main():
                 "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:
             rng = np.random.RandomState(1234)
-            n_s = min(B, 32768)      # bounded sample: stop after ~15 s of CPU work (sustained, not a burst)
-            rate, n_done, secs = cpu_reference_rate(program, pcm, T, weights, x[:n_s].cpu().double(), 128, 15.0, cores)
+            # bounded sample: this workload's own syndromes (cycled if the batch is small), stop after ~15 s of CPU work
+            reps = max(1, -(-131072 // B))
+            xs_cpu = x.cpu().double().repeat(reps, 1)[:131072]
+            rate, n_done, secs = cpu_reference_rate(program, pcm, T, weights, xs_cpu, 128, 15.0, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "syndromes/s", "cores": cores, "kind": "port",
                                     "sample": "%d syndromes of this workload in chunks of 128 (the reference's BATCH_SIZE), "
                                               "fp64, %.1f s, oracle/restate.py on %d torch threads" % (n_done, secs, cores)}
