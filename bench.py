@@ -418,8 +418,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             rng = np.random.RandomState(1234)
             # bounded sample: this workload's own syndromes (cycled if the batch is small), stop after ~15 s of CPU work
-            reps = max(1, -(-131072 // B))
-            xs_cpu = x.cpu().double().repeat(reps, 1)[:131072]
+            n_s = max(128, min(131072, int(5e7 // N)))           # <= 400 MB of fp64 inputs
+            reps = max(1, -(-n_s // B))
+            xs_cpu = x[:n_s].cpu().double().repeat(reps, 1)[:n_s]
             rate, n_done, secs = cpu_reference_rate(program, pcm, T, weights, xs_cpu, 128, 15.0, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "syndromes/s", "cores": cores, "kind": "port",
                                     "sample": "%d syndromes of this workload in chunks of 128 (the reference's BATCH_SIZE), "
