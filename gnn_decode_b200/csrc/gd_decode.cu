@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                     // 1.02: a cubic piece may overshoot its end values slightly inside an interval
                     rtab_R = (float)p.T * (__uint_as_float(*fmax_bits) * 1.02f + 1e-6f);
                     const float rstep = 2.0f * rtab_R / (float)p.rtab_n;
-                    use_rtab = cubic_tab_bound(p.weights + 7 * p.hid + 2, p.hid, rstep) <= 5e-7f;   // feeds the logit directly, not the iteration
+                    use_rtab = cubic_tab_bound(p.weights + 7 * p.hid + 2, p.hid, rstep) <= 4e-6f;   // feeds the logit directly (x degree <= 4), not the iteration: 1000x below the parity bar
                     if (use_rtab) {
                         float4* rdst = reinterpret_cast<float4*>(smem + p.off_rtab);
                         cubic_tab_build(W3, hp, rtab_R, p.rtab_n, rdst, F, tid, nthr);

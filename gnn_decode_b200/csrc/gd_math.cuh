@@ -261,7 +261,7 @@ __device__ __forceinline__ float pwl_eval(const PwlSmem& P, float x) {
 // ends -- node values from the packed direct evaluation, node derivatives from 4th-order central
 // differences.  The interpolation error is bounded by h^4 / 384 * max|d4f/dx4| <= h^4 / 384 * 0.125 *
 // sum_k |w2_k| w1_k^4, evaluated from the weights in the prologue; if the bound exceeds the budget
-// (1e-7 check phase, 5e-7 read-out) the kernel keeps the direct evaluation.  One evaluation is then
+// (1e-7 check phase, 4e-6 read-out) the kernel keeps the direct evaluation.  One evaluation is then
 // ~12 instructions + one 16-byte shared load instead of h x (1.5 MUFU + ~7 FMA).
 struct CubicTab {
     const float4* c;   // [N] (a0, a1, a2, a3): f(x_i + t h) ~= a0 + t (a1 + t (a2 + t a3)), t in [0, 1]

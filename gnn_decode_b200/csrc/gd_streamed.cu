@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(1024, 1) decode_streamed_kernel(const StreamPa
                     __syncthreads();
                     rtab_R = (float)p.T * (__uint_as_float(*fmax_bits) * 1.02f + 1e-6f);
                     const float rstep = 2.0f * rtab_R / (float)p.rtab_n;
-                    use_rtab = cubic_tab_bound(p.weights + 7 * p.hid + 2, p.hid, rstep) <= 5e-7f;
+                    use_rtab = cubic_tab_bound(p.weights + 7 * p.hid + 2, p.hid, rstep) <= 4e-6f;
                     if (use_rtab) {
                         cubic_tab_build(W3, hp, rtab_R, p.rtab_n, rdst, F, tid, nthr);
                         rtab = CubicTab{rdst, 1.0f / rstep, rtab_R / rstep, (float)p.rtab_n - 0.001f};

@@ -229,6 +229,8 @@ def main():
               ckpt=R + "/quantum/new_model/decoder_parameters_epoch3.pkl", loader="train_loader")
     _run_case("v2_4_toricL4_epoch1", "quantum/decoder_v2_4.py", "v2_4", dict(q_small, L="4"),
               ckpt=R + "/quantum/new_model/decoder_parameters_epoch1.pkl", loader="train_loader")
+    _run_case("v2_4_toricL4_epoch67", "quantum/decoder_v2_4.py", "v2_4", dict(q_small, L="4"),
+              ckpt=R + "/quantum/new_model/decoder_parameters_epoch67.pkl", loader="train_loader", seed=67)   # last shipped checkpoint
     _run_case("v2_4_toricL7_epoch3_T5", "quantum/decoder_v2_4.py", "v2_4",
               dict(q_small, L="7", BATCH_SIZE="8", run1="8", run2="8"),
               ckpt=R + "/quantum/new_model/decoder_parameters_epoch3.pkl", loader="train_loader", T=5)
