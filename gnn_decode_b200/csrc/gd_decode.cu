@@ -25,6 +25,7 @@
 #include "gd_decode.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 
 namespace gd {
 
@@ -604,7 +605,25 @@ struct DecodePlan {
 
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePlan* out) {
+// A (tile, R, EB) candidate of the geometry search with its model score
+struct GeomCand {
+    int tile, R, eb;
+    double score;
+};
+
+// force: use exactly this geometry (autotuner / tuned cache); collect: gather every candidate with its score instead
+static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePlan* out, const GeomCand* force = nullptr,
+                       std::vector<GeomCand>* collect = nullptr) {
+    GeomCand tuned_hit;
+    if (!force && !collect && !g->tuned.empty()) {
+        std::lock_guard<std::mutex> lk(const_cast<gd_graph*>(g)->mu);
+        for (const auto& tg : g->tuned)
+            if (tg.program == m->program && tg.hidden == m->hidden && tg.iters == m->iters && tg.flags == m->flags && tg.B == B) {
+                tuned_hit = GeomCand{tg.tile, tg.R, tg.eb, 0.0};
+                force = &tuned_hit;
+                break;
+            }
+    }
     const int V = g->V, C = g->C, N = g->N, Cn = g->C;
     const int64_t E64 = g->E;
     // "bp" here = the sum-product family: no MLP slots, a second node array for the sign counts
@@ -675,12 +694,14 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
             const char* eb = getenv("GD_EB");
             for (int t = 8; t <= tmax && t <= thr_max; t += 8) {
                 if (et && atoi(et) != t) continue;
+                if (force && force->tile != t) continue;
                 if (t < 32 && (32 % t)) continue;
                 const int64_t n_t = (B + t - 1) / t;
                 const int64_t rounds = (n_t + slots - 1) / slots;
                 const double eff_round = (double)B / ((double)rounds * (double)slots * t);
                 for (int r = 1; r * t <= thr_max && r <= E; ++r) {
                     if (er && atoi(er) != r) continue;
+                    if (force && force->R != r) continue;
                     const int thr = r * t;
                     if (thr % 32) continue;
                     double w = wy[7];
@@ -695,10 +716,12 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
                     const double ideal = E * c_edge + 2.0 * E * c_ld;
                     for (int ebk = 4; ebk >= 2; ebk -= 2) {
                         if (eb && atoi(eb) != ebk) continue;
+                        if (force && force->eb != ebk) continue;
                         const int blocks = (n_iter + ebk - 1) / ebk;
                         const double per_thread = (bp ? n_iter : blocks * ebk) * c_edge + node_cost * c_ld;
                         const double eff_bal = ideal / (r * per_thread);
                         const double score = eff_round * eff_bal * w * (ebk == 2 ? (thr >= 384 ? 1.0 : 0.92) : (thr >= 384 ? 0.985 : 1.0));
+                        if (collect) collect->push_back(GeomCand{t, r, ebk, score});
                         if (score > best + 1e-9) { best = score; tile = t; R = r; out->eb = ebk; }
                     }
                 }
@@ -867,4 +890,90 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     }
     if (prev != g->device) cudaSetDevice(prev);
     return rc;
+}
+
+
+// ---- geometry autotuner: measure, don't guess ------------------------------------------------------------------------
+// The (tile, R, EB) model above ranks hundreds of geometries; its top picks are usually within a few percent of each
+// other and occasionally mis-ordered (rotated d = 11: the model's pick is 15 % slower than its 4th candidate).  This
+// entry point times the best few candidates on the caller's own batch and remembers the winner per
+// (graph, model, B); gd_decode_fwd then uses it.  One-time cost: ~2 launches per candidate.
+extern "C" int gd_decode_autotune(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
+                                  int64_t B, int32_t max_candidates, void* stream, gd_launch_info* chosen) {
+    gd_graph* g = const_cast<gd_graph*>(gc);
+    GD_CHECK_ARG(g != nullptr && gd_model_valid(model) && x_dev != nullptr && B > 0, "gd_decode_autotune: bad argument");
+    GD_CHECK_ARG(gd_weights_size(model) == 0 || weights_dev != nullptr, "gd_decode_autotune: weights is NULL");
+    GD_CHECK_ARG(model->program != GD_PROG_NEURAL_BP || model->hidden == g->E, "gd_decode_autotune: NEURAL_BP needs hidden == E");
+    cudaStream_t st = (cudaStream_t)stream;
+    gd_launch_info li;
+    int rc = gd_decode_launch_info(g, model, B, &li);
+    if (rc != GD_OK) return rc;
+    if (chosen) *chosen = li;
+    // only the edge-owner resident kernel has a geometry to tune; the light / streamed kernels plan themselves
+    gd_launch_info probe;
+    if (!li.resident || gd::light_launch_info(g, model, B, &probe)) return GD_OK;
+    std::vector<gd::GeomCand> cands;
+    gd::DecodePlan pl;
+    rc = gd::plan_decode(g, model, B, &pl, nullptr, &cands);
+    if (rc != GD_OK || cands.empty()) return rc;
+    std::sort(cands.begin(), cands.end(), [](const gd::GeomCand& a, const gd::GeomCand& b) { return a.score > b.score; });
+    // keep the best-scored candidate of each distinct (tile, R), EB = 2 and 4 compete inside it
+    std::vector<gd::GeomCand> pick;
+    const int K = max_candidates > 0 ? max_candidates : 24;
+    for (const auto& c : cands) {
+        bool dup = false;
+        for (const auto& q : pick) dup = dup || (q.tile == c.tile && q.R == c.R && q.eb == c.eb);
+        if (!dup) pick.push_back(c);
+        if ((int)pick.size() >= K) break;
+    }
+    int prev = 0;
+    GD_CUDA(cudaGetDevice(&prev));
+    if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
+    float* prob = nullptr;
+    cudaError_t e = cudaMalloc((void**)&prob, (size_t)B * g->V * sizeof(float));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    gd::GeomCand best{0, 0, 0, 0.0};
+    float best_ms = 1e30f;
+    for (size_t i = 0; i < pick.size() && e == cudaSuccess && rc == GD_OK; ++i) {
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            for (size_t q = 0; q < g->tuned.size(); ++q)       // drop a previous entry for this key
+                if (g->tuned[q].program == model->program && g->tuned[q].hidden == model->hidden &&
+                    g->tuned[q].iters == model->iters && g->tuned[q].flags == model->flags && g->tuned[q].B == B) {
+                    g->tuned.erase(g->tuned.begin() + q);
+                    break;
+                }
+            g->tuned.push_back(gd_graph::TunedGeom{model->program, model->hidden, model->iters, model->flags, B, pick[i].tile,
+                                                   pick[i].R, pick[i].eb});
+        }
+        float ms = 1e30f;
+        for (int rep = 0; rep < 3 && rc == GD_OK && e == cudaSuccess; ++rep) {       // first launch warms up
+            cudaEventRecord(e0, st);
+            rc = gd_decode_fwd(g, model, weights_dev, x_dev, prob, nullptr, nullptr, B, st);
+            cudaEventRecord(e1, st);
+            e = cudaEventSynchronize(e1);
+            float t = 0.f;
+            if (e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
+            if (rep > 0 && t < ms) ms = t;
+        }
+        if (ms < best_ms) { best_ms = ms; best = pick[i]; }
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (prob) cudaFree(prob);
+    if (best.tile) {
+        std::lock_guard<std::mutex> lk(g->mu);
+        for (size_t q = 0; q < g->tuned.size(); ++q)
+            if (g->tuned[q].program == model->program && g->tuned[q].hidden == model->hidden && g->tuned[q].iters == model->iters &&
+                g->tuned[q].flags == model->flags && g->tuned[q].B == B) {
+                g->tuned[q].tile = best.tile; g->tuned[q].R = best.R; g->tuned[q].eb = best.eb;
+            }
+    }
+    if (prev != g->device) cudaSetDevice(prev);
+    if (rc != GD_OK) return rc;
+    GD_CUDA(e);
+    if (chosen) gd_decode_launch_info(g, model, B, chosen);
+    return GD_OK;
 }

@@ -288,6 +288,31 @@ class DecoderBase(torch.nn.Module):
             return tuple(t for t in (prob, logit, hard) if t is not None)
         return prob
 
+    def autotune(self, x, graph=None, max_candidates=0):
+        """One-time geometry autotuning for this (decoder, graph, batch size): times the planner's best candidates on x and
+        remembers the fastest for later decode() / decode_host() calls with the same batch size.  Returns the launch info."""
+        g = graph or self._gd_graph
+        if g is None:
+            raise ValueError("no Tanner graph bound: call bind_graph(graph) or pass graph=")
+        _require_cuda(x, "x")
+        x32 = x.detach().to(torch.float32).contiguous()
+        if x32.data_ptr() % 16:
+            x32 = x32.clone()
+        info = _cabi.GdLaunchInfo()
+        model = self.gd_model()
+        w = self.packed_weights(x.device)
+        B = x32.size(0)
+        n_chunks = min(4, max(1, B // 8192))                     # the chunking of gd_decode_host (csrc/gd_host.cu)
+        per = ((B + n_chunks - 1) // n_chunks + 7) // 8 * 8
+        with torch.cuda.device(x.device):
+            for nb in sorted({B, min(per, B), B - (n_chunks - 1) * per if n_chunks > 1 else B}, reverse=True):
+                if nb <= 0:
+                    continue
+                out = info if nb == B else _cabi.GdLaunchInfo()
+                _cabi.check(_cabi.lib().gd_decode_autotune(g.handle, C.byref(model), _ptr(w), _ptr(x32), nb, int(max_candidates),
+                                                           _stream(x.device), C.byref(out)), "gd_decode_autotune")
+        return {k: getattr(info, k) for k, _ in _cabi.GdLaunchInfo._fields_}
+
     def decode_host(self, x_host, prob_out=None, hard_out=None, graph=None):
         """End-to-end call with HOST tensors (pinned for full copy bandwidth): x_host [B, V+C] fp32
         -> prob [B, V] fp32 and/or hard [B, V] uint8 on the host.  Copies are inside the call."""

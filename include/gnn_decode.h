@@ -206,6 +206,12 @@ typedef struct gd_launch_info {
     int32_t n_tiles;
 } gd_launch_info;
 int gd_decode_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out);
+/* Optional one-time geometry autotuning for (graph, model, B): times the best `max_candidates` (0 = 24) geometries of the
+ * planner's model with the caller's own weights and batch (outputs go to a scratch buffer) and remembers the fastest;
+ * later gd_decode_fwd / gd_decode_host calls with the same (model, B) use it.  Synchronises the stream.  Only the
+ * edge-owner resident kernel is tuned; other paths return immediately.  *chosen (may be NULL) receives the result. */
+int gd_decode_autotune(const gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev,
+                       int64_t B, int32_t max_candidates, void* stream, gd_launch_info* chosen);
 
 /* ---- synthetic input: on-GPU Philox4x32-10 sampler with the layout and distribution of
  *      gen_syn (error_generate.py:252-278): per sample s, p = p_list[philox(seed, s) % n_p];

@@ -30,6 +30,8 @@ def time_decode(dec, g, B, iters=5, warm=2):
     x = torch.randn(B, g.N, device=dev)
     x[:, g.V:] = torch.sign(x[:, g.V:])
     x[:, :g.V] = 2.0 + 0.5 * x[:, :g.V]
+    if os.environ.get("GD_AUTOTUNE"):
+        print("   autotuned:", dec.autotune(x, graph=g))
     for _ in range(warm):
         dec.decode(x, graph=g)
     torch.cuda.synchronize()

@@ -286,3 +286,26 @@ def test_v2_4_tabulated_mlps_match_direct_evaluation_and_oracle(scale, T, monkey
     assert (l_tab - l_dir).abs().max().item() <= 2e-5 * (1.0 + rms)
     decided = (ref["logit"].abs() > LOGIT_TIE).repeat(9, 1)
     assert torch.equal(h_tab.cpu()[decided], h_dir.cpu()[decided])
+
+
+def test_autotuned_geometry_gives_identical_results():
+    """gd_decode_autotune times candidate (tile, R, EB) geometries and pins the fastest for (graph, model, B): the
+    arithmetic per syndrome does not depend on the geometry, so results stay bit-identical, and other batch sizes
+    keep the planner's choice."""
+    from gnn_decode_b200.graph import TannerGraph
+    g = Golden("v2_4_toricL5_epoch3")
+    dev = _dev()
+    mod, dec = make_decoder(g)
+    dec = dec.to(dev).eval()
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    x = g.x.repeat(300, 1).to(dev)                                   # 4800 syndromes
+    before = dec.decode(x, graph=tg)
+    info0 = tg.launch_info(dec.gd_model(), x.size(0))
+    info = dec.autotune(x, graph=tg, max_candidates=6)
+    assert info["resident"] == 1 and info["tile"] > 0
+    assert tg.launch_info(dec.gd_model(), x.size(0)) == info        # the tuned geometry is what later launches use
+    assert torch.equal(dec.decode(x, graph=tg), before)
+    assert tg.launch_info(dec.gd_model(), x.size(0) + 8) == tg.launch_info(dec.gd_model(), x.size(0) + 8)
+    other = dec.decode(x[:1000].contiguous(), graph=tg)             # a different B: untouched by the cache
+    assert torch.equal(other, before[:1000])
+    assert isinstance(info0, dict)
