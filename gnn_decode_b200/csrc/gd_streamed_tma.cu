@@ -43,6 +43,7 @@ struct StreamTmaParams {
     int T, V, C, E, N;
     int tile, lanes, W, hid, hp, n_tiles;
     int stage_rows;          // rows of tile floats per pipeline stage
+    int S;                   // pipeline stages per warp (2..4): S - 1 nodes are in flight while one is evaluated
     int vchunk;              // variables per variable-phase item
     int vrows;               // row index of the first prior row inside a variable-phase stage
     int off_w, off_stage;    // shared-memory byte offsets (mbarriers sit at 0)
@@ -93,10 +94,11 @@ __global__ void __launch_bounds__(512, 1) decode_streamed_tma_kernel(const Strea
     const uint32_t row_bytes = (uint32_t)tile * 4u;
     const int stage_floats = p.stage_rows * tile;
     float* const scratch = reinterpret_cast<float*>(smem + p.off_stage);     // all stages, as one array
-    const int scratch_floats = W * 2 * stage_floats;
-    float* const stg0 = scratch + (w * 2) * stage_floats;
-    uint64_t* const bar0 = reinterpret_cast<uint64_t*>(smem) + w * 2;
-    uint32_t par0 = 0, par1 = 0;
+    const int S = p.S;
+    const int scratch_floats = W * S * stage_floats;
+    float* const stg0 = scratch + (w * S) * stage_floats;
+    uint64_t* const bar0 = reinterpret_cast<uint64_t*>(smem) + w * 4;
+    uint32_t parbits = 0;                 // bit s = phase parity of this warp's stage s
     const bool active = lane < p.lanes;
     const int l4 = active ? lane * 4 : 0;
     const GraphTables tb = p.tb;
@@ -140,8 +142,7 @@ __global__ void __launch_bounds__(512, 1) decode_streamed_tma_kernel(const Strea
         }
     }
     if (lane == 0) {
-        tma::bar_init(bar0, 1);
-        tma::bar_init(bar0 + 1, 1);
+        for (int q = 0; q < S; ++q) tma::bar_init(bar0 + q, 1);
         tma::fence_bar_init();
     }
     __syncthreads();
@@ -180,8 +181,8 @@ __global__ void __launch_bounds__(512, 1) decode_streamed_tma_kernel(const Strea
             tma::g2s(dst + (with_m ? 2 * d : d) * tile, xT + (size_t)(V + c) * tile, row_bytes, bar0 + sidx);
     };
     auto wait_stage = [&](int sidx) {
-        if (sidx == 0) { tma::wait(bar0, par0); par0 ^= 1u; }
-        else { tma::wait(bar0 + 1, par1); par1 ^= 1u; }
+        tma::wait(bar0 + sidx, (parbits >> sidx) & 1u);
+        parbits ^= 1u << sidx;
     };
 
     for (int tix = blockIdx.x; tix < p.n_tiles; tix += gridDim.x) {
@@ -215,9 +216,10 @@ __global__ void __launch_bounds__(512, 1) decode_streamed_tma_kernel(const Strea
             // ---- variable phase (or read-out) ----
             {
                 int ci = w, sidx = 0;
-                if (ci < n_vchunks) issue_var(ci, 0, with_m);
-                for (; ci < n_vchunks; ci += W, sidx ^= 1) {
-                    if (ci + W < n_vchunks) issue_var(ci + W, sidx ^ 1, with_m);
+                for (int q = 0; q < S - 1; ++q)                       // prologue: S - 1 items in flight
+                    if (ci + q * W < n_vchunks) issue_var(ci + q * W, q, with_m);
+                for (; ci < n_vchunks; ci += W, sidx = sidx + 1 == S ? 0 : sidx + 1) {
+                    if (ci + (S - 1) * W < n_vchunks) issue_var(ci + (S - 1) * W, sidx == 0 ? S - 1 : sidx - 1, with_m);
                     wait_stage(sidx);
                     const float* st = stg0 + sidx * stage_floats + l4;
                     const int v0 = ci * K, v1 = min(V, v0 + K);
@@ -292,9 +294,10 @@ __global__ void __launch_bounds__(512, 1) decode_streamed_tma_kernel(const Strea
             {
                 const bool ld_m = with_m && !kIsBP;
                 int c = w, sidx = 0;
-                if (c < C) issue_chk(c, 0, ld_m);
-                for (; c < C; c += W, sidx ^= 1) {
-                    if (c + W < C) issue_chk(c + W, sidx ^ 1, ld_m);
+                for (int q = 0; q < S - 1; ++q)
+                    if (c + q * W < C) issue_chk(c + q * W, q, ld_m);
+                for (; c < C; c += W, sidx = sidx + 1 == S ? 0 : sidx + 1) {
+                    if (c + (S - 1) * W < C) issue_chk(c + (S - 1) * W, sidx == 0 ? S - 1 : sidx - 1, ld_m);
                     wait_stage(sidx);
                     const float* st = stg0 + sidx * stage_floats + l4;
                     const int b = __ldg(tb.chk_ptr + c), d = __ldg(tb.chk_ptr + c + 1) - b;
@@ -460,25 +463,35 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
     p.tile = tile;
     p.lanes = tile / 4;
     const int vd = g->max_var_deg > 0 ? g->max_var_deg : 1;
-    int rows = 2 * g->max_chk_deg + 1;
+    int rows = (bp ? 1 : 2) * g->max_chk_deg + 1;          // sum-product fetches no residual rows
     if (rows < vd + 1) rows = vd + 1;
     int K = rows / (vd + 1);
     if (K > 8) K = 8;
     p.stage_rows = rows; p.vchunk = K; p.vrows = K * vd;
     const int stage_bytes = rows * tile * 4;
-    int off = 16 * 2 * 8;                              // up to 16 warps x 2 mbarriers
+    int off = 16 * 4 * 8;                              // up to 16 warps x 4 mbarriers
     p.off_w = off; off += out->npad ? 2 * pwl_smem_floats(out->npad) * 4 : n_slots * 4 * p.hp * 4;
     off = align_up_i(off, 128);
     p.off_stage = off;
-    int Wn = (g->max_smem_optin - off) / (2 * stage_bytes);
+    // stages: as deep as shared memory allows with all 16 warps (sum-product stages are half the size -> 3 stages)
+    int S = 2;
+    {
+        const char* es = getenv("GD_SSTAGES");
+        if (es && atoi(es) >= 2 && atoi(es) <= 4) S = atoi(es);
+        else
+            for (int q = 4; q > 2; --q)
+                if ((g->max_smem_optin - off) / (q * stage_bytes) >= 16) { S = q; break; }
+    }
+    p.S = S;
+    int Wn = (g->max_smem_optin - off) / (S * stage_bytes);
     if (Wn > 16) Wn = 16;
     const char* ew = getenv("GD_SWARPS");
     if (ew && atoi(ew) >= 1 && atoi(ew) < Wn) Wn = atoi(ew);
     if (Wn < 2) return;
-    if ((int64_t)Wn * 2 * rows * tile < 2 * (int64_t)(tile + 2) * 2) return;   // transposition scratch
+    if ((int64_t)Wn * S * rows * tile < 2 * (int64_t)(tile + 2) * 2) return;   // transposition scratch
     p.W = Wn;
     out->threads = Wn * 32;
-    out->smem = off + Wn * 2 * stage_bytes;
+    out->smem = off + Wn * S * stage_bytes;
     p.n_tiles = (int)((B + tile - 1) / tile);
     out->grid = p.n_tiles < g->sm_count ? p.n_tiles : g->sm_count;
     p.slab_floats = ((long long)g->N + 2 * g->E + g->V) * tile;
