@@ -24,6 +24,11 @@ class GdLaunchInfo(C.Structure):
                 ("resident", C.c_int32), ("n_tiles", C.c_int32)]
 
 
+class GdAdam(C.Structure):
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("step", C.c_int32)]
+
+
 _p = C.c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -52,6 +57,9 @@ _SIGNATURES = {
     "gd_loss_v2_4": (C.c_int, [_p, _p, C.c_int32, _p, _p, _p, _p, _p, C.c_int64, _p]),
     "gd_p2p_buffer_floats": (C.c_int64, [C.c_int32]),
     "gd_p2p_allreduce": (C.c_int, [_p, C.c_int32, C.c_int32, _p, _p, C.c_int32, C.c_uint32, C.c_float, _p, _p]),
+    "gd_adam_step": (C.c_int, [C.POINTER(GdAdam), _p, _p, _p, _p, C.c_int64, C.c_float, _p]),
+    "gd_p2p_allreduce_adam": (C.c_int, [_p, C.c_int32, C.c_int32, _p, _p, C.c_int32, C.c_uint32, C.c_float, _p,
+                                        C.POINTER(GdAdam), _p, _p, _p, _p]),
 }
 # entry points added after ABI v1 froze; bound when present (tests assert the header/.so agree)
 _OPTIONAL = {}

@@ -7,7 +7,7 @@
 //   buffer of rank r (floats):  [ slot 0: n_pad ][ slot 1: n_pad ][ flag (uint32, as one float slot) ]
 // Double-buffered by epoch parity: a rank overwrites slot p at step k+2 only after passing the flag wait of step
 // k+1, by which time every peer has finished reading slot p of step k.
-#include "gd_common.cuh"
+#include "gd_adam.cuh"
 
 namespace gd {
 
@@ -20,6 +20,10 @@ struct P2PParams {
     int world, rank, n, n_pad;
     unsigned int epoch;
     float scale;
+    // optional fused optimizer step on the reduced gradient (gd_p2p_allreduce_adam): every rank applies the same
+    // bit-identical update to its replica of the weights, so the replicas never drift
+    float *w, *m, *v;
+    AdamCoef adam;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
@@ -52,7 +56,13 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const P2PParams p) {
         float acc = 0.f;
         for (int r = 0; r < p.world; ++r)                             // fixed rank order on every rank
             acc += __ldcg(p.peer[r] + (size_t)(p.epoch & 1u) * p.n_pad + i);
-        p.dst[i] = acc * p.scale;
+        acc *= p.scale;
+        if (p.dst) p.dst[i] = acc;
+        if (p.w) {
+            float wi = p.w[i], mi = p.m[i], vi = p.v[i];
+            adam_update(p.adam, acc, wi, mi, vi);
+            p.w[i] = wi; p.m[i] = mi; p.v[i] = vi;
+        }
     }
 }
 
@@ -72,7 +82,29 @@ extern "C" int gd_p2p_allreduce(const uint64_t* peer_ptrs_host, int32_t world, i
     gd::P2PParams p;
     for (int r = 0; r < world; ++r) p.peer[r] = reinterpret_cast<float*>((uintptr_t)peer_ptrs_host[r]);
     p.src = src_dev; p.dst = dst_dev; p.err = err_dev; p.world = world; p.rank = rank; p.n = n; p.n_pad = (n + 31) / 32 * 32;
+    p.epoch = epoch; p.scale = scale; p.w = p.m = p.v = nullptr;
+    gd::p2p_allreduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_p2p_allreduce_adam(const uint64_t* peer_ptrs_host, int32_t world, int32_t rank, const float* src_dev,
+                                     float* dst_dev, int32_t n, uint32_t epoch, float scale, int32_t* err_dev,
+                                     const gd_adam* opt, float* weights_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                                     void* stream) {
+    GD_CHECK_ARG(peer_ptrs_host && src_dev && err_dev && opt && weights_dev && exp_avg_dev && exp_avg_sq_dev,
+                 "gd_p2p_allreduce_adam: NULL argument");
+    GD_CHECK_ARG(world >= 1 && world <= gd::kMaxWorld && rank >= 0 && rank < world, "gd_p2p_allreduce_adam: bad rank %d / world %d",
+                 rank, world);
+    GD_CHECK_ARG(n > 0 && epoch > 0 && opt->step >= 1, "gd_p2p_allreduce_adam: n, epoch and step must be positive");
+    GD_CHECK_ARG(opt->beta1 >= 0. && opt->beta1 < 1. && opt->beta2 >= 0. && opt->beta2 < 1. && opt->eps >= 0. && opt->lr >= 0.
+                 && opt->weight_decay >= 0., "gd_p2p_allreduce_adam: invalid hyper-parameters");
+    gd::P2PParams p;
+    for (int r = 0; r < world; ++r) p.peer[r] = reinterpret_cast<float*>((uintptr_t)peer_ptrs_host[r]);
+    p.src = src_dev; p.dst = dst_dev; p.err = err_dev; p.world = world; p.rank = rank; p.n = n; p.n_pad = (n + 31) / 32 * 32;
     p.epoch = epoch; p.scale = scale;
+    p.w = weights_dev; p.m = exp_avg_dev; p.v = exp_avg_sq_dev;
+    p.adam = gd::adam_coef(opt->lr, opt->beta1, opt->beta2, opt->eps, opt->weight_decay, opt->step);
     gd::p2p_allreduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p);
     GD_CUDA(cudaGetLastError());
     return GD_OK;

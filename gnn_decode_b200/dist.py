@@ -104,6 +104,26 @@ class P2PAllReduce(object):
                 "gd_p2p_allreduce")
         return out
 
+    def allreduce_adam(self, flat_grad, adam, weights, exp_avg, exp_avg_sq, flat_out=None, average=True):
+        """The exchange step and the optimizer step as ONE kernel (gd_p2p_allreduce_adam): the flat gradient is summed
+        (or averaged) over the ranks from peer memory and torch.optim.Adam's update is applied to the flat fp32 master
+        `weights` / moments in place.  adam: a _cabi.GdAdam with .step already advanced.  flat_out (optional) receives the
+        reduced gradient."""
+        ct = self._ct
+        for t in (flat_grad, weights, exp_avg, exp_avg_sq):
+            if t.numel() != self.n or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("flat gradient / weights / moments must be contiguous fp32 vectors of %d elements" % self.n)
+        self.epoch += 1
+        st = ct.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            self._cabi.check(self._cabi.lib().gd_p2p_allreduce_adam(
+                self.ptrs, self.world, self.rank, ct.c_void_p(flat_grad.data_ptr()),
+                ct.c_void_p(flat_out.data_ptr()) if flat_out is not None else None, self.n,
+                ct.c_uint32(self.epoch), ct.c_float(1.0 / self.world if average else 1.0), ct.c_void_p(self.err.data_ptr()),
+                ct.byref(adam), ct.c_void_p(weights.data_ptr()), ct.c_void_p(exp_avg.data_ptr()),
+                ct.c_void_p(exp_avg_sq.data_ptr()), st), "gd_p2p_allreduce_adam")
+        return weights
+
     def check(self):
         """Synchronises and raises if a peer failed to arrive in any previous call."""
         if int(self.err.item()) != 0:

@@ -1,7 +1,8 @@
 """Fused training step for the decoder_v2_4 program (BASELINE config 4): forward-with-stash kernel ->
 fused sparse loss + gradient kernel (LossFunc of quantum/decoder_v2_4.py:304-317) -> hand-written backward
-kernel -> parameter .grad, with no autograd graph and no dense H matmul.  The optimizer step (Adam on
-1 283 parameters) and the data-parallel all-reduce (dist.allreduce_flat_grads) stay in PyTorch."""
+kernel -> parameter .grad, with no autograd graph and no dense H matmul.  `train_step_grads` stops at the gradients
+(any torch optimizer can follow); `FusedTrainer` also runs the reference's optimizer (Adam, decoder_v2_4.py:323) as
+a kernel on the flat fp32 master weights -- fused with the peer-memory gradient all-reduce when data-parallel."""
 import ctypes as ct
 
 import numpy as np
@@ -122,3 +123,86 @@ def train_step_grads(decoder, graph, x, y, logical=None, accumulate=False, p2p=N
             p.grad = g.clone()
         off += n
     return loss, prob
+
+
+class FusedTrainer(object):
+    """The body of the reference's training loop (quantum/decoder_v2_4.py:325-341: `pred = decoder(datas)`,
+    `loss = criterion(pred, datas)`, `loss.backward()`, `optimizer.step()` with `Adam(lr=3e-4, weight_decay=1e-9)`, :323)
+    with every stage a kernel of this library and nothing in between: forward-with-stash -> sparse loss + gradient ->
+    backward -> Adam on the flat fp32 master weights (gd_adam_step), or, data-parallel, the peer-memory all-reduce with
+    Adam fused into it (gd_p2p_allreduce_adam).  Five launches per step; all buffers are allocated once per batch size.
+
+    The master weights live in `self.w` (the packed layout the decode kernels read); `sync_module()` writes them back
+    into the decoder's parameters (fp64 in the reference's state_dict) -- call it before `state_dict()` / evaluation
+    through the module.  p2p: a dist.P2PAllReduce (world_size > 1)."""
+
+    def __init__(self, decoder, graph, logical=None, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-9, p2p=None):
+        if decoder._gd_program != _cabi.PROG_V2_4:
+            raise _cabi.GdError("the training kernels exist for the decoder_v2_4 program only")
+        self.decoder, self.graph, self.logical, self.p2p = decoder, graph, logical, p2p
+        dev = graph.device
+        with torch.no_grad():
+            self.w = torch.cat([p.detach().reshape(-1).to(device=dev, dtype=torch.float32) for p in decoder._gd_params()]).contiguous()
+        self.exp_avg = torch.zeros_like(self.w)
+        self.exp_avg_sq = torch.zeros_like(self.w)
+        self.grad = torch.zeros_like(self.w)
+        self.adam = _cabi.GdAdam(lr, betas[0], betas[1], eps, weight_decay, 0)
+        self._bufs = {}
+
+    @property
+    def step_count(self):
+        return int(self.adam.step)
+
+    def _buffers(self, B):
+        b = self._bufs.get(B)
+        if b is None:
+            lib, g, dev = _cabi.lib(), self.graph, self.graph.device
+            model = self.decoder.gd_model()
+            n_stash = lib.gd_stash_floats(g.handle, ct.byref(model), B)
+            n_ws = lib.gd_bwd_workspace_floats(g.handle, ct.byref(model), B)
+            if n_stash < 0 or n_ws < 0:
+                _cabi.check(_cabi.GD_ERR_INVALID, "gd_stash_floats / gd_bwd_workspace_floats")
+            f32 = dict(dtype=torch.float32, device=dev)
+            b = dict(stash=torch.empty(max(n_stash, 1), **f32), ws=torch.empty(max(n_ws, 1), **f32),
+                     prob=torch.empty((B, g.V), **f32), logit=torch.empty((B, g.V), **f32),
+                     per=torch.empty(B, **f32), gl=torch.empty((B, g.V), **f32))
+            self._bufs = {B: b}                      # one batch size at a time: the stash is the big allocation
+        return b
+
+    def step(self, x, y):
+        """x [B, V+C] fp32 CUDA, y [B, V] uint8 CUDA (the sampled error).  One optimizer step; returns the batch loss
+        (0-dim fp64 CUDA tensor, this rank's shard) -- `prob` of the step stays in `self.prob`."""
+        lib, g, dev = _cabi.lib(), self.graph, self.graph.device
+        if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous() or x.data_ptr() % 16:
+            x = x.detach().to(device=dev, dtype=torch.float32).contiguous().clone()
+        B = x.size(0)
+        y8 = y if (y.dtype == torch.uint8 and y.is_contiguous() and y.is_cuda) else y.detach().reshape(B, g.V).to(device=dev, dtype=torch.uint8).contiguous()
+        b = self._buffers(B)
+        model = self.decoder.gd_model()
+        ldev, K = _logical_dev(g, self.logical)
+        st = ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _cabi.check(lib.gd_decode_fwd_train(g.handle, ct.byref(model), _ptr(self.w), _ptr(x), _ptr(b["prob"]), _ptr(b["logit"]),
+                                                _ptr(b["stash"]), B, st), "gd_decode_fwd_train")
+            _cabi.check(lib.gd_loss_v2_4(g.handle, _ptr(ldev), K, _ptr(b["prob"]), _ptr(y8), _ptr(b["per"]), None, _ptr(b["gl"]),
+                                         B, st), "gd_loss_v2_4")
+            _cabi.check(lib.gd_decode_bwd(g.handle, ct.byref(model), _ptr(self.w), _ptr(x), _ptr(b["stash"]), _ptr(b["gl"]),
+                                          _ptr(self.grad), _ptr(b["ws"]), 0, B, st), "gd_decode_bwd")
+            self.adam.step += 1
+            if self.p2p is not None:
+                self.p2p.allreduce_adam(self.grad, self.adam, self.w, self.exp_avg, self.exp_avg_sq)
+            else:
+                _cabi.check(lib.gd_adam_step(ct.byref(self.adam), _ptr(self.w), _ptr(self.grad), _ptr(self.exp_avg),
+                                             _ptr(self.exp_avg_sq), self.w.numel(), 1.0, st), "gd_adam_step")
+        self.prob = b["prob"]
+        return b["per"].double().sum()
+
+    def sync_module(self):
+        """Write the master weights back into the decoder's parameters (state_dict keys / dtypes unchanged)."""
+        off = 0
+        with torch.no_grad():
+            for p in self.decoder._gd_params():
+                n = p.numel()
+                p.copy_(self.w[off:off + n].view(p.shape).to(p.dtype))
+                off += n
+        return self.decoder

@@ -196,6 +196,25 @@ int64_t gd_p2p_buffer_floats(int32_t n);
 int gd_p2p_allreduce(const uint64_t* peer_ptrs_host, int32_t world, int32_t rank, const float* src_dev,
                      float* dst_dev, int32_t n, uint32_t epoch, float scale, int32_t* err_dev, void* stream);
 
+/* ---- optimizer step (replaces torch.optim.Adam(decoder.parameters(), lr=3e-4, weight_decay=1e-9).step(),
+ *      quantum/decoder_v2_4.py:323, 338) on the FLAT fp32 master weight vector (the `weights_dev` layout of
+ *      gd_decode_fwd) in one launch.  Arithmetic of torch.optim.Adam's default path: g += weight_decay * w;
+ *      m += (1-beta1)(g-m); v = beta2 v + (1-beta2) g^2; w -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps).
+ *      step = 1, 2, 3, ... is the step being taken; the gradient is read as grad_scale * grad_dev[i].
+ *      gd_p2p_allreduce_adam = gd_p2p_allreduce with this update applied to the reduced gradient in the same kernel
+ *      (dst_dev may be NULL when the reduced gradient itself is not needed): the exchange step of data-parallel
+ *      training and the optimizer are ONE launch, and every rank applies a bit-identical update. ---- */
+typedef struct gd_adam {
+    double lr, beta1, beta2, eps, weight_decay;   /* doubles, as Python passes them: 1 - beta is formed before rounding to fp32 */
+    int32_t step;
+} gd_adam;
+int gd_adam_step(const gd_adam* opt, float* weights_dev, const float* grad_dev, float* exp_avg_dev,
+                 float* exp_avg_sq_dev, int64_t n, float grad_scale, void* stream);
+int gd_p2p_allreduce_adam(const uint64_t* peer_ptrs_host, int32_t world, int32_t rank, const float* src_dev,
+                          float* dst_dev, int32_t n, uint32_t epoch, float scale, int32_t* err_dev,
+                          const gd_adam* opt, float* weights_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                          void* stream);
+
 /* Launch geometry the library picked for (graph, model, B): for benchmarks / roofline. */
 typedef struct gd_launch_info {
     int32_t tile;            /* syndromes per CTA tile                          */

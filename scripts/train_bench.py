@@ -10,7 +10,7 @@ from gnn_decode_b200.dist import allreduce_flat_grads
 from gnn_decode_b200.graph import TannerGraph
 from gnn_decode_b200.quantum import decoder_v2_4
 from gnn_decode_b200.sampler import sample_syndromes
-from gnn_decode_b200.train import train_step_grads
+from gnn_decode_b200.train import FusedTrainer, train_step_grads
 
 rank, world, lr_ = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr_)
@@ -49,6 +49,22 @@ if world > 1 and os.environ.get("GD_NCCL_ALLREDUCE") is None:
             print("P2PAllReduce unavailable (%s): using NCCL" % e)
 
 
+TRAINER = None
+if FUSED and os.environ.get("GD_TORCH_ADAM") is None and (world == 1 or P2P is not None):
+    TRAINER = FusedTrainer(dec, g, logical_u8, lr=3e-4, weight_decay=1e-9, p2p=P2P)   # Adam as a kernel too (gd_adam_step / fused into the all-reduce)
+
+
+def step_trainer(timers=None):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    loss = TRAINER.step(x, err)
+    ev[1].record()
+    if timers is not None:
+        torch.cuda.synchronize()
+        timers["fwd+loss+bwd+allreduce+adam"] = timers.get("fwd+loss+bwd+allreduce+adam", 0.0) + ev[0].elapsed_time(ev[1])
+    return loss
+
+
 def step_fused(timers=None):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
@@ -66,6 +82,8 @@ def step_fused(timers=None):
 
 
 def step(timers=None):
+    if TRAINER is not None:
+        return step_trainer(timers)
     if FUSED:
         return step_fused(timers)
     opt.zero_grad(set_to_none=False)
@@ -99,7 +117,8 @@ dt = (time.perf_counter() - t0) / n
 if P2P is not None:
     P2P.check()
 if rank == 0:
-    print("gradient all-reduce:", "peer-memory kernel (gd_p2p_allreduce)" if P2P is not None else ("NCCL" if world > 1 else "none (1 GPU)"))
+    print("gradient all-reduce:", "peer-memory kernel (gd_p2p_allreduce)" if P2P is not None else ("NCCL" if world > 1 else "none (1 GPU)"),
+          "| optimizer:", "Adam kernel (FusedTrainer)" if TRAINER is not None else "torch.optim.Adam")
     print("rotated d=%d V=%d C=%d E=%d  B/GPU=%d x %d GPU  T=%d: %.3f ms/step  %.1f steps/s  %.3f M syndromes/s  loss %.2f" %
           (d, g.V, g.C, g.E, B, world, T, dt * 1e3, 1 / dt, world * B / dt / 1e6, l.item()))
     print("  per-step ms:", {k: round(v / n, 3) for k, v in timers.items()})
