@@ -69,7 +69,7 @@ def test_gd_adam_step_matches_oracle(n):
                                      ct.c_void_p(m.data_ptr()), ct.c_void_p(v.data_ptr()), n, 1.0, st))
         wo = o.step(wo, g)
         np.testing.assert_allclose(w.cpu().numpy(), wo, rtol=2e-6, atol=2e-7)
-    np.testing.assert_allclose(m.cpu().numpy(), o.m, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(m.cpu().numpy(), o.m, rtol=1e-5, atol=1e-6 * float(np.abs(o.m).max()))   # cancellation near zero
     np.testing.assert_allclose(v.cpu().numpy(), o.v, rtol=1e-5, atol=1e-12)
 
 
