@@ -49,6 +49,12 @@ struct DecodeParams {
     int ctab_n, off_ctab;   // V2_4: intervals of the check-phase cubic table (0 = direct evaluation) and its smem offset
     float ctab_R;           // half-width of its domain: max check degree - 1
     int off_w, off_tab, off_x, off_node, off_m, off_t;
+    // gated launch (gd_decode_host, see Gate in gd_decode.cuh); all NULL / 0 otherwise
+    const unsigned int* gate_in;
+    unsigned int* gate_out;
+    int* gate_err;
+    unsigned int gate_epoch;
+    int gate_chunk_tiles;
 };
 
 // ---------------- PTX helpers: mbarrier + bulk async copy (TMA 1-D) ----------------
@@ -74,6 +80,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
             smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+// wait until the chunk's host->device copy has landed (flag raised in stream order behind the copy); bounded
+__device__ __forceinline__ void gate_wait(const unsigned int* flag, unsigned int epoch, int* err) {
+    long long spins = 0;
+    while (true) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (++spins > (1ll << 24)) { *err = 1; break; }   // seconds: the copy never came; do not hang the GPU
+        __nanosleep(100);
+    }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -290,13 +307,17 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         const float* xg = p.x + s0 * N;
         const int n_in = nvalid * N;
         const uint32_t bulk_bytes = ((uint32_t)n_in * 4u) & ~15u;
+        if (p.gate_in) {   // gated launch: this tile's chunk may still be on its way from the host
+            if (tid == 0) gate_wait(p.gate_in + tix / p.gate_chunk_tiles, p.gate_epoch, p.gate_err);
+            __syncthreads();
+        }
         // ---- input slab: one bulk async copy (TMA) + scalar tail; zero the state ----
         if (tid == 0) {
             fence_proxy_async();  // order earlier generic reads of xs before the async write
             mbar_arrive_expect_tx(bar, bulk_bytes);
             if (bulk_bytes) bulk_g2s(xs, xg, bulk_bytes, bar);
         }
-        for (int i = (int)(bulk_bytes >> 2) + tid; i < tile * N; i += nthr) xs[i] = i < n_in ? __ldg(xg + i) : 0.f;
+        for (int i = (int)(bulk_bytes >> 2) + tid; i < tile * N; i += nthr) xs[i] = i < n_in ? __ldcg(xg + i) : 0.f;
         for (int i = 0; i < n_iter; ++i) {
             const int e = r + i * R;
             if (e < E) m_st[(size_t)e * tile + s] = 0.f;
@@ -594,6 +615,13 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             }
         }
         if (!(kGRU && p.all_iters)) emit(0);
+        if (p.gate_out) {   // gated launch: publish the tile so the chunk's device->host copy can go
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence_system();
+                atomicAdd(p.gate_out + tix / p.gate_chunk_tiles, 1u);
+            }
+        }
     }
 }
 
@@ -798,7 +826,21 @@ extern "C" int gd_decode_launch_info(const gd_graph* g, const gd_model* model, i
 
 static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
                            float* prob_dev, float* logit_dev, uint8_t* hard_dev, float* stash_dev, int64_t B,
-                           void* stream);
+                           void* stream, const gd::Gate* gate = nullptr);
+
+bool gd::gated_plan(const gd_graph* g, const gd_model* model, int64_t B, int* tile, int* n_tiles) {
+    gd::DecodePlan pl;
+    gd_launch_info probe;
+    if (model->flags != 0 || gd::plan_decode(g, model, B, &pl) != GD_OK || !pl.resident) return false;
+    if (gd::light_launch_info(g, model, B, &probe)) return false;
+    *tile = pl.p.tile; *n_tiles = pl.p.n_tiles;
+    return true;
+}
+
+int gd::decode_fwd_gated(const gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, float* prob_dev,
+                         uint8_t* hard_dev, int64_t B, cudaStream_t st, const gd::Gate& gate) {
+    return decode_fwd_impl(g, model, weights_dev, x_dev, prob_dev, nullptr, hard_dev, nullptr, B, (void*)st, &gate);
+}
 
 extern "C" int gd_decode_fwd(const gd_graph* gc, const gd_model* model, const float* weights_dev,
                              const float* x_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, int64_t B,
@@ -833,7 +875,7 @@ extern "C" int gd_decode_fwd_train(const gd_graph* gc, const gd_model* model, co
 
 static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
                            float* prob_dev, float* logit_dev, uint8_t* hard_dev, float* stash_dev, int64_t B,
-                           void* stream) {
+                           void* stream, const gd::Gate* gate) {
     gd_graph* g = const_cast<gd_graph*>(gc);
     GD_CHECK_ARG(g != nullptr, "gd_decode_fwd: graph is NULL");
     GD_CHECK_ARG(gd_model_valid(model), "gd_decode_fwd: invalid model (program=%d hidden=%d iters=%d)",
@@ -850,6 +892,11 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     if (rc != GD_OK) return rc;
     pl.p.x = x_dev; pl.p.prob = prob_dev; pl.p.logit = logit_dev; pl.p.hard = hard_dev; pl.p.weights = weights_dev;
     pl.p.stash = stash_dev;
+    if (gate) {
+        GD_CHECK_ARG(pl.resident && gate->chunk_tiles > 0, "gd_decode_host: gated launch needs the resident kernel");
+        pl.p.gate_in = gate->in_flags; pl.p.gate_out = gate->out_counts; pl.p.gate_err = gate->err;
+        pl.p.gate_epoch = gate->epoch; pl.p.gate_chunk_tiles = gate->chunk_tiles;
+    }
     pl.p.all_iters = (model->flags & GD_FLAG_ALL_ITERS) ? 1 : 0;
     pl.p.n_vact = getenv("GD_NO_VSKIP") ? (int)g->E : g->n_vact;
     pl.p.vdirect = (g->max_var_deg <= 2 && !getenv("GD_NO_DIRECT")) ? 1 : 0;
@@ -871,7 +918,7 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
         if (prev != g->device) cudaSetDevice(prev);
         return rc;
     }
-    if (!stash_dev) {
+    if (!stash_dev && !gate) {
         // light programs (CGNNI, QGNNI, sum-product): the node-owner kernel of gd_decode_light.cu
         const int lrc = gd::light_decode(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, B, st);
         if (lrc >= 0) {

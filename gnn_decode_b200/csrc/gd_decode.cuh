@@ -16,4 +16,19 @@ bool light_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_l
 int light_decode(const gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev,
                  float* prob_dev, float* logit_dev, uint8_t* hard_dev, int64_t B, cudaStream_t st);
 
+// Gated whole-batch launch for gd_decode_host (gd_host.cu): ONE persistent launch over the full batch whose tiles wait for
+// the host->device copy of their chunk (in_flags[k] >= epoch, raised by a stream memory operation behind the copy) and
+// count completed tiles per chunk (out_counts[k]) so the device->host copy of a chunk can start as soon as its last tile is
+// out.  Only the edge-owner resident kernel supports it.
+struct Gate {
+    const unsigned int* in_flags;
+    unsigned int* out_counts;
+    int* err;                    // host-mapped: set to 1 if a chunk never arrived (bounded spin)
+    unsigned int epoch;
+    int chunk_tiles;             // tiles per chunk: chunk of tile t = t / chunk_tiles
+};
+bool gated_plan(const gd_graph* g, const gd_model* model, int64_t B, int* tile, int* n_tiles);
+int decode_fwd_gated(const gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, float* prob_dev,
+                     uint8_t* hard_dev, int64_t B, cudaStream_t st, const Gate& gate);
+
 }  // namespace gd

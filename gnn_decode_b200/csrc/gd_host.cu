@@ -3,13 +3,31 @@
 // read-back of the prediction.  The batch is cut into chunks that flow through two streams
 // (H2D copy -> fused decode kernel -> D2H copy), so copies of one chunk overlap the kernel of
 // the other and the second kernel's CTAs back-fill the SMs the first one's last wave leaves idle.
-#include "gd_common.cuh"
+//
+// Gated pipeline (edge-owner resident kernel, the headline path): ONE persistent launch over the whole batch instead of one
+// per chunk.  The copy-in stream raises a device flag behind every chunk's H2D copy with a stream memory operation
+// (cuStreamWriteValue32: executed by the front end, no SM needed, so it can never be starved by the resident CTAs); the
+// kernel's tiles wait for their chunk's flag, and count finished tiles per chunk; the copy-out stream blocks on that
+// count (cuStreamWaitValue32) and then copies the chunk's results back.  No per-chunk prologue (weight staging, table
+// builds), no per-chunk tail, and the chunks can be small: the exposed copies shrink to one small chunk each way.
+#include "gd_decode.cuh"
+#include <cuda.h>
 #include <algorithm>
 
 namespace gd {
 
+typedef CUresult (*StreamMemOp32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
 struct HostCtx {
-    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+    // gated pipeline state
+    StreamMemOp32 write32 = nullptr, wait32 = nullptr;
+    int memops = -1;                 // -1 unknown, 0 unavailable, 1 available
+    unsigned int* gate_dev = nullptr;  // [kMaxGateChunks] in_flags | [kMaxGateChunks] out_counts
+    int* gate_err_host = nullptr;    // pinned, mapped
+    int* gate_err_dev = nullptr;
+    cudaEvent_t ev_ready = nullptr;
+    unsigned int epoch = 0;
     float* x_dev = nullptr;
     float* prob_dev = nullptr;
     uint8_t* hard_dev = nullptr;
@@ -18,9 +36,32 @@ struct HostCtx {
     int64_t cap_w = 0;
 };
 
+constexpr int kMaxGateChunks = 32;
+
+// stream memory operations through the driver entry points (no link-time dependency on libcuda); the 32-bit
+// operations are available on every device CUDA 12 supports
+static void probe_memops(HostCtx* c, int device) {
+    c->memops = 0;
+    if (getenv("GD_NO_GATED_HOST")) return;
+    cudaDriverEntryPointQueryResult q;
+    void *w = nullptr, *wt = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &wt, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return;
+    if (!w || !wt) return;
+    if (cudaMalloc((void**)&c->gate_dev, 2 * kMaxGateChunks * sizeof(unsigned int)) != cudaSuccess) return;
+    if (cudaMemset(c->gate_dev, 0, 2 * kMaxGateChunks * sizeof(unsigned int)) != cudaSuccess) return;
+    if (cudaHostAlloc((void**)&c->gate_err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return;
+    *c->gate_err_host = 0;
+    if (cudaHostGetDevicePointer((void**)&c->gate_err_dev, c->gate_err_host, 0) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess) return;
+    c->write32 = reinterpret_cast<StreamMemOp32>(w);
+    c->wait32 = reinterpret_cast<StreamMemOp32>(wt);
+    c->memops = 1;
+}
+
 static cudaError_t ensure(HostCtx* c, const gd_graph* g, int64_t B, int64_t n_w) {
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i)
         if (!c->st[i]) e = cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking);
     if (e == cudaSuccess && B > c->cap_B) {
         if (c->x_dev) cudaFree(c->x_dev);
@@ -46,8 +87,11 @@ static cudaError_t ensure(HostCtx* c, const gd_graph* g, int64_t B, int64_t n_w)
 void gd_host_ctx_destroy(gd_graph* g) {
     gd::HostCtx* c = static_cast<gd::HostCtx*>(g->host_ctx);
     if (!c) return;
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 3; ++i)
         if (c->st[i]) cudaStreamDestroy(c->st[i]);
+    if (c->gate_dev) cudaFree(c->gate_dev);
+    if (c->gate_err_host) cudaFreeHost(c->gate_err_host);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     if (c->x_dev) cudaFree(c->x_dev);
     if (c->prob_dev) cudaFree(c->prob_dev);
     if (c->hard_dev) cudaFree(c->hard_dev);
@@ -78,6 +122,78 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
     cudaError_t e = gd::ensure(c, g, B, n_w);
     lk.unlock();  // gd_decode_fwd takes the same mutex for the streamed workspace
     int rc = GD_OK;
+    if (e == cudaSuccess && c->memops < 0) gd::probe_memops(c, g->device);
+    int tile = 0, n_tiles = 0;
+    if (e == cudaSuccess && c->memops == 1 && B >= 16384 && gd::gated_plan(g, model, B, &tile, &n_tiles)) {
+        // ---- gated pipeline: st[0] = kernel, st[1] = copies in, st[2] = copies out ----
+        const char* ce = getenv("GD_GATE_CHUNKS");
+        int n_chunks = ce && atoi(ce) > 0 ? atoi(ce) : 16;   // measured on B200, rotated d=5 B=65536: 4 -> 19.20, 8 -> 19.41, 16 -> 19.55 M syn/s
+        n_chunks = std::min(std::min(n_chunks, gd::kMaxGateChunks), std::max(1, (int)(B / 4096)));
+        const int chunk_tiles = (n_tiles + n_chunks - 1) / n_chunks;
+        n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
+        const int64_t per = (int64_t)chunk_tiles * tile;
+        unsigned int* in_flags = c->gate_dev;
+        unsigned int* out_counts = c->gate_dev + gd::kMaxGateChunks;
+        const unsigned int epoch = ++c->epoch;
+        *c->gate_err_host = 0;
+        e = cudaMemsetAsync(out_counts, 0, gd::kMaxGateChunks * sizeof(unsigned int), c->st[0]);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_ready, c->st[0]);
+        if (e == cudaSuccess && n_w)
+            e = cudaMemcpyAsync(c->w_dev, weights_host, (size_t)n_w * sizeof(float), cudaMemcpyHostToDevice, c->st[0]);
+        if (e == cudaSuccess) {
+            gd::Gate gate{in_flags, out_counts, c->gate_err_dev, epoch, chunk_tiles};
+            rc = gd::decode_fwd_gated(g, model, c->w_dev, c->x_dev, prob_host ? c->prob_dev : nullptr,
+                                      hard_host ? c->hard_dev : nullptr, B, c->st[0], gate);
+        }
+        bool memop_failed = false;
+        if (e == cudaSuccess && rc == GD_OK) {
+            for (int k = 0; k < n_chunks && e == cudaSuccess; ++k) {
+                const int64_t b0 = (int64_t)k * per, nb = std::min<int64_t>(per, B - b0);
+                e = cudaMemcpyAsync(c->x_dev + b0 * g->N, x_host + b0 * g->N, (size_t)nb * g->N * sizeof(float),
+                                    cudaMemcpyHostToDevice, c->st[1]);
+                if (e == cudaSuccess &&
+                    c->write32((CUstream)c->st[1], (CUdeviceptr)(uintptr_t)(in_flags + k), epoch, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+                    memop_failed = true;
+                if (memop_failed) break;
+            }
+            if (e == cudaSuccess && !memop_failed) e = cudaStreamWaitEvent(c->st[2], c->ev_ready, 0);
+            for (int k = 0; k < n_chunks && e == cudaSuccess && !memop_failed; ++k) {
+                const int64_t b0 = (int64_t)k * per, nb = std::min<int64_t>(per, B - b0);
+                const unsigned int tiles_k = (unsigned int)((nb + tile - 1) / tile);
+                if (c->wait32((CUstream)c->st[2], (CUdeviceptr)(uintptr_t)(out_counts + k), tiles_k, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
+                    memop_failed = true;
+                    break;
+                }
+                if (prob_host)
+                    e = cudaMemcpyAsync(prob_host + b0 * g->V, c->prob_dev + b0 * g->V, (size_t)nb * g->V * sizeof(float),
+                                        cudaMemcpyDeviceToHost, c->st[2]);
+                if (e == cudaSuccess && hard_host)
+                    e = cudaMemcpyAsync(hard_host + b0 * g->V, c->hard_dev + b0 * g->V, (size_t)nb * g->V,
+                                        cudaMemcpyDeviceToHost, c->st[2]);
+            }
+        }
+        if (memop_failed) {
+            // a stream memory operation was refused after the kernel was queued: release every gate from the host side so
+            // the kernel drains, then copy the results back the plain way
+            cudaStreamSynchronize(c->st[1]);
+            std::vector<unsigned int> open(gd::kMaxGateChunks, epoch);
+            cudaMemcpyAsync(in_flags, open.data(), gd::kMaxGateChunks * sizeof(unsigned int), cudaMemcpyHostToDevice, c->st[1]);
+            cudaStreamSynchronize(c->st[1]);
+            c->memops = 0;
+        }
+        cudaError_t s0 = cudaStreamSynchronize(c->st[0]);
+        cudaError_t s1 = cudaStreamSynchronize(c->st[1]);
+        cudaError_t s2 = cudaStreamSynchronize(c->st[2]);   // the kernel always drains, so every queued wait is satisfied
+        if (e == cudaSuccess) e = s0 != cudaSuccess ? s0 : (s1 != cudaSuccess ? s1 : s2);
+        if (prev != g->device) cudaSetDevice(prev);
+        if (rc != GD_OK) return rc;
+        GD_CUDA(e);
+        if (!memop_failed && *c->gate_err_host == 0) return GD_OK;
+        // a gate timed out (the copy-in stream was held up behind the kernel) or a memory operation was refused: results
+        // are not trustworthy -> never gate again on this graph and redo the batch with one launch per chunk
+        c->memops = 0;
+        if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
+    }
     if (e == cudaSuccess && n_w) {
         e = cudaMemcpyAsync(c->w_dev, weights_host, (size_t)n_w * sizeof(float), cudaMemcpyHostToDevice, c->st[0]);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->st[0]);

@@ -309,3 +309,38 @@ def test_autotuned_geometry_gives_identical_results():
     other = dec.decode(x[:1000].contiguous(), graph=tg)             # a different B: untouched by the cache
     assert torch.equal(other, before[:1000])
     assert isinstance(info0, dict)
+
+
+def test_decode_host_gated_pipeline(monkeypatch):
+    """gd_decode_host's gated single-launch pipeline (chunk flags raised by stream memory operations, per-chunk tile
+    counters releasing the copies back): bit-identical to the device path and to the one-launch-per-chunk pipeline, on
+    ragged batch sizes, repeated calls (epoch reuse), changing batch sizes and either output alone."""
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.sampler import sample_syndromes
+    g = Golden("v2_4_toricL4_epoch1")
+    dev = _dev()
+    mod, dec = make_decoder(g)
+    dec = dec.to(dev).eval()
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    dec.bind_graph(tg)
+    x_all, _ = sample_syndromes(tg, 40000, [0.01, 0.04, 0.08, 0.12], noise=0, seed=77)     # every syndrome different
+    ref_p, ref_h = dec.decode(x_all, return_hard=True)
+    ref_p, ref_h = ref_p.cpu(), ref_h.cpu()
+    xh_all = x_all.cpu().pin_memory()
+    for B in (40000, 16384, 20001, 33333, 40000):
+        xh = xh_all[:B]
+        prob_h = torch.zeros(B, g.V, dtype=torch.float32).pin_memory()
+        hard_h = torch.full((B, g.V), 7, dtype=torch.uint8).pin_memory()
+        dec.decode_host(xh, prob_h, hard_h)
+        assert torch.equal(prob_h, ref_p[:B]) and torch.equal(hard_h, ref_h[:B]), B
+    only_h = dec.decode_host(xh_all, hard_out=torch.empty(40000, g.V, dtype=torch.uint8).pin_memory())
+    assert torch.equal(only_h, ref_h)
+    only_p = dec.decode_host(xh_all)
+    assert torch.equal(only_p, ref_p)
+    pageable = dec.decode_host(x_all.cpu()[:17000].clone())                                # pageable host memory works too
+    assert torch.equal(pageable, ref_p[:17000])
+    # the one-launch-per-chunk pipeline (gating disabled for a fresh graph context) gives the same bits
+    monkeypatch.setenv("GD_NO_GATED_HOST", "1")
+    tg2 = TannerGraph(g.edge_index, g.V, g.C, dev)
+    p2 = dec.decode_host(xh_all, graph=tg2)
+    assert torch.equal(p2, ref_p)
