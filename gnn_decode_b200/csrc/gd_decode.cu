@@ -81,17 +81,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
-// wait until the chunk's host->device copy has landed (flag raised in stream order behind the copy); bounded
-__device__ __forceinline__ void gate_wait(const unsigned int* flag, unsigned int epoch, int* err) {
-    long long spins = 0;
-    while (true) {
-        unsigned int v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int)(v - epoch) >= 0) break;
-        if (++spins > (1ll << 24)) { *err = 1; break; }   // seconds: the copy never came; do not hang the GPU
-        __nanosleep(100);
-    }
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -832,7 +821,10 @@ bool gd::gated_plan(const gd_graph* g, const gd_model* model, int64_t B, int* ti
     gd::DecodePlan pl;
     gd_launch_info probe;
     if (model->flags != 0 || gd::plan_decode(g, model, B, &pl) != GD_OK || !pl.resident) return false;
-    if (gd::light_launch_info(g, model, B, &probe)) return false;
+    if (gd::light_launch_info(g, model, B, &probe)) {     // node-owner kernel: gated too
+        *tile = probe.tile; *n_tiles = probe.n_tiles;
+        return true;
+    }
     *tile = pl.p.tile; *n_tiles = pl.p.n_tiles;
     return true;
 }
@@ -918,9 +910,9 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
         if (prev != g->device) cudaSetDevice(prev);
         return rc;
     }
-    if (!stash_dev && !gate) {
+    if (!stash_dev) {
         // light programs (CGNNI, QGNNI, sum-product): the node-owner kernel of gd_decode_light.cu
-        const int lrc = gd::light_decode(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, B, st);
+        const int lrc = gd::light_decode(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, B, st, gate);
         if (lrc >= 0) {
             if (prev != g->device) cudaSetDevice(prev);
             return lrc;

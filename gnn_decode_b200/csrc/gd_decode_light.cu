@@ -36,6 +36,12 @@ struct LightParams {
     int T, V, C, E, N;
     int tile, lanes, R, hid, hp, n_tiles, trows;
     int off_w, off_tab, off_x, off_m, off_t;
+    // gated launch (gd_decode_host, see Gate in gd_decode.cuh); all NULL / 0 otherwise
+    const unsigned int* gate_in;
+    unsigned int* gate_out;
+    int* gate_err;
+    unsigned int gate_epoch;
+    int gate_chunk_tiles;
 };
 
 #define GD_DEGREE_SWITCH4(d, CALL, ...)     \
@@ -156,6 +162,10 @@ __global__ void __launch_bounds__(512, 2) decode_light_kernel(const LightParams 
     for (int tix = blockIdx.x; tix < p.n_tiles; tix += gridDim.x) {
         const long long s0 = (long long)tix * tile;
         const int nvalid = (int)min((long long)tile, p.B - s0);
+        if (p.gate_in) {   // gated launch: this tile's chunk may still be on its way from the host
+            if (tid == 0) gate_wait(p.gate_in + tix / p.gate_chunk_tiles, p.gate_epoch, p.gate_err);
+            __syncthreads();
+        }
         // ---- x[tile][N] (coalesced reads) -> xT[N][tile]; m = 0 ----
         {
             const float* xg = p.x + s0 * N;
@@ -164,7 +174,7 @@ __global__ void __launch_bounds__(512, 2) decode_light_kernel(const LightParams 
                 // conflict-free transpose through the (idle) t region: rows of odd pitch
                 for (int i = tid; i < tile * N; i += nthr) {
                     const int si = i / N, n = i - si * N;
-                    t_st[si * pitch + n] = si < nvalid ? __ldg(xg + i) : 0.f;
+                    t_st[si * pitch + n] = si < nvalid ? __ldcg(xg + i) : 0.f;
                 }
                 __syncthreads();
                 for (int i = tid; i < tile * N; i += nthr) {
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(512, 2) decode_light_kernel(const LightParams 
             } else {
                 for (int i = tid; i < tile * N; i += nthr) {
                     const int si = i / N, n = i - si * N;
-                    xT[n * tile + si] = si < nvalid ? __ldg(xg + i) : 0.f;
+                    xT[n * tile + si] = si < nvalid ? __ldcg(xg + i) : 0.f;
                 }
             }
             for (int i = tid; i < E * tile; i += nthr) m_st[i] = 0.f;
@@ -305,6 +315,10 @@ __global__ void __launch_bounds__(512, 2) decode_light_kernel(const LightParams 
             }
         }
         __syncthreads();
+        if (p.gate_out && tid == 0) {   // gated launch: publish the tile so the chunk's device->host copy can go
+            __threadfence_system();
+            atomicAdd(p.gate_out + tix / p.gate_chunk_tiles, 1u);
+        }
     }
 }
 
@@ -350,13 +364,17 @@ __global__ void __launch_bounds__(512, 2) decode_light_ext_kernel(const LightPar
     for (int tix = blockIdx.x; tix < p.n_tiles; tix += gridDim.x) {
         const long long s0 = (long long)tix * tile;
         const int nvalid = (int)min((long long)tile, p.B - s0);
+        if (p.gate_in) {   // gated launch: this tile's chunk may still be on its way from the host
+            if (tid == 0) gate_wait(p.gate_in + tix / p.gate_chunk_tiles, p.gate_epoch, p.gate_err);
+            __syncthreads();
+        }
         {
             const float* xg = p.x + s0 * N;
             const int pitch = N | 1;
             if (p.trows >= pitch) {
                 for (int i = tid; i < tile * N; i += nthr) {
                     const int si = i / N, n = i - si * N;
-                    t_st[si * pitch + n] = si < nvalid ? __ldg(xg + i) : 0.f;
+                    t_st[si * pitch + n] = si < nvalid ? __ldcg(xg + i) : 0.f;
                 }
                 __syncthreads();
                 for (int i = tid; i < tile * N; i += nthr) {
@@ -366,7 +384,7 @@ __global__ void __launch_bounds__(512, 2) decode_light_ext_kernel(const LightPar
             } else {
                 for (int i = tid; i < tile * N; i += nthr) {
                     const int si = i / N, n = i - si * N;
-                    xT[n * tile + si] = si < nvalid ? __ldg(xg + i) : 0.f;
+                    xT[n * tile + si] = si < nvalid ? __ldcg(xg + i) : 0.f;
                 }
             }
             for (int i = tid; i < E * tile; i += nthr) m_st[i] = 0.f;
@@ -520,6 +538,10 @@ __global__ void __launch_bounds__(512, 2) decode_light_ext_kernel(const LightPar
             }
         }
         __syncthreads();
+        if (p.gate_out && tid == 0) {   // gated launch: publish the tile so the chunk's device->host copy can go
+            __threadfence_system();
+            atomicAdd(p.gate_out + tix / p.gate_chunk_tiles, 1u);
+        }
     }
 }
 
@@ -639,10 +661,14 @@ bool light_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_l
 
 // rc < 0: not applicable (the caller keeps the edge-owner kernel); otherwise a gd_status.
 int light_decode(const gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, float* prob_dev,
-                 float* logit_dev, uint8_t* hard_dev, int64_t B, cudaStream_t st) {
+                 float* logit_dev, uint8_t* hard_dev, int64_t B, cudaStream_t st, const Gate* gate) {
     LightPlan pl;
     plan_light(g, model, B, &pl);
     if (!pl.ok) return -1;
+    if (gate) {
+        pl.p.gate_in = gate->in_flags; pl.p.gate_out = gate->out_counts; pl.p.gate_err = gate->err;
+        pl.p.gate_epoch = gate->epoch; pl.p.gate_chunk_tiles = gate->chunk_tiles;
+    }
     pl.p.x = x_dev; pl.p.prob = prob_dev; pl.p.logit = logit_dev; pl.p.hard = hard_dev; pl.p.weights = weights_dev;
     void (*k)(const LightParams);
     switch (model->program) {

@@ -344,3 +344,31 @@ def test_decode_host_gated_pipeline(monkeypatch):
     tg2 = TannerGraph(g.edge_index, g.V, g.C, dev)
     p2 = dec.decode_host(xh_all, graph=tg2)
     assert torch.equal(p2, ref_p)
+
+
+@pytest.mark.parametrize("name", ["qgnni_toricL4_seeded", "cgnni_bch_seeded", "bp_quantum_toricL4", "cgnni_ldpc_epoch18"])
+def test_decode_host_gated_pipeline_light_programs(name):
+    """The gated pipeline through the node-owner (light) kernels: same bits as the device path."""
+    from gnn_decode_b200.graph import TannerGraph
+    g = Golden(name)
+    dev = _dev()
+    mod, dec = make_decoder(g)
+    dec = dec.to(dev).eval()
+    tg = TannerGraph(g.edge_index, g.V, g.C, dev)
+    dec.bind_graph(tg)
+    B = 36001
+    gen = torch.Generator().manual_seed(9)
+    reps = (B + g.B - 1) // g.B
+    x = g.x.float().repeat(reps, 1)[:B].clone()
+    x[:, :g.V] *= 0.25 + 1.5 * torch.rand(B, 1, generator=gen)            # every syndrome different
+    xh = x.contiguous().pin_memory()
+    ref_p, ref_h = dec.decode(xh.to(dev), return_hard=True)
+    for nb in (B, 16384, B):
+        prob_h = torch.zeros(nb, g.V, dtype=torch.float32).pin_memory()
+        hard_h = torch.full((nb, g.V), 9, dtype=torch.uint8).pin_memory()
+        dec.decode_host(xh[:nb], prob_h, hard_h)
+        if nb == B:
+            assert torch.equal(prob_h, ref_p.cpu()) and torch.equal(hard_h, ref_h.cpu())
+        else:
+            p2, h2 = dec.decode(xh[:nb].to(dev), return_hard=True)
+            assert torch.equal(prob_h, p2.cpu()) and torch.equal(hard_h, h2.cpu())
