@@ -347,6 +347,7 @@ def main():
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     clocks.end()
+    e2e_launches_per_step = int(_cabi.lib().gd_decode_host_last_launches(g.handle))
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -420,7 +421,7 @@ def main():
                         "d2h_bytes_per_step": B * V * 5, "api": "GNNI.decode_host -> gd_decode_host (pinned host buffers)",
                         "matches_device_path": same},
                 "gpu_launches": args.steps * 1,     # timed `value` region: one gd::decode_kernel launch per step
-                "gpu_launches_e2e": args.steps * (min(4, max(1, B // 8192)) if info["resident"] else 1),
+                "gpu_launches_e2e": args.steps * e2e_launches_per_step,   # gd_decode_host_last_launches: 1 = gated single-launch pipeline
                 "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:
             rng = np.random.RandomState(1234)

@@ -28,6 +28,7 @@ struct HostCtx {
     int* gate_err_dev = nullptr;
     cudaEvent_t ev_ready = nullptr;
     unsigned int epoch = 0;
+    int last_launches = 0;           // kernel launches of the last gd_decode_host call (benchmark accounting)
     float* x_dev = nullptr;
     float* prob_dev = nullptr;
     uint8_t* hard_dev = nullptr;
@@ -188,6 +189,7 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
         if (prev != g->device) cudaSetDevice(prev);
         if (rc != GD_OK) return rc;
         GD_CUDA(e);
+        c->last_launches = 1;
         if (!memop_failed && *c->gate_err_host == 0) return GD_OK;
         // a gate timed out (the copy-in stream was held up behind the kernel) or a memory operation was refused: results
         // are not trustworthy -> never gate again on this graph and redo the batch with one launch per chunk
@@ -204,6 +206,7 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
         gd_launch_info li;
         if (gd_decode_launch_info(g, model, B, &li) == GD_OK && !li.resident) n_chunks = 1;  // one shared slab
         int64_t per = ((B + n_chunks - 1) / n_chunks + 7) / 8 * 8;
+        c->last_launches = 0;
         for (int k = 0; k < n_chunks && e == cudaSuccess && rc == GD_OK; ++k) {
             const int64_t b0 = (int64_t)k * per;
             const int64_t nb = std::min<int64_t>(per, B - b0);
@@ -215,6 +218,7 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
             rc = gd_decode_fwd(g, model, c->w_dev, c->x_dev + b0 * g->N, prob_host ? c->prob_dev + b0 * g->V : nullptr,
                                nullptr, hard_host ? c->hard_dev + b0 * g->V : nullptr, nb, st);
             if (rc != GD_OK) break;
+            ++c->last_launches;
             if (prob_host)
                 e = cudaMemcpyAsync(prob_host + b0 * g->V, c->prob_dev + b0 * g->V, (size_t)nb * g->V * sizeof(float),
                                     cudaMemcpyDeviceToHost, st);
@@ -230,4 +234,9 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
     if (rc != GD_OK) return rc;
     GD_CUDA(e);
     return GD_OK;
+}
+
+extern "C" int gd_decode_host_last_launches(const gd_graph* g) {
+    if (!g || !g->host_ctx) return 0;
+    return static_cast<const gd::HostCtx*>(g->host_ctx)->last_launches;
 }

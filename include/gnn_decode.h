@@ -156,6 +156,9 @@ int gd_decode_fwd(const gd_graph* g, const gd_model* model, const float* weights
  * followed by reading the prediction back. weights_host is the packed buffer on the host. */
 int gd_decode_host(const gd_graph* g, const gd_model* model, const float* weights_host,
                    const float* x_host, float* prob_host, uint8_t* hard_host, int64_t B);
+/* Decode-kernel launches the last gd_decode_host call on this graph made: 1 for the gated single-launch pipeline, one per chunk
+ * otherwise (benchmark accounting; streamed codes count one per gd_decode_fwd call). */
+int gd_decode_host_last_launches(const gd_graph* g);
 
 /* ---- training (BASELINE config 4): forward that also stashes the per-iteration activations, and
  *      the hand-written backward (replaces autograd through the loop, decoder_v2_4.py:334-340).
