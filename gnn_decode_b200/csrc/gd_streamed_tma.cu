@@ -463,7 +463,13 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
     p.tile = tile;
     p.lanes = tile / 4;
     const int vd = g->max_var_deg > 0 ? g->max_var_deg : 1;
-    int rows = (bp ? 1 : 2) * g->max_chk_deg + 1;          // sum-product fetches no residual rows
+    // rows per stage: a check item needs deg (+ deg residual rows for the learned programs) + 1; the sum-product family
+    // could do with half, but bigger stages amortise the per-item cost better (variables per item K = rows / (vd + 1)):
+    // measured on B200, sum-product / HGP-1600 / T = 50: 15 rows x 2 stages 28.4 ms, 8 rows x 2 / 3 / 4 stages 33.7 / 32.9 / 33.2 ms
+    const int min_rows = (bp ? 1 : 2) * g->max_chk_deg + 1;
+    int rows = 2 * g->max_chk_deg + 1;
+    const char* er = getenv("GD_SROWS");
+    if (er && atoi(er) >= min_rows && atoi(er) <= 64) rows = atoi(er);
     if (rows < vd + 1) rows = vd + 1;
     int K = rows / (vd + 1);
     if (K > 8) K = 8;
@@ -473,7 +479,7 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
     p.off_w = off; off += out->npad ? 2 * pwl_smem_floats(out->npad) * 4 : n_slots * 4 * p.hp * 4;
     off = align_up_i(off, 128);
     p.off_stage = off;
-    // stages: as deep as shared memory allows with all 16 warps (sum-product stages are half the size -> 3 stages)
+    // stages per warp (2..4, GD_SSTAGES): 2 unless deeper still leaves room for all 16 warps at this stage size
     int S = 2;
     {
         const char* es = getenv("GD_SSTAGES");

@@ -1,7 +1,9 @@
 #!/usr/bin/env bash
 # Reproduce profiles/<tag>_all_workloads: one bench.py line per BASELINE.json config on 1 GPU, the reference arm,
 # and the training step (configs[3]).  Usage: scripts/run_all_configs.sh [out_dir] [tag]
+# GD_SWEEP_FAST=1 skips the 15 s CPU baseline of the secondary workloads (the headline run keeps it).
 set -u
+EXTRA=""; [ -n "${GD_SWEEP_FAST:-}" ] && EXTRA="--no-cpu-baseline"
 OUT=${1:-gpurun_out}; TAG=${2:-run}
 mkdir -p "$OUT"
 python bench.py > "$OUT/${TAG}_bench.json" 2> "$OUT/${TAG}_bench.err"
@@ -9,7 +11,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/${TAG}_bench_refer
 for w in cgnni_ldpc_awgn_B1024 cgnni_bch_awgn_B1024 cgnni_bch_awgn_B65536 \
          v2_4_toric_L5_iidxz_B65536 v2_4_toric_L11_iidxz_B65536 v2_4_rotated_d11_depol_B65536 \
          qgnni_hgp1600_depol_B16384_T50 bp_hgp1600_depol_B16384_T50 v2_4_hgp1600_depol_B8192; do
-  python bench.py --workload "$w" --steps 10 > "$OUT/${TAG}_bench_$w.json" 2>> "$OUT/${TAG}_bench.err"
+  python bench.py --workload "$w" --steps 10 $EXTRA > "$OUT/${TAG}_bench_$w.json" 2>> "$OUT/${TAG}_bench.err"
 done
 python scripts/train_bench.py 7 4096 > "$OUT/${TAG}_train_bench.txt" 2>&1
 python - "$OUT" "$TAG" <<'PY'
