@@ -46,6 +46,7 @@ _SIGNATURES = {
     "gd_decode_fwd": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, _p, C.c_int64, _p]),
     "gd_decode_host": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, C.c_int64]),
     "gd_decode_host_last_launches": (C.c_int, [_p]),
+    "gd_decode_tables_info": (C.c_int, [_p, C.POINTER(GdModel), C.c_int64, C.POINTER(C.c_int32)]),
     "gd_decode_launch_info": (C.c_int, [_p, C.POINTER(GdModel), C.c_int64, C.POINTER(GdLaunchInfo)]),
     "gd_decode_autotune": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, C.c_int64, C.c_int32, _p, C.POINTER(GdLaunchInfo)]),
     "gd_sample": (C.c_int, [_p, C.c_int32, _p, C.c_int32, C.c_uint64, C.c_uint64, _p, _p, C.c_int64, _p]),

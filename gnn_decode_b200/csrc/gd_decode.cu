@@ -48,6 +48,9 @@ struct DecodeParams {
     int rtab_n, off_rtab;   // V2_4: intervals of the read-out MLP's cubic table (0 = direct) and its smem offset
     int ctab_n, off_ctab;   // V2_4: intervals of the check-phase cubic table (0 = direct evaluation) and its smem offset
     float ctab_R;           // half-width of its domain: max check degree - 1
+    // V2_4: cubic tables of the variable-phase MLP's sections f(ext, prior = const), one per distinct prior value a CTA
+    // meets (inputs made like the reference's gen_syn carry one prior per syndrome, drawn from a short list)
+    int vtab_n, vtab_k, off_vtab, off_vmeta;
     int off_w, off_tab, off_x, off_node, off_m, off_t;
     // gated launch (gd_decode_host, see Gate in gd_decode.cuh); all NULL / 0 otherwise
     const unsigned int* gate_in;
@@ -280,6 +283,41 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             }
         }
     }
+    // V2_4 variable phase (decoder_v2_4.py:254-255, mlp([ext, prior])): when every variable of a syndrome carries the same
+    // prior (the reference's gen_syn: x = log((1-p)/p) for all of them) the update is a function of ext alone, f_p(ext).
+    // A CTA keeps cubic tables of f_p for the distinct p it meets (up to vtab_k; later tiles reuse them); syndromes with
+    // non-uniform priors, more distinct values than slots, or |ext| beyond the tabulated domain take the direct path.
+    // Domain half-width: the largest R whose interpolation-error bound (same formula, first-input weights) is <= 2e-7.
+    bool use_vtab = false;
+    float vtab_R = 0.f, vtab_inv_h = 0.f;
+    float* const vt_vals = reinterpret_cast<float*>(smem + p.off_vmeta + 16);      // [16] prior of table k
+    int* const vt_cnt = reinterpret_cast<int*>(smem + p.off_vmeta);               // tables built so far
+    int* const vt_lane = reinterpret_cast<int*>(smem + p.off_vmeta + 16 + 16 * 4); // [tile] table of lane s (-1: direct)
+    if constexpr (PROG == GD_PROG_V2_4) {
+        if (p.vtab_n > 0 && !p.stash && use_ctab && tile <= 128 && E * tile >= p.vtab_n + 8) {
+            float m4 = 0.f;
+            for (int k = 0; k < p.hid; ++k) {
+                float a = __ldg(p.weights + 2 * k);                       // w1[k][0]: the ext input
+                a *= a;
+                m4 = fmaf(fabsf(__ldg(p.weights + 3 * p.hid + k)), a * a, m4);
+            }
+            const float hmax = sqrtf(sqrtf(2e-7f * 384.0f / (0.125f * fmaxf(m4, 1e-20f))));
+            vtab_R = fminf(0.5f * (float)p.vtab_n * hmax, 1e4f);
+#ifdef GD_VTAB_DEBUG
+            if (p.B == 4242 && blockIdx.x == 0 && tid == 0) printf("vtab: m4=%g hmax=%g R_budget=%g\n", m4, hmax, vtab_R);
+#endif
+            use_vtab = vtab_R >= 0.5f;                                    // a narrower domain would mostly fall back
+            if (use_rtab && rtab_R > 0.f) vtab_R = fminf(vtab_R, rtab_R * (float)(p.vdirect ? 1 : 8));   // |m| <= rtab_R: no need to go wider
+            vtab_inv_h = 0.5f * (float)p.vtab_n / vtab_R;
+            if (tid == 0) *vt_cnt = 0;
+        }
+#ifdef GD_VTAB_DEBUG
+        if (p.B == 4242 && blockIdx.x == 0 && tid == 0) {
+            vt_cnt[1] = vt_cnt[2] = 0;
+            printf("vtab: n=%d k=%d use=%d R=%f rtab_R=%f use_rtab=%d use_ctab=%d\n", p.vtab_n, p.vtab_k, (int)use_vtab, vtab_R, rtab_R, (int)use_rtab, (int)use_ctab);
+        }
+#endif
+    }
     fence_proxy_async();   // the prologue used the slab region as generic-proxy scratch; the bulk copies (async proxy) come next
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -315,6 +353,45 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         parity ^= 1u;
         __syncthreads();
         const float* xrow = xs + (size_t)s * N;  // prior = xrow[0..V), check input = xrow[V..V+C)
+        int my_vtab = -1;
+        if constexpr (PROG == GD_PROG_V2_4) {
+            if (use_vtab) {
+                const int old_cnt = *vt_cnt;
+                float* const lane_prior = t_st;                              // t is idle until the first variable phase
+                if (r == 0) {
+                    const float pv = xrow[0];
+                    bool uni = s < nvalid;
+                    for (int v = 1; v < V; ++v) uni = uni && (__float_as_uint(xrow[v]) == __float_as_uint(pv));
+                    lane_prior[s] = pv;
+                    vt_lane[s] = uni ? 0 : -1;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int cnt = old_cnt;
+                    for (int q = 0; q < tile; ++q) {
+                        if (vt_lane[q] < 0) continue;
+                        const unsigned int pb = __float_as_uint(lane_prior[q]);
+                        int k = 0;
+                        while (k < cnt && __float_as_uint(vt_vals[k]) != pb) ++k;
+                        if (k == cnt) {
+                            if (cnt < p.vtab_k) vt_vals[cnt++] = lane_prior[q];
+                            else k = -1;
+                        }
+                        vt_lane[q] = k;
+                    }
+                    *vt_cnt = cnt;
+                }
+                __syncthreads();
+                const int new_cnt = *vt_cnt;
+                for (int k = old_cnt; k < new_cnt; ++k)                       // CTA-uniform bounds
+                    cubic_tab_build<true>(W1, hp, vtab_R, p.vtab_n, reinterpret_cast<float4*>(smem + p.off_vtab) + (size_t)k * p.vtab_n,
+                                          t_st, tid, nthr, vt_vals[k]);
+                my_vtab = vt_lane[s];
+                __syncthreads();
+            }
+        }
+        const CubicTab vtab{reinterpret_cast<const float4*>(smem + p.off_vtab) + (size_t)(my_vtab > 0 ? my_vtab : 0) * p.vtab_n,
+                            vtab_inv_h, vtab_R * vtab_inv_h, (float)p.vtab_n - 0.001f};
 
         // read-out as a callable: GRU_CA with GD_FLAG_ALL_ITERS emits one prediction per iteration
         auto emit = [&](const long long out_off) {
@@ -451,8 +528,21 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         }
                         x1[j] = xrow[v];
                     }
-                    if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, true, (NPOLY > 0 ? NPOLY : 0)>(W1, hp, x0, x1, o);
-                    else mlp_softplus<kEB, true>(W1, hp, x0, x1, o);
+                    bool vt_ok = my_vtab >= 0;
+#pragma unroll
+                    for (int j = 0; j < kEB; ++j) vt_ok = vt_ok && fabsf(x0[j]) <= vtab_R;
+                    if (!vt_ok) {
+                        if constexpr (NPOLY >= 0) mlp_softplus_x2<kEB, true, (NPOLY > 0 ? NPOLY : 0)>(W1, hp, x0, x1, o);
+                        else mlp_softplus<kEB, true>(W1, hp, x0, x1, o);
+                    }
+                    if (my_vtab >= 0) {     // per item, so a result never depends on which items share a register batch
+#pragma unroll
+                        for (int j = 0; j < kEB; ++j)
+                            if (vt_ok || fabsf(x0[j]) <= vtab_R) o[j] = cubic_tab_eval(vtab, x0[j]);
+                    }
+#ifdef GD_VTAB_DEBUG
+                    if (p.B == 4242 && blockIdx.x == 0) atomicAdd(reinterpret_cast<int*>(smem + p.off_vmeta) + (vt_ok ? 1 : 2), 1);
+#endif
 #pragma unroll
                     for (int j = 0; j < kEB; ++j)
                         if (ee[j] < E) {
@@ -604,6 +694,10 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             }
         }
         if (!(kGRU && p.all_iters)) emit(0);
+#ifdef GD_VTAB_DEBUG
+        if (p.B == 4242 && blockIdx.x == 0 && tid == 0)
+            printf("vtab tile %d: tables=%d groups table=%d direct=%d lane0=%d\n", tix, vt_cnt[0], vt_cnt[1], vt_cnt[2], vt_lane[0]);
+#endif
         if (p.gate_out) {   // gated launch: publish the tile so the chunk's device->host copy can go
             __syncthreads();
             if (tid == 0) {
@@ -689,6 +783,24 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     }
     const bool fits16 = E64 < 65536 && V < 65535 && C < 65535;
     const int tab_bytes = (int)(9 * E64 + V + C + 2) * 2;
+    if (p.ctab_n > 0 && !getenv("GD_NO_VTAB")) {
+        const char* en = getenv("GD_VTAB_N");
+        const char* ek = getenv("GD_VTAB_K");
+        // 12 tables x 512 intervals (96 KB): the reference draws p from a list of 10 (decoder_v2_4.py:187).  Measured on B200,
+        // rotated d=5, B=65536, 10 distinct priors: direct 3.43 ms; 4 x 1024 3.68 (6 of 10 priors overflow the slots);
+        // 12 x 384 1.21; 10..12 x 512..640 0.81 ms.  With 4 distinct priors 4 x 1024 takes 0.69 ms.
+        int vn = en ? atoi(en) : 512, vk = ek ? atoi(ek) : 12;
+        if (vn < 64 || vn > 4096) vn = 512;
+        if (vk < 1 || vk > 16) vk = 12;
+        const int vbytes = vk * vn * 16 + 16 + 16 * 4 + 128 * 4;
+        const int64_t per_syn_est = ((int64_t)N + maxvc + 2 * E64) * 4;
+        // only where it leaves room for tiles of >= 16 syndromes (larger codes keep the direct variable phase)
+        if (fits16 && (smem_max - align_up(off + vbytes + tab_bytes, 128)) / per_syn_est >= 16) {
+            p.vtab_n = vn; p.vtab_k = vk;
+            p.off_vtab = off; off += vk * vn * 16;
+            p.off_vmeta = off; off += 16 + 16 * 4 + 128 * 4;
+        }
+    }
     // resident layout first
     int tile = 0, resident = 0, R = 0;
     if (fits16 && off + tab_bytes < smem_max) {
@@ -810,6 +922,19 @@ extern "C" int gd_decode_launch_info(const gd_graph* g, const gd_model* model, i
     if (gd::light_launch_info(g, model, B, out)) return GD_OK;      // node-owner kernel for the light programs
     out->tile = pl.p.tile; out->threads = pl.threads; out->grid = pl.grid; out->smem_bytes = pl.smem;
     out->resident = pl.resident; out->n_tiles = pl.p.n_tiles;
+    return GD_OK;
+}
+
+extern "C" int gd_decode_tables_info(const gd_graph* g, const gd_model* model, int64_t B, int32_t* out4) {
+    GD_CHECK_ARG(g && out4, "gd_decode_tables_info: NULL argument");
+    GD_CHECK_ARG(gd_model_valid(model) && B > 0, "gd_decode_tables_info: invalid model / B");
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    gd::DecodePlan pl;
+    gd_launch_info probe;
+    int rc = gd::plan_decode(g, model, B, &pl);
+    if (rc != GD_OK) return rc;
+    if (!pl.resident || gd::light_launch_info(g, model, B, &probe)) return GD_OK;
+    out4[0] = pl.p.ctab_n; out4[1] = pl.p.rtab_n; out4[2] = pl.p.vtab_n; out4[3] = pl.p.vtab_k;
     return GD_OK;
 }
 

@@ -141,28 +141,31 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
         if (e == cudaSuccess) e = cudaEventRecord(c->ev_ready, c->st[0]);
         if (e == cudaSuccess && n_w)
             e = cudaMemcpyAsync(c->w_dev, weights_host, (size_t)n_w * sizeof(float), cudaMemcpyHostToDevice, c->st[0]);
-        if (e == cudaSuccess) {
+        // Enqueue order: every copy-in and flag write FIRST, then the kernel, then the copy-out waits.  Under a tool that makes
+        // kernel launches block the host (ncu replay, CUDA_LAUNCH_BLOCKING=1) the gated kernel then still finds all of its
+        // inputs on their way; launched first it would spin until its bound with the copies not even queued.
+        bool memop_failed = false, launched = false;
+        for (int k = 0; k < n_chunks && e == cudaSuccess && !memop_failed; ++k) {
+            const int64_t b0 = (int64_t)k * per, nb = std::min<int64_t>(per, B - b0);
+            e = cudaMemcpyAsync(c->x_dev + b0 * g->N, x_host + b0 * g->N, (size_t)nb * g->N * sizeof(float),
+                                cudaMemcpyHostToDevice, c->st[1]);
+            if (e == cudaSuccess &&
+                c->write32((CUstream)c->st[1], (CUdeviceptr)(uintptr_t)(in_flags + k), epoch, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+                memop_failed = true;
+        }
+        if (e == cudaSuccess && !memop_failed) {
             gd::Gate gate{in_flags, out_counts, c->gate_err_dev, epoch, chunk_tiles};
             rc = gd::decode_fwd_gated(g, model, c->w_dev, c->x_dev, prob_host ? c->prob_dev : nullptr,
                                       hard_host ? c->hard_dev : nullptr, B, c->st[0], gate);
+            launched = rc == GD_OK;
         }
-        bool memop_failed = false;
-        if (e == cudaSuccess && rc == GD_OK) {
-            for (int k = 0; k < n_chunks && e == cudaSuccess; ++k) {
-                const int64_t b0 = (int64_t)k * per, nb = std::min<int64_t>(per, B - b0);
-                e = cudaMemcpyAsync(c->x_dev + b0 * g->N, x_host + b0 * g->N, (size_t)nb * g->N * sizeof(float),
-                                    cudaMemcpyHostToDevice, c->st[1]);
-                if (e == cudaSuccess &&
-                    c->write32((CUstream)c->st[1], (CUdeviceptr)(uintptr_t)(in_flags + k), epoch, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
-                    memop_failed = true;
-                if (memop_failed) break;
-            }
-            if (e == cudaSuccess && !memop_failed) e = cudaStreamWaitEvent(c->st[2], c->ev_ready, 0);
+        if (launched) {
+            e = cudaStreamWaitEvent(c->st[2], c->ev_ready, 0);
             for (int k = 0; k < n_chunks && e == cudaSuccess && !memop_failed; ++k) {
                 const int64_t b0 = (int64_t)k * per, nb = std::min<int64_t>(per, B - b0);
                 const unsigned int tiles_k = (unsigned int)((nb + tile - 1) / tile);
                 if (c->wait32((CUstream)c->st[2], (CUdeviceptr)(uintptr_t)(out_counts + k), tiles_k, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
-                    memop_failed = true;
+                    memop_failed = true;      // the kernel still drains (all its flags are queued); results are redone below
                     break;
                 }
                 if (prob_host)
@@ -172,15 +175,6 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
                     e = cudaMemcpyAsync(hard_host + b0 * g->V, c->hard_dev + b0 * g->V, (size_t)nb * g->V,
                                         cudaMemcpyDeviceToHost, c->st[2]);
             }
-        }
-        if (memop_failed) {
-            // a stream memory operation was refused after the kernel was queued: release every gate from the host side so
-            // the kernel drains, then copy the results back the plain way
-            cudaStreamSynchronize(c->st[1]);
-            std::vector<unsigned int> open(gd::kMaxGateChunks, epoch);
-            cudaMemcpyAsync(in_flags, open.data(), gd::kMaxGateChunks * sizeof(unsigned int), cudaMemcpyHostToDevice, c->st[1]);
-            cudaStreamSynchronize(c->st[1]);
-            c->memops = 0;
         }
         cudaError_t s0 = cudaStreamSynchronize(c->st[0]);
         cudaError_t s1 = cudaStreamSynchronize(c->st[1]);

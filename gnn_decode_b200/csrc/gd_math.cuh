@@ -290,13 +290,17 @@ __device__ __forceinline__ float cubic_tab_bound(const float* w, int h, float st
 }
 // Build the table with the whole CTA (contains __syncthreads()).  W: the MLP staged (pre-scaled) in shared
 // memory; F: n + 6 floats of shared scratch.  Returns this thread's max |f| over the nodes it touched.
+// TWO_IN: W is a 2 -> h -> 1 MLP and the table is its section f(., x1v) at a fixed second input.
+template <bool TWO_IN = false>
 __device__ __forceinline__ float cubic_tab_build(const MlpSmem& W, int hp, float Rdom, int n, float4* dst, float* F,
-                                                 int tid, int nthr) {
+                                                 int tid, int nthr, float x1v = 0.f) {
     const float step = 2.0f * Rdom / (float)n;
     for (int j0 = tid * 2; j0 < n + 5; j0 += nthr * 2) {          // nodes -2 .. n+2, two per thread per pass
         const float xa[2] = {-Rdom + step * (float)(j0 - 2), -Rdom + step * (float)(j0 - 1)};
+        const float xb[2] = {x1v, x1v};
         float oa[2];
-        mlp_softplus_x2<2, false, 2>(W, hp, xa, xa, oa);
+        if constexpr (TWO_IN) mlp_softplus_x2<2, true, 2>(W, hp, xa, xb, oa);
+        else mlp_softplus_x2<2, false, 2>(W, hp, xa, xa, oa);
         F[j0] = oa[0];
         F[j0 + 1] = oa[1];
     }

@@ -97,6 +97,13 @@ class TannerGraph(object):
         _cabi.check(_cabi.lib().gd_decode_launch_info(self._h, ct.byref(model), int(B), ct.byref(info)))
         return {k: getattr(info, k) for k, _ in info._fields_}
 
+    def tables_info(self, model, B):
+        """(check-phase intervals, read-out intervals, variable-phase intervals, variable-phase table slots) the resident
+        decoder_v2_4 kernel plans; 0 = direct evaluation (gd_decode_tables_info)."""
+        out = (ct.c_int32 * 4)()
+        _cabi.check(_cabi.lib().gd_decode_tables_info(self._h, ct.byref(model), int(B), out))
+        return tuple(int(v) for v in out)
+
 
 # ---- resolving the graph behind a PyG-batched edge_index ---------------------------------------
 _batched_cache = {}

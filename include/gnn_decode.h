@@ -228,6 +228,10 @@ typedef struct gd_launch_info {
     int32_t n_tiles;
 } gd_launch_info;
 int gd_decode_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out);
+/* Cubic tables the resident GD_PROG_V2_4 kernel plans for (graph, model, B): out4 = {check-phase intervals, read-out
+ * intervals, variable-phase intervals per table, variable-phase table slots}; 0 = that MLP is evaluated directly (the
+ * kernel additionally checks an interpolation-error bound from the weights at launch and falls back if it fails). */
+int gd_decode_tables_info(const gd_graph* g, const gd_model* model, int64_t B, int32_t* out4);
 /* Optional one-time geometry autotuning for (graph, model, B): times the best `max_candidates` (0 = 24) geometries of the
  * planner's model with the caller's own weights and batch (outputs go to a scratch buffer) and remembers the fastest;
  * later gd_decode_fwd / gd_decode_host calls with the same (model, B) use it.  Synchronises the stream.  Only the

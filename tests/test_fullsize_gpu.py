@@ -87,3 +87,54 @@ def test_hgp_streamed_full_batch_properties():
     assert int(w1.sum()) > 0 and int(cnt[0]) == 0                            # single errors: syndrome always cleared
     total = count_failures(g, err, hard)
     assert int(total[0]) < 0.10 * B                                          # sanity: plain BP well below threshold
+
+
+def test_variable_phase_tables_and_their_fallbacks(monkeypatch):
+    """decoder_v2_4's variable-phase MLP is read from per-prior cubic tables when every variable of a syndrome carries the
+    same prior.  Every way out of that fast path must give the reference's numbers too:
+    (a) uniform priors, few distinct values: tables (vs the oracle, and vs the direct kernel GD_NO_VTAB=1);
+    (b) a different prior on every variable: nothing is tabulated -> bit-identical to the direct kernel;
+    (c) more distinct per-syndrome priors than table slots: some syndromes tabulated, the rest direct;
+    (d) a mix of uniform and non-uniform syndromes in the same tiles;
+    and the table look-up may not make a result depend on which syndromes share a tile (batch slices bit-identical)."""
+    pcm = codes.rotated_surface_pcm(5)
+    g = TannerGraph.from_pcm(pcm, DEV)
+    V = g.V
+    dec, w = _v2_4(15)
+    B = 20000
+    info = g.tables_info(dec.gd_model(), B)
+    assert info[2] > 0 and info[3] >= 10, info            # the reference's list of 10 error rates fits the table slots
+    x, _ = sample_syndromes(g, B, [0.01 * k for k in range(1, 11)], noise=1, seed=5)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    cases = {"uniform10": x.clone()}
+    xb = x.clone()
+    xb[:, :V] = 2.0 + 3.0 * torch.rand(B, V, device=DEV, generator=gen)
+    cases["per_variable"] = xb
+    xc = x.clone()
+    xc[:, :V] = (2.0 + 3.0 * torch.rand(B, 1, device=DEV, generator=gen)).expand(B, V)      # B distinct per-syndrome priors
+    cases["many_distinct"] = xc
+    xd = x.clone()
+    odd = torch.arange(B, device=DEV) % 3 == 1
+    xd[odd, 7] += 0.25                                                                       # one variable off: not uniform
+    cases["mixed"] = xd
+    idx = torch.from_numpy(np.random.RandomState(1).choice(B, 40, replace=False)).to(DEV)
+    out = {}
+    for name, xx in cases.items():
+        prob, logit, hard = dec.decode(xx, graph=g, return_logits=True, return_hard=True)
+        out[name] = (prob, logit, hard)
+        _subset_vs_oracle("v2_4", pcm, xx, logit, w, 15, idx, RTOL)
+        if name in ("uniform10", "mixed"):              # few distinct priors: slices are bit-identical (table content depends on the prior only)
+            for lo, n in ((0, 8), (777, 1234), (B - 501, 501)):
+                assert torch.equal(dec.decode(xx[lo:lo + n].contiguous(), graph=g), prob[lo:lo + n]), (name, lo)
+    monkeypatch.setenv("GD_NO_VTAB", "1")
+    assert g.tables_info(dec.gd_model(), B)[2] == 0
+    for name, xx in cases.items():
+        prob, logit, hard = out[name]
+        p2, l2, h2 = dec.decode(xx, graph=g, return_logits=True, return_hard=True)
+        if name == "per_variable":
+            assert torch.equal(prob, p2) and torch.equal(hard, h2)
+        else:
+            scale = 1.0 + l2.pow(2).mean().sqrt().item()
+            assert (logit - l2).abs().max().item() <= 0.05 * RTOL * scale, name      # tables vs direct: 20x inside the parity bar
+            decided = l2.abs() > 1e-3
+            assert torch.equal(hard[decided], h2[decided]), name
