@@ -31,7 +31,7 @@ __device__ __forceinline__ void gate_wait(const unsigned int* flag, unsigned int
         unsigned int v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int)(v - epoch) >= 0) break;
-        if (++spins > (1ll << 24)) { *err = 1; break; }   // seconds: the copy never came; do not hang the GPU
+        if (++spins > (1ll << 22)) { *err = 1; break; }   // seconds: the copy never came; do not hang the GPU
         __nanosleep(100);
     }
 }
