@@ -368,16 +368,21 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                 __syncthreads();
                 if (tid == 0) {
                     int cnt = old_cnt;
-                    for (int q = 0; q < tile; ++q) {
+                    bool overflow = false;
+                    for (int q = 0; q < tile && !overflow; ++q) {
                         if (vt_lane[q] < 0) continue;
                         const unsigned int pb = __float_as_uint(lane_prior[q]);
                         int k = 0;
                         while (k < cnt && __float_as_uint(vt_vals[k]) != pb) ++k;
                         if (k == cnt) {
                             if (cnt < p.vtab_k) vt_vals[cnt++] = lane_prior[q];
-                            else k = -1;
+                            else overflow = true;
                         }
                         vt_lane[q] = k;
+                    }
+                    if (overflow) {       // more distinct priors than slots: the whole tile goes direct (warps would diverge otherwise)
+                        cnt = old_cnt;
+                        for (int q = 0; q < tile; ++q) vt_lane[q] = -1;
                     }
                     *vt_cnt = cnt;
                 }
@@ -789,16 +794,26 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
         // 12 tables x 512 intervals (96 KB): the reference draws p from a list of 10 (decoder_v2_4.py:187).  Measured on B200,
         // rotated d=5, B=65536, 10 distinct priors: direct 3.43 ms; 4 x 1024 3.68 (6 of 10 priors overflow the slots);
         // 12 x 384 1.21; 10..12 x 512..640 0.81 ms.  With 4 distinct priors 4 x 1024 takes 0.69 ms.
-        int vn = en ? atoi(en) : 512, vk = ek ? atoi(ek) : 12;
+        int vn = en ? atoi(en) : 512;
         if (vn < 64 || vn > 4096) vn = 512;
-        if (vk < 1 || vk > 16) vk = 12;
-        const int vbytes = vk * vn * 16 + 16 + 16 * 4 + 128 * 4;
         const int64_t per_syn_est = ((int64_t)N + maxvc + 2 * E64) * 4;
-        // only where it leaves room for tiles of >= 16 syndromes (larger codes keep the direct variable phase)
-        if (fits16 && (smem_max - align_up(off + vbytes + tab_bytes, 128)) / per_syn_est >= 16) {
-            p.vtab_n = vn; p.vtab_k = vk;
-            p.off_vtab = off; off += vk * vn * 16;
-            p.off_vmeta = off; off += 16 + 16 * 4 + 128 * 4;
+        const int64_t t_without = fits16 ? (smem_max - align_up(off + tab_bytes, 128)) / per_syn_est / 8 * 8 : 0;
+        // slots: as many (12, 8, 6) as still leave tiles as large as the code gets anyway, up to 16 syndromes (rotated d = 5 / 7
+        // and toric L = 5 take 12; rotated d = 11 takes 8, toric L = 11 takes 6).  A tile whose syndromes carry more distinct
+        // priors than there are slots takes the direct evaluation as a whole (no mixed warps).
+        static const int ks[] = {12, 8, 6};
+        for (int ki = 0; ki < 3 && t_without >= 8; ++ki) {
+            int vk = ek ? atoi(ek) : ks[ki];
+            if (vk < 1 || vk > 16) vk = ks[ki];
+            const int vbytes = vk * vn * 16 + 16 + 16 * 4 + 128 * 4;
+            const int64_t t_with = (smem_max - align_up(off + vbytes + tab_bytes, 128)) / per_syn_est / 8 * 8;
+            if (t_with >= 8 && t_with >= (t_without < 16 ? t_without : 16)) {
+                p.vtab_n = vn; p.vtab_k = vk;
+                p.off_vtab = off; off += vk * vn * 16;
+                p.off_vmeta = off; off += 16 + 16 * 4 + 128 * 4;
+                break;
+            }
+            if (ek) break;
         }
     }
     // resident layout first
