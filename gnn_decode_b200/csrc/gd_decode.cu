@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     int* const vt_cnt = reinterpret_cast<int*>(smem + p.off_vmeta);               // tables built so far
     int* const vt_lane = reinterpret_cast<int*>(smem + p.off_vmeta + 16 + 16 * 4); // [tile] table of lane s (-1: direct)
     if constexpr (PROG == GD_PROG_V2_4) {
-        if (p.vtab_n > 0 && !p.stash && use_ctab && tile <= 128 && E * tile >= p.vtab_n + 8) {
+        if (p.vtab_n > 0 && use_ctab && tile <= 128 && E * tile >= p.vtab_n + 8) {
             float m4 = 0.f;
             for (int k = 0; k < p.hid; ++k) {
                 float a = __ldg(p.weights + 2 * k);                       // w1[k][0]: the ext input
