@@ -362,17 +362,23 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                     const float pv = xrow[0];
                     bool uni = s < nvalid;
                     for (int v = 1; v < V; ++v) uni = uni && (__float_as_uint(xrow[v]) == __float_as_uint(pv));
+                    int k = -1;                                           // -1: direct (non-uniform priors / padding lane)
+                    if (uni) {                                            // every lane searches the cache itself, in parallel
+                        k = 0;
+                        while (k < old_cnt && __float_as_uint(vt_vals[k]) != __float_as_uint(pv)) ++k;
+                        if (k == old_cnt) k = -2;                         // -2: uniform, but its prior has no table yet
+                    }
                     lane_prior[s] = pv;
-                    vt_lane[s] = uni ? 0 : -1;
+                    vt_lane[s] = k;
                 }
                 __syncthreads();
-                if (tid == 0) {
+                if (tid == 0) {                                           // only priors met for the first time are inserted serially
                     int cnt = old_cnt;
                     bool overflow = false;
                     for (int q = 0; q < tile && !overflow; ++q) {
-                        if (vt_lane[q] < 0) continue;
+                        if (vt_lane[q] != -2) continue;
                         const unsigned int pb = __float_as_uint(lane_prior[q]);
-                        int k = 0;
+                        int k = old_cnt;
                         while (k < cnt && __float_as_uint(vt_vals[k]) != pb) ++k;
                         if (k == cnt) {
                             if (cnt < p.vtab_k) vt_vals[cnt++] = lane_prior[q];
