@@ -69,3 +69,43 @@ def test_pcm_text_round_trip(tmp_path, codes_npz):
     assert np.array_equal(codes.read_pcm_txt(str(f)), pcm)
     assert np.array_equal(codes.read_pcm_txt(str(f)), codes_npz["bch_63_45_H"])
     assert np.array_equal(codes.read_pcm_txt(str(f), transpose=True), pcm.T)
+
+
+def test_hgp_1600_64_logicals():
+    """Logical operators of the [[1600,64]] hypergraph-product code (the input of gd_eval_failures for BASELINE config 5):
+    2k = 128 rows that commute with every check, are independent of the stabilizers, and pair up symplectically with full
+    rank.  The reference's H_Prep (error_generate.py:145-248) is O(n^3) Python; the bit-packed incremental elimination
+    here takes about a second."""
+    import time
+    pcm = codes.hgp_pcm()
+    n = 1600
+    Hz, Hx = pcm[:768, :n], pcm[768:, n:]
+    t0 = time.time()
+    lg = codes.css_logicals(Hz, Hx)
+    assert time.time() - t0 < 30
+    assert lg.shape == (128, 2 * n)
+    lz, lx = lg[:64, :n], lg[64:, n:]
+    assert not lg[:64, n:].any() and not lg[64:, :n].any()
+    assert not ((Hx.astype(int) @ lz.T.astype(int)) % 2).any()             # logical Z commutes with the X checks
+    assert not ((Hz.astype(int) @ lx.T.astype(int)) % 2).any()
+    assert codes.gf2_rank(np.vstack([Hz, lz])) == codes.gf2_rank(Hz) + 64  # outside the stabilizer group
+    assert codes.gf2_rank(np.vstack([Hx, lx])) == codes.gf2_rank(Hx) + 64
+    assert codes.gf2_rank((lz.astype(int) @ lx.T.astype(int)) % 2) == 64   # 64 anticommuting pairs
+
+
+def test_complete_basis_matches_rank_definition():
+    """_complete_basis keeps exactly the rows that raise the rank of [sub; rows kept so far], in row order."""
+    rng = np.random.RandomState(3)
+    for _ in range(25):
+        c = rng.randint(2, 70)
+        sub = (rng.rand(rng.randint(0, 6), c) < 0.4).astype(np.uint8)
+        full = (rng.rand(rng.randint(1, 12), c) < 0.4).astype(np.uint8)
+        got = codes._complete_basis(sub, full)
+        cur, want = sub.reshape(-1, c), []
+        for v in full:
+            cand = np.vstack([cur, v[None]])
+            if codes.gf2_rank(cand) > (codes.gf2_rank(cur) if cur.size else 0):
+                want.append(v)
+                cur = cand
+        want = np.array(want, dtype=np.uint8).reshape(-1, c)
+        assert got.shape == want.shape and (got == want).all()
