@@ -52,6 +52,7 @@ _SIGNATURES = {
     "gd_sample": (C.c_int, [_p, C.c_int32, _p, C.c_int32, C.c_uint64, C.c_uint64, _p, _p, C.c_int64, _p]),
     "gd_eval_failures": (C.c_int, [_p, _p, C.c_int32, _p, _p, C.c_int64, _p, _p]),
     "gd_microbench": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.POINTER(C.c_double)]),
+    "gd_set_option": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32]),
     "gd_stash_floats": (C.c_int64, [_p, C.POINTER(GdModel), C.c_int64]),
     "gd_decode_fwd_train": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, _p, C.c_int64, _p]),
     "gd_bwd_workspace_floats": (C.c_int64, [_p, C.POINTER(GdModel), C.c_int64]),

@@ -62,6 +62,7 @@ struct gd_graph {
     float* gstate;
     size_t gstate_bytes;
     void* host_ctx;             // gd_decode_host pipeline state (see gd_host.cu)
+    void* lean_ctx;             // check-owner table kernel: per-(R) metadata, workspace pool (see gd_lean.cu)
     // geometries measured by gd_decode_autotune (guarded by mu): key = {program, hidden, iters, flags, B}
     struct TunedGeom { int32_t program, hidden, iters, flags; int64_t B; int32_t tile, R, eb; };
     std::vector<TunedGeom> tuned;

@@ -23,6 +23,8 @@
 #include "gd_common.cuh"
 #include "gd_math.cuh"
 #include "gd_decode.cuh"
+#include "gd_lean.cuh"
+#include "gd_options.cuh"
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -58,6 +60,11 @@ struct DecodeParams {
     int* gate_err;
     unsigned int gate_epoch;
     int gate_chunk_tiles;
+    // deferred pass behind the check-owner table kernel (gd_lean.cu): decode only the listed syndromes (*defer_count > 0),
+    // the whole batch (-1) or nothing (0); all NULL otherwise
+    const int* defer_count;
+    const int* defer_idx;
+    uint32_t* hard_bits;    // optional packed hard decisions [B][ceil(V/32)]
 };
 
 // ---------------- PTX helpers: mbarrier + bulk async copy (TMA 1-D) ----------------
@@ -140,6 +147,18 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     float* t_st = reinterpret_cast<float*>(smem + p.off_t);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int s = tid % tile, r = tid / tile;
+    long long B_eff = p.B;
+    int n_tiles = p.n_tiles;
+    const int* didx = nullptr;
+    if (p.defer_count) {
+        const int cnt = *p.defer_count;
+        if (cnt == 0) return;                                  // nothing was deferred: no prologue either
+        if (cnt > 0) {
+            B_eff = cnt;
+            didx = p.defer_idx;
+            n_tiles = (cnt + tile - 1) / tile;
+        }
+    }
 
     // ---- prologue: tables and (pre-scaled) weights into shared memory ----
     Tables tb;
@@ -294,7 +313,8 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     int* const vt_cnt = reinterpret_cast<int*>(smem + p.off_vmeta);               // tables built so far
     int* const vt_lane = reinterpret_cast<int*>(smem + p.off_vmeta + 16 + 16 * 4); // [tile] table of lane s (-1: direct)
     if constexpr (PROG == GD_PROG_V2_4) {
-        if (p.vtab_n > 0 && use_ctab && tile <= 128 && E * tile >= p.vtab_n + 8) {
+        // (a deferred LIST is evaluated directly, per item: its results must not depend on what else was deferred)
+        if (p.vtab_n > 0 && use_ctab && tile <= 128 && E * tile >= p.vtab_n + 8 && !didx) {
             float m4 = 0.f;
             for (int k = 0; k < p.hid; ++k) {
                 float a = __ldg(p.weights + 2 * k);                       // w1[k][0]: the ext input
@@ -303,20 +323,11 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             }
             const float hmax = sqrtf(sqrtf(2e-7f * 384.0f / (0.125f * fmaxf(m4, 1e-20f))));
             vtab_R = fminf(0.5f * (float)p.vtab_n * hmax, 1e4f);
-#ifdef GD_VTAB_DEBUG
-            if (p.B == 4242 && blockIdx.x == 0 && tid == 0) printf("vtab: m4=%g hmax=%g R_budget=%g\n", m4, hmax, vtab_R);
-#endif
             use_vtab = vtab_R >= 0.5f;                                    // a narrower domain would mostly fall back
             if (use_rtab && rtab_R > 0.f) vtab_R = fminf(vtab_R, rtab_R * (float)(p.vdirect ? 1 : 8));   // |m| <= rtab_R: no need to go wider
             vtab_inv_h = 0.5f * (float)p.vtab_n / vtab_R;
             if (tid == 0) *vt_cnt = 0;
         }
-#ifdef GD_VTAB_DEBUG
-        if (p.B == 4242 && blockIdx.x == 0 && tid == 0) {
-            vt_cnt[1] = vt_cnt[2] = 0;
-            printf("vtab: n=%d k=%d use=%d R=%f rtab_R=%f use_rtab=%d use_ctab=%d\n", p.vtab_n, p.vtab_k, (int)use_vtab, vtab_R, rtab_R, (int)use_rtab, (int)use_ctab);
-        }
-#endif
     }
     fence_proxy_async();   // the prologue used the slab region as generic-proxy scratch; the bulk copies (async proxy) come next
     if (tid == 0) {
@@ -328,12 +339,12 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     uint32_t parity = 0;
     const int n_iter = (E + R - 1) / R;  // edges per thread (interleaved ownership e = r + i*R)
 
-    for (int tix = blockIdx.x; tix < p.n_tiles; tix += gridDim.x) {
+    for (int tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
         const long long s0 = (long long)tix * tile;
-        const int nvalid = (int)min((long long)tile, p.B - s0);
+        const int nvalid = (int)min((long long)tile, B_eff - s0);
         const float* xg = p.x + s0 * N;
         const int n_in = nvalid * N;
-        const uint32_t bulk_bytes = ((uint32_t)n_in * 4u) & ~15u;
+        const uint32_t bulk_bytes = didx ? 0u : ((uint32_t)n_in * 4u) & ~15u;
         if (p.gate_in) {   // gated launch: this tile's chunk may still be on its way from the host
             if (tid == 0) gate_wait(p.gate_in + tix / p.gate_chunk_tiles, p.gate_epoch, p.gate_err);
             __syncthreads();
@@ -344,7 +355,14 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             mbar_arrive_expect_tx(bar, bulk_bytes);
             if (bulk_bytes) bulk_g2s(xs, xg, bulk_bytes, bar);
         }
-        for (int i = (int)(bulk_bytes >> 2) + tid; i < tile * N; i += nthr) xs[i] = i < n_in ? __ldcg(xg + i) : 0.f;
+        if (didx) {                                            // listed syndromes: gather their rows
+            for (int i = tid; i < tile * N; i += nthr) {
+                const int q = i / N;
+                xs[i] = q < nvalid ? __ldcg(p.x + (long long)__ldg(didx + s0 + q) * N + (i - q * N)) : 0.f;
+            }
+        } else {
+            for (int i = (int)(bulk_bytes >> 2) + tid; i < tile * N; i += nthr) xs[i] = i < n_in ? __ldcg(xg + i) : 0.f;
+        }
         for (int i = 0; i < n_iter; ++i) {
             const int e = r + i * R;
             if (e < E) m_st[(size_t)e * tile + s] = 0.f;
@@ -467,7 +485,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             {
                 const int total = nvalid * V;
                 const long long g0 = out_off + s0 * V;  // s0 * V is a multiple of 8 elements: tile % 8 == 0
-                const bool vec_ok = (g0 & 3) == 0;
+                const bool vec_ok = (g0 & 3) == 0 && !didx;
                 constexpr bool kClamp = (PROG == GD_PROG_CGNNI || PROG == GD_PROG_BP_CLASSICAL || PROG == GD_PROG_GRU_CA);
                 for (int i = tid * 4; i < total; i += nthr * 4) {
                     float l[4], pr[4];
@@ -486,10 +504,26 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                                 make_uchar4(pr[0] > 0.5f, pr[1] > 0.5f, pr[2] > 0.5f, pr[3] > 0.5f);
                     } else {
                         for (int j = 0; j < n; ++j) {
-                            if (p.prob) p.prob[g0 + i + j] = pr[j];
-                            if (p.logit) p.logit[g0 + i + j] = l[j];
-                            if (p.hard) p.hard[g0 + i + j] = pr[j] > 0.5f;
+                            long long o = g0 + i + j;
+                            if (didx) {                        // scatter back to the listed rows
+                                const int q = (i + j) / V;
+                                o = out_off + (long long)__ldg(didx + s0 + q) * V + (i + j - q * V);
+                            }
+                            if (p.prob) p.prob[o] = pr[j];
+                            if (p.logit) p.logit[o] = l[j];
+                            if (p.hard) p.hard[o] = pr[j] > 0.5f;
                         }
+                    }
+                }
+                if (p.hard_bits) {
+                    const int vw = (V + 31) >> 5;
+                    for (int i = tid; i < nvalid * vw; i += nthr) {
+                        const int q = i / vw, w = i - q * vw;
+                        uint32_t word = 0u;
+                        for (int b = 0; b < 32 && w * 32 + b < V; ++b)
+                            word |= (sigmoid_neg(stage[q * V + w * 32 + b]) > 0.5f ? 1u : 0u) << b;
+                        const long long row = didx ? (long long)__ldg(didx + s0 + q) : s0 + q;
+                        p.hard_bits[row * vw + w] = word;     // (single read-out only: not combined with GD_FLAG_ALL_ITERS)
                     }
                 }
             }
@@ -551,9 +585,6 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         for (int j = 0; j < kEB; ++j)
                             if (vt_ok || fabsf(x0[j]) <= vtab_R) o[j] = cubic_tab_eval(vtab, x0[j]);
                     }
-#ifdef GD_VTAB_DEBUG
-                    if (p.B == 4242 && blockIdx.x == 0) atomicAdd(reinterpret_cast<int*>(smem + p.off_vmeta) + (vt_ok ? 1 : 2), 1);
-#endif
 #pragma unroll
                     for (int j = 0; j < kEB; ++j)
                         if (ee[j] < E) {
@@ -705,10 +736,6 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             }
         }
         if (!(kGRU && p.all_iters)) emit(0);
-#ifdef GD_VTAB_DEBUG
-        if (p.B == 4242 && blockIdx.x == 0 && tid == 0)
-            printf("vtab tile %d: tables=%d groups table=%d direct=%d lane0=%d\n", tix, vt_cnt[0], vt_cnt[1], vt_cnt[2], vt_lane[0]);
-#endif
         if (p.gate_out) {   // gated launch: publish the tile so the chunk's device->host copy can go
             __syncthreads();
             if (tid == 0) {
@@ -765,8 +792,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     // CTAs per SM: two half-size CTAs let one CTA's light phases (node sums, table look-ups, barriers) overlap the
     // other's MUFU-bound variable phase
     {
-        const char* ec = getenv("GD_CPS");
-        out->cps = ec ? atoi(ec) : 1;
+        out->cps = (int)opt_int(OPT_CPS, 1);
         if (out->cps < 1 || out->cps > 4) out->cps = 1;
     }
     const int smem_max = out->cps == 1 ? g->max_smem_optin : (g->max_smem_sm - 1024 * out->cps) / out->cps;
@@ -774,19 +800,17 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     int off = 16;                                  // mbarrier
     // ReLU programs with h < 32: piecewise-linear tables (3 * NPAD floats per MLP) instead of the SoA weight rows
     const bool relu_prog = m->program == GD_PROG_CGNNI || m->program == GD_PROG_QGNNI || gru;
-    out->npad = (relu_prog && hid < 32 && !getenv("GD_NO_PWL")) ? (hid < 16 ? 16 : 32) : 0;
+    out->npad = (relu_prog && hid < 32 && !opt_on(OPT_NO_PWL)) ? (hid < 16 ? 16 : 32) : 0;
     p.wslot = 4 * hp > 3 * out->npad ? 4 * hp : 3 * out->npad;
     p.off_w = off; off += n_slots * p.wslot * 4 + (gru ? 24 * 4 : 0); off = align_up(off, 16);
-    if (m->program == GD_PROG_V2_4 && !getenv("GD_NO_CTAB") && !getenv("GD_NO_RTAB")) {
-        const char* en = getenv("GD_RTAB_N");
-        p.rtab_n = en ? atoi(en) : 2048;
+    if (m->program == GD_PROG_V2_4 && !opt_on(OPT_NO_CTAB) && !opt_on(OPT_NO_RTAB)) {
+        p.rtab_n = (int)opt_int(OPT_RTAB_N, 2048);
         if (p.rtab_n < 16 || p.rtab_n > 8192) p.rtab_n = 2048;
         p.off_rtab = off;
         off += p.rtab_n * 16;
     }
-    if (m->program == GD_PROG_V2_4 && !getenv("GD_NO_CTAB")) {
-        const char* en = getenv("GD_CTAB_N");
-        p.ctab_n = en ? atoi(en) : 512;
+    if (m->program == GD_PROG_V2_4 && !opt_on(OPT_NO_CTAB)) {
+        p.ctab_n = (int)opt_int(OPT_CTAB_N, 512);
         if (p.ctab_n < 16 || p.ctab_n > 4096) p.ctab_n = 512;
         p.ctab_R = (float)(g->max_chk_deg > 1 ? g->max_chk_deg - 1 : 1);
         p.off_ctab = off;
@@ -794,13 +818,12 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     }
     const bool fits16 = E64 < 65536 && V < 65535 && C < 65535;
     const int tab_bytes = (int)(9 * E64 + V + C + 2) * 2;
-    if (p.ctab_n > 0 && !getenv("GD_NO_VTAB")) {
-        const char* en = getenv("GD_VTAB_N");
-        const char* ek = getenv("GD_VTAB_K");
+    if (p.ctab_n > 0 && !opt_on(OPT_NO_VTAB)) {
+        const long long ek = opt_int(OPT_VTAB_K, 0);
         // 12 tables x 512 intervals (96 KB): the reference draws p from a list of 10 (decoder_v2_4.py:187).  Measured on B200,
         // rotated d=5, B=65536, 10 distinct priors: direct 3.43 ms; 4 x 1024 3.68 (6 of 10 priors overflow the slots);
         // 12 x 384 1.21; 10..12 x 512..640 0.81 ms.  With 4 distinct priors 4 x 1024 takes 0.69 ms.
-        int vn = en ? atoi(en) : 512;
+        int vn = (int)opt_int(OPT_VTAB_N, 512);
         if (vn < 64 || vn > 4096) vn = 512;
         const int64_t per_syn_est = ((int64_t)N + maxvc + 2 * E64) * 4;
         const int64_t t_without = fits16 ? (smem_max - align_up(off + tab_bytes, 128)) / per_syn_est / 8 * 8 : 0;
@@ -809,7 +832,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
         // priors than there are slots takes the direct evaluation as a whole (no mixed warps).
         static const int ks[] = {12, 8, 6};
         for (int ki = 0; ki < 3 && t_without >= 8; ++ki) {
-            int vk = ek ? atoi(ek) : ks[ki];
+            int vk = ek > 0 ? (int)ek : ks[ki];
             if (vk < 1 || vk > 16) vk = ks[ki];
             const int vbytes = vk * vn * 16 + 16 + 16 * 4 + 128 * 4;
             const int64_t t_with = (smem_max - align_up(off + vbytes + tab_bytes, 128)) / per_syn_est / 8 * 8;
@@ -819,7 +842,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
                 p.off_vmeta = off; off += 16 + 16 * 4 + 128 * 4;
                 break;
             }
-            if (ek) break;
+            if (ek > 0) break;
         }
     }
     // resident layout first
@@ -839,18 +862,16 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
             static const int wx[] = {32, 128, 256, 384, 512, 640, 896, 1024};
             static const double wy[] = {0.20, 0.62, 0.80, 0.90, 0.96, 0.985, 1.0, 1.0};
             double best = -1.0;
-            const char* et = getenv("GD_TILE");
-            const char* er = getenv("GD_R");
-            const char* eb = getenv("GD_EB");
+            const long long et = opt_int(OPT_TILE, 0), er = opt_int(OPT_R, 0), eb = opt_int(OPT_EB, 0);
             for (int t = 8; t <= tmax && t <= thr_max; t += 8) {
-                if (et && atoi(et) != t) continue;
+                if (et > 0 && et != t) continue;
                 if (force && force->tile != t) continue;
                 if (t < 32 && (32 % t)) continue;
                 const int64_t n_t = (B + t - 1) / t;
                 const int64_t rounds = (n_t + slots - 1) / slots;
                 const double eff_round = (double)B / ((double)rounds * (double)slots * t);
                 for (int r = 1; r * t <= thr_max && r <= E; ++r) {
-                    if (er && atoi(er) != r) continue;
+                    if (er > 0 && er != r) continue;
                     if (force && force->R != r) continue;
                     const int thr = r * t;
                     if (thr % 32) continue;
@@ -865,7 +886,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
                     const double node_cost = (double)((V + r - 1) / r) * g->max_var_deg + (double)((Cn + r - 1) / r) * g->max_chk_deg;
                     const double ideal = E * c_edge + 2.0 * E * c_ld;
                     for (int ebk = 4; ebk >= 2; ebk -= 2) {
-                        if (eb && atoi(eb) != ebk) continue;
+                        if (eb > 0 && eb != ebk) continue;
                         if (force && force->eb != ebk) continue;
                         const int blocks = (n_iter + ebk - 1) / ebk;
                         const double per_thread = (bp ? n_iter : blocks * ebk) * c_edge + node_cost * c_ld;
@@ -889,7 +910,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
             p.scratch_bytes = o2 - p.off_x;
         }
     }
-    if (!resident || getenv("GD_FORCE_STREAMED")) {
+    if (!resident || opt_on(OPT_FORCE_STREAMED)) {
         out->resident = 0;
         return GD_OK;           // caller takes the streamed kernel (gd_streamed.cu)
     }
@@ -908,8 +929,7 @@ static int launch_decode(const DecodePlan& pl, cudaStream_t st) {
     if constexpr (PROG == GD_PROG_V2_4) {
         // NPOLY: how many of every 4 hidden-unit pairs take the FMA-pipe polynomial lg2 (-1 = scalar MUFU loop).
         // Measured on B200 (profiles/r01_npoly_sweep.txt): 2 is best (8.70 vs 6.84 M syndromes/s for -1).
-        const char* en = getenv("GD_NPOLY");
-        const int np = en ? atoi(en) : 2;
+        const int np = (int)opt_int(OPT_NPOLY, 2);
 #define GD_PICK(MT, EBV)                                                                               \
         (np < 0 ? decode_kernel<PROG, MT, EBV, -1> : np == 3 ? decode_kernel<PROG, MT, EBV, 3> : decode_kernel<PROG, MT, EBV, 2>)
         if (pl.threads > 512 || pl.cps > 1) k = pl.eb == 2 ? GD_PICK(1024, 2) : GD_PICK(1024, 4);   // the <= 64-register build
@@ -940,6 +960,7 @@ extern "C" int gd_decode_launch_info(const gd_graph* g, const gd_model* model, i
     int rc = gd::plan_decode(g, model, B, &pl);
     if (rc != GD_OK) return rc;
     if (!pl.resident) return gd::streamed_launch_info(g, model, B, out);
+    if (gd::lean_launch_info(g, model, B, out)) return GD_OK;       // check-owner table kernel (decoder_v2_4, surface / toric codes)
     if (gd::light_launch_info(g, model, B, out)) return GD_OK;      // node-owner kernel for the light programs
     out->tile = pl.p.tile; out->threads = pl.threads; out->grid = pl.grid; out->smem_bytes = pl.smem;
     out->resident = pl.resident; out->n_tiles = pl.p.n_tiles;
@@ -961,12 +982,14 @@ extern "C" int gd_decode_tables_info(const gd_graph* g, const gd_model* model, i
 
 static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
                            float* prob_dev, float* logit_dev, uint8_t* hard_dev, float* stash_dev, int64_t B,
-                           void* stream, const gd::Gate* gate = nullptr);
+                           void* stream, const gd::Gate* gate = nullptr, const gd::DeferList* dl = nullptr,
+                           uint32_t* hard_bits_dev = nullptr);
 
 bool gd::gated_plan(const gd_graph* g, const gd_model* model, int64_t B, int* tile, int* n_tiles) {
     gd::DecodePlan pl;
     gd_launch_info probe;
     if (model->flags != 0 || gd::plan_decode(g, model, B, &pl) != GD_OK || !pl.resident) return false;
+    if (gd::lean_launch_info(g, model, B, &probe)) return false;   // the check-owner table kernel is launched per chunk
     if (gd::light_launch_info(g, model, B, &probe)) {     // node-owner kernel: gated too
         *tile = probe.tile; *n_tiles = probe.n_tiles;
         return true;
@@ -1011,9 +1034,16 @@ extern "C" int gd_decode_fwd_train(const gd_graph* gc, const gd_model* model, co
     return decode_fwd_impl(gc, model, weights_dev, x_dev, prob_dev, logit_dev, nullptr, stash_dev, B, stream);
 }
 
+int gd::decode_fwd_deferred(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, float* prob_dev,
+                            float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev, int64_t B, cudaStream_t st,
+                            const gd::DeferList& dl) {
+    return decode_fwd_impl(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, nullptr, B, (void*)st, nullptr, &dl,
+                           hard_bits_dev);
+}
+
 static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
                            float* prob_dev, float* logit_dev, uint8_t* hard_dev, float* stash_dev, int64_t B,
-                           void* stream, const gd::Gate* gate) {
+                           void* stream, const gd::Gate* gate, const gd::DeferList* dl, uint32_t* hard_bits_dev) {
     gd_graph* g = const_cast<gd_graph*>(gc);
     GD_CHECK_ARG(g != nullptr, "gd_decode_fwd: graph is NULL");
     GD_CHECK_ARG(gd_model_valid(model), "gd_decode_fwd: invalid model (program=%d hidden=%d iters=%d)",
@@ -1025,20 +1055,38 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     GD_CHECK_ARG(((uintptr_t)x_dev & 15) == 0, "gd_decode_fwd: x must be 16-byte aligned");
     GD_CHECK_ARG(((uintptr_t)prob_dev & 15) == 0 && ((uintptr_t)logit_dev & 15) == 0 && ((uintptr_t)hard_dev & 3) == 0,
                  "gd_decode_fwd: outputs must be 16-byte (prob, logit) / 4-byte (hard) aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int prev = 0;
+    GD_CUDA(cudaGetDevice(&prev));
+    if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
+    if (!stash_dev && !gate && !dl) {
+        // decoder_v2_4 on surface / toric codes: the check-owner table kernel (gd_lean.cu); what it cannot serve comes back
+        // here through decode_fwd_deferred
+        const int lrc = gd::lean_decode(g, model, weights_dev, x_dev, nullptr, nullptr, prob_dev, logit_dev, hard_dev, hard_bits_dev,
+                                        B, st);
+        if (lrc >= 0) {
+            if (prev != g->device) cudaSetDevice(prev);
+            return lrc;
+        }
+    }
     gd::DecodePlan pl;
     int rc = gd::plan_decode(g, model, B, &pl);
-    if (rc != GD_OK) return rc;
+    if (rc != GD_OK) {
+        if (prev != g->device) cudaSetDevice(prev);
+        return rc;
+    }
     pl.p.x = x_dev; pl.p.prob = prob_dev; pl.p.logit = logit_dev; pl.p.hard = hard_dev; pl.p.weights = weights_dev;
-    pl.p.stash = stash_dev;
+    pl.p.stash = stash_dev; pl.p.hard_bits = hard_bits_dev;
+    if (dl) { pl.p.defer_count = dl->count; pl.p.defer_idx = dl->idx; }
     if (gate) {
         GD_CHECK_ARG(pl.resident && gate->chunk_tiles > 0, "gd_decode_host: gated launch needs the resident kernel");
         pl.p.gate_in = gate->in_flags; pl.p.gate_out = gate->out_counts; pl.p.gate_err = gate->err;
         pl.p.gate_epoch = gate->epoch; pl.p.gate_chunk_tiles = gate->chunk_tiles;
     }
     pl.p.all_iters = (model->flags & GD_FLAG_ALL_ITERS) ? 1 : 0;
-    pl.p.n_vact = getenv("GD_NO_VSKIP") ? (int)g->E : g->n_vact;
-    pl.p.vdirect = (g->max_var_deg <= 2 && !getenv("GD_NO_DIRECT")) ? 1 : 0;
-    pl.p.cdirect = (g->max_chk_deg <= 4 && !getenv("GD_NO_DIRECT")) ? 1 : 0;
+    pl.p.n_vact = gd::opt_on(gd::OPT_NO_VSKIP) ? (int)g->E : g->n_vact;
+    pl.p.vdirect = (g->max_var_deg <= 2 && !gd::opt_on(gd::OPT_NO_DIRECT)) ? 1 : 0;
+    pl.p.cdirect = (g->max_chk_deg <= 4 && !gd::opt_on(gd::OPT_NO_DIRECT)) ? 1 : 0;
     GD_CHECK_ARG(model->program != GD_PROG_NEURAL_BP || model->hidden == g->E,
                  "gd_decode_fwd: GD_PROG_NEURAL_BP needs model.hidden == E (%lld per-edge weights), got %d",
                  (long long)g->E, model->hidden);
@@ -1047,16 +1095,12 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
                       "shared memory", model->program);
         return GD_ERR_UNSUPPORTED;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    int prev = 0;
-    GD_CUDA(cudaGetDevice(&prev));
-    if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
     if (!pl.resident) {
         rc = gd::streamed_decode(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, B, st);
         if (prev != g->device) cudaSetDevice(prev);
         return rc;
     }
-    if (!stash_dev) {
+    if (!stash_dev && !dl) {
         // light programs (CGNNI, QGNNI, sum-product): the node-owner kernel of gd_decode_light.cu
         const int lrc = gd::light_decode(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, B, st, gate);
         if (lrc >= 0) {
@@ -1096,7 +1140,7 @@ extern "C" int gd_decode_autotune(const gd_graph* gc, const gd_model* model, con
     if (chosen) *chosen = li;
     // only the edge-owner resident kernel has a geometry to tune; the light / streamed kernels plan themselves
     gd_launch_info probe;
-    if (!li.resident || gd::light_launch_info(g, model, B, &probe)) return GD_OK;
+    if (!li.resident || gd::lean_launch_info(g, model, B, &probe) || gd::light_launch_info(g, model, B, &probe)) return GD_OK;
     std::vector<gd::GeomCand> cands;
     gd::DecodePlan pl;
     rc = gd::plan_decode(g, model, B, &pl, nullptr, &cands);

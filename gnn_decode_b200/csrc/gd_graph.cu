@@ -75,7 +75,7 @@ extern "C" int gd_graph_create(const int64_t* ei, int64_t E, int32_t V, int32_t 
     gd_graph* g = new (std::nothrow) gd_graph();
     GD_CHECK_ARG(g != nullptr, "gd_graph_create: out of host memory");
     g->V = V; g->C = C; g->N = V + C; g->E = E; g->device = device;
-    g->gstate = nullptr; g->gstate_bytes = 0; g->host_ctx = nullptr; g->blob_dev = nullptr;
+    g->gstate = nullptr; g->gstate_bytes = 0; g->host_ctx = nullptr; g->lean_ctx = nullptr; g->blob_dev = nullptr;
     g->h_edge_var.resize((size_t)E);
     g->h_edge_chk.resize((size_t)E);
     for (int64_t e = 0; e < E; ++e) {
@@ -142,6 +142,7 @@ extern "C" int gd_graph_create(const int64_t* ei, int64_t E, int32_t V, int32_t 
 }
 
 void gd_host_ctx_destroy(gd_graph* g);  // gd_host.cu
+void gd_lean_ctx_destroy(gd_graph* g);  // gd_lean.cu
 
 extern "C" void gd_graph_destroy(gd_graph* g) {
     if (!g) return;
@@ -149,6 +150,7 @@ extern "C" void gd_graph_destroy(gd_graph* g) {
     bool have_prev = cudaGetDevice(&prev) == cudaSuccess;
     cudaSetDevice(g->device);
     gd_host_ctx_destroy(g);
+    gd_lean_ctx_destroy(g);
     if (g->gstate) cudaFree(g->gstate);
     if (g->blob_dev) cudaFree(g->blob_dev);
     if (have_prev) cudaSetDevice(prev);

@@ -1,0 +1,874 @@
+// decoder_v2_4 (quantum/decoder_v2_4.py:272-294) on surface / toric codes as a CHECK-OWNER, TABLE-ONLY kernel.
+//
+// On these codes every variable has <= 2 checks and every check <= 4 variables, and the reference's inputs (gen_syn,
+// quantum/error_generate.py:252-278) carry ONE prior value per syndrome (drawn from a short list) plus +-1 check inputs.
+// One iteration of GNNI.forward (decoder_v2_4.py:280-283) then collapses, per edge e = (v, c), to
+//     t_e   = g_p(m_sib(e))                   g_p(x) = tanh(ggc1.mlp([x, prior]) / 2), sib(e) = the other edge of v
+//                                             (no sibling: ext == 0 in every iteration, t_e = g_p(0))
+//     m_e  += s_c * f2(sum of t over the other edges of c)          f2 = ggc2.mlp, s_c = the check's +-1 input
+// and the read-out (decoder_v2_4.py:291-292) to logit_v = prior + sum_{e at v} f3(m_e), f3 = mlp.  g_p, f2 and f3 are
+// smooth scalar functions on compact, known domains (|ext| <= 3, |m| <= T max|f2|): they are tabulated ONCE per call in
+// double precision (exact node values AND derivatives -> cubic Hermite pieces, a-posteriori error measured at the
+// interval midpoints and checked against a budget), by two small kernels, and the decode kernel evaluates nothing else:
+//   * a thread owns CHECKS of one syndrome (lanes = 32 syndromes of a group, a group's R warps = its check owners);
+//     the whole iteration is one fused pass over the owned checks -- read the sibling messages, look up t, sum, look up
+//     f2, update m -- against a double-buffered message array in shared memory: ONE barrier per iteration, and it is a
+//     NAMED barrier over the group's R warps only: the G groups of a CTA share the tables but run independently, so one
+//     group's barrier wait is another group's issue slot;
+//   * tanh is folded into the variable-phase table (no MUFU in the loop), the check-phase table is replicated once per
+//     16-byte bank group (lane & 7), so its 128-bit look-ups are conflict-free;
+//   * inputs are read in packed form (prior float + check-sign bits, produced by the prep kernel from x [B, V+C] or
+//     handed in directly by gd_decode_packed_*): nothing but the messages lives in shared memory.
+// What binds it is the shared-memory crossbar (table look-ups); see DESIGN.md.
+//
+// Syndromes the tables cannot serve -- non-uniform priors, check inputs other than +-1, non-finite priors -- are listed
+// by the prep kernel and decoded afterwards by the edge-owner kernel's direct evaluation (gd_decode.cu), per item; a batch
+// with more distinct priors than table slots, or weights whose tables miss the error budget, goes there as a whole.
+#include "gd_lean.cuh"
+#include "gd_decode.cuh"
+#include "gd_math.cuh"
+#include "gd_options.cuh"
+#include <algorithm>
+#include <string.h>
+
+namespace gd {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kMaxSlots = 12;
+constexpr int kHdrBytes = 512;
+constexpr float kBudgetC = 1e-7f;     // check table: feeds the iteration (+ half an fp32 ulp of its values: 6e-8 max|f2|)
+constexpr float kBudgetV = 1e-6f;     // variable table, in units of tanh output (the MUFU tanh it replaces: ~2e-7)
+constexpr float kBudgetR = 4e-6f;     // read-out table: adds <= 2 terms to the final logit (+ 1e-7 of its scale)
+
+static_assert(sizeof(LeanHeader) <= kHdrBytes, "header");
+
+struct LeanParams {
+    // packed inputs
+    const float* prior;          // [B]
+    const int* slot;             // [B] table slot of the syndrome, < 0: deferred
+    const uint32_t* sgn;         // [B][nw] bit c = check c's input is -1
+    float* prob; float* logit; uint8_t* hard; uint32_t* hard_bits;
+    LeanHeader* hdr;
+    const float4* ctab; const float4* rtab; const float4* vtab;   // global tables: (n + 2) pieces each, piece 0 = interval -1
+    const uint32_t* meta;        // device metadata blob of this (graph, R)
+    long long B;
+    int T, V, C, E, nw, vw, P;   // P = odd pitch of the staged logits
+    int R, G, NCH;               // owners per group, groups per CTA, checks per owner (padded)
+    int ct_n, rt_n, vt_n, vt_k;
+    int n_tiles;                 // tiles of 32 syndromes
+    int off_me, off_ms, off_mi, off_var, off_ct, off_rt, off_vt, off_state;   // shared-memory byte offsets
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// shared-memory access by 32-bit address
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t a) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f128(uint32_t a) {   // read-only tables: free to move
+    float4 v;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+// message state: volatile, so these keep their order around the group barriers
+template <int OFF>
+__device__ __forceinline__ float lds_state(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_state(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v));
+}
+__device__ __forceinline__ float lds_state_rt(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_state_rt(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void group_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// One cubic piece: w = interval coordinate (piece i covers [i - 0.5, i + 0.5)), base = shared address of piece 0 as seen
+// by this lane MINUS 0x4B400000 * STRIDE (mod 2^32: the magic-number add leaves the piece index in the low mantissa bits of
+// v, so bits(v) * STRIDE + base lands on the piece), STRIDE = bytes between pieces.  8 instructions + one 128-bit load,
+// no conversion instruction.
+template <int STRIDE>
+__device__ __forceinline__ float lean_cubic(uint32_t base, float w) {
+    const float v = w + 12582912.0f;
+    const float tau = w - (v - 12582912.0f);
+    const float4 c = lds_f128((uint32_t)__float_as_int(v) * (uint32_t)STRIDE + base);
+    return fmaf(fmaf(fmaf(c.w, tau, c.z), tau, c.y), tau, c.x);
+}
+template <int STRIDE>
+__device__ __forceinline__ uint32_t lean_base(uint32_t piece0) {
+    uint32_t b = piece0 - 0x4B400000u * (uint32_t)STRIDE;
+    asm volatile("" : "+r"(b));          // keep it ONE register: ptxas would otherwise re-add the constant at every look-up
+    return b;
+}
+
+struct LeanTabs {
+    uint32_t vt_base;          // lean_base of this lane's variable-phase table
+    uint32_t ct_base;          // lean_base of this lane's replica of the check table
+    float vt_inv_h, vt_off;
+    float ct_inv_h, ct_off;
+    float t0;                  // g_p(0): the message of a variable without a sibling edge
+};
+
+// No clamps: |m| <= T max|f2| < Rm by construction (check inputs are exactly +-1 here) and |ext| <= 3 up to rounding; the
+// tables carry one extra piece on either side.
+__device__ __forceinline__ float lean_vt(const LeanTabs& tb, float m) {
+    return lean_cubic<16>(tb.vt_base, fmaf(m, tb.vt_inv_h, tb.vt_off));
+}
+__device__ __forceinline__ float lean_ct(const LeanTabs& tb, float ext) {
+    return lean_cubic<128>(tb.ct_base, fmaf(ext, tb.ct_inv_h, tb.ct_off));
+}
+
+// one check of degree DEG whose first NSIB edges have a sibling edge at their variable (the metadata lists those first):
+// CUR = byte offset of the buffer read, NXT = written
+template <int DEG, int NSIB, int CUR, int NXT>
+__device__ __forceinline__ void lean_check(const uint4 eo, const uint4 so, uint32_t st_lane, const LeanTabs& tb, uint32_t sgn) {
+    const uint32_t eoa[4] = {eo.x, eo.y, eo.z, eo.w}, soa[4] = {so.x, so.y, so.z, so.w};
+    float t[4], mo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        t[j] = j < NSIB ? lean_vt(tb, lds_state<CUR>(st_lane + soa[j])) : (j < DEG ? tb.t0 : 0.f);
+        mo[j] = j < DEG ? lds_state<CUR>(st_lane + eoa[j]) : 0.f;
+    }
+    const float a = t[0] + t[1], b = t[2] + t[3];
+    const float ext[4] = {t[1] + b, t[0] + b, a + t[3], a + t[2]};
+#pragma unroll
+    for (int j = 0; j < DEG; ++j) {
+        const float o = lean_ct(tb, ext[j]);
+        sts_state<NXT>(st_lane + eoa[j], mo[j] + __uint_as_float(__float_as_uint(o) ^ sgn));
+    }
+}
+
+template <int CUR>
+__device__ __forceinline__ void lean_iteration(const LeanParams& p, uint32_t me, uint32_t ms, uint32_t mi, uint32_t st_lane,
+                                               const LeanTabs& tb, uint32_t mybits) {
+    constexpr int NXT = 128 - CUR;
+#pragma unroll 1
+    for (int k = 0; k < p.NCH; ++k) {
+        const uint32_t kind = lds_u32(mi + 4u * k) & 63u;      // degree | siblings << 3  (warp-uniform)
+        if (kind == 0) break;                                  // padding checks are last
+        const uint4 eo = lds_u128(me + 16u * k), so = lds_u128(ms + 16u * k);
+        const uint32_t sgn = (mybits >> k) << 31;
+        switch (kind) {
+#define GD_LEAN_CASE(D, S) case ((D) | ((S) << 3)): lean_check<D, S, CUR, NXT>(eo, so, st_lane, tb, sgn); break;
+            GD_LEAN_CASE(4, 4) GD_LEAN_CASE(4, 3) GD_LEAN_CASE(4, 2) GD_LEAN_CASE(4, 1) GD_LEAN_CASE(4, 0)
+            GD_LEAN_CASE(3, 3) GD_LEAN_CASE(3, 2) GD_LEAN_CASE(3, 1) GD_LEAN_CASE(3, 0)
+            GD_LEAN_CASE(2, 2) GD_LEAN_CASE(2, 1) GD_LEAN_CASE(2, 0)
+            GD_LEAN_CASE(1, 1) GD_LEAN_CASE(1, 0)
+#undef GD_LEAN_CASE
+            default: break;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const LeanHeader* H = p.hdr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- can the tables serve this call at all? (identical decision in every thread of the grid) ----
+    const int n_slots = H->n_slots;
+    const float fmax = __uint_as_float(H->fmax_bits), f3max = __uint_as_float(H->f3max_bits);
+    bool ok = !H->overflow && n_slots <= p.vt_k && __uint_as_float(H->err_c_bits) <= kBudgetC + 6e-8f * fmax &&
+              __uint_as_float(H->err_r_bits) <= kBudgetR + 1e-7f * f3max && isfinite(fmax) && isfinite(f3max);
+    for (int k = 0; k < n_slots && k < 16; ++k) ok = ok && __uint_as_float(H->err_v_bits[k]) <= kBudgetV;
+    if (!ok) {
+        if (blockIdx.x == 0 && tid == 0) p.hdr->defer_count = -1;     // everything goes to the edge-owner kernel
+        return;
+    }
+    if (n_slots == 0) return;                                         // nothing eligible: all listed as deferred already
+
+    // ---- prologue: metadata and tables into shared memory ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.meta);
+        uint4* dst = reinterpret_cast<uint4*>(smem + p.off_me);
+        const int n16 = (p.off_ct - p.off_me) >> 4;
+        for (int i = tid; i < n16; i += blockDim.x) dst[i] = src[i];
+        float4* ct = reinterpret_cast<float4*>(smem + p.off_ct);
+        for (int i = tid; i < (p.ct_n + 2) * 8; i += blockDim.x) ct[i] = p.ctab[i >> 3];          // 8 replicas: one per bank group
+        float4* rt = reinterpret_cast<float4*>(smem + p.off_rt);
+        for (int i = tid; i < p.rt_n + 2; i += blockDim.x) rt[i] = p.rtab[i];
+        float4* vt = reinterpret_cast<float4*>(smem + p.off_vt);
+        for (int i = tid; i < n_slots * (p.vt_n + 2); i += blockDim.x) vt[i] = p.vtab[i];
+    }
+    __syncthreads();
+    if (warp >= p.G * p.R) return;
+    const int grp = warp / p.R, r = warp - grp * p.R;
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t me = s_base + p.off_me + (uint32_t)(r * p.NCH) * 16u;
+    const uint32_t ms = s_base + p.off_ms + (uint32_t)(r * p.NCH) * 16u;
+    const uint32_t mi = s_base + p.off_mi + (uint32_t)(r * p.NCH) * 4u;
+    const uint32_t st_lane = s_base + p.off_state + (uint32_t)grp * (uint32_t)p.E * 256u + (uint32_t)lane * 4u;
+    const int bar_id = 1 + grp, bar_n = 32 * p.R;
+    const float Rm = (float)p.T * (fmax * 1.02f + 1e-6f);
+    LeanTabs tb;
+    tb.vt_inv_h = 0.5f * (float)p.vt_n / Rm;
+    tb.vt_off = Rm * tb.vt_inv_h - 0.5f;
+    tb.ct_inv_h = (float)p.ct_n / 6.0f;
+    tb.ct_off = 3.0f * tb.ct_inv_h - 0.5f;
+    tb.ct_base = lean_base<128>(s_base + p.off_ct + 128u + (uint32_t)(lane & 7) * 16u);
+    const float rt_inv_h = 0.5f * (float)p.rt_n / Rm, rt_off = Rm * rt_inv_h - 0.5f;
+    const uint32_t rt_base = lean_base<16>(s_base + p.off_rt + 16u);
+    const int fin = (p.T & 1) * 128, oth = 128 - fin;          // buffer holding the final messages / free for the staged logits
+
+    // tiles are dealt to the CTAs first (every SM gets n_tiles / grid of them, +-1), then round-robin to a CTA's groups
+    for (int tile = blockIdx.x + gridDim.x * grp; tile < p.n_tiles; tile += gridDim.x * p.G) {
+        const long long s0 = (long long)tile * 32;
+        const long long sg = s0 + lane;
+        const bool valid = sg < p.B;
+        const int slot = valid ? __ldg(p.slot + sg) : -1;
+        if (!__any_sync(0xffffffffu, slot >= 0)) continue;     // same decision in all R warps of the group (same 32 syndromes)
+        const bool live = slot >= 0;
+        const float prior = live ? __ldg(p.prior + sg) : 0.f;
+        tb.vt_base = lean_base<16>(s_base + p.off_vt + (uint32_t)(live ? slot : 0) * (uint32_t)(p.vt_n + 2) * 16u + 16u);
+        tb.t0 = lean_vt(tb, 0.f);
+        uint32_t mybits = 0;                                    // bit k = the sign bit of my k-th check's input
+        for (int k = 0; k < p.NCH; ++k) {
+            const uint32_t info = lds_u32(mi + 4u * k);
+            if ((info & 7u) == 0) break;
+            const int c = (int)(info >> 8);
+            const uint32_t wv = live ? __ldg(p.sgn + sg * p.nw + (c >> 5)) : 0u;
+            mybits |= ((wv >> (c & 31)) & 1u) << k;
+        }
+        // ---- iteration 0: m == 0 everywhere, so every t is g_p(0) and a check's edges share one look-up ----
+        for (int k = 0; k < p.NCH; ++k) {
+            const int deg = (int)(lds_u32(mi + 4u * k) & 7u);
+            if (deg == 0) break;
+            const uint4 eo = lds_u128(me + 16u * k);
+            const float o = lean_ct(tb, (float)(deg - 1) * tb.t0);
+            const float mv = __uint_as_float(__float_as_uint(o) ^ ((mybits >> k) << 31));
+            const uint32_t eoa[4] = {eo.x, eo.y, eo.z, eo.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < deg) sts_state<128>(st_lane + eoa[j], mv);
+        }
+        group_bar(bar_id, bar_n);
+        int it = 1;
+        for (; it + 1 < p.T; it += 2) {
+            lean_iteration<128>(p, me, ms, mi, st_lane, tb, mybits);
+            group_bar(bar_id, bar_n);
+            lean_iteration<0>(p, me, ms, mi, st_lane, tb, mybits);
+            group_bar(bar_id, bar_n);
+        }
+        if (it < p.T) {
+            lean_iteration<128>(p, me, ms, mi, st_lane, tb, mybits);
+            group_bar(bar_id, bar_n);
+        }
+        // ---- read-out: logit_v = prior + sum over the variable's edges of f3(m_e); staged with an odd pitch in the free buffer ----
+        const uint32_t st_grp = st_lane - (uint32_t)lane * 4u;
+        for (int v = r; v < p.V; v += p.R) {
+            const uint2 ve = lds_u64(s_base + p.off_var + 8u * v);
+            float acc = prior;
+            if (ve.x != kNone) acc += lean_cubic<16>(rt_base, fminf(fmaxf(fmaf(lds_state_rt(st_lane + ve.x + fin), rt_inv_h, rt_off), -1.4f), (float)p.rt_n + 0.4f));
+            if (ve.y != kNone) acc += lean_cubic<16>(rt_base, fminf(fmaxf(fmaf(lds_state_rt(st_lane + ve.y + fin), rt_inv_h, rt_off), -1.4f), (float)p.rt_n + 0.4f));
+            const uint32_t q = (uint32_t)lane * (uint32_t)p.P + (uint32_t)v;
+            sts_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth, acc);
+        }
+        group_bar(bar_id, bar_n);
+        // ---- outputs (the group's 32 syndromes are one contiguous block of rows) ----
+        {
+            const int nvalid = (int)min(32ll, p.B - s0);
+            const int total = nvalid * p.V;
+            const long long g0 = s0 * p.V;                     // multiple of 32 elements: 16-byte aligned
+            const float invV = 1.0f / (float)p.V;
+            const int gt = r * 32 + lane, gn = 32 * p.R;
+            auto stage = [&](int i) -> float {
+                const int s = (int)(((float)i + 0.5f) * invV), v = i - s * p.V;
+                const uint32_t q = (uint32_t)s * (uint32_t)p.P + (uint32_t)v;
+                return lds_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth);
+            };
+            for (int i = gt * 4; i < total; i += gn * 4) {
+                float l[4], pr[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {               // total is a multiple of 4 only when nvalid * V is
+                    l[j] = i + j < total ? stage(i + j) : 0.f;
+                    pr[j] = sigmoid_neg(l[j]);
+                }
+                if (i + 4 <= total) {
+                    if (p.prob) *reinterpret_cast<float4*>(p.prob + g0 + i) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+                    if (p.logit) *reinterpret_cast<float4*>(p.logit + g0 + i) = make_float4(l[0], l[1], l[2], l[3]);
+                    if (p.hard)
+                        *reinterpret_cast<uchar4*>(p.hard + g0 + i) = make_uchar4(pr[0] > 0.5f, pr[1] > 0.5f, pr[2] > 0.5f, pr[3] > 0.5f);
+                } else {
+                    for (int j = 0; i + j < total; ++j) {
+                        if (p.prob) p.prob[g0 + i + j] = pr[j];
+                        if (p.logit) p.logit[g0 + i + j] = l[j];
+                        if (p.hard) p.hard[g0 + i + j] = pr[j] > 0.5f;
+                    }
+                }
+            }
+            if (p.hard_bits) {                                  // packed hard decisions: bit v of row s
+                for (int s = r; s < nvalid; s += p.R)
+                    for (int w = 0; w < p.vw; ++w) {
+                        const int v = w * 32 + lane;
+                        const uint32_t q = (uint32_t)s * (uint32_t)p.P + (uint32_t)v;
+                        const float lv = v < p.V ? lds_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth) : 1.0f;
+                        const uint32_t word = __ballot_sync(0xffffffffu, sigmoid_neg(lv) > 0.5f);
+                        if (lane == 0) p.hard_bits[(s0 + s) * p.vw + w] = word;
+                    }
+            }
+        }
+        group_bar(bar_id, bar_n);                               // the staged logits are consumed before the next tile writes
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Table construction in double precision.  One warp evaluates one point: lanes over the hidden units.
+struct MlpD {
+    const float* w1; int w1s; const float* w1b; const float* b1; const float* w2; float b2; int h;
+};
+__device__ __forceinline__ void mlp_eval_warp(const MlpD& M, double prior, double x, int lane, double& f, double& df) {
+    double sf = 0.0, sd = 0.0;
+    for (int k = lane; k < M.h; k += 32) {
+        const double a = (double)M.w1[k * M.w1s];
+        double c = (double)M.b1[k];
+        if (M.w1b) c += (double)M.w1b[k * M.w1s] * prior;
+        const double z = a * x + c;
+        double sp, sg;
+        if (z > 20.0) { sp = z; sg = 1.0; }                      // torch.nn.Softplus(beta=1, threshold=20)
+        else {
+            const double e = exp(-fabs(z));
+            sp = fmax(z, 0.0) + log1p(e);
+            sg = z >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
+        }
+        const double w2 = (double)M.w2[k];
+        sf += w2 * sp;
+        sd += w2 * a * sg;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sf += __shfl_xor_sync(0xffffffffu, sf, o);
+        sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    }
+    f = sf + (double)M.b2;
+    df = sd;
+}
+__device__ __forceinline__ void atomic_max_float_up(unsigned int* dst, double v) {
+    const float f = __double2float_ru(fabs(v));                 // non-negative floats order like their bit patterns
+    atomicMax(dst, __float_as_uint(f));
+}
+
+constexpr int kChunk = 32;     // pieces per CTA of the table kernels
+
+// Build pieces [i0, i0 + n_int) (piece index = interval index + 1) of one table into dst; CTA of 256 threads.
+// tanh_fold: tabulate tanh(f / 2) instead of f.  Returns nothing; error / max go to the header by atomics.
+__device__ void build_chunk(const MlpD& M, double prior, bool tanh_fold, double Rdom, int n, int i0, int n_int, float4* dst,
+                            unsigned int* fmax_bits, unsigned int* err_bits, double2* nodes /* smem [kChunk + 1] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const double h = 2.0 * Rdom / (double)n;
+    for (int j = warp; j <= n_int; j += nwarp) {                  // nodes of intervals i0 - 1 + j
+        const double x = -Rdom + h * (double)(i0 - 1 + j);
+        double f, df;
+        mlp_eval_warp(M, prior, x, lane, f, df);
+        if (lane == 0 && fmax_bits) atomic_max_float_up(fmax_bits, f);
+        if (tanh_fold) {
+            const double g = tanh(0.5 * f);
+            df = 0.5 * (1.0 - g * g) * df;
+            f = g;
+        }
+        if (lane == 0) nodes[j] = make_double2(f, h * df);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_int; j += blockDim.x) {
+        const double f0 = nodes[j].x, d0 = nodes[j].y, f1 = nodes[j + 1].x, d1 = nodes[j + 1].y;
+        const double c0 = f0, c1 = d0, c2 = 3.0 * (f1 - f0) - 2.0 * d0 - d1, c3 = 2.0 * (f0 - f1) + d0 + d1;
+        // re-centred on the interval midpoint: p(tau), tau in [-0.5, 0.5]
+        dst[i0 + j] = make_float4((float)(c0 + 0.5 * c1 + 0.25 * c2 + 0.125 * c3), (float)(c1 + c2 + 0.75 * c3),
+                                  (float)(c2 + 1.5 * c3), (float)c3);
+    }
+    // a-posteriori error at the midpoints (where the Hermite remainder peaks) of every 4th interval
+    for (int j = warp * 4 + 1; j < n_int; j += nwarp * 4) {
+        const double x = -Rdom + h * ((double)(i0 - 1 + j) + 0.5);
+        double f, df;
+        mlp_eval_warp(M, prior, x, lane, f, df);
+        if (tanh_fold) f = tanh(0.5 * f);
+        const double f0 = nodes[j].x, d0 = nodes[j].y, f1 = nodes[j + 1].x, d1 = nodes[j + 1].y;
+        const double c2 = 3.0 * (f1 - f0) - 2.0 * d0 - d1, c3 = 2.0 * (f0 - f1) + d0 + d1;
+        const float a0 = (float)(f0 + 0.5 * d0 + 0.25 * c2 + 0.125 * c3);
+        if (lane == 0) atomic_max_float_up(err_bits, (double)a0 - f);
+    }
+}
+
+// prior look-up / insertion into the header's slot list; returns the slot or -1 (list full)
+__device__ __forceinline__ int slot_of(LeanHeader* H, unsigned int bits, int vt_k) {
+    for (int k = 0; k < vt_k; ++k) {
+        unsigned int cur = *reinterpret_cast<volatile unsigned int*>(&H->slot_bits[k]);
+        if (cur == kNone) {
+            cur = atomicCAS(&H->slot_bits[k], kNone, bits);
+            if (cur == kNone) {
+                atomicMax(&H->n_slots, k + 1);
+                return k;
+            }
+        }
+        if (cur == bits) return k;
+    }
+    return -1;
+}
+
+struct PrepParams {
+    const float* x;              // [B, N] or NULL (packed inputs given)
+    const float* weights;
+    float* prior_out;            // [B]   (x given)
+    uint32_t* sgn_out;           // [B][nw]
+    const float* prior_in;       // [B]   (packed inputs)
+    int* slot; int* defer_idx;
+    LeanHeader* hdr;
+    float4* ctab;
+    long long B;
+    int V, C, N, nw, hid, ct_n, vt_k, n_ct_blocks;
+};
+
+// Prep kernel: the first n_ct_blocks CTAs tabulate the check-phase MLP (and its max, which sizes the other tables'
+// domains); the others bring the inputs into packed form -- prior value, table slot, check-sign bits -- discover the
+// distinct priors and list the syndromes the tables cannot serve.
+__global__ void __launch_bounds__(256) lean_prep_kernel(const PrepParams p) {
+    __shared__ double2 nodes[kChunk + 1];
+    LeanHeader* H = p.hdr;
+    if ((int)blockIdx.x < p.n_ct_blocks) {
+        const float* w = p.weights + 4 * p.hid + 1;             // ggc2.mlp
+        const MlpD M{w, 1, nullptr, w + p.hid, w + 2 * p.hid, w[3 * p.hid], p.hid};
+        const int i0 = blockIdx.x * kChunk, n_int = min(kChunk, p.ct_n + 2 - i0);
+        if (n_int > 0) build_chunk(M, 0.0, false, 3.0, p.ct_n, i0, n_int, p.ctab, &H->fmax_bits, &H->err_c_bits, nodes);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)(blockIdx.x - p.n_ct_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)(gridDim.x - p.n_ct_blocks) * (blockDim.x >> 5);
+    if (p.x) {
+        for (long long s = wid; s < p.B; s += nwarps) {          // a warp per syndrome
+            const float* row = p.x + s * p.N;
+            const float p0 = __ldg(row);
+            bool good = true;
+            for (int v = lane; v < p.V; v += 32) good = good && (__float_as_uint(__ldg(row + v)) == __float_as_uint(p0));
+            for (int w = 0; w < p.nw; ++w) {
+                const int c = w * 32 + lane;
+                const float val = c < p.C ? __ldg(row + p.V + c) : 1.0f;
+                good = good && (val == 1.0f || val == -1.0f);
+                const uint32_t word = __ballot_sync(0xffffffffu, val < 0.f);
+                if (lane == 0) p.sgn_out[s * p.nw + w] = word;
+            }
+            good = __all_sync(0xffffffffu, good) && isfinite(p0);
+            if (lane == 0) {
+                int slot = -1;
+                if (good) {
+                    slot = slot_of(H, __float_as_uint(p0), p.vt_k);
+                    if (slot < 0) H->overflow = 1;
+                } else {
+                    p.defer_idx[atomicAdd(&H->defer_count, 1)] = (int)s;
+                }
+                p.prior_out[s] = p0;
+                p.slot[s] = slot;
+            }
+        }
+    } else {
+        for (long long s = wid * 32 + lane; s < p.B; s += nwarps * 32) {   // a thread per syndrome
+            const float p0 = __ldg(p.prior_in + s);
+            int slot = -1;
+            if (isfinite(p0)) {
+                slot = slot_of(H, __float_as_uint(p0), p.vt_k);
+                if (slot < 0) H->overflow = 1;
+            } else {
+                p.defer_idx[atomicAdd(&H->defer_count, 1)] = (int)s;
+            }
+            p.slot[s] = slot;
+        }
+    }
+}
+
+struct TabParams {
+    const float* weights;
+    LeanHeader* hdr;
+    float4* rtab; float4* vtab;
+    int hid, T, rt_n, vt_n, vt_k, rt_blocks, vt_blocks_per_slot;
+};
+
+// Table kernel: read-out table and one variable-phase table per discovered prior, on [-Rm, Rm], Rm = T max|mlp2| (a bound on
+// |m|: m starts at 0 and gains mlp2(ext) * (+-1) per iteration).
+__global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
+    __shared__ double2 nodes[kChunk + 1];
+    LeanHeader* H = p.hdr;
+    const float fmax = __uint_as_float(H->fmax_bits);
+    const double Rm = (double)((float)p.T * (fmax * 1.02f + 1e-6f));        // the decode kernel forms the same float
+    if (!(Rm > 0.0) || !isfinite(Rm)) return;
+    if ((int)blockIdx.x < p.rt_blocks) {
+        const float* w = p.weights + 7 * p.hid + 2;             // mlp (read-out)
+        const MlpD M{w, 1, nullptr, w + p.hid, w + 2 * p.hid, w[3 * p.hid], p.hid};
+        const int i0 = blockIdx.x * kChunk, n_int = min(kChunk, p.rt_n + 2 - i0);
+        if (n_int > 0) build_chunk(M, 0.0, false, Rm, p.rt_n, i0, n_int, p.rtab, &H->f3max_bits, &H->err_r_bits, nodes);
+        return;
+    }
+    const int b = blockIdx.x - p.rt_blocks, k = b / p.vt_blocks_per_slot, cb = b - k * p.vt_blocks_per_slot;
+    if (k >= H->n_slots || H->overflow) return;
+    const float* w = p.weights;                                 // ggc1.mlp: w1 [h, 2] | b1 | w2 | b2
+    const MlpD M{w, 2, w + 1, w + 2 * p.hid, w + 3 * p.hid, w[4 * p.hid], p.hid};
+    const double prior = (double)__uint_as_float(H->slot_bits[k]);
+    const int i0 = cb * kChunk, n_int = min(kChunk, p.vt_n + 2 - i0);
+    if (n_int > 0)
+        build_chunk(M, prior, true, Rm, p.vt_n, i0, n_int, p.vtab + (size_t)k * (p.vt_n + 2), nullptr, &H->err_v_bits[k], nodes);
+}
+
+// packed inputs -> x rows for the syndromes the edge-owner kernel has to redo (gd_decode_packed_*)
+__global__ void lean_unpack_kernel(const float* prior, const uint32_t* sgn, const LeanHeader* H, const int* defer_idx, float* x,
+                                   long long B, int V, int C, int nw) {
+    const int cnt = H->defer_count;
+    if (cnt == 0) return;
+    const long long n = cnt < 0 ? B : cnt;
+    const int N = V + C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * N; i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i / N;
+        const int j = (int)(i - q * N);
+        const long long s = cnt < 0 ? q : defer_idx[q];
+        float v;
+        if (j < V) v = prior[s];
+        else {
+            const int c = j - V;
+            v = ((sgn[s * nw + (c >> 5)] >> (c & 31)) & 1u) ? -1.0f : 1.0f;
+        }
+        x[s * N + j] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side: owner assignment, metadata, plan, workspace
+struct LeanMeta {
+    int R = 0, NCH = 0;
+    uint32_t* dev = nullptr;
+    size_t bytes = 0;
+    int off_ms = 0, off_mi = 0, off_var = 0;   // byte offsets inside the blob (me at 0)
+    double balance = 0.0;
+};
+struct LeanGeom { int R = 0, G = 0, NCH = 0, rt_n = 0, vt_k = 0, ct_n = 0, vt_n = 0; long long opt_epoch = -1; bool valid = false; };
+struct LeanCtx {
+    std::vector<LeanMeta*> metas;          // one per R ever planned (stable addresses)
+    LeanGeom geom;                         // geometry search result, redone when an option changes
+    cudaMemPool_t pool = nullptr;
+};
+
+struct LeanPlan {
+    LeanParams p;
+    int threads, grid, smem;
+    const LeanMeta* meta;
+};
+
+static int align_up_i(int x, int a) { return (x + a - 1) / a * a; }
+
+// owners' check lists: longest-processing-time assignment by degree (ties: ascending check id) -> balanced edge counts
+static void assign_owners(const gd_graph* g, int R, std::vector<std::vector<int>>& own, int* nch, double* balance) {
+    std::vector<int> order;
+    for (int c = 0; c < g->C; ++c)
+        if (g->h_chk_ptr[c + 1] > g->h_chk_ptr[c]) order.push_back(c);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return g->h_chk_ptr[a + 1] - g->h_chk_ptr[a] > g->h_chk_ptr[b + 1] - g->h_chk_ptr[b];
+    });
+    own.assign(R, {});
+    std::vector<int> load(R, 0);
+    for (int c : order) {
+        int best = 0;
+        for (int r = 1; r < R; ++r)
+            if (load[r] < load[best] || (load[r] == load[best] && own[r].size() < own[best].size())) best = r;
+        own[best].push_back(c);
+        load[best] += g->h_chk_ptr[c + 1] - g->h_chk_ptr[c];
+    }
+    int mx = 0, mxn = 0;
+    for (int r = 0; r < R; ++r) {
+        mx = std::max(mx, load[r]);
+        mxn = std::max(mxn, (int)own[r].size());
+    }
+    *nch = mxn;
+    *balance = mx ? (double)g->E / ((double)R * mx) : 0.0;
+}
+
+static const LeanMeta* get_meta(gd_graph* g, int R) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (!g->lean_ctx) g->lean_ctx = new LeanCtx();
+    LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
+    for (const LeanMeta* q : ctx->metas)
+        if (q->R == R) return q->dev ? q : nullptr;
+    LeanMeta* mp = new LeanMeta();
+    LeanMeta& m = *mp;
+    m.R = R;
+    std::vector<std::vector<int>> own;
+    assign_owners(g, R, own, &m.NCH, &m.balance);
+    const int n = R * m.NCH;
+    m.off_ms = n * 16;
+    m.off_mi = 2 * n * 16;
+    m.off_var = align_up_i(m.off_mi + n * 4, 16);
+    m.bytes = (size_t)align_up_i(m.off_var + g->V * 8, 16);
+    std::vector<uint32_t> blob(m.bytes / 4, 0u);
+    uint32_t* me = blob.data();
+    uint32_t* ms = blob.data() + m.off_ms / 4;
+    uint32_t* mi = blob.data() + m.off_mi / 4;
+    uint32_t* var = blob.data() + m.off_var / 4;
+    auto sibling = [&](int e) -> uint32_t {
+        const int v = g->h_edge_var[e], b = g->h_var_ptr[v], d = g->h_var_ptr[v + 1] - b;
+        if (d < 2) return kNone;
+        return (uint32_t)(g->h_var_edges[b] == e ? g->h_var_edges[b + 1] : g->h_var_edges[b]) * 256u;
+    };
+    for (int r = 0; r < R; ++r)
+        for (int k = 0; k < m.NCH; ++k) {
+            const int i = r * m.NCH + k;
+            for (int j = 0; j < 4; ++j) me[4 * i + j] = 0u, ms[4 * i + j] = kNone;
+            mi[i] = 0u;
+            if (k >= (int)own[r].size()) continue;
+            const int c = own[r][k], b = g->h_chk_ptr[c], d = g->h_chk_ptr[c + 1] - b;
+            int j = 0, nsib = 0;
+            for (int pass = 0; pass < 2; ++pass)               // edges whose variable has a second edge first
+                for (int q = 0; q < d; ++q) {
+                    const int e = g->h_chk_edges[b + q];
+                    const uint32_t sb = sibling(e);
+                    if ((sb != kNone) != (pass == 0)) continue;
+                    me[4 * i + j] = (uint32_t)e * 256u;
+                    ms[4 * i + j] = sb;
+                    nsib += sb != kNone;
+                    ++j;
+                }
+            mi[i] = (uint32_t)d | ((uint32_t)nsib << 3) | ((uint32_t)c << 8);
+        }
+    for (int v = 0; v < g->V; ++v) {
+        const int b = g->h_var_ptr[v], d = g->h_var_ptr[v + 1] - b;
+        var[2 * v] = d > 0 ? (uint32_t)g->h_var_edges[b] * 256u : kNone;
+        var[2 * v + 1] = d > 1 ? (uint32_t)g->h_var_edges[b + 1] * 256u : kNone;
+    }
+    if (cudaMalloc((void**)&m.dev, m.bytes) != cudaSuccess ||
+        cudaMemcpy(m.dev, blob.data(), m.bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (m.dev) cudaFree(m.dev);
+        m.dev = nullptr;
+        cudaGetLastError();
+    }
+    ctx->metas.push_back(mp);
+    return mp->dev ? mp : nullptr;
+}
+
+static bool lean_applicable(const gd_graph* g, const gd_model* m) {
+    if (m->program != GD_PROG_V2_4 || m->flags != 0 || m->iters < 1 || opt_on(OPT_NO_LEAN)) return false;
+    if (g->max_var_deg > 2 || g->max_chk_deg > 4 || g->E >= (1 << 23) / 256) return false;
+    if ((g->V | 1) > g->E) return false;                        // the staged logits reuse the free message buffer
+    return true;
+}
+
+// the search itself (host work proportional to C * 32^2: done once per graph and option set, not per call)
+static bool lean_search(gd_graph* g, LeanGeom* out) {
+    const int E = (int)g->E, V = g->V;
+    const int ct_n = (int)std::min<long long>(1024, std::max<long long>(32, opt_int(OPT_LEAN_CTAB_N, 128)));
+    const int vt_n = (int)std::min<long long>(4096, std::max<long long>(64, opt_int(OPT_LEAN_VTAB_N, 512)));
+    const int state = E * 256;
+    const int smem_max = g->max_smem_optin;
+    struct Cand { int R, G, NCH, rt_n, vt_k; double score; };
+    Cand best{0, 0, 0, 0, 0, -1.0};
+    static const int rts[] = {2048, 1024}, ks[] = {12, 10, 8, 6};
+    const long long force_R = opt_int(OPT_LEAN_R, 0), force_G = opt_int(OPT_LEAN_G, 0);
+    const long long force_rt = opt_int(OPT_LEAN_RTAB_N, 0), force_k = opt_int(OPT_LEAN_VTAB_K, 0);
+    for (int R = 1; R <= 32; ++R) {
+        if (force_R > 0 && R != force_R) continue;
+        std::vector<std::vector<int>> own;
+        int nch;
+        double bal;
+        assign_owners(g, R, own, &nch, &bal);
+        if (nch > 32 || nch == 0) continue;                      // sign bits of the owned checks live in one register
+        const int meta = align_up_i(align_up_i(2 * R * nch * 16 + R * nch * 4, 16) + V * 8, 16);
+        for (int ri = 0; ri < 2; ++ri)
+            for (int ki = 0; ki < 4; ++ki) {
+                const int rt_n = force_rt > 0 ? (int)force_rt : rts[ri], vt_k = force_k > 0 ? (int)std::min<long long>(force_k, kMaxSlots) : ks[ki];
+                const int fixed = align_up_i(meta + (ct_n + 2) * 128 + (rt_n + 2) * 16 + vt_k * (vt_n + 2) * 16, 128);
+                int G = (smem_max - fixed) / state;
+                G = std::min(G, std::min(32 / R, 15));
+                if (force_G > 0) G = G >= force_G ? (int)force_G : 0;
+                if (G < 1) continue;
+                const int warps = G * R;
+                // enough warps to cover the look-up latency, balanced owners, then: keep the big tables, more groups
+                double score = std::min(1.0, warps / 24.0) * (0.4 + 0.6 * bal);
+                score *= 1.0 - 0.03 * ri - 0.02 * ki;
+                score *= 1.0 + 0.01 * std::min(G, 8);
+                if (score > best.score) best = Cand{R, G, nch, rt_n, vt_k, score};
+            }
+    }
+    out->valid = true;                                          // "does not fit" is a cached answer too (R == 0)
+    out->R = best.R; out->G = best.G; out->NCH = best.NCH; out->rt_n = best.rt_n; out->vt_k = best.vt_k;
+    out->ct_n = ct_n; out->vt_n = vt_n;
+    return true;
+}
+
+static bool lean_fill(gd_graph* g, const gd_model* m, int64_t B, const LeanGeom& best, const LeanMeta* meta, LeanPlan* out) {
+    const int E = (int)g->E, V = g->V, ct_n = best.ct_n, vt_n = best.vt_n, state = E * 256;
+    const int smem_max = g->max_smem_optin;
+    LeanParams& p = out->p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.T = m->iters; p.V = V; p.C = g->C; p.E = E;
+    p.nw = (g->C + 31) / 32; p.vw = (V + 31) / 32; p.P = V | 1;
+    p.R = best.R; p.G = best.G; p.NCH = meta->NCH;
+    p.ct_n = ct_n; p.rt_n = best.rt_n; p.vt_n = vt_n; p.vt_k = best.vt_k;
+    p.n_tiles = (int)((B + 31) / 32);
+    p.meta = meta->dev;
+    p.off_me = 0; p.off_ms = meta->off_ms; p.off_mi = meta->off_mi; p.off_var = meta->off_var;
+    p.off_ct = (int)meta->bytes;
+    p.off_rt = p.off_ct + (ct_n + 2) * 128;
+    p.off_vt = p.off_rt + (best.rt_n + 2) * 16;
+    p.off_state = align_up_i(p.off_vt + best.vt_k * (vt_n + 2) * 16, 128);
+    out->smem = p.off_state + best.G * state;
+    out->threads = 32 * best.G * best.R;
+    out->grid = std::min(g->sm_count, std::max(1, p.n_tiles));
+    out->meta = meta;
+    return out->smem <= smem_max;
+}
+
+// Geometry: R owners (warps) per group of 32 syndromes, G groups per CTA.  The kernel is bound by the shared-memory
+// crossbar, so what matters is enough resident warps (>= ~24) with balanced owners; more groups = more independent
+// barrier domains.  Table sizes shrink (read-out 2048 -> 1024 intervals, slots 12 -> 10 -> 8 -> 6) only as far as
+// needed to seat at least one group.
+static bool lean_plan(gd_graph* g, const gd_model* m, int64_t B, LeanPlan* out) {
+    if (!lean_applicable(g, m)) return false;
+    LeanGeom geom;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        if (!g->lean_ctx) g->lean_ctx = new LeanCtx();
+        geom = static_cast<LeanCtx*>(g->lean_ctx)->geom;
+    }
+    if (!geom.valid || geom.opt_epoch != opt_epoch()) {
+        if (!lean_search(g, &geom)) return false;
+        geom.opt_epoch = opt_epoch();
+        std::lock_guard<std::mutex> lk(g->mu);
+        static_cast<LeanCtx*>(g->lean_ctx)->geom = geom;
+    }
+    if (geom.R == 0) return false;
+    const LeanMeta* meta = get_meta(g, geom.R);
+    if (!meta) return false;
+    return lean_fill(g, m, B, geom, meta, out);
+}
+
+bool lean_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out) {
+    LeanPlan pl;
+    if (!lean_plan(const_cast<gd_graph*>(g), model, B, &pl)) return false;
+    out->tile = 32 * pl.p.G; out->threads = pl.threads; out->grid = pl.grid; out->smem_bytes = pl.smem;
+    out->resident = 1; out->n_tiles = (pl.p.n_tiles + pl.p.G - 1) / pl.p.G;
+    return true;
+}
+
+static cudaMemPool_t lean_pool(gd_graph* g) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (!g->lean_ctx) g->lean_ctx = new LeanCtx();
+    LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
+    if (!ctx->pool) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = g->device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess) {
+            ctx->pool = nullptr;
+            cudaGetLastError();
+            return nullptr;
+        }
+        unsigned long long keep = ~0ull;                          // never hand the workspace back between calls
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return ctx->pool;
+}
+
+int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* prior_dev,
+                const uint32_t* synd_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev,
+                int64_t B, cudaStream_t st) {
+    LeanPlan pl;
+    if (!lean_plan(g, model, B, &pl)) return -1;
+    cudaMemPool_t pool = lean_pool(g);
+    if (!pool) return -1;
+    LeanParams& p = pl.p;
+    const int N = g->N;
+    // workspace: header | ctab | rtab | vtab | slot | prior | sgn | defer_idx | (x for the deferred pass of packed calls)
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_hdr = take(kHdrBytes), o_ct = take((size_t)(p.ct_n + 2) * 16), o_rt = take((size_t)(p.rt_n + 2) * 16);
+    const size_t o_vt = take((size_t)p.vt_k * (p.vt_n + 2) * 16), o_slot = take((size_t)B * 4);
+    const size_t o_prior = take(x_dev ? (size_t)B * 4 : 0), o_sgn = take(x_dev ? (size_t)B * p.nw * 4 : 0);
+    const size_t o_defer = take((size_t)B * 4), o_x = take(x_dev ? 0 : (size_t)B * N * 4);
+    unsigned char* ws = nullptr;
+    GD_CUDA(cudaMallocFromPoolAsync((void**)&ws, off, pool, st));
+    LeanHeader* hdr = reinterpret_cast<LeanHeader*>(ws + o_hdr);
+    cudaError_t e = cudaMemsetAsync(hdr, 0, kHdrBytes, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(hdr->slot_bits, 0xFF, sizeof(hdr->slot_bits), st);
+    int rc = GD_OK;
+    if (e == cudaSuccess) {
+        PrepParams pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.x = x_dev; pp.weights = weights_dev; pp.hdr = hdr; pp.ctab = reinterpret_cast<float4*>(ws + o_ct);
+        pp.prior_out = reinterpret_cast<float*>(ws + o_prior); pp.sgn_out = reinterpret_cast<uint32_t*>(ws + o_sgn);
+        pp.prior_in = prior_dev; pp.slot = reinterpret_cast<int*>(ws + o_slot); pp.defer_idx = reinterpret_cast<int*>(ws + o_defer);
+        pp.B = B; pp.V = g->V; pp.C = g->C; pp.N = N; pp.nw = p.nw; pp.hid = model->hidden; pp.ct_n = p.ct_n; pp.vt_k = p.vt_k;
+        pp.n_ct_blocks = (p.ct_n + 2 + kChunk - 1) / kChunk;
+        const long long units = x_dev ? B : (B + 31) / 32;       // warps of work
+        const int pack_blocks = (int)std::min<long long>((units + 7) / 8, (long long)g->sm_count * 8);
+        lean_prep_kernel<<<pp.n_ct_blocks + std::max(1, pack_blocks), 256, 0, st>>>(pp);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        TabParams tp;
+        tp.weights = weights_dev; tp.hdr = hdr; tp.rtab = reinterpret_cast<float4*>(ws + o_rt);
+        tp.vtab = reinterpret_cast<float4*>(ws + o_vt); tp.hid = model->hidden; tp.T = model->iters; tp.rt_n = p.rt_n;
+        tp.vt_n = p.vt_n; tp.vt_k = p.vt_k; tp.rt_blocks = (p.rt_n + 2 + kChunk - 1) / kChunk;
+        tp.vt_blocks_per_slot = (p.vt_n + 2 + kChunk - 1) / kChunk;
+        lean_tables_kernel<<<tp.rt_blocks + p.vt_k * tp.vt_blocks_per_slot, 256, 0, st>>>(tp);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        p.prior = x_dev ? reinterpret_cast<const float*>(ws + o_prior) : prior_dev;
+        p.sgn = x_dev ? reinterpret_cast<const uint32_t*>(ws + o_sgn) : synd_dev;
+        p.slot = reinterpret_cast<const int*>(ws + o_slot);
+        p.prob = prob_dev; p.logit = logit_dev; p.hard = hard_dev; p.hard_bits = hard_bits_dev;
+        p.hdr = hdr;
+        p.ctab = reinterpret_cast<const float4*>(ws + o_ct); p.rtab = reinterpret_cast<const float4*>(ws + o_rt);
+        p.vtab = reinterpret_cast<const float4*>(ws + o_vt);
+        e = cudaFuncSetAttribute(lean_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
+        if (e == cudaSuccess) {
+            lean_decode_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(p);
+            e = cudaGetLastError();
+        }
+    }
+    // the syndromes the tables could not serve: edge-owner kernel, direct evaluation, per item
+    const float* x_for_deferred = x_dev;
+    if (e == cudaSuccess && !x_dev) {
+        float* xw = reinterpret_cast<float*>(ws + o_x);
+        lean_unpack_kernel<<<g->sm_count * 4, 256, 0, st>>>(prior_dev, synd_dev, hdr, reinterpret_cast<const int*>(ws + o_defer), xw,
+                                                            B, g->V, g->C, p.nw);
+        e = cudaGetLastError();
+        x_for_deferred = xw;
+    }
+    if (e == cudaSuccess) {
+        const DeferList dl{&hdr->defer_count, reinterpret_cast<const int*>(ws + o_defer)};
+        rc = decode_fwd_deferred(g, model, weights_dev, x_for_deferred, prob_dev, logit_dev, hard_dev, hard_bits_dev, B, st, dl);
+    }
+    cudaError_t ef = cudaFreeAsync(ws, st);
+    if (rc != GD_OK) return rc;
+    GD_CUDA(e);
+    GD_CUDA(ef);
+    return GD_OK;
+}
+
+}  // namespace gd
+
+void gd_lean_ctx_destroy(gd_graph* g) {
+    gd::LeanCtx* ctx = static_cast<gd::LeanCtx*>(g->lean_ctx);
+    if (!ctx) return;
+    for (gd::LeanMeta* m : ctx->metas) {
+        if (m->dev) cudaFree(m->dev);
+        delete m;
+    }
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    delete ctx;
+    g->lean_ctx = nullptr;
+}

@@ -1,0 +1,41 @@
+// Internal interface of the check-owner table kernel for decoder_v2_4 on surface / toric codes (gd_lean.cu).
+#pragma once
+#include "gd_common.cuh"
+
+namespace gd {
+
+// Device-side header of one lean decode call (lives in the call's workspace).  Written by the prep / table kernels,
+// read by the decode kernel and by the deferred pass of the edge-owner kernel (gd_decode.cu).
+struct LeanHeader {
+    int n_slots;                 // distinct eligible priors found (<= slots of the plan)
+    int overflow;                // more distinct priors than table slots: the whole batch takes the edge-owner kernel
+    int defer_count;             // syndromes listed in defer_idx; -1 = all of them, in batch order
+    int pad0;
+    unsigned int fmax_bits;      // max |mlp2| over the check table's nodes (float bits, rounded up)
+    unsigned int f3max_bits;     // max |mlp3| over the read-out table's nodes
+    unsigned int err_c_bits;     // a-posteriori interpolation error of the check table (sampled interval midpoints)
+    unsigned int err_r_bits;     // ... of the read-out table
+    unsigned int err_v_bits[16]; // ... of each variable-phase table (in units of tanh output)
+    unsigned int slot_bits[16];  // prior value (float bits) of table slot k; 0xFFFFFFFF = free
+};
+
+// Edge-owner kernel pass over the syndromes the lean kernel deferred (gd_decode.cu).
+struct DeferList {
+    const int* count;            // &LeanHeader::defer_count
+    const int* idx;              // [B] syndrome indices (valid when *count > 0)
+};
+
+// returns -1 when the lean path does not apply to (graph, model) -- the caller then takes the edge-owner kernel --
+// otherwise a gd_status.  Exactly one of x_dev / (prior_dev, synd_dev) is given.
+int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* prior_dev,
+                const uint32_t* synd_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev,
+                int64_t B, cudaStream_t st);
+bool lean_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out);
+
+// gd_decode.cu: run the edge-owner resident kernel over a deferred list (no variable-phase tables: per-item direct
+// evaluation, so a deferred syndrome's result never depends on what else was deferred)
+int decode_fwd_deferred(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, float* prob_dev,
+                        float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev, int64_t B, cudaStream_t st,
+                        const DeferList& dl);
+
+}  // namespace gd

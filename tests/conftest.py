@@ -17,6 +17,44 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device: skip (not fail) them on a box without one."""
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class _GdOptions(object):
+    """Set / unset library tunables (gnn_decode_b200.options) for one test; everything touched is unset again afterwards."""
+
+    def __init__(self):
+        self.touched = set()
+
+    def set(self, name, value=1):
+        from gnn_decode_b200 import options
+        options.set_option(name, value)
+        self.touched.add(name)
+
+    def unset(self, name):
+        from gnn_decode_b200 import options
+        options.unset_option(name)
+
+    def restore(self):
+        from gnn_decode_b200 import options
+        for name in self.touched:
+            options.unset_option(name)
+
+
+@pytest.fixture
+def gd_opt():
+    o = _GdOptions()
+    yield o
+    o.restore()
+
+
 def golden_cases():
     return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
                   if not f.endswith("codes.npz") and not os.path.basename(f).startswith(("grad_", "ext_")))

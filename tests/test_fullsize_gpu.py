@@ -89,7 +89,7 @@ def test_hgp_streamed_full_batch_properties():
     assert int(total[0]) < 0.10 * B                                          # sanity: plain BP well below threshold
 
 
-def test_variable_phase_tables_and_their_fallbacks(monkeypatch):
+def test_variable_phase_tables_and_their_fallbacks(gd_opt):
     """decoder_v2_4's variable-phase MLP is read from per-prior cubic tables when every variable of a syndrome carries the
     same prior.  Every way out of that fast path must give the reference's numbers too:
     (a) uniform priors, few distinct values: tables (vs the oracle, and vs the direct kernel GD_NO_VTAB=1);
@@ -126,7 +126,7 @@ def test_variable_phase_tables_and_their_fallbacks(monkeypatch):
         if name in ("uniform10", "mixed"):              # few distinct priors: slices are bit-identical (table content depends on the prior only)
             for lo, n in ((0, 8), (777, 1234), (B - 501, 501)):
                 assert torch.equal(dec.decode(xx[lo:lo + n].contiguous(), graph=g), prob[lo:lo + n]), (name, lo)
-    monkeypatch.setenv("GD_NO_VTAB", "1")
+    gd_opt.set("GD_NO_VTAB")
     assert g.tables_info(dec.gd_model(), B)[2] == 0
     for name, xx in cases.items():
         prob, logit, hard = out[name]

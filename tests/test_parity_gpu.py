@@ -205,7 +205,7 @@ def test_fp32_and_fp64_inputs_agree():
 
 @pytest.mark.parametrize("name", ["v2_4_toricL4_epoch1", "qgnni_toricL4_seeded", "cgnni_bch_seeded", "cgnni_ldpc_epoch18",
                                   "bp_quantum_toricL4", "bp_classical_bch"])
-def test_streamed_kernel_matches_resident_and_reference(name, monkeypatch):
+def test_streamed_kernel_matches_resident_and_reference(name, gd_opt):
     """The global-memory (streamed) kernel used for codes too large for shared memory, forced on
     a small code: same logits as the oracle (same bar) and hard decisions identical to the
     resident kernel."""
@@ -217,11 +217,11 @@ def test_streamed_kernel_matches_resident_and_reference(name, monkeypatch):
     tg = TannerGraph(g.edge_index, g.V, g.C, dev)
     x = g.x.repeat(5, 1).to(dev)                                   # 80..160 syndromes: ragged tiles
     p_res, l_res, h_res = dec.decode(x, graph=tg, return_logits=True, return_hard=True)
-    monkeypatch.setenv("GD_FORCE_STREAMED", "1")
+    gd_opt.set("GD_FORCE_STREAMED")
     assert tg.launch_info(dec.gd_model(), x.size(0))["resident"] == 0
     p_str, l_str, h_str = dec.decode(x, graph=tg, return_logits=True, return_hard=True)
     p_str2 = dec.decode(x, graph=tg)
-    monkeypatch.delenv("GD_FORCE_STREAMED")
+    gd_opt.unset("GD_FORCE_STREAMED")
     assert torch.equal(p_str, p_str2)                               # deterministic
     ref = restate.decode(g.program, g.edge_index, g.V, g.C, g.x, g.weights, T=g.T, dtype=torch.float64)
     bp = g.program.startswith("bp")
@@ -259,7 +259,7 @@ def test_hgp_1600_streamed_matches_oracle():
 
 
 @pytest.mark.parametrize("scale,T", [(1.0, 15), (6.0, 4), (1.0, 60)])
-def test_v2_4_tabulated_mlps_match_direct_evaluation_and_oracle(scale, T, monkeypatch):
+def test_v2_4_tabulated_mlps_match_direct_evaluation_and_oracle(scale, T, gd_opt):
     """decoder_v2_4's 1->128->1 check-phase and read-out MLPs run from per-launch cubic tables when the
     in-kernel error bound allows.  (a) tabulated == direct evaluation (GD_NO_CTAB) far inside
     the logit tolerance; (b) with first-layer weights scaled up the bound fails and the kernel must fall back
@@ -277,9 +277,9 @@ def test_v2_4_tabulated_mlps_match_direct_evaluation_and_oracle(scale, T, monkey
     tg = TannerGraph(g.edge_index, g.V, g.C, dev)
     x = g.x.repeat(9, 1).to(dev)
     _, l_tab, h_tab = dec.decode(x, graph=tg, return_logits=True, return_hard=True)
-    monkeypatch.setenv("GD_NO_CTAB", "1")
+    gd_opt.set("GD_NO_CTAB")
     _, l_dir, h_dir = dec.decode(x, graph=tg, return_logits=True, return_hard=True)
-    monkeypatch.delenv("GD_NO_CTAB")
+    gd_opt.unset("GD_NO_CTAB")
     ref = restate.decode("v2_4", g.edge_index, g.V, g.C, g.x, w, T=T, dtype=torch.float64)
     for l in (l_tab, l_dir):
         worst, max_err = _logit_close(l[:g.B], ref["logit"], RTOL)
@@ -313,7 +313,7 @@ def test_autotuned_geometry_gives_identical_results():
     assert isinstance(info0, dict)
 
 
-def test_decode_host_gated_pipeline(monkeypatch):
+def test_decode_host_gated_pipeline(gd_opt):
     """gd_decode_host's gated single-launch pipeline (chunk flags raised by stream memory operations, per-chunk tile
     counters releasing the copies back): bit-identical to the device path and to the one-launch-per-chunk pipeline, on
     ragged batch sizes, repeated calls (epoch reuse), changing batch sizes and either output alone."""
@@ -342,7 +342,7 @@ def test_decode_host_gated_pipeline(monkeypatch):
     pageable = dec.decode_host(x_all.cpu()[:17000].clone())                                # pageable host memory works too
     assert torch.equal(pageable, ref_p[:17000])
     # the one-launch-per-chunk pipeline (gating disabled for a fresh graph context) gives the same bits
-    monkeypatch.setenv("GD_NO_GATED_HOST", "1")
+    gd_opt.set("GD_NO_GATED_HOST")
     tg2 = TannerGraph(g.edge_index, g.V, g.C, dev)
     p2 = dec.decode_host(xh_all, graph=tg2)
     assert torch.equal(p2, ref_p)

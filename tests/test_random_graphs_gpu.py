@@ -39,7 +39,7 @@ def _decoder(program, T, E):
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
 @pytest.mark.parametrize("program", ["v2_4", "qgnni", "cgnni", "bp_quantum", "bp_classical", "neural_bp", "gru_ca"])
-def test_random_graph_matches_oracle(program, seed, monkeypatch):
+def test_random_graph_matches_oracle(program, seed, gd_opt):
     rng = np.random.RandomState(100 * seed + 7)
     C, V = rng.randint(3, 14), rng.randint(6, 40)
     pcm = _random_pcm(rng, C, V, max_row=(12 if seed == 2 else 6))
@@ -62,9 +62,9 @@ def test_random_graph_matches_oracle(program, seed, monkeypatch):
     modes = ["resident"] + (["streamed"] if program not in ("neural_bp", "gru_ca") else [])
     for mode in modes:
         if mode == "streamed":
-            monkeypatch.setenv("GD_FORCE_STREAMED", "1")
+            gd_opt.set("GD_FORCE_STREAMED")
         _, logit, hard = dec.decode(x.to(DEV), graph=g, return_logits=True, return_hard=True)
-        monkeypatch.delenv("GD_FORCE_STREAMED", raising=False)
+        gd_opt.unset("GD_FORCE_STREAMED")
         got = logit.double().cpu()
         ok = (got - ref).abs() <= rtol * ref.abs() + atol
         if bp:   # saturated sum-product messages: compare where the reference itself is not at its clamp
@@ -75,7 +75,7 @@ def test_random_graph_matches_oracle(program, seed, monkeypatch):
 
 
 @pytest.mark.parametrize("mode", ["v2_4-resident", "qgnni-light", "bp-light", "qgnni-streamed", "bp-streamed", "v2_4-streamed"])
-def test_repeated_launches_are_bit_identical(mode, monkeypatch):
+def test_repeated_launches_are_bit_identical(mode, gd_opt):
     """compute-sanitizer is not available on the GPU pool, so data races are hunted the blunt way: 25 launches of
     every kernel family on a ragged batch, concurrently on two streams, must all be bit-identical."""
     from gnn_decode_b200.quantum import decoder_v2_4, QGNNI, BP
@@ -88,9 +88,9 @@ def test_repeated_launches_are_bit_identical(mode, monkeypatch):
     B = 5003 if kern != "streamed" else 1203
     x, _ = sample_syndromes(g, B, [0.03, 0.08], noise=1 if prog == "v2_4" else 0, seed=4)
     if kern == "light":
-        monkeypatch.setenv("GD_FORCE_LIGHT", "1")
+        gd_opt.set("GD_FORCE_LIGHT")
     if kern == "streamed":
-        monkeypatch.setenv("GD_FORCE_STREAMED", "1")
+        gd_opt.set("GD_FORCE_STREAMED")
     first = dec.decode(x, graph=g, return_logits=True)[1].clone()
     streams = [torch.cuda.Stream(DEV), torch.cuda.Stream(DEV)]
     torch.cuda.synchronize()

@@ -164,7 +164,7 @@ def test_fused_loss_and_train_step_match_reference(name):
         assert (p.grad - first[k]).abs().max().item() <= 1e-5 * first[k].abs().max().item() + 1e-12
 
 
-def test_degree_one_variables_and_table_adjoint_do_not_change_gradients(monkeypatch):
+def test_degree_one_variables_and_table_adjoint_do_not_change_gradients(gd_opt):
     """Rotated surface codes have degree-1 variables (the toric gradient fixtures do not): their variable-phase
     messages are iteration-invariant, so the backward sums their upstream gradient over the iterations and runs
     the MLP once; the check-phase MLP goes through its cubic table and the table's adjoint.  Both are pure
@@ -186,8 +186,8 @@ def test_degree_one_variables_and_table_adjoint_do_not_change_gradients(monkeypa
     x, err = sample_syndromes(g, 333, [0.03, 0.08, 0.12], noise=1, seed=5)
     loss_a, _ = train_step_grads(dec, g, x, err, logical)
     ga = {k: p.grad.clone() for k, p in dec.named_parameters()}
-    monkeypatch.setenv("GD_NO_VSKIP", "1")
-    monkeypatch.setenv("GD_NO_CTAB", "1")
+    gd_opt.set("GD_NO_VSKIP")
+    gd_opt.set("GD_NO_CTAB")
     loss_b, _ = train_step_grads(dec, g, x, err, logical)
     gb = {k: p.grad.clone() for k, p in dec.named_parameters()}
     assert abs(loss_a.item() - loss_b.item()) <= 1e-5 * abs(loss_b.item())
