@@ -44,6 +44,14 @@ _SIGNATURES = {
     "gd_propagate_features": (C.c_int, [C.c_int32, C.c_int32]),
     "gd_propagate_fwd": (C.c_int, [_p, C.POINTER(GdModel), C.c_int32, C.c_int32, _p, _p, _p, _p, C.c_int64, _p]),
     "gd_decode_fwd": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, _p, C.c_int64, _p]),
+    "gd_decode_packed_fwd": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, _p, C.c_int64, _p]),
+    "gd_pipeline_create": (C.c_int, [_p, C.POINTER(GdModel), _p, C.c_int64, C.c_int32, C.POINTER(_p)]),
+    "gd_pipeline_destroy": (None, [_p]),
+    "gd_pipeline_set_weights": (C.c_int, [_p, _p]),
+    "gd_pipeline_submit": (C.c_int, [_p, _p, _p, _p, C.c_int64, C.POINTER(C.c_int32)]),
+    "gd_pipeline_submit_packed": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.POINTER(C.c_int32)]),
+    "gd_pipeline_wait": (C.c_int, [_p, C.c_int32]),
+    "gd_pipeline_drain": (C.c_int, [_p]),
     "gd_decode_host": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, C.c_int64]),
     "gd_decode_host_last_launches": (C.c_int, [_p]),
     "gd_decode_tables_info": (C.c_int, [_p, C.POINTER(GdModel), C.c_int64, C.POINTER(C.c_int32)]),

@@ -16,6 +16,7 @@
 //     wgrad reduction"), ready for one NCCL all-reduce of 10h+3 floats.
 #include "gd_common.cuh"
 #include "gd_math.cuh"
+#include "gd_options.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -499,8 +500,8 @@ static int plan_bwd(const gd_graph* g, const gd_model* m, int64_t B, BwdPlan* ou
     p.np_pad = align_up_b((int)gd_weights_size(m), 32);
     const int tab_bytes = (5 * E + V + C + 2) * 2;
     int fixed = align_up_b(tab_bytes, 128);
-    p.n_vact = getenv("GD_NO_VSKIP") ? E : g->n_vact;
-    if (!getenv("GD_NO_CTAB") && !getenv("GD_NO_BWD_CTAB")) {
+    p.n_vact = opt_on(OPT_NO_VSKIP) ? E : g->n_vact;
+    if (!opt_on(OPT_NO_CTAB) && !opt_on(OPT_NO_BWD_CTAB)) {
         p.ctab_n = 512;
         p.ctab_R = (float)(g->max_chk_deg > 1 ? g->max_chk_deg - 1 : 1);
         const int hp = (m->hidden + 7) / 8 * 8;

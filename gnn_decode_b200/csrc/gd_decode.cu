@@ -1009,6 +1009,55 @@ extern "C" int gd_decode_fwd(const gd_graph* gc, const gd_model* model, const fl
     return decode_fwd_impl(gc, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, nullptr, B, stream);
 }
 
+// ---- packed form of the same decode (include/gnn_decode.h): what the reference's x actually carries per syndrome is ONE
+// prior value and C check signs (gen_syn, quantum/error_generate.py:258, 270-276) ----
+namespace {
+struct PackedRun {
+    const gd_graph* g; const gd_model* model; const float* w; float* prob; uint32_t* bits; int64_t B; void* stream;
+};
+int packed_run(void* ctx, const float* x_dev) {
+    const PackedRun* r = static_cast<const PackedRun*>(ctx);
+    return decode_fwd_impl(r->g, r->model, r->w, x_dev, r->prob, nullptr, nullptr, nullptr, r->B, r->stream, nullptr, nullptr, r->bits);
+}
+}  // namespace
+
+extern "C" int gd_decode_packed_fwd(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* prior_dev,
+                                    const uint32_t* synd_dev, float* prob_dev, uint32_t* hard_bits_dev, int64_t B, void* stream) {
+    gd_graph* g = const_cast<gd_graph*>(gc);
+    GD_CHECK_ARG(g != nullptr, "gd_decode_packed_fwd: graph is NULL");
+    GD_CHECK_ARG(gd_model_valid(model), "gd_decode_packed_fwd: invalid model");
+    GD_CHECK_ARG(B >= 0 && B < ((int64_t)1 << 31), "gd_decode_packed_fwd: B=%lld out of range", (long long)B);
+    if (B == 0) return GD_OK;
+    GD_CHECK_ARG(prior_dev && synd_dev, "gd_decode_packed_fwd: prior / syndrome bits are NULL");
+    GD_CHECK_ARG(prob_dev || hard_bits_dev, "gd_decode_packed_fwd: no output requested");
+    GD_CHECK_ARG(gd_weights_size(model) == 0 || weights_dev != nullptr, "gd_decode_packed_fwd: weights is NULL");
+    GD_CHECK_ARG(((uintptr_t)prob_dev & 15) == 0 && ((uintptr_t)hard_bits_dev & 3) == 0 && ((uintptr_t)synd_dev & 3) == 0,
+                 "gd_decode_packed_fwd: prob must be 16-byte, bit arrays 4-byte aligned");
+    if (model->program != GD_PROG_V2_4) {
+        gd::set_error("gd_decode_packed_fwd: packed inputs are implemented for GD_PROG_V2_4 only");
+        return GD_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int prev = 0;
+    GD_CUDA(cudaGetDevice(&prev));
+    if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
+    int rc = gd::lean_decode(g, model, weights_dev, nullptr, prior_dev, synd_dev, prob_dev, nullptr, nullptr, hard_bits_dev, B, st);
+    if (rc < 0) {                // not a surface / toric code: expand and take the edge-owner kernel
+        gd_launch_info li;
+        rc = gd_decode_launch_info(g, model, B, &li);
+        if (rc == GD_OK && !li.resident) {
+            gd::set_error("gd_decode_packed_fwd: this code's edge state does not fit shared memory (streamed path has no packed form)");
+            rc = GD_ERR_UNSUPPORTED;
+        }
+        if (rc == GD_OK) {
+            PackedRun r{g, model, weights_dev, prob_dev, hard_bits_dev, B, stream};
+            rc = gd::packed_via_unpack(g, prior_dev, synd_dev, B, st, packed_run, &r);
+        }
+    }
+    if (prev != g->device) cudaSetDevice(prev);
+    return rc;
+}
+
 extern "C" int64_t gd_stash_floats(const gd_graph* g, const gd_model* model, int64_t B) {
     if (!g || !gd_model_valid(model) || B < 0) {
         gd::set_error("gd_stash_floats: invalid argument");

@@ -16,6 +16,7 @@
 // Requires the canonical variable-sorted edge order (H.to_sparse()); other graphs keep the edge-owner kernel.
 #include "gd_common.cuh"
 #include "gd_math.cuh"
+#include "gd_options.cuh"
 #include "gd_decode.cuh"
 #include "gd_nodemath.cuh"
 #include <stdlib.h>
@@ -560,10 +561,10 @@ static void plan_light(const gd_graph* g, const gd_model* m, int64_t B, LightPla
     const int prog = m->program;
     const bool ext = prog == GD_PROG_NEURAL_BP || prog == GD_PROG_GRU_CA;
     if (prog != GD_PROG_CGNNI && prog != GD_PROG_QGNNI && prog != GD_PROG_BP_QUANTUM && prog != GD_PROG_BP_CLASSICAL && !ext) return;
-    if (prog == GD_PROG_GRU_CA && (m->hidden >= 32 || (m->flags & GD_FLAG_ALL_ITERS) || getenv("GD_NO_PWL"))) return;
+    if (prog == GD_PROG_GRU_CA && (m->hidden >= 32 || (m->flags & GD_FLAG_ALL_ITERS) || opt_on(OPT_NO_PWL))) return;
     if (prog == GD_PROG_NEURAL_BP && m->hidden != g->E) return;      // the caller's argument check reports it
-    if (getenv("GD_NO_LIGHT") || getenv("GD_FORCE_STREAMED")) return;
-    if ((B + 15) / 16 < g->sm_count && !getenv("GD_FORCE_LIGHT")) return;   // cannot fill the GPU at any tile size: skip the search
+    if (opt_on(OPT_NO_LIGHT) || opt_on(OPT_FORCE_STREAMED)) return;
+    if ((B + 15) / 16 < g->sm_count && !opt_on(OPT_FORCE_LIGHT)) return;   // cannot fill the GPU at any tile size: skip the search
     if (g->E >= 65536 || g->V >= 65535 || g->C >= 65535) return;
     for (size_t i = 0; i < g->h_var_edges.size(); ++i)
         if (g->h_var_edges[i] != (int32_t)i) return;           // needs the canonical variable-sorted edge order
@@ -571,7 +572,7 @@ static void plan_light(const gd_graph* g, const gd_model* m, int64_t B, LightPla
     p.B = B; p.T = m->iters; p.V = g->V; p.C = g->C; p.E = (int)g->E; p.N = g->N; p.tb = g->t;
     p.hid = bp ? 0 : m->hidden;
     p.hp = align_up_l(p.hid, 4);
-    out->npad = (!bp && m->hidden < 32 && !getenv("GD_NO_PWL")) ? (m->hidden < 16 ? 16 : 32) : 0;
+    out->npad = (!bp && m->hidden < 32 && !opt_on(OPT_NO_PWL)) ? (m->hidden < 16 ? 16 : 32) : 0;
     p.trows = g->E > g->V ? (int)g->E : g->V;                  // the t region doubles as the logit rows lg[V][tile]
     int off = 0;
     p.off_w = off;
@@ -589,12 +590,11 @@ static void plan_light(const gd_graph* g, const gd_model* m, int64_t B, LightPla
     // graphs whose balance falls below 0.3 keep the edge-owner kernel.
     int best_tile = 0, best_cps = 1, best_R = 1;
     double best_cost = 1e300, best_bal = 0.0;
-    const char* et = getenv("GD_LTILE");
-    const char* er = getenv("GD_LR");
+    const long long et = opt_int(OPT_LTILE, 0), er = opt_int(OPT_LR, 0);
     const int maxn = g->V > g->C ? g->V : g->C;
     std::vector<int> load;
     for (int t = 16; t <= 128; t *= 2) {
-        if (et && atoi(et) != t) continue;
+        if (et > 0 && et != t) continue;
         const int64_t smem = fixed + per_syn * t;
         if (smem > g->max_smem_optin) break;
         const int lanes = t / 4;
@@ -604,7 +604,7 @@ static void plan_light(const gd_graph* g, const gd_model* m, int64_t B, LightPla
         for (int ci = 0; ci < 8; ++ci) {
             const int R = cand[ci];
             if (R < 1 || R > r_max) continue;
-            if (er && atoi(er) != R) continue;
+            if (er > 0 && er != R) continue;
             bool dup = false;
             for (int cj = 0; cj < ci; ++cj) dup = dup || cand[cj] == R;
             if (dup) continue;
@@ -631,7 +631,7 @@ static void plan_light(const gd_graph* g, const gd_model* m, int64_t B, LightPla
             if (cost < best_cost * (1.0 - 1e-12)) { best_cost = cost; best_tile = t; best_cps = cps; best_R = R; best_bal = bal; }
         }
     }
-    if (!best_tile || (best_bal < 0.3 && !getenv("GD_FORCE_LIGHT"))) return;
+    if (!best_tile || (best_bal < 0.3 && !opt_on(OPT_FORCE_LIGHT))) return;
     p.tile = best_tile;
     p.lanes = best_tile / 4;
     p.R = best_R;
@@ -645,7 +645,7 @@ static void plan_light(const gd_graph* g, const gd_model* m, int64_t B, LightPla
     const int slots = g->sm_count * best_cps;
     // Small batches are latency-bound: four syndromes per lane leave 4x fewer threads than the edge-owner kernel's
     // one-syndrome-per-lane mapping (toy LDPC, B = 1024: 48 vs 35 us).  Take over only when the GPU is filled.
-    if (p.n_tiles < slots && !getenv("GD_FORCE_LIGHT")) return;
+    if (p.n_tiles < slots && !opt_on(OPT_FORCE_LIGHT)) return;
     out->grid = p.n_tiles < slots ? p.n_tiles : slots;
     out->ok = true;
 }

@@ -11,6 +11,7 @@
 // count (cuStreamWaitValue32) and then copies the chunk's results back.  No per-chunk prologue (weight staging, table
 // builds), no per-chunk tail, and the chunks can be small: the exposed copies shrink to one small chunk each way.
 #include "gd_decode.cuh"
+#include "gd_options.cuh"
 #include <cuda.h>
 #include <algorithm>
 
@@ -19,6 +20,7 @@ namespace gd {
 typedef CUresult (*StreamMemOp32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 
 struct HostCtx {
+    std::mutex call_mu;              // one gd_decode_host call at a time per graph: the staging buffers, gate flags and epochs are shared
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};
     // gated pipeline state
     StreamMemOp32 write32 = nullptr, wait32 = nullptr;
@@ -43,7 +45,7 @@ constexpr int kMaxGateChunks = 32;
 // operations are available on every device CUDA 12 supports
 static void probe_memops(HostCtx* c, int device) {
     c->memops = 0;
-    if (getenv("GD_NO_GATED_HOST")) return;
+    if (opt_on(OPT_NO_GATED_HOST)) return;
     cudaDriverEntryPointQueryResult q;
     void *w = nullptr, *wt = nullptr;
     if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return;
@@ -120,15 +122,16 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
     std::unique_lock<std::mutex> lk(g->mu);
     if (!g->host_ctx) g->host_ctx = new gd::HostCtx();
     gd::HostCtx* c = static_cast<gd::HostCtx*>(g->host_ctx);
-    cudaError_t e = gd::ensure(c, g, B, n_w);
     lk.unlock();  // gd_decode_fwd takes the same mutex for the streamed workspace
+    // one call at a time per graph from here on: the staging buffers, streams, gate flags and epochs are shared state
+    std::lock_guard<std::mutex> call_lk(c->call_mu);
+    cudaError_t e = gd::ensure(c, g, B, n_w);
     int rc = GD_OK;
     if (e == cudaSuccess && c->memops < 0) gd::probe_memops(c, g->device);
     int tile = 0, n_tiles = 0;
     if (e == cudaSuccess && c->memops == 1 && B >= 16384 && gd::gated_plan(g, model, B, &tile, &n_tiles)) {
         // ---- gated pipeline: st[0] = kernel, st[1] = copies in, st[2] = copies out ----
-        const char* ce = getenv("GD_GATE_CHUNKS");
-        int n_chunks = ce && atoi(ce) > 0 ? atoi(ce) : 16;   // measured on B200, rotated d=5 B=65536: 4 -> 19.20, 8 -> 19.41, 16 -> 19.55 M syn/s
+        int n_chunks = (int)std::max<long long>(1, gd::opt_int(gd::OPT_GATE_CHUNKS, 16));   // measured on B200, rotated d=5 B=65536: 4 -> 19.20, 8 -> 19.41, 16 -> 19.55 M syn/s
         n_chunks = std::min(std::min(n_chunks, gd::kMaxGateChunks), std::max(1, (int)(B / 4096)));
         const int chunk_tiles = (n_tiles + n_chunks - 1) / n_chunks;
         n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
@@ -148,9 +151,7 @@ extern "C" int gd_decode_host(const gd_graph* gc, const gd_model* model, const f
         // goes undetected the gates time out (seconds), the batch is redone by the chunked pipeline and gating is turned off.
         // (Nsight Compute marks its target with NV_NSIGHT_INJECTION_PORT_BASE / NV_COMPUTE_PROFILER_PERFWORKS_DIR; other
         // injectors use CUDA_INJECTION64_PATH)
-        const bool kernel_first = !getenv("CUDA_INJECTION64_PATH") && !getenv("NV_NSIGHT_INJECTION_PORT_BASE") &&
-                                  !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") && !getenv("CUDA_LAUNCH_BLOCKING") &&
-                                  !getenv("GD_GATE_COPIES_FIRST");
+        const bool kernel_first = !gd::opt_on(gd::OPT_LAUNCH_BLOCKING) && !gd::opt_on(gd::OPT_GATE_COPIES_FIRST);
         bool memop_failed = false, launched = false;
         auto launch = [&]() {
             gd::Gate gate{in_flags, out_counts, c->gate_err_dev, epoch, chunk_tiles};

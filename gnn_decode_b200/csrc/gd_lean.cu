@@ -49,6 +49,7 @@ struct LeanParams {
     const uint32_t* sgn;         // [B][nw] bit c = check c's input is -1
     float* prob; float* logit; uint8_t* hard; uint32_t* hard_bits;
     LeanHeader* hdr;
+    LeanCall* call;
     const float4* ctab; const float4* rtab; const float4* vtab;   // global tables: (n + 2) pieces each, piece 0 = interval -1
     const uint32_t* meta;        // device metadata blob of this (graph, R)
     long long B;
@@ -186,13 +187,21 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
     // ---- can the tables serve this call at all? (identical decision in every thread of the grid) ----
     const int n_slots = H->n_slots;
     const float fmax = __uint_as_float(H->fmax_bits), f3max = __uint_as_float(H->f3max_bits);
-    bool ok = !H->overflow && n_slots <= p.vt_k && __uint_as_float(H->err_c_bits) <= kBudgetC + 6e-8f * fmax &&
+    const bool overflow = p.call->overflow != 0;
+    bool ok = !overflow && n_slots <= p.vt_k && __uint_as_float(H->err_c_bits) <= kBudgetC + 6e-8f * fmax &&
               __uint_as_float(H->err_r_bits) <= kBudgetR + 1e-7f * f3max && isfinite(fmax) && isfinite(f3max);
     for (int k = 0; k < n_slots && k < 16; ++k) ok = ok && __uint_as_float(H->err_v_bits[k]) <= kBudgetV;
-    if (!ok) {
-        if (blockIdx.x == 0 && tid == 0) p.hdr->defer_count = -1;     // everything goes to the edge-owner kernel
-        return;
+    if (blockIdx.x == 0 && tid == 0) {
+        if (overflow) {        // the prior list is full of values this batch does not (only) use: start it afresh next call
+            p.hdr->n_slots = 0;
+            p.hdr->built_mask = 0u;
+            for (int k = 0; k < 16; ++k) { p.hdr->slot_bits[k] = kNone; p.hdr->err_v_bits[k] = 0u; }
+        } else {
+            p.hdr->built_mask = n_slots >= 32 ? 0xFFFFFFFFu : ((1u << n_slots) - 1u);   // the table kernel finished before this one
+        }
+        if (!ok) p.call->defer_count = -1;                     // everything goes to the edge-owner kernel
     }
+    if (!ok) return;
     if (n_slots == 0) return;                                         // nothing eligible: all listed as deferred already
 
     // ---- prologue: metadata and tables into shared memory ----
@@ -405,20 +414,65 @@ __device__ void build_chunk(const MlpD& M, double prior, bool tanh_fold, double 
     }
 }
 
-// prior look-up / insertion into the header's slot list; returns the slot or -1 (list full)
-__device__ __forceinline__ int slot_of(LeanHeader* H, unsigned int bits, int vt_k) {
+// prior look-up / insertion into the header's slot list; returns the slot or -1 (list full).  `mirror` is the CTA's copy of
+// the list in shared memory: after the first few syndromes every look-up is answered there (all warps of the grid polling
+// the one global cache line serialises on a single L2 slice: 125 us for 65536 syndromes, measured).
+__device__ __forceinline__ int slot_of(LeanHeader* H, unsigned int* mirror, unsigned int bits, int vt_k) {
     for (int k = 0; k < vt_k; ++k) {
-        unsigned int cur = *reinterpret_cast<volatile unsigned int*>(&H->slot_bits[k]);
+        unsigned int cur = *reinterpret_cast<volatile unsigned int*>(&mirror[k]);
+        if (cur == bits) return k;
+        if (cur != kNone) continue;
+        cur = *reinterpret_cast<volatile unsigned int*>(&H->slot_bits[k]);
         if (cur == kNone) {
             cur = atomicCAS(&H->slot_bits[k], kNone, bits);
             if (cur == kNone) {
                 atomicMax(&H->n_slots, k + 1);
-                return k;
+                cur = bits;
             }
         }
+        *reinterpret_cast<volatile unsigned int*>(&mirror[k]) = cur;    // slots are never reassigned within a call
         if (cur == bits) return k;
     }
     return -1;
+}
+
+// 64-bit mix (splitmix64 finaliser)
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// First kernel of a call (one CTA): content hash of the weights and table geometry against the cache entry's; on a
+// mismatch the entry is reset (its tables are rebuilt by the next two kernels).  Also clears the per-call state.
+__global__ void __launch_bounds__(256) lean_begin_kernel(const float* weights, int n_w, int T, int ct_n, int rt_n, int vt_n,
+                                                          LeanHeader* H, LeanCall* call) {
+    __shared__ unsigned long long part[8];
+    unsigned long long h = 0;
+    for (int i = threadIdx.x; i < n_w; i += blockDim.x)
+        h += mix64((unsigned long long)__float_as_uint(weights[i]) ^ ((unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull));
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        h = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) h += part[i];
+        h += mix64(((unsigned long long)T << 48) ^ ((unsigned long long)ct_n << 32) ^ ((unsigned long long)rt_n << 16) ^ (unsigned long long)vt_n ^
+                   ((unsigned long long)n_w << 56));
+        if (h == 0) h = 1;
+        if (H->hash != h) {
+            H->hash = h;
+            H->rebuild = 1;
+            H->n_slots = 0;
+            H->built_mask = 0u;
+            H->fmax_bits = H->f3max_bits = H->err_c_bits = H->err_r_bits = 0u;
+            for (int k = 0; k < 16; ++k) { H->slot_bits[k] = kNone; H->err_v_bits[k] = 0u; }
+        } else {
+            H->rebuild = 0;
+        }
+        call->overflow = 0;
+        call->defer_count = 0;
+    }
 }
 
 struct PrepParams {
@@ -429,6 +483,7 @@ struct PrepParams {
     const float* prior_in;       // [B]   (packed inputs)
     int* slot; int* defer_idx;
     LeanHeader* hdr;
+    LeanCall* call;
     float4* ctab;
     long long B;
     int V, C, N, nw, hid, ct_n, vt_k, n_ct_blocks;
@@ -439,39 +494,53 @@ struct PrepParams {
 // distinct priors and list the syndromes the tables cannot serve.
 __global__ void __launch_bounds__(256) lean_prep_kernel(const PrepParams p) {
     __shared__ double2 nodes[kChunk + 1];
+    __shared__ volatile unsigned int mirror_v[16];
+    unsigned int* mirror = const_cast<unsigned int*>(mirror_v);
     LeanHeader* H = p.hdr;
     if ((int)blockIdx.x < p.n_ct_blocks) {
+        if (!H->rebuild) return;                                // same weights as the last call on this entry: the table stands
         const float* w = p.weights + 4 * p.hid + 1;             // ggc2.mlp
         const MlpD M{w, 1, nullptr, w + p.hid, w + 2 * p.hid, w[3 * p.hid], p.hid};
         const int i0 = blockIdx.x * kChunk, n_int = min(kChunk, p.ct_n + 2 - i0);
         if (n_int > 0) build_chunk(M, 0.0, false, 3.0, p.ct_n, i0, n_int, p.ctab, &H->fmax_bits, &H->err_c_bits, nodes);
         return;
     }
+    if (threadIdx.x < 16) mirror[threadIdx.x] = threadIdx.x < p.vt_k ? H->slot_bits[threadIdx.x] : 0u;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)(blockIdx.x - p.n_ct_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)(gridDim.x - p.n_ct_blocks) * (blockDim.x >> 5);
     if (p.x) {
         for (long long s = wid; s < p.B; s += nwarps) {          // a warp per syndrome
             const float* row = p.x + s * p.N;
-            const float p0 = __ldg(row);
-            bool good = true;
-            for (int v = lane; v < p.V; v += 32) good = good && (__float_as_uint(__ldg(row + v)) == __float_as_uint(p0));
+            // ~60 instructions per syndrome: independent lane-strided loads (no short-circuit &&, which would chain one memory
+            // latency per load), one ballot per word of check signs, one vote, and the prior looked up by 16 lanes at once
+            const unsigned int p0b = __float_as_uint(__ldg(row));
+            unsigned int bad = 0u;
+#pragma unroll 4
+            for (int v = lane; v < p.V; v += 32) bad |= __float_as_uint(__ldg(row + v)) ^ p0b;
             for (int w = 0; w < p.nw; ++w) {
                 const int c = w * 32 + lane;
                 const float val = c < p.C ? __ldg(row + p.V + c) : 1.0f;
-                good = good && (val == 1.0f || val == -1.0f);
+                bad |= (val == 1.0f || val == -1.0f) ? 0u : 1u;
                 const uint32_t word = __ballot_sync(0xffffffffu, val < 0.f);
                 if (lane == 0) p.sgn_out[s * p.nw + w] = word;
             }
-            good = __all_sync(0xffffffffu, good) && isfinite(p0);
-            if (lane == 0) {
-                int slot = -1;
-                if (good) {
-                    slot = slot_of(H, __float_as_uint(p0), p.vt_k);
-                    if (slot < 0) H->overflow = 1;
-                } else {
-                    p.defer_idx[atomicAdd(&H->defer_count, 1)] = (int)s;
+            const float p0 = __uint_as_float(p0b);
+            const bool good = __all_sync(0xffffffffu, bad == 0u) && isfinite(p0);
+            int slot = -1;
+            if (good) {
+                const unsigned int hit = __ballot_sync(0xffffffffu, lane < p.vt_k && mirror_v[lane & 15] == p0b);
+                if (hit) slot = __ffs(hit) - 1;
+                else {                                          // first sight of this prior in this CTA
+                    if (lane == 0) slot = slot_of(H, mirror, p0b, p.vt_k);
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    __syncwarp();
                 }
+            }
+            if (lane == 0) {
+                if (good && slot < 0) p.call->overflow = 1;
+                if (!good) p.defer_idx[atomicAdd(&p.call->defer_count, 1)] = (int)s;
                 p.prior_out[s] = p0;
                 p.slot[s] = slot;
             }
@@ -481,10 +550,10 @@ __global__ void __launch_bounds__(256) lean_prep_kernel(const PrepParams p) {
             const float p0 = __ldg(p.prior_in + s);
             int slot = -1;
             if (isfinite(p0)) {
-                slot = slot_of(H, __float_as_uint(p0), p.vt_k);
-                if (slot < 0) H->overflow = 1;
+                slot = slot_of(H, mirror, __float_as_uint(p0), p.vt_k);
+                if (slot < 0) p.call->overflow = 1;
             } else {
-                p.defer_idx[atomicAdd(&H->defer_count, 1)] = (int)s;
+                p.defer_idx[atomicAdd(&p.call->defer_count, 1)] = (int)s;
             }
             p.slot[s] = slot;
         }
@@ -494,6 +563,7 @@ __global__ void __launch_bounds__(256) lean_prep_kernel(const PrepParams p) {
 struct TabParams {
     const float* weights;
     LeanHeader* hdr;
+    const LeanCall* call;
     float4* rtab; float4* vtab;
     int hid, T, rt_n, vt_n, vt_k, rt_blocks, vt_blocks_per_slot;
 };
@@ -507,6 +577,7 @@ __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
     const double Rm = (double)((float)p.T * (fmax * 1.02f + 1e-6f));        // the decode kernel forms the same float
     if (!(Rm > 0.0) || !isfinite(Rm)) return;
     if ((int)blockIdx.x < p.rt_blocks) {
+        if (!H->rebuild) return;
         const float* w = p.weights + 7 * p.hid + 2;             // mlp (read-out)
         const MlpD M{w, 1, nullptr, w + p.hid, w + 2 * p.hid, w[3 * p.hid], p.hid};
         const int i0 = blockIdx.x * kChunk, n_int = min(kChunk, p.rt_n + 2 - i0);
@@ -514,7 +585,7 @@ __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
         return;
     }
     const int b = blockIdx.x - p.rt_blocks, k = b / p.vt_blocks_per_slot, cb = b - k * p.vt_blocks_per_slot;
-    if (k >= H->n_slots || H->overflow) return;
+    if (k >= H->n_slots || p.call->overflow || ((H->built_mask >> k) & 1u)) return;   // nothing new to tabulate
     const float* w = p.weights;                                 // ggc1.mlp: w1 [h, 2] | b1 | w2 | b2
     const MlpD M{w, 2, w + 1, w + 2 * p.hid, w + 3 * p.hid, w[4 * p.hid], p.hid};
     const double prior = (double)__uint_as_float(H->slot_bits[k]);
@@ -524,9 +595,9 @@ __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
 }
 
 // packed inputs -> x rows for the syndromes the edge-owner kernel has to redo (gd_decode_packed_*)
-__global__ void lean_unpack_kernel(const float* prior, const uint32_t* sgn, const LeanHeader* H, const int* defer_idx, float* x,
+__global__ void lean_unpack_kernel(const float* prior, const uint32_t* sgn, const LeanCall* H, const int* defer_idx, float* x,
                                    long long B, int V, int C, int nw) {
-    const int cnt = H->defer_count;
+    const int cnt = H ? H->defer_count : -1;                    // no call state: unpack everything
     if (cnt == 0) return;
     const long long n = cnt < 0 ? B : cnt;
     const int N = V + C;
@@ -554,10 +625,26 @@ struct LeanMeta {
     double balance = 0.0;
 };
 struct LeanGeom { int R = 0, G = 0, NCH = 0, rt_n = 0, vt_k = 0, ct_n = 0, vt_n = 0; long long opt_epoch = -1; bool valid = false; };
+// One table set on the device, keyed on the host by (stream, weights pointer, T, table sizes) and VALIDATED on the device
+// by a content hash (lean_begin_kernel): a stale or recycled entry simply rebuilds itself.  An entry is only ever used in
+// stream order; when the least recently used one is handed to another stream, that stream first waits for its last use.
+struct LeanEntry {
+    cudaStream_t st = nullptr;
+    const float* w = nullptr;
+    int T = 0, hid = 0, ct_n = 0, rt_n = 0, vt_n = 0, vt_k = 0;
+    unsigned char* dev = nullptr;          // header | ctab | rtab | vtab
+    size_t o_ct = 0, o_rt = 0, o_vt = 0;
+    cudaEvent_t ev = nullptr;
+    unsigned long long last_use = 0;
+};
+constexpr int kMaxEntries = 4;
 struct LeanCtx {
     std::vector<LeanMeta*> metas;          // one per R ever planned (stable addresses)
     LeanGeom geom;                         // geometry search result, redone when an option changes
     cudaMemPool_t pool = nullptr;
+    std::mutex enq;                        // one call at a time enqueues on a graph (entries are shared state)
+    std::vector<LeanEntry*> entries;
+    unsigned long long tick = 0;
 };
 
 struct LeanPlan {
@@ -781,6 +868,52 @@ static cudaMemPool_t lean_pool(gd_graph* g) {
     return ctx->pool;
 }
 
+// pick (or make) the table set for this call; the caller holds ctx->enq
+static LeanEntry* lean_entry(gd_graph* g, LeanCtx* ctx, const LeanParams& p, const gd_model* model, const float* w, cudaStream_t st) {
+    LeanEntry* hit = nullptr;
+    LeanEntry* lru = nullptr;
+    for (LeanEntry* e : ctx->entries) {
+        if (e->st == st && e->w == w && e->T == model->iters && e->hid == model->hidden && e->ct_n == p.ct_n && e->rt_n == p.rt_n &&
+            e->vt_n == p.vt_n && e->vt_k == p.vt_k)
+            hit = e;
+        if (!lru || e->last_use < lru->last_use) lru = e;
+    }
+    if (!hit) {
+        const bool same_shape = lru && lru->ct_n == p.ct_n && lru->rt_n == p.rt_n && lru->vt_n == p.vt_n && lru->vt_k == p.vt_k;
+        if ((int)ctx->entries.size() < kMaxEntries || !same_shape) {
+            if ((int)ctx->entries.size() >= kMaxEntries) {          // table sizes changed (options): drop the oldest entry
+                cudaEventSynchronize(lru->ev);
+                cudaFree(lru->dev);
+                cudaEventDestroy(lru->ev);
+                ctx->entries.erase(std::find(ctx->entries.begin(), ctx->entries.end(), lru));
+                delete lru;
+            }
+            hit = new LeanEntry();
+            size_t off = 0;
+            auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+            take(kHdrBytes);
+            hit->o_ct = take((size_t)(p.ct_n + 2) * 16);
+            hit->o_rt = take((size_t)(p.rt_n + 2) * 16);
+            hit->o_vt = take((size_t)p.vt_k * (p.vt_n + 2) * 16);
+            if (cudaMalloc((void**)&hit->dev, off) != cudaSuccess || cudaMemsetAsync(hit->dev, 0, kHdrBytes, st) != cudaSuccess ||
+                cudaEventCreateWithFlags(&hit->ev, cudaEventDisableTiming) != cudaSuccess) {
+                if (hit->dev) cudaFree(hit->dev);
+                delete hit;
+                cudaGetLastError();
+                return nullptr;
+            }
+            ctx->entries.push_back(hit);
+        } else {
+            hit = lru;                                            // recycle: its hash will not match, so it rebuilds itself
+            if (hit->st != st && cudaStreamWaitEvent(st, hit->ev, 0) != cudaSuccess) return nullptr;
+        }
+        hit->st = st; hit->w = w; hit->T = model->iters; hit->hid = model->hidden;
+        hit->ct_n = p.ct_n; hit->rt_n = p.rt_n; hit->vt_n = p.vt_n; hit->vt_k = p.vt_k;
+    }
+    hit->last_use = ++ctx->tick;
+    return hit;
+}
+
 int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* prior_dev,
                 const uint32_t* synd_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev,
                 int64_t B, cudaStream_t st) {
@@ -788,25 +921,32 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
     if (!lean_plan(g, model, B, &pl)) return -1;
     cudaMemPool_t pool = lean_pool(g);
     if (!pool) return -1;
+    LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
+    std::lock_guard<std::mutex> enq(ctx->enq);
     LeanParams& p = pl.p;
+    LeanEntry* ent = lean_entry(g, ctx, p, model, weights_dev, st);
+    if (!ent) return -1;
     const int N = g->N;
-    // workspace: header | ctab | rtab | vtab | slot | prior | sgn | defer_idx | (x for the deferred pass of packed calls)
+    // per-call workspace: call state | slot | prior | sgn | defer_idx | (x for the deferred pass of packed calls)
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_hdr = take(kHdrBytes), o_ct = take((size_t)(p.ct_n + 2) * 16), o_rt = take((size_t)(p.rt_n + 2) * 16);
-    const size_t o_vt = take((size_t)p.vt_k * (p.vt_n + 2) * 16), o_slot = take((size_t)B * 4);
+    const size_t o_call = take(sizeof(LeanCall)), o_slot = take((size_t)B * 4);
     const size_t o_prior = take(x_dev ? (size_t)B * 4 : 0), o_sgn = take(x_dev ? (size_t)B * p.nw * 4 : 0);
     const size_t o_defer = take((size_t)B * 4), o_x = take(x_dev ? 0 : (size_t)B * N * 4);
     unsigned char* ws = nullptr;
     GD_CUDA(cudaMallocFromPoolAsync((void**)&ws, off, pool, st));
-    LeanHeader* hdr = reinterpret_cast<LeanHeader*>(ws + o_hdr);
-    cudaError_t e = cudaMemsetAsync(hdr, 0, kHdrBytes, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(hdr->slot_bits, 0xFF, sizeof(hdr->slot_bits), st);
+    LeanHeader* hdr = reinterpret_cast<LeanHeader*>(ent->dev);
+    LeanCall* call = reinterpret_cast<LeanCall*>(ws + o_call);
+    float4* ctab = reinterpret_cast<float4*>(ent->dev + ent->o_ct);
+    float4* rtab = reinterpret_cast<float4*>(ent->dev + ent->o_rt);
+    float4* vtab = reinterpret_cast<float4*>(ent->dev + ent->o_vt);
     int rc = GD_OK;
+    lean_begin_kernel<<<1, 256, 0, st>>>(weights_dev, (int)gd_weights_size(model), model->iters, p.ct_n, p.rt_n, p.vt_n, hdr, call);
+    cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
         PrepParams pp;
         memset(&pp, 0, sizeof(pp));
-        pp.x = x_dev; pp.weights = weights_dev; pp.hdr = hdr; pp.ctab = reinterpret_cast<float4*>(ws + o_ct);
+        pp.x = x_dev; pp.weights = weights_dev; pp.hdr = hdr; pp.call = call; pp.ctab = ctab;
         pp.prior_out = reinterpret_cast<float*>(ws + o_prior); pp.sgn_out = reinterpret_cast<uint32_t*>(ws + o_sgn);
         pp.prior_in = prior_dev; pp.slot = reinterpret_cast<int*>(ws + o_slot); pp.defer_idx = reinterpret_cast<int*>(ws + o_defer);
         pp.B = B; pp.V = g->V; pp.C = g->C; pp.N = N; pp.nw = p.nw; pp.hid = model->hidden; pp.ct_n = p.ct_n; pp.vt_k = p.vt_k;
@@ -818,8 +958,8 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
     }
     if (e == cudaSuccess) {
         TabParams tp;
-        tp.weights = weights_dev; tp.hdr = hdr; tp.rtab = reinterpret_cast<float4*>(ws + o_rt);
-        tp.vtab = reinterpret_cast<float4*>(ws + o_vt); tp.hid = model->hidden; tp.T = model->iters; tp.rt_n = p.rt_n;
+        tp.weights = weights_dev; tp.hdr = hdr; tp.call = call; tp.rtab = rtab; tp.vtab = vtab;
+        tp.hid = model->hidden; tp.T = model->iters; tp.rt_n = p.rt_n;
         tp.vt_n = p.vt_n; tp.vt_k = p.vt_k; tp.rt_blocks = (p.rt_n + 2 + kChunk - 1) / kChunk;
         tp.vt_blocks_per_slot = (p.vt_n + 2 + kChunk - 1) / kChunk;
         lean_tables_kernel<<<tp.rt_blocks + p.vt_k * tp.vt_blocks_per_slot, 256, 0, st>>>(tp);
@@ -830,29 +970,50 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         p.sgn = x_dev ? reinterpret_cast<const uint32_t*>(ws + o_sgn) : synd_dev;
         p.slot = reinterpret_cast<const int*>(ws + o_slot);
         p.prob = prob_dev; p.logit = logit_dev; p.hard = hard_dev; p.hard_bits = hard_bits_dev;
-        p.hdr = hdr;
-        p.ctab = reinterpret_cast<const float4*>(ws + o_ct); p.rtab = reinterpret_cast<const float4*>(ws + o_rt);
-        p.vtab = reinterpret_cast<const float4*>(ws + o_vt);
+        p.hdr = hdr; p.call = call;
+        p.ctab = ctab; p.rtab = rtab; p.vtab = vtab;
         e = cudaFuncSetAttribute(lean_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
         if (e == cudaSuccess) {
             lean_decode_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(p);
             e = cudaGetLastError();
         }
     }
+    cudaEventRecord(ent->ev, st);                                // the entry's tables are free again after this point of the stream
     // the syndromes the tables could not serve: edge-owner kernel, direct evaluation, per item
     const float* x_for_deferred = x_dev;
     if (e == cudaSuccess && !x_dev) {
         float* xw = reinterpret_cast<float*>(ws + o_x);
-        lean_unpack_kernel<<<g->sm_count * 4, 256, 0, st>>>(prior_dev, synd_dev, hdr, reinterpret_cast<const int*>(ws + o_defer), xw,
+        lean_unpack_kernel<<<g->sm_count * 4, 256, 0, st>>>(prior_dev, synd_dev, call, reinterpret_cast<const int*>(ws + o_defer), xw,
                                                             B, g->V, g->C, p.nw);
         e = cudaGetLastError();
         x_for_deferred = xw;
     }
     if (e == cudaSuccess) {
-        const DeferList dl{&hdr->defer_count, reinterpret_cast<const int*>(ws + o_defer)};
+        const DeferList dl{&call->defer_count, reinterpret_cast<const int*>(ws + o_defer)};
         rc = decode_fwd_deferred(g, model, weights_dev, x_for_deferred, prob_dev, logit_dev, hard_dev, hard_bits_dev, B, st, dl);
     }
     cudaError_t ef = cudaFreeAsync(ws, st);
+    if (rc != GD_OK) return rc;
+    GD_CUDA(e);
+    GD_CUDA(ef);
+    return GD_OK;
+}
+
+// Packed inputs for a (graph, model) the table kernel does not serve: expand them to x [B, V+C] in a pooled workspace and hand
+// that to `run` (the edge-owner kernel); the workspace is released in stream order.
+int packed_via_unpack(gd_graph* g, const float* prior_dev, const uint32_t* synd_dev, int64_t B, cudaStream_t st,
+                      int (*run)(void* ctx, const float* x_dev), void* ctx) {
+    cudaMemPool_t pool = lean_pool(g);
+    if (!pool) {
+        set_error("gd_decode_packed_fwd: no memory pool on device %d", g->device);
+        return GD_ERR_CUDA;
+    }
+    float* xw = nullptr;
+    GD_CUDA(cudaMallocFromPoolAsync((void**)&xw, (size_t)B * g->N * sizeof(float), pool, st));
+    lean_unpack_kernel<<<g->sm_count * 4, 256, 0, st>>>(prior_dev, synd_dev, nullptr, nullptr, xw, B, g->V, g->C, (g->C + 31) / 32);
+    cudaError_t e = cudaGetLastError();
+    int rc = e == cudaSuccess ? run(ctx, xw) : GD_OK;
+    cudaError_t ef = cudaFreeAsync(xw, st);
     if (rc != GD_OK) return rc;
     GD_CUDA(e);
     GD_CUDA(ef);
@@ -867,6 +1028,11 @@ void gd_lean_ctx_destroy(gd_graph* g) {
     for (gd::LeanMeta* m : ctx->metas) {
         if (m->dev) cudaFree(m->dev);
         delete m;
+    }
+    for (gd::LeanEntry* e : ctx->entries) {
+        if (e->ev) { cudaEventSynchronize(e->ev); cudaEventDestroy(e->ev); }
+        if (e->dev) cudaFree(e->dev);
+        delete e;
     }
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;

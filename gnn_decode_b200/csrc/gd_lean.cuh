@@ -4,12 +4,13 @@
 
 namespace gd {
 
-// Device-side header of one lean decode call (lives in the call's workspace).  Written by the prep / table kernels,
-// read by the decode kernel and by the deferred pass of the edge-owner kernel (gd_decode.cu).
+// Device-side state of one table set (lives in a cache entry of the graph, persists across calls): the tables are rebuilt
+// only when the content hash of (weights, T, table sizes) changes, variable-phase tables are added as new priors show up.
 struct LeanHeader {
-    int n_slots;                 // distinct eligible priors found (<= slots of the plan)
-    int overflow;                // more distinct priors than table slots: the whole batch takes the edge-owner kernel
-    int defer_count;             // syndromes listed in defer_idx; -1 = all of them, in batch order
+    unsigned long long hash;     // what the tables were built from
+    int rebuild;                 // this call found other weights: check / read-out tables are rebuilt, the prior list was reset
+    int n_slots;                 // distinct priors in the list (<= slots of the plan)
+    unsigned int built_mask;     // slots whose variable-phase table is complete
     int pad0;
     unsigned int fmax_bits;      // max |mlp2| over the check table's nodes (float bits, rounded up)
     unsigned int f3max_bits;     // max |mlp3| over the read-out table's nodes
@@ -18,10 +19,15 @@ struct LeanHeader {
     unsigned int err_v_bits[16]; // ... of each variable-phase table (in units of tanh output)
     unsigned int slot_bits[16];  // prior value (float bits) of table slot k; 0xFFFFFFFF = free
 };
+// per call (workspace)
+struct LeanCall {
+    int overflow;                // more distinct priors than table slots: the whole batch takes the edge-owner kernel
+    int defer_count;             // syndromes listed in defer_idx; -1 = all of them, in batch order
+};
 
 // Edge-owner kernel pass over the syndromes the lean kernel deferred (gd_decode.cu).
 struct DeferList {
-    const int* count;            // &LeanHeader::defer_count
+    const int* count;            // &LeanCall::defer_count
     const int* idx;              // [B] syndrome indices (valid when *count > 0)
 };
 
@@ -30,6 +36,8 @@ struct DeferList {
 int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* prior_dev,
                 const uint32_t* synd_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev,
                 int64_t B, cudaStream_t st);
+int packed_via_unpack(gd_graph* g, const float* prior_dev, const uint32_t* synd_dev, int64_t B, cudaStream_t st,
+                      int (*run)(void* ctx, const float* x_dev), void* ctx);
 bool lean_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out);
 
 // gd_decode.cu: run the edge-owner resident kernel over a deferred list (no variable-phase tables: per-item direct

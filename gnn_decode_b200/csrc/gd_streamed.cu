@@ -13,6 +13,7 @@
 //     one broadcast transaction per warp), MLP weights sit in shared memory.
 #include "gd_common.cuh"
 #include "gd_math.cuh"
+#include "gd_options.cuh"
 #include "gd_decode.cuh"
 #include <stdlib.h>
 #include <string.h>
@@ -311,9 +312,9 @@ static int plan_streamed(const gd_graph* g, const gd_model* m, int64_t B, Stream
     p.hid = bp ? 0 : m->hidden; p.hp = (p.hid + 7) / 8 * 8; p.tb = g->t;
     const int n_slots = bp ? 0 : (m->program == GD_PROG_V2_4 ? 3 : 2);
     out->smem = n_slots * 4 * p.hp * 4 + 16;
-    if (m->program == GD_PROG_V2_4 && !getenv("GD_NO_CTAB")) {
+    if (m->program == GD_PROG_V2_4 && !opt_on(OPT_NO_CTAB)) {
         p.ctab_n = 512;
-        p.rtab_n = getenv("GD_NO_RTAB") ? 0 : 2048;
+        p.rtab_n = opt_on(OPT_NO_RTAB) ? 0 : 2048;
         p.ctab_R = (float)(g->max_chk_deg > 1 ? g->max_chk_deg - 1 : 1);
         const int big = p.ctab_n > p.rtab_n ? p.ctab_n : p.rtab_n;
         out->smem += (p.ctab_n + p.rtab_n) * 16 + (big + 8) * 4 + 16;
@@ -329,13 +330,11 @@ static int plan_streamed(const gd_graph* g, const gd_model* m, int64_t B, Stream
             if (eff > best + 1e-9) { best = eff; tile = t; }
         }
     }
-    const char* et = getenv("GD_STILE");
-    if (et) tile = atoi(et);
+    if (opt_on(OPT_STILE)) tile = (int)opt_int(OPT_STILE, tile);
     if (tile < 8 || tile > 512 || (tile % 8)) tile = 32;
     p.tile = tile;
     int maxthr = 1024;
-    const char* em = getenv("GD_STHREADS");
-    if (em) maxthr = atoi(em);
+    maxthr = (int)opt_int(OPT_STHREADS, maxthr);
     int R = maxthr / tile;
     const int maxn = g->V > g->C ? g->V : g->C;
     if (R > maxn) R = maxn;

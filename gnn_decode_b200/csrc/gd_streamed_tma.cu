@@ -23,6 +23,7 @@
 //     the sign bit of the stored value instead of a second array.
 #include "gd_common.cuh"
 #include "gd_math.cuh"
+#include "gd_options.cuh"
 #include "gd_decode.cuh"
 #include "gd_nodemath.cuh"
 #include <stdlib.h>
@@ -430,7 +431,7 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
     StreamTmaParams& p = out->p;
     memset(&p, 0, sizeof(p));
     out->ok = false;
-    if (getenv("GD_STREAM_LEGACY")) return;
+    if (opt_on(OPT_STREAM_LEGACY)) return;
     for (size_t i = 0; i < g->h_var_edges.size(); ++i)
         if (g->h_var_edges[i] != (int32_t)i) return;
     const bool bp = m->program == GD_PROG_BP_QUANTUM || m->program == GD_PROG_BP_CLASSICAL;
@@ -443,7 +444,7 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
     // batch fills all 32 lanes of every SM; smaller batches take the register-batched kernel.
     if (m->program == GD_PROG_V2_4 && B < (int64_t)128 * g->sm_count) return;
     out->npad = 0;
-    if ((m->program == GD_PROG_CGNNI || m->program == GD_PROG_QGNNI) && m->hidden < 32 && !getenv("GD_NO_PWL"))
+    if ((m->program == GD_PROG_CGNNI || m->program == GD_PROG_QGNNI) && m->hidden < 32 && !opt_on(OPT_NO_PWL))
         out->npad = m->hidden < 16 ? 16 : 32;
     // tile: multiple of 4 (a lane owns one float4 of a row), <= 128.  Cost model: the kernel is
     // HBM-bound, a tile's time ~ its bytes ~ tile (with a floor: a warp instruction costs the
@@ -458,8 +459,8 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
             if (cost <= best * (1.0 + 1e-12)) { best = cost; tile = t; }
         }
     }
-    const char* et = getenv("GD_STILE");
-    if (et && atoi(et) >= 4 && atoi(et) <= 128 && atoi(et) % 4 == 0) tile = atoi(et);
+    const long long et = opt_int(OPT_STILE, 0);
+    if (et >= 4 && et <= 128 && et % 4 == 0) tile = (int)et;
     p.tile = tile;
     p.lanes = tile / 4;
     const int vd = g->max_var_deg > 0 ? g->max_var_deg : 1;
@@ -468,8 +469,8 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
     // measured on B200, sum-product / HGP-1600 / T = 50: 15 rows x 2 stages 28.4 ms, 8 rows x 2 / 3 / 4 stages 33.7 / 32.9 / 33.2 ms
     const int min_rows = (bp ? 1 : 2) * g->max_chk_deg + 1;
     int rows = 2 * g->max_chk_deg + 1;
-    const char* er = getenv("GD_SROWS");
-    if (er && atoi(er) >= min_rows && atoi(er) <= 64) rows = atoi(er);
+    const long long er = opt_int(OPT_SROWS, 0);
+    if (er >= min_rows && er <= 64) rows = (int)er;
     if (rows < vd + 1) rows = vd + 1;
     int K = rows / (vd + 1);
     if (K > 8) K = 8;
@@ -482,8 +483,8 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
     // stages per warp (2..4, GD_SSTAGES): 2 unless deeper still leaves room for all 16 warps at this stage size
     int S = 2;
     {
-        const char* es = getenv("GD_SSTAGES");
-        if (es && atoi(es) >= 2 && atoi(es) <= 4) S = atoi(es);
+        const long long es = opt_int(OPT_SSTAGES, 0);
+        if (es >= 2 && es <= 4) S = (int)es;
         else
             for (int q = 4; q > 2; --q)
                 if ((g->max_smem_optin - off) / (q * stage_bytes) >= 16) { S = q; break; }
@@ -491,8 +492,8 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
     p.S = S;
     int Wn = (g->max_smem_optin - off) / (S * stage_bytes);
     if (Wn > 16) Wn = 16;
-    const char* ew = getenv("GD_SWARPS");
-    if (ew && atoi(ew) >= 1 && atoi(ew) < Wn) Wn = atoi(ew);
+    const long long ew = opt_int(OPT_SWARPS, 0);
+    if (ew >= 1 && ew < Wn) Wn = (int)ew;
     if (Wn < 2) return;
     if ((int64_t)Wn * S * rows * tile < 2 * (int64_t)(tile + 2) * 2) return;   // transposition scratch
     p.W = Wn;

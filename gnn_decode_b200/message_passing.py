@@ -288,6 +288,29 @@ class DecoderBase(torch.nn.Module):
             return tuple(t for t in (prob, logit, hard) if t is not None)
         return prob
 
+    def decode_packed(self, prior, synd_bits, graph=None, return_prob=False):
+        """Packed form of decode() (gd_decode_packed_fwd): prior [B] fp32 CUDA = the one prior LLR every variable of the
+        syndrome carries (gen_syn, quantum/error_generate.py:258), synd_bits [B, ceil(C/32)] int32 CUDA with bit c set where
+        check c fired (input -1).  Returns hard_bits [B, ceil(V/32)] int32 (bit v = prob > 0.5), and prob [B, V] if asked."""
+        g = graph or self._gd_graph
+        if g is None:
+            raise ValueError("no Tanner graph bound: call bind_graph(graph) or pass graph=")
+        _require_cuda(prior, "prior")
+        _require_cuda(synd_bits, "synd_bits")
+        B, nw, vw = prior.numel(), (g.C + 31) // 32, (g.V + 31) // 32
+        if prior.dtype != torch.float32 or synd_bits.dtype != torch.int32 or tuple(synd_bits.shape) != (B, nw):
+            raise ValueError("prior must be fp32 [B], synd_bits int32 [B, %d]" % nw)
+        prior, synd_bits = prior.contiguous(), synd_bits.contiguous()
+        dev = prior.device
+        bits = torch.empty((B, vw), dtype=torch.int32, device=dev)
+        prob = torch.empty((B, g.V), dtype=torch.float32, device=dev) if return_prob else None
+        model = self.gd_model()
+        w = self.packed_weights(dev)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().gd_decode_packed_fwd(g.handle, C.byref(model), _ptr(w), _ptr(prior), _ptr(synd_bits), _ptr(prob),
+                                                         _ptr(bits), B, _stream(dev)), "gd_decode_packed_fwd")
+        return (bits, prob) if return_prob else bits
+
     def autotune(self, x, graph=None, max_candidates=0):
         """One-time geometry autotuning for this (decoder, graph, batch size): times the planner's best candidates on x and
         remembers the fastest for later decode() / decode_host() calls with the same batch size.  Returns the launch info."""

@@ -150,15 +150,50 @@ int gd_decode_fwd(const gd_graph* g, const gd_model* model, const float* weights
                   const float* x_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev,
                   int64_t B, void* stream);
 
+/* The same decode with PACKED inputs and outputs.  What the reference's x carries per syndrome (gen_syn,
+ * quantum/error_generate.py:258, 270-276) is ONE prior value log((1-p)/p), repeated on all V variables, and C check signs:
+ *   prior_dev     [B] fp32            the prior LLR of the syndrome's variables
+ *   synd_dev      [B, ceil(C/32)] u32 bit c (of word c / 32) set = check c fired, i.e. its input is -1
+ *   prob_dev      [B, V] fp32         optional, as gd_decode_fwd
+ *   hard_bits_dev [B, ceil(V/32)] u32 optional, bit v set = (prob > 0.5): the hard decision of variable v
+ * 8 + 8 bytes per syndrome instead of 296 + 250 at rotated d = 5.  Results are bit-identical to gd_decode_fwd on the
+ * expanded x.  GD_PROG_V2_4, resident codes only (GD_ERR_UNSUPPORTED otherwise). */
+int gd_decode_packed_fwd(const gd_graph* g, const gd_model* model, const float* weights_dev, const float* prior_dev,
+                         const uint32_t* synd_dev, float* prob_dev, uint32_t* hard_bits_dev, int64_t B, void* stream);
+
 /* Same computation with HOST buffers: host->device copy of x, the kernel, device->host copy of
  * the requested outputs, pipelined in chunks over internal streams; returns when the outputs
- * are complete.  Replaces `datas.to(device); pred = decoder(datas)` (decoder_v2_4.py:332-334)
+ * are complete.  Calls on one graph are serialised internally (they share its staging buffers); use one gd_pipeline
+ * per caller for concurrency.  Replaces `datas.to(device); pred = decoder(datas)` (decoder_v2_4.py:332-334)
  * followed by reading the prediction back. weights_host is the packed buffer on the host. */
 int gd_decode_host(const gd_graph* g, const gd_model* model, const float* weights_host,
                    const float* x_host, float* prob_host, uint8_t* hard_host, int64_t B);
 /* Decode-kernel launches the last gd_decode_host call on this graph made: 1 for the gated single-launch pipeline, one per chunk
  * otherwise (benchmark accounting; streamed codes count one per gd_decode_fwd call). */
 int gd_decode_host_last_launches(const gd_graph* g);
+
+/* ---- the same end-to-end call as an ASYNCHRONOUS PIPELINE for callers that stream batches: batch k+1 is copied in
+ *      while batch k decodes and batch k-1 is copied out (three internal streams chained by events, `depth` slots of
+ *      device buffers, all decode kernels on one stream so the decoder's tables are built once).  The weights are
+ *      copied at creation (gd_pipeline_set_weights replaces them in stream order).  submit returns at once unless all
+ *      `depth` slots are in flight (then it waits for the oldest batch); gd_pipeline_wait(ticket) returns when that
+ *      batch's outputs are complete in host memory; host buffers must stay valid until then and should be pinned
+ *      (pageable memory works, the copies then stage synchronously).  One pipeline may be driven from several host
+ *      threads (calls are serialised).
+ *      gd_pipeline_submit        x_host [B, V+C] fp32 -> prob_host [B, V] fp32 and / or hard_host [B, V] uint8
+ *      gd_pipeline_submit_packed prior_host [B] fp32 + synd_host [B, ceil(C/32)] u32 -> hard_bits_host [B, ceil(V/32)] u32
+ *                                and / or prob_host (the layouts of gd_decode_packed_fwd): 16 bytes per syndrome over
+ *                                PCIe instead of 546 at rotated d = 5.  GD_PROG_V2_4 only. ---- */
+typedef struct gd_pipeline gd_pipeline;
+int gd_pipeline_create(const gd_graph* g, const gd_model* model, const float* weights_host, int64_t max_B, int32_t depth,
+                       gd_pipeline** out);
+void gd_pipeline_destroy(gd_pipeline* p);
+int gd_pipeline_set_weights(gd_pipeline* p, const float* weights_host);
+int gd_pipeline_submit(gd_pipeline* p, const float* x_host, float* prob_host, uint8_t* hard_host, int64_t B, int32_t* ticket);
+int gd_pipeline_submit_packed(gd_pipeline* p, const float* prior_host, const uint32_t* synd_host, float* prob_host,
+                              uint32_t* hard_bits_host, int64_t B, int32_t* ticket);
+int gd_pipeline_wait(gd_pipeline* p, int32_t ticket);
+int gd_pipeline_drain(gd_pipeline* p);   /* wait for every batch submitted so far */
 
 /* ---- training (BASELINE config 4): forward that also stashes the per-iteration activations, and
  *      the hand-written backward (replaces autograd through the loop, decoder_v2_4.py:334-340).

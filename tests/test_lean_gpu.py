@@ -1,0 +1,203 @@
+"""The check-owner table kernel for decoder_v2_4 on surface / toric codes (csrc/gd_lean.cu): per-item routing between the tables
+and the edge-owner kernel's direct evaluation, table reuse across calls and its invalidation, the packed entry point."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden
+from gnn_decode_b200 import codes, options, packing
+from gnn_decode_b200.graph import TannerGraph
+from gnn_decode_b200.quantum import decoder_v2_4
+from gnn_decode_b200.sampler import sample_syndromes
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+P10 = [0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.1]
+
+
+def _setup(d=5, T=15, case="v2_4_toricL5_epoch3"):
+    g = TannerGraph.from_pcm(codes.rotated_surface_pcm(d), DEV)
+    dec = decoder_v2_4.GNNI(T)
+    w = Golden(case).weights
+    dec.load_state_dict(w)
+    return g, dec.to(DEV).eval().bind_graph(g), w
+
+
+def _lean_runs(g, dec, B):
+    info = g.launch_info(dec.gd_model(), B)
+    with options.option("GD_NO_LEAN"):
+        old = g.launch_info(dec.gd_model(), B)
+    return info != old
+
+
+def test_lean_kernel_is_the_one_running():
+    g, dec, _ = _setup()
+    assert _lean_runs(g, dec, 4096)
+
+
+def test_per_item_routing_and_batch_invariance():
+    """Rows the tables cannot serve (per-variable priors, a check input that is not +-1, a non-finite prior) are decoded by the
+    edge-owner kernel's direct path, per item: every row's result is independent of what else is in the batch."""
+    g, dec, w = _setup()
+    B = 3000
+    x, _ = sample_syndromes(g, B, P10, noise=1, seed=11)
+    xm = x.clone()
+    rows_pv = torch.arange(5, B, 7, device=DEV)
+    xm[rows_pv, :g.V] += 0.01 * torch.arange(g.V, device=DEV, dtype=torch.float32)          # per-variable priors
+    rows_sg = torch.arange(3, B, 11, device=DEV)
+    xm[rows_sg, g.V + 2] *= 0.5                                                              # a check input of +-0.5
+    special = torch.zeros(B, dtype=torch.bool, device=DEV)
+    special[rows_pv] = True
+    special[rows_sg] = True
+    p_mix, l_mix, h_mix = dec.decode(xm, return_logits=True, return_hard=True)
+    p_clean = dec.decode(x)
+    assert torch.equal(p_mix[~special], p_clean[~special])                                   # table rows: unaffected by their neighbours
+    with options.option("GD_NO_LEAN"), options.option("GD_NO_VTAB"):
+        p_dir = dec.decode(xm)
+    assert torch.equal(p_mix[special], p_dir[special])                                       # deferred rows: exactly the direct evaluation
+    # slices of the batch give the same bits
+    for lo, n in ((0, 8), (100, 1000), (B - 333, 333)):
+        assert torch.equal(dec.decode(xm[lo:lo + n].contiguous()), p_mix[lo:lo + n])
+    # and everything matches the oracle
+    idx = torch.cat([rows_pv[:8], rows_sg[:8], torch.arange(0, 16, device=DEV)])
+    ei = torch.from_numpy(codes.edge_index_of(codes.rotated_surface_pcm(5)))
+    ref = restate.decode("v2_4", ei, g.V, g.C, xm[idx].double().cpu(), w, T=15)["logit"]
+    err = (l_mix[idx].double().cpu() - ref).abs()
+    assert float((err / ref.abs().clamp_min(1.0)).max()) <= 1e-4              # 1e-4 relative; absolute below |logit| = 1
+    xn = x.clone()
+    xn[17, :g.V] = float("nan")
+    pn = dec.decode(xn)
+    assert torch.equal(pn[:17], p_clean[:17]) and torch.equal(pn[18:], p_clean[18:])
+
+
+def test_more_priors_than_slots_takes_the_edge_owner_kernel():
+    g, dec, _ = _setup()
+    B = 2048
+    x, _ = sample_syndromes(g, B, [0.01 + 0.004 * i for i in range(20)], noise=1, seed=5)
+    assert torch.unique(x[:, 0]).numel() > 12
+    p = dec.decode(x)
+    with options.option("GD_NO_LEAN"):
+        p_old = dec.decode(x)
+    assert torch.equal(p, p_old)
+    x2, _ = sample_syndromes(g, B, P10, noise=1, seed=6)                                     # the prior list starts afresh afterwards
+    p2 = dec.decode(x2)
+    with options.option("GD_NO_LEAN"):
+        p2_old = dec.decode(x2)
+    assert not torch.equal(p2, p2_old)
+    assert float((p2 - p2_old).abs().max()) < 1e-4
+
+
+def test_tables_follow_the_weights():
+    """Tables persist across calls (keyed by a content hash on the device): changing the weights in place, or swapping
+    checkpoints, must rebuild them."""
+    g, dec, w = _setup()
+    x, _ = sample_syndromes(g, 1024, P10[:4], noise=1, seed=3)
+    outs = {}
+    for name in ("v2_4_toricL5_epoch3", "v2_4_toricL4_epoch1", "v2_4_toricL5_epoch3"):
+        dec.load_state_dict(Golden(name).weights)
+        p = dec.decode(x)
+        with options.option("GD_NO_LEAN"):
+            p_old = dec.decode(x)
+        assert float((p - p_old).abs().max()) < 1e-4, name
+        if name in outs:
+            assert torch.equal(outs[name], p)
+        outs[name] = p
+    assert not torch.equal(outs["v2_4_toricL5_epoch3"], outs["v2_4_toricL4_epoch1"])
+    with torch.no_grad():                                  # in-place change of the packed weight buffer's source
+        dec.mlp[2].bias.add_(0.25)
+    p = dec.decode(x)
+    with options.option("GD_NO_LEAN"):
+        p_old = dec.decode(x)
+    assert float((p - p_old).abs().max()) < 1e-4
+    assert not torch.equal(p, outs["v2_4_toricL5_epoch3"])
+
+
+def test_collapsed_checkpoint_misses_the_table_budget_and_falls_back():
+    """epoch67 (|logit| up to ~600, T max|mlp2| = 70): the variable-phase tables miss their 1e-6 budget, so the whole batch
+    is decoded by the edge-owner kernel -- bit-identical to running it directly."""
+    g, dec, _ = _setup(case="v2_4_toricL4_epoch67")
+    x, _ = sample_syndromes(g, 2000, P10[:6], noise=1, seed=8)
+    p = dec.decode(x)
+    with options.option("GD_NO_LEAN"):
+        p_old = dec.decode(x)
+    assert torch.equal(p, p_old)
+
+
+@pytest.mark.parametrize("d", [3, 5, 7])
+def test_packed_entry_point_is_bit_identical(d):
+    g, dec, _ = _setup(d)
+    B = 5000 + d
+    x, _ = sample_syndromes(g, B, P10, noise=1, seed=d)
+    prob, hard = dec.decode(x, return_hard=True)
+    prior, bits = packing.pack_x(x, g.V)
+    hb, pp = dec.decode_packed(prior, bits, return_prob=True)
+    assert torch.equal(pp, prob)
+    assert torch.equal(packing.unpack_bits(hb, g.V), hard)
+    hb2 = dec.decode_packed(prior, bits)
+    assert torch.equal(hb2, hb)
+    # more priors than slots, through the packed call: the expanded rows go to the edge-owner kernel
+    x20, _ = sample_syndromes(g, 1500, [0.01 + 0.004 * i for i in range(20)], noise=1, seed=1)
+    p20, h20 = dec.decode(x20, return_hard=True)
+    pr, sb = packing.pack_x(x20, g.V)
+    hb20, pp20 = dec.decode_packed(pr, sb, return_prob=True)
+    assert torch.equal(pp20, p20) and torch.equal(packing.unpack_bits(hb20, g.V), h20)
+
+
+def test_two_streams_share_a_graph():
+    g, dec, _ = _setup()
+    x1, _ = sample_syndromes(g, 4000, P10, noise=1, seed=21)
+    x2, _ = sample_syndromes(g, 3000, P10[:3], noise=1, seed=22)
+    r1, r2 = dec.decode(x1), dec.decode(x2)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(DEV), torch.cuda.Stream(DEV)
+    outs = []
+    for _ in range(10):
+        with torch.cuda.stream(s1):
+            a = dec.decode(x1)
+        with torch.cuda.stream(s2):
+            b = dec.decode(x2)
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a, r1) and torch.equal(b, r2)
+
+
+def test_pipeline_matches_the_device_path():
+    """gd_pipeline_*: batches of changing size streamed through the asynchronous host pipeline, packed and fp32 forms, give
+    the bits of the device-resident call."""
+    from gnn_decode_b200.pipeline import DecodePipeline
+    g, dec, _ = _setup()
+    pipe = DecodePipeline(dec, g, max_B=6000, depth=3)
+    batches = []
+    for i, B in enumerate([6000, 17, 4096, 5999, 1, 3000, 6000, 2500]):
+        x, _ = sample_syndromes(g, B, P10, noise=1, seed=100 + i)
+        prob, hard = dec.decode(x, return_hard=True)
+        prior, synd = packing.pack_x(x, g.V)
+        rec = {"x": x.cpu().pin_memory(), "prior": prior.cpu().pin_memory(), "synd": synd.cpu().pin_memory(), "prob": prob.cpu(),
+               "hard": hard.cpu(), "bits_out": torch.empty((B, (g.V + 31) // 32), dtype=torch.int32).pin_memory(),
+               "prob_out": torch.empty((B, g.V), dtype=torch.float32).pin_memory(),
+               "prob_out2": torch.empty((B, g.V), dtype=torch.float32).pin_memory(),
+               "hard_out": torch.empty((B, g.V), dtype=torch.uint8).pin_memory()}
+        batches.append(rec)
+    tickets = []
+    for rec in batches:                                      # packed submissions, all in flight before the first wait
+        tickets.append(pipe.submit_packed(rec["prior"], rec["synd"], hard_bits_out=rec["bits_out"], prob_out=rec["prob_out"]))
+    for t, rec in zip(tickets, batches):
+        pipe.wait(t)
+        assert torch.equal(rec["prob_out"], rec["prob"])
+        assert torch.equal(packing.unpack_bits(rec["bits_out"], g.V), rec["hard"])
+    tickets = [pipe.submit(rec["x"], prob_out=rec["prob_out2"], hard_out=rec["hard_out"]) for rec in batches]
+    pipe.drain()
+    for rec in batches:
+        assert torch.equal(rec["prob_out2"], rec["prob"]) and torch.equal(rec["hard_out"], rec["hard"])
+    with pytest.raises(ValueError):
+        pipe.submit_packed(torch.zeros(7000), torch.zeros((7000, 1), dtype=torch.int32), hard_bits_out=torch.zeros((7000, 2), dtype=torch.int32))
+    # new weights reach the pipeline in stream order
+    dec.load_state_dict(Golden("v2_4_toricL4_epoch1").weights)
+    pipe.refresh_weights()
+    rec = batches[0]
+    x = rec["x"].to(DEV)
+    p_new = dec.decode(x).cpu()
+    pipe.wait(pipe.submit(rec["x"], prob_out=rec["prob_out2"]))
+    assert torch.equal(rec["prob_out2"], p_new) and not torch.equal(p_new, rec["prob"])
