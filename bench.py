@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autotune", action="store_true", help="keep the planner's model geometry (skip gd_decode_autotune)")
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only (skip the short passes over the other BASELINE configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -268,26 +269,104 @@ def main():
 
     # ------------------------------------------------------------------ our arm (GPU)
     import torch.distributed as dist
-    from gnn_decode_b200 import _cabi
-    from gnn_decode_b200.graph import TannerGraph
-    from gnn_decode_b200.sampler import sample_syndromes
-
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    _pin_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    line = run_workload(args.workload, args, dev, rank, world, clocks, headline=True)
+    extras = []
+    if not args.no_extras:
+        for name in EXTRA_WORKLOADS:
+            if name == args.workload:
+                continue
+            try:
+                extras.append(run_workload(name, args, dev, rank, world, None, headline=False))
+            except Exception as ex:  # noqa: BLE001  (an extra must never cost the headline line)
+                extras.append({"workload": name, "error": "%s: %s" % (type(ex).__name__, ex)})
+        try:
+            extras.append(run_training(args, dev, rank, world))
+        except Exception as ex:  # noqa: BLE001
+            extras.append({"workload": TRAIN_WORKLOAD, "error": "%s: %s" % (type(ex).__name__, ex)})
+    if rank == 0:
+        clk = clocks.stop()
+        if line.get("_clock_probe_s"):
+            clk["load_probe_s"] = line.pop("_clock_probe_s")
+        line.pop("_clock_probe_s", None)
+        line["clocks"] = clk
+        if extras:
+            line["extra_workloads"] = extras
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# the other BASELINE.json configs, run short after the headline and embedded as `extra_workloads`
+EXTRA_WORKLOADS = ["cgnni_ldpc_awgn_B1024", "cgnni_bch_awgn_B1024", "v2_4_toric_L11_iidxz_B65536", "v2_4_rotated_d11_depol_B65536",
+                   "qgnni_hgp1600_depol_B16384_T50", "bp_hgp1600_depol_B16384_T50"]
+TRAIN_WORKLOAD = "train_v2_4_rotated_d7_B4096"
+
+
+def _pin_to_gpu_numa_node(index):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU.  No-op when the topology is not exposed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def lean_wavefronts_per_syndrome(pcm, T):
+    """Algorithmic shared-memory wavefronts (128 B each) per syndrome of the check-owner table kernel: per
+    iteration and edge one message read, one message write and one 128-bit check-table look-up (4 wavefronts per warp),
+    plus, where the variable has a second edge, one sibling read and one 128-bit variable-table look-up; the first
+    iteration (all messages zero) is one look-up per check; the read-out is one read + one look-up per edge and a staged
+    logit per variable.  Counted per warp of 32 syndromes, conflict-free, metadata broadcasts not counted."""
+    deg = pcm.sum(0)
+    E = int(pcm.sum())
+    E_sib = int(deg[deg >= 2].sum())
+    Cn, V = pcm.shape
+    per_warp = (T - 1) * (6 * E + 5 * E_sib) + (E + 4 * Cn) + 5 * E + 2 * V
+    return per_warp / 32.0
+
+
+def run_workload(name, args, dev, rank, world, clocks, headline):
+    from gnn_decode_b200 import _cabi, options, packing
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.pipeline import DecodePipeline
+    from gnn_decode_b200.sampler import sample_syndromes
+    program, code_spec, T, B, noise, p_list = WORKLOADS[name]
+    pcm = build_pcm(code_spec)
+    Cn, V = pcm.shape
+    N = V + Cn
+    E = int(pcm.sum())
+    weights, weights_src = load_weights(program)
+    cores = os.cpu_count() or 1
+    steps = args.steps if headline else max(3, min(args.steps, 10))
+    warmup = args.warmup if headline else 3
+    local_rank = dev.index
     g = TannerGraph.from_pcm(pcm, dev)
     dec = make_decoder(program, T, weights).to(dev).eval()
     dec.bind_graph(g)
     model = dec.gd_model()
     info = g.launch_info(model, B)
-
-    # synthetic inputs, resident in HBM before the timed region; each rank its own Philox range
     x, err = sample_syndromes(g, B, p_list, noise=noise, seed=1234, first_sample=rank * B)
-    if not args.no_autotune:
-        # one-time setup, outside every timed region: time the planner's best candidate geometries on this batch (and on
-        # the host pipeline's chunk size) and keep the fastest -- "measure, don't guess"; no effect on light / streamed paths
-        dec.autotune(x)
+    lean = False
+    if program == "v2_4":
+        with options.option("GD_NO_LEAN"):
+            lean = g.launch_info(model, B) != info
+    if not args.no_autotune and not lean:
+        dec.autotune(x)                      # edge-owner kernel only: one-time geometry measurement, outside every timed region
         info = g.launch_info(model, B)
     prob = torch.empty((B, V), dtype=torch.float32, device=dev)
     hard = torch.empty((B, V), dtype=torch.uint8, device=dev)
@@ -297,184 +376,295 @@ def main():
     lib = _cabi.lib()
     stream = torch.cuda.current_stream(dev)
 
-    def step():
-        _cabi.check(lib.gd_decode_fwd(g.handle, C.byref(model), wptr, C.c_void_p(x.data_ptr()),
-                                      C.c_void_p(prob.data_ptr()), None, C.c_void_p(hard.data_ptr()), B,
+    def step(xx=x):
+        _cabi.check(lib.gd_decode_fwd(g.handle, C.byref(model), wptr, C.c_void_p(xx.data_ptr()),
+                                      C.c_void_p(prob.data_ptr()), None, C.c_void_p(hard.data_ptr()), xx.size(0),
                                       C.c_void_p(stream.cuda_stream)))
 
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
+            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    for _ in range(args.warmup):
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    for _ in range(warmup):
         flush.fill_(1)
         step()
     barrier()
-    clocks.begin()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if clocks is not None and rank == 0:
+        clocks.begin()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for e0, e1 in evs:
         flush.fill_(1)                       # evict the inputs from L2 (untimed)
         e0.record(stream)
         step()
         e1.record(stream)
     barrier()
-    clocks.end()
-    # The timed region can be shorter than the clock sampler's period (30 steps of the default workload take ~25 ms, nvidia-smi
-    # reports every 20 ms): keep exactly the same step running, untimed, for 0.3 s more so that the clocks / throttle reasons are
-    # sampled under this load.  Nothing measured here enters `value`.
     clock_probe_s = 0.0
-    if clocks.windows[-1][1] - clocks.windows[-1][0] < 0.3:
-        clocks.begin()
-        t_probe = time.monotonic()
-        while time.monotonic() - t_probe < 0.3:
-            for _ in range(8):
-                step()
-            torch.cuda.synchronize(dev)
+    if clocks is not None and rank == 0:
         clocks.end()
-        clock_probe_s = round(time.monotonic() - t_probe, 3)
+        # The timed region can be shorter than the clock sampler's period (nvidia-smi reports every 20 ms): keep exactly the same
+        # step running, untimed, for 0.3 s more so the clocks / throttle reasons are sampled under this load.
+        if clocks.windows[-1][1] - clocks.windows[-1][0] < 0.3:
+            clocks.begin()
+            t_probe = time.monotonic()
+            while time.monotonic() - t_probe < 0.3:
+                for _ in range(8):
+                    step()
+                torch.cuda.synchronize(dev)
+            clocks.end()
+            clock_probe_s = round(time.monotonic() - t_probe, 3)
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-    total_ms = sum(kernel_ms)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = t.item()
-    ms_per_step = total_ms_max / args.steps
-    value = world * B * args.steps / (total_ms_max * 1e-3)
+    total_ms_max = allmax(sum(kernel_ms))
+    ms_per_step = total_ms_max / steps
+    value = world * B * steps / (total_ms_max * 1e-3)
+    prob_ref, hard_ref = prob.cpu(), hard.cpu()
 
-    # ---- end-to-end through the host-buffer call ----
+    # ---- end to end: pinned host buffers -> device -> decode -> host, every step, through the asynchronous pipeline ----
+    depth = 3
+    pipe = DecodePipeline(dec, g, max_B=B, depth=depth)
     xh = x.cpu().pin_memory()
-    prob_h = torch.empty((B, V), dtype=torch.float32).pin_memory()
-    hard_h = torch.empty((B, V), dtype=torch.uint8).pin_memory()
-    for _ in range(2):
-        dec.decode_host(xh, prob_h, hard_h)
+    e2e = {}
+    if program == "v2_4":
+        # packed form: what x carries per syndrome is one prior float + C check-sign bits; V hard-decision bits come back
+        prior_d, synd_d = packing.pack_x(x, V)
+        prior_h, synd_h = prior_d.cpu().pin_memory(), synd_d.cpu().pin_memory()
+        bits_h = [torch.empty((B, (V + 31) // 32), dtype=torch.int32).pin_memory() for _ in range(depth)]
+        for i in range(depth):
+            pipe.submit_packed(prior_h, synd_h, hard_bits_out=bits_h[i])
+        pipe.drain()
+        barrier()
+        if clocks is not None and rank == 0:
+            clocks.begin()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            pipe.submit_packed(prior_h, synd_h, hard_bits_out=bits_h[i % depth])   # H2D of this step's inputs + decode + D2H of its result
+        pipe.drain()
+        dt = allmax(time.perf_counter() - t0)
+        if clocks is not None and rank == 0:
+            clocks.end()
+        same_bits = bool(torch.equal(packing.unpack_bits(bits_h[(steps - 1) % depth], V), hard_ref))
+        e2e = {"value": world * B * steps / dt, "unit": "syndromes/s",
+               "h2d_bytes_per_step": B * (4 + 4 * ((Cn + 31) // 32)), "d2h_bytes_per_step": B * 4 * ((V + 31) // 32),
+               "api": "DecodePipeline.submit_packed -> gd_pipeline_submit_packed (pinned host buffers; prior float + check-sign bits "
+                      "in, hard-decision bits out; %d batches in flight)" % depth,
+               "matches_device_path": same_bits}
+    # the reference's own layout: x [B, V+C] fp32 in, prob fp32 + hard bytes out
+    prob_h = [torch.empty((B, V), dtype=torch.float32).pin_memory() for _ in range(depth)]
+    hard_h = [torch.empty((B, V), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+    n_e2e = steps if headline else max(3, steps // 2)
+    for i in range(depth):
+        pipe.submit(xh, prob_out=prob_h[i], hard_out=hard_h[i])
+    pipe.drain()
     barrier()
-    clocks.begin()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        dec.decode_host(xh, prob_h, hard_h)     # returns when the host outputs are complete
+    for i in range(n_e2e):
+        pipe.submit(xh, prob_out=prob_h[i % depth], hard_out=hard_h[i % depth])
+    pipe.drain()
+    dt = allmax(time.perf_counter() - t0)
+    same = bool(torch.equal(prob_h[(n_e2e - 1) % depth], prob_ref) and torch.equal(hard_h[(n_e2e - 1) % depth], hard_ref))
+    fp32_form = {"value": world * B * n_e2e / dt, "unit": "syndromes/s", "h2d_bytes_per_step": B * N * 4, "d2h_bytes_per_step": B * V * 5,
+                 "api": "DecodePipeline.submit -> gd_pipeline_submit (x [B, V+C] fp32 in, prob fp32 + hard uint8 out; %d batches in flight)" % depth,
+                 "matches_device_path": same}
+    if e2e:
+        e2e["fp32_form"] = fp32_form
+    else:
+        e2e = fp32_form
+    if headline:
+        # the blocking single call of round 1, for continuity
+        dec.decode_host(xh, prob_h[0], hard_h[0])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(3, steps // 3)):
+            dec.decode_host(xh, prob_h[0], hard_h[0])
+        dt = allmax(time.perf_counter() - t0)
+        e2e["blocking_call"] = {"value": world * B * max(3, steps // 3) / dt, "unit": "syndromes/s",
+                                "api": "GNNI.decode_host -> gd_decode_host (one synchronous call per batch, fp32 layout)",
+                                "matches_device_path": bool(torch.equal(prob_h[0], prob_ref))}
+    del pipe
+
+    out = {"metric": "decoded syndromes/sec", "value": value, "unit": "syndromes/s", "n_gpus": world,
+           "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    if rank != 0:
+        return out
+    config = {"workload": name, "program": PROGRAM_NAMES[program], "code": "%s-%d" % code_spec,
+              "V": V, "C": Cn, "E": E, "T": T, "batch_per_gpu": B,
+              "noise": ["iid-xz", "depolarizing", "awgn (all-zero codeword)", "awgn (all-one codeword)"][noise],
+              "l2": "L2 flushed (256 MiB write) between timed steps", "weights": weights_src, "launch": info,
+              "parallelism": "batch-sharded x%d, no collective" % world}
+    # ---- rooflines ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    io_bytes = B * (4 * N + 4 * V + V)                       # x in, prob + hard out, per launch
+    med_ms = statistics.median(kernel_ms)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r02_decode_kernel_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(name)
+    n_kernels = 1
+    if info["resident"]:
+        alg_bytes = io_bytes
+        kname = "gd::lean_decode_kernel (+ begin / prep / tables / deferred-pass launches)" if lean else "gd::decode_kernel<%s, resident>" % program
+        n_kernels = 5 if lean else 1
+        note = "fused resident kernel: ~%d B/syndrome of HBM traffic, so HBM is not the binding resource; see pipe" % (alg_bytes // B)
+    else:
+        # streamed path: per edge and iteration m: R,R,W  t: W,R = 20 B for the learned programs, 16 B for
+        # sum-product (sign rides in t); the first iteration reads no m (m == 0).
+        per_edge = (16 * T - 4) if program.startswith("bp") else (20 * T - 8)
+        alg_bytes = io_bytes + B * E * max(per_edge, 0)
+        kname = "gd::decode_streamed_tma_kernel<%s>" % program
+        note = "streamed global-memory path: %.2f MB of edge-state traffic per syndrome" % (E * per_edge / 1e6)
+    achieved = alg_bytes / (med_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": kname,
+                "kernel_ms": med_ms, "algorithmic_bytes_per_launch": alg_bytes, "note": note}
+    if lean:
+        r = (C.c_double * 2)()
+        _cabi.check(lib.gd_microbench(7, 4096, local_rank, r))    # conflict-free 128-bit shared-memory loads: wavefronts / s
+        wf_peak = r[0]
+        wf = lean_wavefronts_per_syndrome(pcm, T) * B
+        measured = None
+        mpath = os.path.join(ROOT, "profiles", "r02_lean_kernel_ncu.json")
+        if os.path.exists(mpath):
+            measured = json.load(open(mpath)).get(name)
+        roofline["pipe"] = {
+            "name": "shared-memory data pipe (l1tex LSU wavefronts, 128 B per cycle per SM): the decoder evaluates nothing but table "
+                    "look-ups -- all three Softplus MLPs and the tanh are cubic tables built in double precision once per weight "
+                    "set (DESIGN.md 4.0) -- so 128-bit table loads and the message reads / writes are the whole kernel",
+            "achieved": wf / (med_ms * 1e-3) / 1e12, "peak": wf_peak / 1e12, "unit": "T wavefronts/s",
+            "frac": wf / (med_ms * 1e-3) / wf_peak,
+            "what": "ALGORITHMIC (conflict-free) wavefronts per launch = %.0f per syndrome x %d syndromes, over the time of the WHOLE "
+                    "step (5 launches: hash check, input packing, table refresh, decode, deferred pass); bank conflicts of the "
+                    "variable-phase look-ups (random 16-byte indices, 8 lanes per phase) add ~40%% real wavefronts on top" % (wf / B, B),
+            "peak_source": "gd_microbench kind=7 (conflict-free LDS.128 stream), measured live on this GPU",
+            "ncu": measured}
+    elif program == "v2_4":
+        r = (C.c_double * 2)()
+        _cabi.check(lib.gd_microbench(1, 4096, local_rank, r))   # ex2+lg2 pairs / s: the Softplus unit rate
+        deg = pcm.sum(0)
+        n_vact = int(deg[deg >= 2].sum())
+        hid = dec.mlp[0].out_features
+        units = B * hid * (T * n_vact + (E - n_vact)) if info["resident"] else B * hid * T * E
+        roofline["pipe"] = {"name": "xu (MUFU): Softplus hidden units of the 2-input variable-phase MLP evaluated directly (check-phase and "
+                                    "read-out MLPs are cubic tables); peak = the 2-MUFU-per-unit (ex2+lg2) rate",
+                            "achieved": units / (med_ms * 1e-3) / 1e12, "peak": r[0] / 1e12, "unit": "T Softplus units/s",
+                            "frac": units / (med_ms * 1e-3) / r[0],
+                            "peak_source": "gd_microbench kind=1 (ex2+lg2 pairs/s), measured live on this GPU", "units_per_launch": units}
+    out.update({"config": config, "e2e": e2e, "gpu_launches": steps * n_kernels, "roofline": roofline})
+    if headline and lean:
+        # the general path beside the fast one: the same batch with per-variable priors (no syndrome is table-eligible, every
+        # one is decoded by the edge-owner kernel's direct evaluation)
+        xg = x.clone()
+        xg[:, :V] += 1e-3 * torch.arange(V, device=dev, dtype=torch.float32)
+        for _ in range(2):
+            step(xg)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            step(xg)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        out["general_path"] = {"value": 3 * B / (e0.elapsed_time(e1) * 1e-3), "unit": "syndromes/s (1 GPU)",
+                               "what": "same batch with per-variable priors: nothing is table-eligible, every syndrome takes the "
+                                       "edge-owner kernel's direct (MUFU) evaluation of the variable-phase MLP"}
+    if headline:
+        out["_clock_probe_s"] = clock_probe_s
+    if headline and not args.no_cpu_baseline and world == 1:
+        rng = np.random.RandomState(1234)  # noqa: F841
+        # bounded sample: this workload's own syndromes (cycled if the batch is small), stop after ~15 s of CPU work
+        n_s = max(128, min(131072, int(5e7 // N)))           # <= 400 MB of fp64 inputs
+        reps = max(1, -(-n_s // B))
+        xs_cpu = x[:n_s].cpu().double().repeat(reps, 1)[:n_s]
+        rate, n_done, secs = cpu_reference_rate(program, pcm, T, weights, xs_cpu, 128, 15.0, cores)
+        out["cpu_baseline"] = {"value": rate, "unit": "syndromes/s", "cores": cores, "kind": "port",
+                               "sample": "%d syndromes of this workload in chunks of 128 (the reference's BATCH_SIZE), "
+                                         "fp64, %.1f s, oracle/restate.py on %d torch threads" % (n_done, secs, cores)}
+    if not headline:
+        out = {"workload": name, "value": out["value"], "unit": "syndromes/s", "ms_per_step": ms_per_step, "steps": steps,
+               "n_gpus": world, "e2e": e2e, "roofline": {k: roofline[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel")},
+               "config": {k: config[k] for k in ("program", "code", "V", "C", "E", "T", "batch_per_gpu", "noise", "launch")}}
+        if "pipe" in roofline:
+            out["roofline"]["pipe"] = {k: roofline["pipe"][k] for k in ("achieved", "peak", "unit", "frac")}
+    return out
+
+
+def run_training(args, dev, rank, world):
+    """BASELINE configs[3]: one training step of the decoder_v2_4 program on the rotated surface code d = 7, B = 4096 per GPU:
+    forward with stash, sparse loss, hand-written backward, gradient all-reduce (one peer-memory kernel with Adam fused in;
+    NCCL when symmetric memory is unavailable), Adam."""
+    import torch.distributed as dist
+    from gnn_decode_b200 import codes
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.quantum import decoder_v2_4
+    from gnn_decode_b200.sampler import sample_syndromes
+    from gnn_decode_b200.train import FusedTrainer
+    d, B, T = 7, 4096, 15
+    Hz, Hx = codes.rotated_surface_checks(d)
+    pcm = codes.css_pcm(Hz, Hx)
+    logical = codes.css_logicals(Hz, Hx)
+    g = TannerGraph.from_pcm(pcm, dev)
+    torch.manual_seed(0)
+    dec = decoder_v2_4.GNNI(T).to(dev).train().bind_graph(g)
+    p2p, how = None, "none (1 GPU)"
+    if world > 1:
+        how = "NCCL all-reduce of the flat gradient (1 283 floats)"
+        try:
+            from gnn_decode_b200.dist import P2PAllReduce
+            p2p = P2PAllReduce(sum(p.numel() for p in dec._gd_params()), dev)
+            how = "peer-memory kernel over NVLink (gd_p2p_allreduce_adam: exchange + Adam in one launch)"
+        except Exception as ex:  # noqa: BLE001
+            how += " [peer-memory kernel unavailable: %s]" % type(ex).__name__
+    trainer = FusedTrainer(dec, g, logical, lr=3e-4, weight_decay=1e-9, p2p=p2p)
+    x, err = sample_syndromes(g, B, [0.01, 0.03, 0.05, 0.08], noise=1, seed=1, first_sample=rank * B)
+    for _ in range(3):
+        trainer.step(x, err)
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    clocks.end()
-    e2e_launches_per_step = int(_cabi.lib().gd_decode_host_last_launches(g.handle))
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        loss = trainer.step(x, err)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / t.item()
-    clk = clocks.stop() if rank == 0 else None
-    if clk is not None and clock_probe_s:
-        clk["load_probe_s"] = clock_probe_s      # untimed continuation of the same step, sampled together with the timed windows
-    same = bool(torch.equal(prob_h, prob.cpu()) and torch.equal(hard_h, hard.cpu()))
-
-    if rank == 0:
-        # ---- rooflines ----
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-        else:
-            hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        io_bytes = B * (4 * N + 4 * V + V)                       # x in, prob + hard out, per launch
-        med_ms = statistics.median(kernel_ms)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_decode_kernel_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload)
-        if info["resident"]:
-            alg_bytes = io_bytes
-            kname = "gd::decode_kernel<%s, resident>" % program
-            note = ("fused resident kernel: ~%d B/syndrome, so HBM is not the binding resource; see pipe" % (alg_bytes // B)
-                    if program == "v2_4" else "fused resident kernel: ~%d B/syndrome; FP32-issue bound, not HBM" % (alg_bytes // B))
-        else:
-            # streamed path: per edge and iteration m: R,R,W  t: W,R = 20 B for the learned
-            # programs, 16 B for sum-product (sign rides in t); the first iteration reads no m (m == 0).
-            per_edge = (16 * T - 4) if program.startswith("bp") else (20 * T - 8)
-            alg_bytes = io_bytes + B * E * max(per_edge, 0)
-            kname = "gd::decode_streamed_tma_kernel<%s>" % program
-            note = "streamed global-memory path: %.2f MB of edge-state traffic per syndrome" % (E * per_edge / 1e6)
-        achieved = alg_bytes / (med_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": kname,
-                    "kernel_ms": med_ms, "algorithmic_bytes_per_launch": alg_bytes, "note": note}
-        if program == "v2_4":
-            r = (C.c_double * 2)()
-            _cabi.check(lib.gd_microbench(1, 4096, local_rank, r))   # ex2+lg2 pairs / s: the Softplus unit rate
-            unit_peak = r[0]
-            deg = pcm.sum(0)
-            n_vact = int(deg[deg >= 2].sum())                        # edges on variables of degree >= 2
-            if info["resident"]:
-                # direct (MUFU) Softplus evaluations per launch: only the 2-input variable-phase MLP -- every
-                # iteration for edges on variables of degree >= 2, once for degree-1 variables; the 1 -> h -> 1
-                # check-phase and read-out MLPs are cubic tables
-                units = B * dec.mlp[0].out_features * (T * n_vact + (E - n_vact))
-                what = ("xu (MUFU): Softplus hidden units evaluated on the direct path = the 2-input variable-phase MLP only "
-                        "(check-phase + read-out MLPs are cubic tables, degree-1 variables are evaluated once); peak = the "
-                        "2-MUFU-per-unit (ex2+lg2) rate; the kernel needs 1.5 MUFU/unit (half of the lg2 run as an FMA-pipe "
-                        "polynomial), so frac can exceed 1")
-            else:
-                units = B * dec.mlp[0].out_features * T * E
-                what = ("xu (MUFU): Softplus hidden units evaluated on the direct path = the 2-input variable-phase MLP, every "
-                        "edge and iteration (streamed path; check-phase + read-out MLPs are cubic tables); peak = the "
-                        "2-MUFU-per-unit (ex2+lg2) rate")
-            tabs = (C.c_int32 * 4)()
-            _cabi.check(lib.gd_decode_tables_info(g.handle, C.byref(model), B, tabs))
-            priors = torch.unique(x[:, :V])
-            vtab_on = bool(tabs[2] > 0 and priors.numel() <= tabs[3] and bool((x[:, :V] == x[:, :1]).all()))
-            unit_rate = units / (med_ms * 1e-3)
-            if vtab_on:
-                # every syndrome of this batch carries one prior on all its variables and the batch has no more distinct priors
-                # than the kernel has table slots, so the variable phase is tabulated as well: no MLP runs on the MUFU pipe
-                ref_units = B * E * (T * 256 + 128)
-                roofline["pipe"] = {
-                    "name": "none: all three Softplus MLPs are evaluated from cubic tables in shared memory (check phase, read-out, and -- "
-                            "since every syndrome carries one prior value on all its variables, as the reference's gen_syn makes them, and "
-                            "the batch has %d distinct priors <= %d table slots -- the variable phase, DESIGN.md 4.1); the MUFU pipe only "
-                            "sees one tanh per edge-iteration and the table builds. What binds the kernel now is shared-memory look-ups, "
-                            "issue and barriers (ncu summary under profiles/); the numbers below are the EQUIVALENT rate: the "
-                            "reference's Softplus units per launch / kernel time, against the measured MUFU rate an un-tabulated kernel "
-                            "could not exceed" % (priors.numel(), tabs[3]),
-                    "tabulated": {"check_phase_intervals": tabs[0], "readout_intervals": tabs[1],
-                                  "variable_phase_intervals": tabs[2], "variable_phase_table_slots": tabs[3]},
-                    "achieved": ref_units / (med_ms * 1e-3) / 1e12, "peak": unit_peak / 1e12, "unit": "T Softplus units/s (equivalent)",
-                    "frac": ref_units / (med_ms * 1e-3) / unit_peak,
-                    "peak_source": "gd_microbench kind=1 (ex2+lg2 pairs/s), measured live on this GPU",
-                    "units_per_launch": 0, "reference_units_per_launch": ref_units}
-            else:
-                roofline["pipe"] = {"name": what, "achieved": unit_rate / 1e12,
-                                    "peak": unit_peak / 1e12, "unit": "T Softplus units/s", "frac": unit_rate / unit_peak,
-                                    "frac_of_1p5_mufu_bound": unit_rate / (unit_peak * 2.0 / 1.5),
-                                    "peak_source": "gd_microbench kind=1 (ex2+lg2 pairs/s), measured live on this GPU",
-                                    "units_per_launch": units,
-                                    "reference_units_per_launch": B * E * (T * 256 + 128)}
-        line = {"metric": "decoded syndromes/sec", "value": value, "unit": "syndromes/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, launch=info, parallelism="batch-sharded x%d, no collective" % world,
-                               geometry="planner model" if args.no_autotune else "autotuned before warm-up (gd_decode_autotune)"),
-                "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": "syndromes/s", "h2d_bytes_per_step": B * N * 4,
-                        "d2h_bytes_per_step": B * V * 5, "api": "GNNI.decode_host -> gd_decode_host (pinned host buffers)",
-                        "matches_device_path": same},
-                "gpu_launches": args.steps * 1,     # timed `value` region: one gd::decode_kernel launch per step
-                "gpu_launches_e2e": args.steps * e2e_launches_per_step,   # gd_decode_host_last_launches: 1 = gated single-launch pipeline
-                "roofline": roofline}
-        if not args.no_cpu_baseline and world == 1:
-            rng = np.random.RandomState(1234)
-            # bounded sample: this workload's own syndromes (cycled if the batch is small), stop after ~15 s of CPU work
-            n_s = max(128, min(131072, int(5e7 // N)))           # <= 400 MB of fp64 inputs
-            reps = max(1, -(-n_s // B))
-            xs_cpu = x[:n_s].cpu().double().repeat(reps, 1)[:n_s]
-            rate, n_done, secs = cpu_reference_rate(program, pcm, T, weights, xs_cpu, 128, 15.0, cores)
-            line["cpu_baseline"] = {"value": rate, "unit": "syndromes/s", "cores": cores, "kind": "port",
-                                    "sample": "%d syndromes of this workload in chunks of 128 (the reference's BATCH_SIZE), "
-                                              "fp64, %.1f s, oracle/restate.py on %d torch threads" % (n_done, secs, cores)}
-        print(json.dumps(line))
+    ms = t.item() / n
+    ar_us = None
     if world > 1:
-        dist.destroy_process_group()
-    return 0
+        flat = torch.zeros(trainer.w.numel(), dtype=torch.float32, device=dev)
+        fn = (lambda: p2p(flat)) if p2p is not None else (lambda: dist.all_reduce(flat))
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(50):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ar_us = e0.elapsed_time(e1) / 50 * 1e3
+        if p2p is not None:
+            p2p.check()
+    return {"workload": TRAIN_WORKLOAD, "value": world * B / (ms * 1e-3), "unit": "syndromes/s", "ms_per_step": ms,
+            "steps_per_s": 1e3 / ms, "steps": n, "n_gpus": world, "loss": float(loss.item()),
+            "gradient_allreduce": how, "allreduce_us": ar_us,
+            "config": {"program": PROGRAM_NAMES["v2_4"], "code": "rotated-7", "V": g.V, "C": g.C, "E": g.E, "T": T, "batch_per_gpu": B,
+                       "step": "forward(+stash) + loss + backward + all-reduce + Adam(lr 3e-4, wd 1e-9), fp32 master weights"}}
 
 
 def _host_sample(pcm, noise, p_list, n, rng):

@@ -515,16 +515,43 @@ __global__ void __launch_bounds__(256) lean_prep_kernel(const PrepParams p) {
             const float* row = p.x + s * p.N;
             // ~60 instructions per syndrome: independent lane-strided loads (no short-circuit &&, which would chain one memory
             // latency per load), one ballot per word of check signs, one vote, and the prior looked up by 16 lanes at once
+            // all loads of a pass are issued before the first one is used (the SM issues in order: a load -> use -> load loop
+            // pays one memory latency per load; measured 25 us vs 46 us for 65536 syndromes before the other fixes)
+            constexpr int kU = 4;
             const unsigned int p0b = __float_as_uint(__ldg(row));
             unsigned int bad = 0u;
-#pragma unroll 4
-            for (int v = lane; v < p.V; v += 32) bad |= __float_as_uint(__ldg(row + v)) ^ p0b;
-            for (int w = 0; w < p.nw; ++w) {
-                const int c = w * 32 + lane;
-                const float val = c < p.C ? __ldg(row + p.V + c) : 1.0f;
-                bad |= (val == 1.0f || val == -1.0f) ? 0u : 1u;
-                const uint32_t word = __ballot_sync(0xffffffffu, val < 0.f);
-                if (lane == 0) p.sgn_out[s * p.nw + w] = word;
+            float sv[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {                      // first kU words of check inputs (all of them up to C = 128)
+                const int c = u * 32 + lane;
+                sv[u] = (u < p.nw && c < p.C) ? __ldg(row + p.V + c) : 1.0f;
+            }
+            for (int v0 = 0; v0 < p.V; v0 += 32 * kU) {
+                unsigned int a[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int v = v0 + u * 32 + lane;
+                    a[u] = __float_as_uint(__ldg(row + (v < p.V ? v : 0)));      // lanes past V re-read row[0]
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) bad |= a[u] ^ p0b;
+            }
+            for (int w0 = 0; w0 < p.nw; w0 += kU) {
+                if (w0 > 0) {
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int c = (w0 + u) * 32 + lane;
+                        sv[u] = (w0 + u < p.nw && c < p.C) ? __ldg(row + p.V + c) : 1.0f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (w0 + u < p.nw) {                        // warp-uniform
+                        bad |= (sv[u] == 1.0f || sv[u] == -1.0f) ? 0u : 1u;
+                        const uint32_t word = __ballot_sync(0xffffffffu, sv[u] < 0.f);
+                        if (lane == 0) p.sgn_out[s * p.nw + w0 + u] = word;
+                    }
+                }
             }
             const float p0 = __uint_as_float(p0b);
             const bool good = __all_sync(0xffffffffu, bad == 0u) && isfinite(p0);

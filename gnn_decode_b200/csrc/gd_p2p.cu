@@ -16,7 +16,7 @@ struct P2PParams {
     float* peer[kMaxWorld];       // peer[r] = rank r's symmetric buffer mapped into this process
     const float* src;
     float* dst;
-    int* err;                     // set to 1 when a peer never showed up (bounded spin)
+    int* err;                     // set to 1 when a peer never showed up (bounded spin); dst and the weights are then left untouched
     int world, rank, n, n_pad;
     unsigned int epoch;
     float scale;
@@ -36,7 +36,9 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 }
 
 __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const P2PParams p) {
+    __shared__ int timed_out;
     const int tid = threadIdx.x;
+    if (tid == 0) timed_out = 0;
     float* mine = p.peer[p.rank] + (size_t)(p.epoch & 1u) * p.n_pad;
     for (int i = tid; i < p.n; i += blockDim.x) mine[i] = p.src[i];
     __threadfence_system();
@@ -47,11 +49,14 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const P2PParams p) {
         long long spins = 0;
         // epochs only grow; (int) difference tolerates wrap-around
         while ((int)(ld_acquire_sys(flag) - p.epoch) < 0) {
-            if (++spins > (1ll << 27)) { *p.err = 1; break; }        // ~ seconds: a peer is gone, do not hang the GPU
+            // 2^24 polls of >= 64 ns each plus the system-scope load: tens of seconds.  A peer is gone: do not hang the
+            // GPU, and do NOT touch dst / the weights with a partial sum (the flag is CTA-uniform after the barrier)
+            if (++spins > (1ll << 24)) { *p.err = 1; timed_out = 1; break; }
             __nanosleep(64);
         }
     }
     __syncthreads();
+    if (timed_out) return;
     for (int i = tid; i < p.n; i += blockDim.x) {
         float acc = 0.f;
         for (int r = 0; r < p.world; ++r)                             // fixed rank order on every rank

@@ -142,11 +142,18 @@ def graph_from_batched(edge_index, n_node_rows, rows=None, cols=None, chk_is_off
     device to be the block-diagonal replication of the first graph (the reference silently
     assumes it)."""
     device = edge_index.device if device is None else torch.device(device)
+    # Two-level cache.  The address / shape / version of the batched tensor only REMEMBERS where its first graph ends; a hit
+    # is then validated against the CONTENT of that first-graph slice (the caching allocator hands a freed block to a new
+    # tensor of the same shape with version 0: another code with the same V / C / E must not decode with a stale graph).
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, n_node_rows, rows, cols,
            bool(chk_is_offset), str(device))
     hit = _batched_cache.get(key)
     if hit is not None:
-        return hit
+        g, B, per_bytes = hit
+        head = edge_index[:, :g.E].detach().to("cpu", torch.int64).contiguous()
+        if head.numpy().tobytes() == per_bytes:
+            return g, B
+        del _batched_cache[key]
     total = int(edge_index.size(1))
     if rows is not None and cols is not None:
         V, Cn = int(rows), int(cols)
@@ -164,7 +171,8 @@ def graph_from_batched(edge_index, n_node_rows, rows=None, cols=None, chk_is_off
                              "to the decoder constructor")
         V, Cn, E = dims
         B = total // E
-    per = edge_index[:, :E].detach().to("cpu", torch.int64).clone()
+    per = edge_index[:, :E].detach().to("cpu", torch.int64).contiguous().clone()
+    per_bytes = per.numpy().tobytes()                      # as it sits in the batched tensor (check ids possibly offset)
     if chk_is_offset:
         per[1] -= V
     g = _graph_intern(per, V, Cn, device)
@@ -175,7 +183,7 @@ def graph_from_batched(edge_index, n_node_rows, rows=None, cols=None, chk_is_off
                              "(%d mismatching entries)" % bad)
     if len(_batched_cache) > 64:
         _batched_cache.clear()
-    _batched_cache[key] = (g, B)
+    _batched_cache[key] = (g, B, per_bytes)
     return g, B
 
 

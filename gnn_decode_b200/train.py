@@ -134,9 +134,17 @@ class FusedTrainer(object):
 
     The master weights live in `self.w` (the packed layout the decode kernels read); `sync_module()` writes them back
     into the decoder's parameters (fp64 in the reference's state_dict) -- call it before `state_dict()` / evaluation
-    through the module.  p2p: a dist.P2PAllReduce (world_size > 1)."""
+    through the module.  Data-parallel (an initialised process group with world_size > 1): the flat gradient is summed over
+    the ranks by p2p (a dist.P2PAllReduce, one kernel with Adam fused in) or, without it, by ONE NCCL all-reduce; rank 0's
+    weights and moments are broadcast at construction so every replica starts, and therefore stays, bit-identical.
+    average: divide the summed gradient by world_size.  The reference's loss is a batch SUM (decoder_v2_4.py:314-315), so
+    average=False reproduces `W ranks x batch B == one GPU x batch W B` exactly; the default True keeps the per-step
+    gradient scale independent of the number of GPUs (Adam is nearly scale-invariant: only eps = 1e-8 and
+    weight_decay = 1e-9 see the difference).  check_every: synchronise and raise if a peer missed an all-reduce, every that
+    many steps (and in sync_module())."""
 
-    def __init__(self, decoder, graph, logical=None, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-9, p2p=None):
+    def __init__(self, decoder, graph, logical=None, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-9, p2p=None,
+                 average=True, check_every=256):
         if decoder._gd_program != _cabi.PROG_V2_4:
             raise _cabi.GdError("the training kernels exist for the decoder_v2_4 program only")
         self.decoder, self.graph, self.logical, self.p2p = decoder, graph, logical, p2p
@@ -148,6 +156,12 @@ class FusedTrainer(object):
         self.grad = torch.zeros_like(self.w)
         self.adam = _cabi.GdAdam(lr, betas[0], betas[1], eps, weight_decay, 0)
         self._bufs = {}
+        self.average, self.check_every = bool(average), int(check_every)
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if self.world > 1:
+            for t in (self.w, self.exp_avg, self.exp_avg_sq):
+                dist.broadcast(t, src=0)
 
     @property
     def step_count(self):
@@ -189,16 +203,24 @@ class FusedTrainer(object):
             _cabi.check(lib.gd_decode_bwd(g.handle, ct.byref(model), _ptr(self.w), _ptr(x), _ptr(b["stash"]), _ptr(b["gl"]),
                                           _ptr(self.grad), _ptr(b["ws"]), 0, B, st), "gd_decode_bwd")
             self.adam.step += 1
+            scale = 1.0 / self.world if self.average else 1.0
             if self.p2p is not None:
-                self.p2p.allreduce_adam(self.grad, self.adam, self.w, self.exp_avg, self.exp_avg_sq)
+                self.p2p.allreduce_adam(self.grad, self.adam, self.w, self.exp_avg, self.exp_avg_sq, average=self.average)
+                if self.check_every > 0 and self.adam.step % self.check_every == 0:
+                    self.p2p.check()
             else:
+                if self.world > 1:                 # the path's only exchange: one NCCL all-reduce of the flat gradient
+                    import torch.distributed as dist
+                    dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
                 _cabi.check(lib.gd_adam_step(ct.byref(self.adam), _ptr(self.w), _ptr(self.grad), _ptr(self.exp_avg),
-                                             _ptr(self.exp_avg_sq), self.w.numel(), 1.0, st), "gd_adam_step")
+                                             _ptr(self.exp_avg_sq), self.w.numel(), scale if self.world > 1 else 1.0, st), "gd_adam_step")
         self.prob = b["prob"]
         return b["per"].double().sum()
 
     def sync_module(self):
         """Write the master weights back into the decoder's parameters (state_dict keys / dtypes unchanged)."""
+        if self.p2p is not None:
+            self.p2p.check()
         off = 0
         with torch.no_grad():
             for p in self.decoder._gd_params():

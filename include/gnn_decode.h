@@ -229,7 +229,8 @@ int gd_loss_v2_4(const gd_graph* g, const uint8_t* logical_dev, int32_t K, const
  *      have mapped; peer_ptrs_host[r] is rank r's buffer as seen from THIS process.  The kernel publishes src in the
  *      caller's buffer, raises its epoch flag, waits (bounded) for the peers and writes dst[i] = scale * sum over ranks
  *      in rank order -- bit-identical on every rank.  epoch must be 1, 2, 3, ... on successive calls, the same on all
- *      ranks; *err_dev is set to 1 if a peer never arrived. ---- */
+ *      ranks; if a peer never arrives (bounded wait, tens of seconds) *err_dev is set to 1 and NOTHING is written: dst and,
+ *      for gd_p2p_allreduce_adam, the weights and moments keep their values -- check err_dev before trusting a step. ---- */
 int64_t gd_p2p_buffer_floats(int32_t n);
 int gd_p2p_allreduce(const uint64_t* peer_ptrs_host, int32_t world, int32_t rank, const float* src_dev,
                      float* dst_dev, int32_t n, uint32_t epoch, float scale, int32_t* err_dev, void* stream);
@@ -299,7 +300,9 @@ int gd_eval_failures(const gd_graph* g, const uint8_t* logical_dev, int32_t K,
                      unsigned long long* counts_dev, void* stream);
 
 /* ---- measurement support: throughput of the pipes that bound the resident decoders
- *      (kind 0 MUFU ex2, 1 ex2+lg2, 2 FFMA, 3 one Softplus hidden unit, 4 packed FFMA2).
+ *      (kind 0 MUFU ex2, 1 ex2+lg2, 2 FFMA, 3 one Softplus hidden unit, 4 packed FFMA2, 5 rcp, 6 ex2+rcp+lg2,
+ *      7 shared-memory wavefronts: conflict-free 128-bit loads, units = 128-byte wavefronts -- the pipe that binds the
+ *      table-only decoder of surface / toric codes).
  *      result[0] = units / s over the whole GPU, result[1] = ms of the timed launch. ---- */
 int gd_microbench(int32_t kind, int32_t iters, int device, double* result);
 

@@ -1,6 +1,6 @@
-"""bench.py's output contract: (a) the reference arm (`--impl reference`, the oracle port on the host cores) runs without a
-GPU and prints the agreed JSON line; (b) the last line recorded on a B200 (profiles/r01l_bench.json) carries every key the
-driver reads."""
+"""bench.py's output contract: the reference arm (`--impl reference`, the oracle port on the host cores) runs without a
+GPU and prints the agreed JSON line; the roofline numerator of the table kernel is what DESIGN.md says it is.  (The GPU arm's
+line is checked where a GPU exists: tests/test_bench_gpu.py.)"""
 import json
 import os
 import subprocess
@@ -33,16 +33,11 @@ def test_reference_arm_runs_on_cpu_and_prints_the_contract_line():
     assert d["config"]["workload"] == "v2_4_rotated_d5_depol_B65536"        # BASELINE.json configs[1]
 
 
-def test_recorded_b200_line_has_every_key():
-    d = json.loads(open(os.path.join(ROOT, "profiles", "r01l_bench.json")).read().strip().splitlines()[-1])
-    _check_common(d)
-    assert d["n_gpus"] == 1 and d["dtype"] == "f32" and d["gpu_launches"] == d["steps"] > 0
-    r = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] in ("hbm", "tensor")
-    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    c = d["clocks"]
-    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(c)
-    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
-    assert d["e2e"]["value"] < d["value"]                                    # copies inside the timed region
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+def test_wavefront_count_of_the_table_kernel():
+    """bench.py's algorithmic shared-memory wavefront count (the roofline numerator of the check-owner table kernel) on the
+    headline code: rotated d = 5 has 80 edges, 60 of them on variables with a second edge, 24 checks, 50 variables."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from gnn_decode_b200 import codes
+    pcm = codes.rotated_surface_pcm(5)
+    assert bench.lean_wavefronts_per_syndrome(pcm, 15) == (14 * (6 * 80 + 5 * 60) + (80 + 4 * 24) + 5 * 80 + 2 * 50) / 32.0
