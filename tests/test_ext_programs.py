@@ -72,11 +72,8 @@ def test_restatement_matches_live_reference(script, program):
 
 # ------------------------------------------------------------------------------------------ GPU
 def _close(got, want, rtol):
-    want = want.double()
-    got = got.double().cpu()
-    atol = 1e-4 * (1.0 + want.pow(2).mean().sqrt().item())
-    err = (got - want).abs()
-    return (err / (rtol * want.abs() + atol)).max().item(), err.max().item()
+    from conftest import logit_worst
+    return logit_worst(got, want, rtol)
 
 
 class _Data(object):

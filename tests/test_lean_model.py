@@ -1,0 +1,50 @@
+"""The algorithm of the check-owner table kernel (csrc/gd_lean.cu), emulated in numpy (oracle/lean_model.py: same tables,
+same fp32 recurrence), against the fp64 oracle on the golden inputs -- checks on the CPU that (a) the per-edge recurrence
+    t_e = g_p(m_sib(e)),  m_e += s_c f2(sum of the other t of the check),  logit_v = prior + sum f3(m_e)
+IS decoder_v2_4's GNNI.forward on graphs with variable degree <= 2 / check degree <= 4, and (b) the table sizes the kernel
+ships with (128 / 512 / 2048 pieces) meet their error budgets on the shipped checkpoints."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, logit_worst
+from oracle import lean_model, restate
+
+
+@pytest.mark.parametrize("name", ["v2_4_toricL4_epoch1", "v2_4_toricL5_epoch3", "v2_4_toricL7_epoch3_T5"])
+def test_table_recurrence_matches_the_oracle(name):
+    g = Golden(name)
+    w = {k: v.numpy() for k, v in g.weights.items()}
+    out = lean_model.decode(g.edge_index.numpy(), g.V, g.C, g.x.numpy(), w, g.T)
+    ref = restate.decode("v2_4", g.edge_index, g.V, g.C, g.x, g.weights, T=g.T)["logit"]
+    worst, max_err = logit_worst(torch.from_numpy(out["logit"]), ref)
+    assert worst <= 0.5, (worst, max_err)                       # measured: <= 0.06 of the bar
+    e = out["errs"]
+    fmax = e["Rm"] / g.T / 1.02
+    assert e["c"] <= lean_model.BUDGET_C + 6e-8 * fmax           # check table: 1e-7 + half an fp32 ulp of its values
+    assert e["r"] <= lean_model.BUDGET_R + 1e-7 * e["f3max"]
+    assert max(e["v"].values()) <= lean_model.BUDGET_V
+
+
+def test_collapsed_checkpoint_misses_the_variable_table_budget():
+    """epoch67 (T max|mlp2| = 70): 512 pieces cannot hold tanh(mlp1 / 2) to 1e-6 -- the kernel must notice (it then hands the
+    batch to the edge-owner kernel; tests/test_lean_gpu.py)."""
+    g = Golden("v2_4_toricL4_epoch67")
+    w = {k: v.numpy() for k, v in g.weights.items()}
+    out = lean_model.decode(g.edge_index.numpy(), g.V, g.C, g.x.numpy()[:4], w, g.T)
+    assert max(out["errs"]["v"].values()) > lean_model.BUDGET_V
+
+
+def test_midpoint_error_estimate_is_the_true_error():
+    """The kernel measures a table's error at the interval midpoints only; on a dense grid the true error is no larger
+    (the Hermite remainder (t (1 - t))^2 f''''/24 peaks there)."""
+    g = Golden("v2_4_toricL5_epoch3")
+    gw = lambda k: g.weights[k].numpy().astype(np.float32).astype(np.float64)
+    a, c, w2, b2 = gw("ggc2.mlp.0.weight")[:, 0], gw("ggc2.mlp.0.bias"), gw("ggc2.mlp.2.weight")[0], float(gw("ggc2.mlp.2.bias")[0])
+    n = 128
+    coef, err_mid, _ = lean_model.build_table(a, c, w2, b2, 3.0, n)
+    x = np.linspace(-3.0, 3.0, 20001)
+    f, _ = lean_model.mlp_f_df(a, c, w2, b2, x)
+    inv_h = n / 6.0
+    got = lean_model.eval_table(coef, inv_h, 3.0 * inv_h - 0.5, x)
+    assert np.abs(got.astype(np.float64) - f).max() <= err_mid + 2.4e-7      # + fp32 evaluation rounding (|f| ~ 2-3)

@@ -3,8 +3,8 @@
 Bars (BASELINE.json north_star):
   * graph / index tables: bit-exact;
   * hard decisions: bit-exact wherever the reference's own logit is not within LOGIT_TIE of 0;
-  * soft logits: |cuda_fp32 - reference| <= RTOL * |reference| + ATOL, RTOL = 1e-4, with the
-    absolute floor ATOL = 1e-4 * (1 + rms of the reference logits of that case) for values near 0.
+  * soft logits: |cuda_fp32 - reference| <= RTOL * max(|reference|, 1), RTOL = 1e-4 (conftest.logit_bound: relative
+    above |logit| = 1, the same number absolute below it).
     The sum-product (BP) programs are ill-conditioned in the saturated regime (the fp32 reference
     itself is ~1e-2 away from the fp64 evaluation of its own formulas there), so for them the bar is
     RTOL_BP against the fp64 oracle plus hard-decision equality.
@@ -13,12 +13,12 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import Golden, golden_cases, make_decoder
+from conftest import Golden, golden_cases, logit_worst, make_decoder
 from oracle import restate
 
 pytestmark = pytest.mark.gpu
 
-RTOL, RTOL_BP, LOGIT_TIE = 1e-4, 2e-3, 1e-3
+RTOL, RTOL_BP, LOGIT_TIE = 1e-4, 5e-4, 1e-3     # measured: v2_4 <= 0.08 x, sum-product <= 0.05 x these bars (profiles/r02_parity_envelope.txt)
 
 
 def _dev():
@@ -27,13 +27,7 @@ def _dev():
 
 
 def _logit_close(got, want, rtol):
-    want = want.double()
-    got = got.double().cpu()
-    atol = 1e-4 * (1.0 + want.pow(2).mean().sqrt().item())
-    err = (got - want).abs()
-    bound = rtol * want.abs() + atol
-    worst = (err / bound).max().item()
-    return worst, err.max().item()
+    return logit_worst(got, want, rtol)
 
 
 class _Data(object):

@@ -3,7 +3,7 @@ of the REFERENCE's own train step (loss = criterion(decoder(datas), datas); loss
 quantum/decoder_v2_4.py:331-335) stored in tests/golden/grad_*.npz, and against the oracle.
 
 Bar: fp32 kernels vs the fp64 reference, per parameter tensor
-     max |g_cuda - g_ref| <= GRAD_RTOL * max |g_ref|  (GRAD_RTOL = 2e-3), loss within 1e-5 relative;
+     max |g_cuda - g_ref| <= GRAD_RTOL * max |g_ref|  (GRAD_RTOL = 1e-4          # measured worst case over the fixtures: 1.1e-5 (profiles/r02_parity_envelope.txt); round 1 used 2e-3), loss within 1e-5 relative;
      gradients bit-reproducible run to run (fixed-order two-stage reduction, no atomics)."""
 import math
 import os
@@ -16,7 +16,7 @@ from conftest import GOLDEN
 from oracle import restate
 
 pytestmark = pytest.mark.gpu
-GRAD_RTOL = 2e-3
+GRAD_RTOL = 1e-4          # measured worst case over the fixtures: 1.1e-5 (profiles/r02_parity_envelope.txt); round 1 used 2e-3
 DEV = "cuda:0"
 
 
