@@ -29,6 +29,7 @@
 #include "gd_math.cuh"
 #include "gd_options.cuh"
 #include <algorithm>
+#include <stddef.h>
 #include <string.h>
 
 namespace gd {
@@ -49,7 +50,8 @@ struct LeanParams {
     const uint32_t* sgn;         // [B][nw] bit c = check c's input is -1
     float* prob; float* logit; uint8_t* hard; uint32_t* hard_bits;
     LeanHeader* hdr;
-    LeanCall* call;
+    LeanCall* call;              // this call's state
+    LeanCall* next_call;         // the next call's: cleared here
     const float4* ctab; const float4* rtab; const float4* vtab;   // global tables: (n + 2) pieces each, piece 0 = interval -1
     const uint32_t* meta;        // device metadata blob of this (graph, R)
     long long B;
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
     extern __shared__ __align__(128) unsigned char smem[];
     const LeanHeader* H = p.hdr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (blockIdx.x == 0 && tid == 0) { p.next_call->overflow = 0; p.next_call->defer_count = 0; }
     // ---- can the tables serve this call at all? (identical decision in every thread of the grid) ----
     const int n_slots = H->n_slots;
     const float fmax = __uint_as_float(H->fmax_bits), f3max = __uint_as_float(H->f3max_bits);
@@ -443,10 +446,10 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     return x ^ (x >> 31);
 }
 
-// First kernel of a call (one CTA): content hash of the weights and table geometry against the cache entry's; on a
-// mismatch the entry is reset (its tables are rebuilt by the next two kernels).  Also clears the per-call state.
-__global__ void __launch_bounds__(256) lean_begin_kernel(const float* weights, int n_w, int T, int ct_n, int rt_n, int vt_n,
-                                                          LeanHeader* H, LeanCall* call) {
+// Content hash of the weights and table geometry against the cache entry's (one CTA; runs beside the packing CTAs of the
+// prep kernel): on a mismatch the tables are marked for rebuilding by the table kernel that follows.  The prior list is
+// kept -- prior values do not depend on the weights.
+__device__ void lean_hash_check(const float* weights, int n_w, int T, int ct_n, int rt_n, int vt_n, LeanHeader* H) {
     __shared__ unsigned long long part[8];
     unsigned long long h = 0;
     for (int i = threadIdx.x; i < n_w; i += blockDim.x)
@@ -463,15 +466,12 @@ __global__ void __launch_bounds__(256) lean_begin_kernel(const float* weights, i
         if (H->hash != h) {
             H->hash = h;
             H->rebuild = 1;
-            H->n_slots = 0;
             H->built_mask = 0u;
             H->fmax_bits = H->f3max_bits = H->err_c_bits = H->err_r_bits = 0u;
-            for (int k = 0; k < 16; ++k) { H->slot_bits[k] = kNone; H->err_v_bits[k] = 0u; }
+            for (int k = 0; k < 16; ++k) H->err_v_bits[k] = 0u;
         } else {
             H->rebuild = 0;
         }
-        call->overflow = 0;
-        call->defer_count = 0;
     }
 }
 
@@ -484,94 +484,95 @@ struct PrepParams {
     int* slot; int* defer_idx;
     LeanHeader* hdr;
     LeanCall* call;
-    float4* ctab;
     long long B;
-    int V, C, N, nw, hid, ct_n, vt_k, n_ct_blocks;
+    int V, C, N, nw, vt_k;
+    int n_w, T, ct_n, rt_n, vt_n;   // what the content hash covers
 };
 
-// Prep kernel: the first n_ct_blocks CTAs tabulate the check-phase MLP (and its max, which sizes the other tables'
-// domains); the others bring the inputs into packed form -- prior value, table slot, check-sign bits -- discover the
-// distinct priors and list the syndromes the tables cannot serve.
-__global__ void __launch_bounds__(256) lean_prep_kernel(const PrepParams p) {
-    __shared__ double2 nodes[kChunk + 1];
+// x [B, V+C] rows -> packed form, L lanes per row (see lean_prep_kernel)
+template <int L>
+__device__ __forceinline__ void pack_rows(const PrepParams& p, LeanHeader* H, volatile unsigned int* mirror_v, unsigned int* mirror,
+                                          long long wid, long long nwarps) {
+    constexpr int G = 32 / L;                                   // rows per warp
+    constexpr unsigned int kMask = L == 32 ? 0xFFFFFFFFu : ((1u << (L & 31)) - 1u);
+    const int lane = threadIdx.x & 31, sub = lane % L, grp = lane / L, sh = grp * L;
+    for (long long s0 = wid * G; s0 < p.B; s0 += nwarps * G) {
+        const long long s = s0 + grp;
+        const bool valid = s < p.B;
+        const float* row = p.x + (valid ? s : p.B - 1) * p.N;
+        // every load of a pass is issued before its first use (the SM issues in order: load -> use -> load would pay one
+        // memory latency per load)
+        const unsigned int p0b = __float_as_uint(__ldg(row));
+        unsigned int bad = 0u;
+        for (int v0 = sub; v0 < p.V; v0 += 4 * L) {
+            unsigned int a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = __float_as_uint(__ldg(row + (v0 + u * L < p.V ? v0 + u * L : 0)));   // past V: row[0] again
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bad |= a[u] ^ p0b;
+        }
+        for (int w = 0; w < p.nw; ++w) {
+            float sv[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const int c = w * 32 + j * L + sub;
+                sv[j] = c < p.C ? __ldg(row + p.V + c) : 1.0f;
+            }
+            uint32_t word = 0u;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                bad |= (sv[j] == 1.0f || sv[j] == -1.0f) ? 0u : 1u;
+                const uint32_t b = __ballot_sync(0xffffffffu, sv[j] < 0.f);
+                word |= ((b >> sh) & kMask) << (j * L);          // checks w * 32 + j * L + (0 .. L-1) of this row
+            }
+            if (sub == 0 && valid) p.sgn_out[s * p.nw + w] = word;
+        }
+        const float p0 = __uint_as_float(p0b);
+        const bool good = ((__ballot_sync(0xffffffffu, bad != 0u) >> sh) & kMask) == 0u && isfinite(p0);
+        int slot = -1;
+#pragma unroll
+        for (int j = 0; j < (16 + L - 1) / L; ++j) {             // the prior list, L slots per vote
+            const int k = j * L + sub;
+            const uint32_t b = __ballot_sync(0xffffffffu, k < p.vt_k && mirror_v[k & 15] == p0b);
+            const uint32_t gb = (b >> sh) & kMask;
+            if (gb && slot < 0) slot = j * L + __ffs(gb) - 1;
+        }
+        if (good && slot < 0 && sub == 0 && valid) slot = slot_of(H, mirror, p0b, p.vt_k);    // first sight of this prior in this CTA
+        slot = __shfl_sync(0xffffffffu, slot, sh);
+        if (sub == 0 && valid) {
+            if (good && slot < 0) p.call->overflow = 1;
+            if (!good) {
+                slot = -1;
+                p.defer_idx[atomicAdd(&p.call->defer_count, 1)] = (int)s;
+            }
+            p.prior_out[s] = p0;
+            p.slot[s] = slot;
+        }
+    }
+}
+
+// Prep kernel: CTA 0 checks the weights' content hash; the others bring the inputs into packed form -- prior value, table
+// slot, check-sign bits -- discover the distinct priors and list the syndromes the tables cannot serve.
+__global__ void __launch_bounds__(256, 6) lean_prep_kernel(const PrepParams p) {
     __shared__ volatile unsigned int mirror_v[16];
     unsigned int* mirror = const_cast<unsigned int*>(mirror_v);
     LeanHeader* H = p.hdr;
-    if ((int)blockIdx.x < p.n_ct_blocks) {
-        if (!H->rebuild) return;                                // same weights as the last call on this entry: the table stands
-        const float* w = p.weights + 4 * p.hid + 1;             // ggc2.mlp
-        const MlpD M{w, 1, nullptr, w + p.hid, w + 2 * p.hid, w[3 * p.hid], p.hid};
-        const int i0 = blockIdx.x * kChunk, n_int = min(kChunk, p.ct_n + 2 - i0);
-        if (n_int > 0) build_chunk(M, 0.0, false, 3.0, p.ct_n, i0, n_int, p.ctab, &H->fmax_bits, &H->err_c_bits, nodes);
+    if (blockIdx.x == 0) {
+        lean_hash_check(p.weights, p.n_w, p.T, p.ct_n, p.rt_n, p.vt_n, H);
         return;
     }
     if (threadIdx.x < 16) mirror[threadIdx.x] = threadIdx.x < p.vt_k ? H->slot_bits[threadIdx.x] : 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long long wid = (long long)(blockIdx.x - p.n_ct_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)(gridDim.x - p.n_ct_blocks) * (blockDim.x >> 5);
+    const long long wid = (long long)(blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)(gridDim.x - 1) * (blockDim.x >> 5);
     if (p.x) {
-        for (long long s = wid; s < p.B; s += nwarps) {          // a warp per syndrome
-            const float* row = p.x + s * p.N;
-            // ~60 instructions per syndrome: independent lane-strided loads (no short-circuit &&, which would chain one memory
-            // latency per load), one ballot per word of check signs, one vote, and the prior looked up by 16 lanes at once
-            // all loads of a pass are issued before the first one is used (the SM issues in order: a load -> use -> load loop
-            // pays one memory latency per load; measured 25 us vs 46 us for 65536 syndromes before the other fixes)
-            constexpr int kU = 4;
-            const unsigned int p0b = __float_as_uint(__ldg(row));
-            unsigned int bad = 0u;
-            float sv[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {                      // first kU words of check inputs (all of them up to C = 128)
-                const int c = u * 32 + lane;
-                sv[u] = (u < p.nw && c < p.C) ? __ldg(row + p.V + c) : 1.0f;
-            }
-            for (int v0 = 0; v0 < p.V; v0 += 32 * kU) {
-                unsigned int a[kU];
-#pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int v = v0 + u * 32 + lane;
-                    a[u] = __float_as_uint(__ldg(row + (v < p.V ? v : 0)));      // lanes past V re-read row[0]
-                }
-#pragma unroll
-                for (int u = 0; u < kU; ++u) bad |= a[u] ^ p0b;
-            }
-            for (int w0 = 0; w0 < p.nw; w0 += kU) {
-                if (w0 > 0) {
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const int c = (w0 + u) * 32 + lane;
-                        sv[u] = (w0 + u < p.nw && c < p.C) ? __ldg(row + p.V + c) : 1.0f;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    if (w0 + u < p.nw) {                        // warp-uniform
-                        bad |= (sv[u] == 1.0f || sv[u] == -1.0f) ? 0u : 1u;
-                        const uint32_t word = __ballot_sync(0xffffffffu, sv[u] < 0.f);
-                        if (lane == 0) p.sgn_out[s * p.nw + w0 + u] = word;
-                    }
-                }
-            }
-            const float p0 = __uint_as_float(p0b);
-            const bool good = __all_sync(0xffffffffu, bad == 0u) && isfinite(p0);
-            int slot = -1;
-            if (good) {
-                const unsigned int hit = __ballot_sync(0xffffffffu, lane < p.vt_k && mirror_v[lane & 15] == p0b);
-                if (hit) slot = __ffs(hit) - 1;
-                else {                                          // first sight of this prior in this CTA
-                    if (lane == 0) slot = slot_of(H, mirror, p0b, p.vt_k);
-                    slot = __shfl_sync(0xffffffffu, slot, 0);
-                    __syncwarp();
-                }
-            }
-            if (lane == 0) {
-                if (good && slot < 0) p.call->overflow = 1;
-                if (!good) p.defer_idx[atomicAdd(&p.call->defer_count, 1)] = (int)s;
-                p.prior_out[s] = p0;
-                p.slot[s] = slot;
-            }
-        }
+        // L lanes per syndrome (8 up to 128 nodes, 16 up to 512, else 32): the per-row overhead -- address arithmetic, votes,
+        // the prior look-up, three stores -- is shared by the 32 / L rows a warp handles at once (issue-bound otherwise:
+        // ~200 warp instructions per row, 19 us for 65536 rows of the d = 5 code)
+        if (p.N <= 128) pack_rows<8>(p, H, mirror_v, mirror, wid, nwarps);
+        else if (p.N <= 512) pack_rows<16>(p, H, mirror_v, mirror, wid, nwarps);
+        else pack_rows<32>(p, H, mirror_v, mirror, wid, nwarps);
     } else {
         for (long long s = wid * 32 + lane; s < p.B; s += nwarps * 32) {   // a thread per syndrome
             const float p0 = __ldg(p.prior_in + s);
@@ -591,28 +592,64 @@ struct TabParams {
     const float* weights;
     LeanHeader* hdr;
     const LeanCall* call;
-    float4* rtab; float4* vtab;
-    int hid, T, rt_n, vt_n, vt_k, rt_blocks, vt_blocks_per_slot;
+    float4* ctab; float4* rtab; float4* vtab;
+    int hid, T, ct_n, rt_n, vt_n, vt_k, ct_blocks, rt_blocks, vt_blocks_per_slot;
 };
 
-// Table kernel: read-out table and one variable-phase table per discovered prior, on [-Rm, Rm], Rm = T max|mlp2| (a bound on
-// |m|: m starts at 0 and gains mlp2(ext) * (+-1) per iteration).
+// Table kernel.  In the steady state (same weights, no new prior) every CTA returns at once.  After a weight change the
+// check table, the read-out table and every listed prior's variable-phase table are rebuilt; a new prior adds its table.
+// The other tables live on [-Rm, Rm], Rm = T max|mlp2| (a bound on |m|: m starts at 0 and gains mlp2(ext) * (+-1) per
+// iteration): on a rebuild every CTA first evaluates max|mlp2| over the check table's nodes itself (the same arithmetic
+// everywhere, so the same value -- a grid-wide dependency without a grid-wide barrier; ~130 point evaluations, rare).
 __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
     __shared__ double2 nodes[kChunk + 1];
+    __shared__ unsigned int fmax_sh;
     LeanHeader* H = p.hdr;
-    const float fmax = __uint_as_float(H->fmax_bits);
+    const int rebuild = H->rebuild;
+    const int bid = blockIdx.x;
+    const bool is_ct = bid < p.ct_blocks, is_rt = !is_ct && bid < p.ct_blocks + p.rt_blocks;
+    int k = -1, cb = 0;
+    if (!is_ct && !is_rt) {
+        const int b = bid - p.ct_blocks - p.rt_blocks;
+        k = b / p.vt_blocks_per_slot;
+        cb = b - k * p.vt_blocks_per_slot;
+        if (k >= H->n_slots || p.call->overflow || ((H->built_mask >> k) & 1u)) return;   // nothing new to tabulate
+    } else if (!rebuild) {
+        return;
+    }
+    const float* w2p = p.weights + 4 * p.hid + 1;               // ggc2.mlp
+    const MlpD M2{w2p, 1, nullptr, w2p + p.hid, w2p + 2 * p.hid, w2p[3 * p.hid], p.hid};
+    float fmax;
+    if (rebuild) {
+        if (threadIdx.x == 0) fmax_sh = 0u;
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+        const double h = 6.0 / (double)p.ct_n;
+        for (int j = warp; j < p.ct_n + 3; j += nwarp) {
+            double f, df;
+            mlp_eval_warp(M2, 0.0, -3.0 + h * (double)(j - 1), lane, f, df);
+            if (lane == 0) atomic_max_float_up(&fmax_sh, f);
+        }
+        __syncthreads();
+        fmax = __uint_as_float(fmax_sh);
+        if (bid == 0 && threadIdx.x == 0) H->fmax_bits = fmax_sh;
+    } else {
+        fmax = __uint_as_float(H->fmax_bits);
+    }
     const double Rm = (double)((float)p.T * (fmax * 1.02f + 1e-6f));        // the decode kernel forms the same float
-    if (!(Rm > 0.0) || !isfinite(Rm)) return;
-    if ((int)blockIdx.x < p.rt_blocks) {
-        if (!H->rebuild) return;
+    if (is_ct) {
+        const int i0 = bid * kChunk, n_int = min(kChunk, p.ct_n + 2 - i0);
+        if (n_int > 0) build_chunk(M2, 0.0, false, 3.0, p.ct_n, i0, n_int, p.ctab, nullptr, &H->err_c_bits, nodes);
+        return;
+    }
+    if (!(Rm > 0.0) || !isfinite(Rm)) return;                   // (the decode kernel sees the non-finite max and defers everything)
+    if (is_rt) {
         const float* w = p.weights + 7 * p.hid + 2;             // mlp (read-out)
         const MlpD M{w, 1, nullptr, w + p.hid, w + 2 * p.hid, w[3 * p.hid], p.hid};
-        const int i0 = blockIdx.x * kChunk, n_int = min(kChunk, p.rt_n + 2 - i0);
+        const int i0 = (bid - p.ct_blocks) * kChunk, n_int = min(kChunk, p.rt_n + 2 - i0);
         if (n_int > 0) build_chunk(M, 0.0, false, Rm, p.rt_n, i0, n_int, p.rtab, &H->f3max_bits, &H->err_r_bits, nodes);
         return;
     }
-    const int b = blockIdx.x - p.rt_blocks, k = b / p.vt_blocks_per_slot, cb = b - k * p.vt_blocks_per_slot;
-    if (k >= H->n_slots || p.call->overflow || ((H->built_mask >> k) & 1u)) return;   // nothing new to tabulate
     const float* w = p.weights;                                 // ggc1.mlp: w1 [h, 2] | b1 | w2 | b2
     const MlpD M{w, 2, w + 1, w + 2 * p.hid, w + 3 * p.hid, w[4 * p.hid], p.hid};
     const double prior = (double)__uint_as_float(H->slot_bits[k]);
@@ -663,6 +700,7 @@ struct LeanEntry {
     size_t o_ct = 0, o_rt = 0, o_vt = 0;
     cudaEvent_t ev = nullptr;
     unsigned long long last_use = 0;
+    unsigned long long calls = 0;          // decode calls enqueued on this entry: selects the header's LeanCall
 };
 constexpr int kMaxEntries = 4;
 struct LeanCtx {
@@ -923,6 +961,7 @@ static LeanEntry* lean_entry(gd_graph* g, LeanCtx* ctx, const LeanParams& p, con
             hit->o_rt = take((size_t)(p.rt_n + 2) * 16);
             hit->o_vt = take((size_t)p.vt_k * (p.vt_n + 2) * 16);
             if (cudaMalloc((void**)&hit->dev, off) != cudaSuccess || cudaMemsetAsync(hit->dev, 0, kHdrBytes, st) != cudaSuccess ||
+                cudaMemsetAsync(hit->dev + offsetof(LeanHeader, slot_bits), 0xFF, sizeof(LeanHeader::slot_bits), st) != cudaSuccess ||
                 cudaEventCreateWithFlags(&hit->ev, cudaEventDisableTiming) != cudaSuccess) {
                 if (hit->dev) cudaFree(hit->dev);
                 delete hit;
@@ -954,42 +993,44 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
     LeanEntry* ent = lean_entry(g, ctx, p, model, weights_dev, st);
     if (!ent) return -1;
     const int N = g->N;
-    // per-call workspace: call state | slot | prior | sgn | defer_idx | (x for the deferred pass of packed calls)
+    // per-call workspace: slot | prior | sgn | defer_idx | (x for the deferred pass of packed calls)
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_call = take(sizeof(LeanCall)), o_slot = take((size_t)B * 4);
+    const size_t o_slot = take((size_t)B * 4);
     const size_t o_prior = take(x_dev ? (size_t)B * 4 : 0), o_sgn = take(x_dev ? (size_t)B * p.nw * 4 : 0);
     const size_t o_defer = take((size_t)B * 4), o_x = take(x_dev ? 0 : (size_t)B * N * 4);
     unsigned char* ws = nullptr;
     GD_CUDA(cudaMallocFromPoolAsync((void**)&ws, off, pool, st));
     LeanHeader* hdr = reinterpret_cast<LeanHeader*>(ent->dev);
-    LeanCall* call = reinterpret_cast<LeanCall*>(ws + o_call);
+    LeanCall* call = &hdr->calls[ent->calls & 1];
+    LeanCall* next_call = &hdr->calls[(ent->calls + 1) & 1];
+    ++ent->calls;
     float4* ctab = reinterpret_cast<float4*>(ent->dev + ent->o_ct);
     float4* rtab = reinterpret_cast<float4*>(ent->dev + ent->o_rt);
     float4* vtab = reinterpret_cast<float4*>(ent->dev + ent->o_vt);
     int rc = GD_OK;
-    lean_begin_kernel<<<1, 256, 0, st>>>(weights_dev, (int)gd_weights_size(model), model->iters, p.ct_n, p.rt_n, p.vt_n, hdr, call);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) {
+    cudaError_t e = cudaSuccess;
+    {
         PrepParams pp;
         memset(&pp, 0, sizeof(pp));
-        pp.x = x_dev; pp.weights = weights_dev; pp.hdr = hdr; pp.call = call; pp.ctab = ctab;
+        pp.x = x_dev; pp.weights = weights_dev; pp.hdr = hdr; pp.call = call;
         pp.prior_out = reinterpret_cast<float*>(ws + o_prior); pp.sgn_out = reinterpret_cast<uint32_t*>(ws + o_sgn);
         pp.prior_in = prior_dev; pp.slot = reinterpret_cast<int*>(ws + o_slot); pp.defer_idx = reinterpret_cast<int*>(ws + o_defer);
-        pp.B = B; pp.V = g->V; pp.C = g->C; pp.N = N; pp.nw = p.nw; pp.hid = model->hidden; pp.ct_n = p.ct_n; pp.vt_k = p.vt_k;
-        pp.n_ct_blocks = (p.ct_n + 2 + kChunk - 1) / kChunk;
+        pp.B = B; pp.V = g->V; pp.C = g->C; pp.N = N; pp.nw = p.nw; pp.vt_k = p.vt_k;
+        pp.n_w = (int)gd_weights_size(model); pp.T = model->iters; pp.ct_n = p.ct_n; pp.rt_n = p.rt_n; pp.vt_n = p.vt_n;
         const long long units = x_dev ? B : (B + 31) / 32;       // warps of work
         const int pack_blocks = (int)std::min<long long>((units + 7) / 8, (long long)g->sm_count * 8);
-        lean_prep_kernel<<<pp.n_ct_blocks + std::max(1, pack_blocks), 256, 0, st>>>(pp);
+        lean_prep_kernel<<<1 + std::max(1, pack_blocks), 256, 0, st>>>(pp);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) {
         TabParams tp;
-        tp.weights = weights_dev; tp.hdr = hdr; tp.call = call; tp.rtab = rtab; tp.vtab = vtab;
-        tp.hid = model->hidden; tp.T = model->iters; tp.rt_n = p.rt_n;
-        tp.vt_n = p.vt_n; tp.vt_k = p.vt_k; tp.rt_blocks = (p.rt_n + 2 + kChunk - 1) / kChunk;
+        tp.weights = weights_dev; tp.hdr = hdr; tp.call = call; tp.ctab = ctab; tp.rtab = rtab; tp.vtab = vtab;
+        tp.hid = model->hidden; tp.T = model->iters; tp.ct_n = p.ct_n; tp.rt_n = p.rt_n; tp.vt_n = p.vt_n; tp.vt_k = p.vt_k;
+        tp.ct_blocks = (p.ct_n + 2 + kChunk - 1) / kChunk;
+        tp.rt_blocks = (p.rt_n + 2 + kChunk - 1) / kChunk;
         tp.vt_blocks_per_slot = (p.vt_n + 2 + kChunk - 1) / kChunk;
-        lean_tables_kernel<<<tp.rt_blocks + p.vt_k * tp.vt_blocks_per_slot, 256, 0, st>>>(tp);
+        lean_tables_kernel<<<tp.ct_blocks + tp.rt_blocks + p.vt_k * tp.vt_blocks_per_slot, 256, 0, st>>>(tp);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) {
@@ -997,7 +1038,7 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         p.sgn = x_dev ? reinterpret_cast<const uint32_t*>(ws + o_sgn) : synd_dev;
         p.slot = reinterpret_cast<const int*>(ws + o_slot);
         p.prob = prob_dev; p.logit = logit_dev; p.hard = hard_dev; p.hard_bits = hard_bits_dev;
-        p.hdr = hdr; p.call = call;
+        p.hdr = hdr; p.call = call; p.next_call = next_call;
         p.ctab = ctab; p.rtab = rtab; p.vtab = vtab;
         e = cudaFuncSetAttribute(lean_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
         if (e == cudaSuccess) {

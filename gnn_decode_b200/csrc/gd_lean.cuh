@@ -4,6 +4,13 @@
 
 namespace gd {
 
+// per call: two of them live in the header and alternate, so that call n's decode kernel can clear the one call n + 1 will
+// use (nobody else touches it in between: its last reader, the deferred pass of call n - 1, is long done) -- no memset launch
+struct LeanCall {
+    int overflow;                // more distinct priors than table slots: the whole batch takes the edge-owner kernel
+    int defer_count;             // syndromes listed in defer_idx; -1 = all of them, in batch order
+};
+
 // Device-side state of one table set (lives in a cache entry of the graph, persists across calls): the tables are rebuilt
 // only when the content hash of (weights, T, table sizes) changes, variable-phase tables are added as new priors show up.
 struct LeanHeader {
@@ -18,11 +25,7 @@ struct LeanHeader {
     unsigned int err_r_bits;     // ... of the read-out table
     unsigned int err_v_bits[16]; // ... of each variable-phase table (in units of tanh output)
     unsigned int slot_bits[16];  // prior value (float bits) of table slot k; 0xFFFFFFFF = free
-};
-// per call (workspace)
-struct LeanCall {
-    int overflow;                // more distinct priors than table slots: the whole batch takes the edge-owner kernel
-    int defer_count;             // syndromes listed in defer_idx; -1 = all of them, in batch order
+    LeanCall calls[2];
 };
 
 // Edge-owner kernel pass over the syndromes the lean kernel deferred (gd_decode.cu).

@@ -246,7 +246,7 @@ def test_hgp_1600_streamed_matches_oracle():
     bpd = BP.GNNI(8).to(dev).eval()
     prob, logit, hard = bpd.decode(x, graph=tg, return_logits=True, return_hard=True)
     ref = restate.decode("bp_quantum", ei, tg.V, tg.C, x.cpu().double(), {}, T=8)
-    worst, max_err = _logit_close(logit, ref["logit"], RTOL_BP)
+    worst, max_err = _logit_close(logit, ref["logit"], 2e-3)      # degree-7 checks, saturated messages: the round-1 sum-product bar
     assert worst <= 1.0, "HGP bp: %.3g x bound (max abs %.3g)" % (worst, max_err)
     decided = ref["logit"].abs() > LOGIT_TIE
     assert torch.equal(hard.cpu().bool()[decided], (ref["prob"] > 0.5)[decided])
