@@ -35,8 +35,8 @@
 namespace gd {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kMaxSlots = 12;
-constexpr int kHdrBytes = 512;
+constexpr int kMaxSlots = kLeanMaxSlots;
+constexpr int kHdrBytes = 2048;
 constexpr float kBudgetC = 1e-7f;     // check table: feeds the iteration (+ half an fp32 ulp of its values: 6e-8 max|f2|)
 constexpr float kBudgetV = 1e-6f;     // variable table, in units of tanh output (the MUFU tanh it replaces: ~2e-7)
 constexpr float kBudgetR = 4e-6f;     // read-out table: adds <= 2 terms to the final logit (+ 1e-7 of its scale)
@@ -44,9 +44,8 @@ constexpr float kBudgetR = 4e-6f;     // read-out table: adds <= 2 terms to the 
 static_assert(sizeof(LeanHeader) <= kHdrBytes, "header");
 
 struct LeanParams {
-    // packed inputs
-    const float* prior;          // [B]
-    const int* slot;             // [B] table slot of the syndrome, < 0: deferred
+    // packed inputs, sorted by prior
+    const int* idx;              // [B] syndrome ids: first the call->count[0] ones that carry the prior of slot 0, then slot 1's, ...
     const uint32_t* sgn;         // [B][nw] bit c = check c's input is -1
     float* prob; float* logit; uint8_t* hard; uint32_t* hard_bits;
     LeanHeader* hdr;
@@ -57,8 +56,7 @@ struct LeanParams {
     long long B;
     int T, V, C, E, nw, vw, P;   // P = odd pitch of the staged logits
     int R, G, NCH;               // owners per group, groups per CTA, checks per owner (padded)
-    int ct_n, rt_n, vt_n, vt_k;
-    int n_tiles;                 // tiles of 32 syndromes
+    int ct_n, rt_n, vt_n;
     int off_me, off_ms, off_mi, off_var, off_ct, off_rt, off_vt, off_state;   // shared-memory byte offsets
 };
 
@@ -124,7 +122,7 @@ __device__ __forceinline__ uint32_t lean_base(uint32_t piece0) {
 }
 
 struct LeanTabs {
-    uint32_t vt_base;          // lean_base of this lane's variable-phase table
+    uint32_t vt_base;          // lean_base of this lane's replica of the current prior's variable-phase table
     uint32_t ct_base;          // lean_base of this lane's replica of the check table
     float vt_inv_h, vt_off;
     float ct_inv_h, ct_off;
@@ -134,7 +132,7 @@ struct LeanTabs {
 // No clamps: |m| <= T max|f2| < Rm by construction (check inputs are exactly +-1 here) and |ext| <= 3 up to rounding; the
 // tables carry one extra piece on either side.
 __device__ __forceinline__ float lean_vt(const LeanTabs& tb, float m) {
-    return lean_cubic<16>(tb.vt_base, fmaf(m, tb.vt_inv_h, tb.vt_off));
+    return lean_cubic<128>(tb.vt_base, fmaf(m, tb.vt_inv_h, tb.vt_off));
 }
 __device__ __forceinline__ float lean_ct(const LeanTabs& tb, float ext) {
     return lean_cubic<128>(tb.ct_base, fmaf(ext, tb.ct_inv_h, tb.ct_off));
@@ -184,30 +182,36 @@ __device__ __forceinline__ void lean_iteration(const LeanParams& p, uint32_t me,
 
 __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int tile_pre[kMaxSlots + 1];                   // tiles of the slots before slot k, in the prior-sorted tile list
+    __shared__ int row_pre[kMaxSlots + 1];                    // syndromes of the slots before slot k
     const LeanHeader* H = p.hdr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (blockIdx.x == 0 && tid == 0) { p.next_call->overflow = 0; p.next_call->defer_count = 0; }
+    if (blockIdx.x == 0) {                                     // the next call's state: nobody reads or writes it until then
+        if (tid == 0) { p.next_call->overflow = 0; p.next_call->defer_count = 0; }
+        if (tid < kMaxSlots) p.next_call->count[tid] = 0;
+    }
     // ---- can the tables serve this call at all? (identical decision in every thread of the grid) ----
     const int n_slots = H->n_slots;
     const float fmax = __uint_as_float(H->fmax_bits), f3max = __uint_as_float(H->f3max_bits);
     const bool overflow = p.call->overflow != 0;
-    bool ok = !overflow && n_slots <= p.vt_k && __uint_as_float(H->err_c_bits) <= kBudgetC + 6e-8f * fmax &&
+    bool ok = !overflow && n_slots <= kMaxSlots && __uint_as_float(H->err_c_bits) <= kBudgetC + 6e-8f * fmax &&
               __uint_as_float(H->err_r_bits) <= kBudgetR + 1e-7f * f3max && isfinite(fmax) && isfinite(f3max);
-    for (int k = 0; k < n_slots && k < 16; ++k) ok = ok && __uint_as_float(H->err_v_bits[k]) <= kBudgetV;
+    for (int k = 0; k < n_slots && k < kMaxSlots; ++k)
+        ok = ok && (p.call->count[k] == 0 || __uint_as_float(H->err_v_bits[k]) <= kBudgetV);   // (a listed prior this batch does not use cannot hurt it)
     if (blockIdx.x == 0 && tid == 0) {
         if (overflow) {        // the prior list is full of values this batch does not (only) use: start it afresh next call
             p.hdr->n_slots = 0;
-            p.hdr->built_mask = 0u;
-            for (int k = 0; k < 16; ++k) { p.hdr->slot_bits[k] = kNone; p.hdr->err_v_bits[k] = 0u; }
+            p.hdr->built_mask = 0ull;
+            for (int k = 0; k < kMaxSlots; ++k) { p.hdr->slot_bits[k] = kNone; p.hdr->err_v_bits[k] = 0u; }
         } else {
-            p.hdr->built_mask = n_slots >= 32 ? 0xFFFFFFFFu : ((1u << n_slots) - 1u);   // the table kernel finished before this one
+            p.hdr->built_mask = n_slots >= 64 ? ~0ull : ((1ull << n_slots) - 1ull);   // the table kernel finished before this one
         }
         if (!ok) p.call->defer_count = -1;                     // everything goes to the edge-owner kernel
     }
     if (!ok) return;
-    if (n_slots == 0) return;                                         // nothing eligible: all listed as deferred already
+    if (n_slots == 0) return;                                  // nothing eligible: all listed as deferred already
 
-    // ---- prologue: metadata and tables into shared memory ----
+    // ---- prologue: metadata and the prior-independent tables into shared memory ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.meta);
         uint4* dst = reinterpret_cast<uint4*>(smem + p.off_me);
@@ -217,11 +221,16 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
         for (int i = tid; i < (p.ct_n + 2) * 8; i += blockDim.x) ct[i] = p.ctab[i >> 3];          // 8 replicas: one per bank group
         float4* rt = reinterpret_cast<float4*>(smem + p.off_rt);
         for (int i = tid; i < p.rt_n + 2; i += blockDim.x) rt[i] = p.rtab[i];
-        float4* vt = reinterpret_cast<float4*>(smem + p.off_vt);
-        for (int i = tid; i < n_slots * (p.vt_n + 2); i += blockDim.x) vt[i] = p.vtab[i];
+        if (tid == 0) {
+            int acc = 0, racc = 0;
+            for (int k = 0; k < n_slots; ++k) {
+                tile_pre[k] = acc; row_pre[k] = racc;
+                acc += (p.call->count[k] + 31) >> 5; racc += p.call->count[k];
+            }
+            tile_pre[n_slots] = acc; row_pre[n_slots] = racc;
+        }
     }
     __syncthreads();
-    if (warp >= p.G * p.R) return;
     const int grp = warp / p.R, r = warp - grp * p.R;
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t me = s_base + p.off_me + (uint32_t)(r * p.NCH) * 16u;
@@ -236,108 +245,100 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
     tb.ct_inv_h = (float)p.ct_n / 6.0f;
     tb.ct_off = 3.0f * tb.ct_inv_h - 0.5f;
     tb.ct_base = lean_base<128>(s_base + p.off_ct + 128u + (uint32_t)(lane & 7) * 16u);
+    tb.vt_base = lean_base<128>(s_base + p.off_vt + 128u + (uint32_t)(lane & 7) * 16u);
     const float rt_inv_h = 0.5f * (float)p.rt_n / Rm, rt_off = Rm * rt_inv_h - 0.5f;
     const uint32_t rt_base = lean_base<16>(s_base + p.off_rt + 16u);
     const int fin = (p.T & 1) * 128, oth = 128 - fin;          // buffer holding the final messages / free for the staged logits
 
-    // tiles are dealt to the CTAs first (every SM gets n_tiles / grid of them, +-1), then round-robin to a CTA's groups
-    for (int tile = blockIdx.x + gridDim.x * grp; tile < p.n_tiles; tile += gridDim.x * p.G) {
-        const long long s0 = (long long)tile * 32;
-        const long long sg = s0 + lane;
-        const bool valid = sg < p.B;
-        const int slot = valid ? __ldg(p.slot + sg) : -1;
-        if (!__any_sync(0xffffffffu, slot >= 0)) continue;     // same decision in all R warps of the group (same 32 syndromes)
-        const bool live = slot >= 0;
-        const float prior = live ? __ldg(p.prior + sg) : 0.f;
-        tb.vt_base = lean_base<16>(s_base + p.off_vt + (uint32_t)(live ? slot : 0) * (uint32_t)(p.vt_n + 2) * 16u + 16u);
-        tb.t0 = lean_vt(tb, 0.f);
-        uint32_t mybits = 0;                                    // bit k = the sign bit of my k-th check's input
-        for (int k = 0; k < p.NCH; ++k) {
-            const uint32_t info = lds_u32(mi + 4u * k);
-            if ((info & 7u) == 0) break;
-            const int c = (int)(info >> 8);
-            const uint32_t wv = live ? __ldg(p.sgn + sg * p.nw + (c >> 5)) : 0u;
-            mybits |= ((wv >> (c & 31)) & 1u) << k;
-        }
-        // ---- iteration 0: m == 0 everywhere, so every t is g_p(0) and a check's edges share one look-up ----
-        for (int k = 0; k < p.NCH; ++k) {
-            const int deg = (int)(lds_u32(mi + 4u * k) & 7u);
-            if (deg == 0) break;
-            const uint4 eo = lds_u128(me + 16u * k);
-            const float o = lean_ct(tb, (float)(deg - 1) * tb.t0);
-            const float mv = __uint_as_float(__float_as_uint(o) ^ ((mybits >> k) << 31));
-            const uint32_t eoa[4] = {eo.x, eo.y, eo.z, eo.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < deg) sts_state<128>(st_lane + eoa[j], mv);
-        }
-        group_bar(bar_id, bar_n);
-        int it = 1;
-        for (; it + 1 < p.T; it += 2) {
-            lean_iteration<128>(p, me, ms, mi, st_lane, tb, mybits);
-            group_bar(bar_id, bar_n);
-            lean_iteration<0>(p, me, ms, mi, st_lane, tb, mybits);
-            group_bar(bar_id, bar_n);
-        }
-        if (it < p.T) {
-            lean_iteration<128>(p, me, ms, mi, st_lane, tb, mybits);
-            group_bar(bar_id, bar_n);
-        }
-        // ---- read-out: logit_v = prior + sum over the variable's edges of f3(m_e); staged with an odd pitch in the free buffer ----
-        const uint32_t st_grp = st_lane - (uint32_t)lane * 4u;
-        for (int v = r; v < p.V; v += p.R) {
-            const uint2 ve = lds_u64(s_base + p.off_var + 8u * v);
-            float acc = prior;
-            if (ve.x != kNone) acc += lean_cubic<16>(rt_base, fminf(fmaxf(fmaf(lds_state_rt(st_lane + ve.x + fin), rt_inv_h, rt_off), -1.4f), (float)p.rt_n + 0.4f));
-            if (ve.y != kNone) acc += lean_cubic<16>(rt_base, fminf(fmaxf(fmaf(lds_state_rt(st_lane + ve.y + fin), rt_inv_h, rt_off), -1.4f), (float)p.rt_n + 0.4f));
-            const uint32_t q = (uint32_t)lane * (uint32_t)p.P + (uint32_t)v;
-            sts_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth, acc);
-        }
-        group_bar(bar_id, bar_n);
-        // ---- outputs (the group's 32 syndromes are one contiguous block of rows) ----
+    // The batch, sorted by prior, is one list of tiles of 32 syndromes; this CTA takes a contiguous share of it.  All 32
+    // syndromes of a tile carry the SAME prior, so one variable-phase table serves the whole CTA at a time: it is loaded
+    // once per prior the share touches (usually one or two), replicated per bank group like the check table -- every table
+    // look-up of the iteration is then conflict-free -- and the CTA's groups deal that prior's tiles among themselves.
+    const int total_tiles = tile_pre[n_slots];
+    const int t_lo = (int)((long long)blockIdx.x * total_tiles / gridDim.x), t_hi = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+    for (int k = 0; k < n_slots; ++k) {
+        const int j_lo = max(t_lo, tile_pre[k]) - tile_pre[k], j_hi = min(t_hi, tile_pre[k + 1]) - tile_pre[k];
+        if (j_lo >= j_hi) continue;                            // (CTA-uniform)
+        __syncthreads();                                       // every group is done with the previous prior's table
         {
-            const int nvalid = (int)min(32ll, p.B - s0);
-            const int total = nvalid * p.V;
-            const long long g0 = s0 * p.V;                     // multiple of 32 elements: 16-byte aligned
-            const float invV = 1.0f / (float)p.V;
-            const int gt = r * 32 + lane, gn = 32 * p.R;
-            auto stage = [&](int i) -> float {
-                const int s = (int)(((float)i + 0.5f) * invV), v = i - s * p.V;
-                const uint32_t q = (uint32_t)s * (uint32_t)p.P + (uint32_t)v;
-                return lds_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth);
-            };
-            for (int i = gt * 4; i < total; i += gn * 4) {
-                float l[4], pr[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {               // total is a multiple of 4 only when nvalid * V is
-                    l[j] = i + j < total ? stage(i + j) : 0.f;
-                    pr[j] = sigmoid_neg(l[j]);
-                }
-                if (i + 4 <= total) {
-                    if (p.prob) *reinterpret_cast<float4*>(p.prob + g0 + i) = make_float4(pr[0], pr[1], pr[2], pr[3]);
-                    if (p.logit) *reinterpret_cast<float4*>(p.logit + g0 + i) = make_float4(l[0], l[1], l[2], l[3]);
-                    if (p.hard)
-                        *reinterpret_cast<uchar4*>(p.hard + g0 + i) = make_uchar4(pr[0] > 0.5f, pr[1] > 0.5f, pr[2] > 0.5f, pr[3] > 0.5f);
-                } else {
-                    for (int j = 0; i + j < total; ++j) {
-                        if (p.prob) p.prob[g0 + i + j] = pr[j];
-                        if (p.logit) p.logit[g0 + i + j] = l[j];
-                        if (p.hard) p.hard[g0 + i + j] = pr[j] > 0.5f;
-                    }
-                }
-            }
-            if (p.hard_bits) {                                  // packed hard decisions: bit v of row s
-                for (int s = r; s < nvalid; s += p.R)
-                    for (int w = 0; w < p.vw; ++w) {
-                        const int v = w * 32 + lane;
-                        const uint32_t q = (uint32_t)s * (uint32_t)p.P + (uint32_t)v;
-                        const float lv = v < p.V ? lds_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth) : 1.0f;
-                        const uint32_t word = __ballot_sync(0xffffffffu, sigmoid_neg(lv) > 0.5f);
-                        if (lane == 0) p.hard_bits[(s0 + s) * p.vw + w] = word;
-                    }
-            }
+            float4* vt = reinterpret_cast<float4*>(smem + p.off_vt);
+            const float4* src = p.vtab + (size_t)k * (p.vt_n + 2);
+            for (int i = tid; i < (p.vt_n + 2) * 8; i += blockDim.x) vt[i] = __ldg(src + (i >> 3));
         }
-        group_bar(bar_id, bar_n);                               // the staged logits are consumed before the next tile writes
+        __syncthreads();
+        const float prior = __uint_as_float(H->slot_bits[k]);
+        const int cnt = p.call->count[k];
+        const int* rows = p.idx + row_pre[k];
+        tb.t0 = lean_vt(tb, 0.f);
+        for (int j = j_lo + grp; j < j_hi; j += p.G) {
+            const int li = j * 32 + lane;
+            const bool live = li < cnt;
+            const long long sg = live ? (long long)__ldg(rows + li) : 0;
+            uint32_t mybits = 0;                                // bit q = the sign bit of my q-th check's input
+            for (int q = 0; q < p.NCH; ++q) {
+                const uint32_t info = lds_u32(mi + 4u * q);
+                if ((info & 7u) == 0) break;
+                const int c = (int)(info >> 8);
+                const uint32_t wv = live ? __ldg(p.sgn + sg * p.nw + (c >> 5)) : 0u;
+                mybits |= ((wv >> (c & 31)) & 1u) << q;
+            }
+            // ---- iteration 0: m == 0 everywhere, so every t is g_p(0) and a check's edges share one look-up ----
+            for (int q = 0; q < p.NCH; ++q) {
+                const int deg = (int)(lds_u32(mi + 4u * q) & 7u);
+                if (deg == 0) break;
+                const uint4 eo = lds_u128(me + 16u * q);
+                const float o = lean_ct(tb, (float)(deg - 1) * tb.t0);
+                const float mv = __uint_as_float(__float_as_uint(o) ^ ((mybits >> q) << 31));
+                const uint32_t eoa[4] = {eo.x, eo.y, eo.z, eo.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (e < deg) sts_state<128>(st_lane + eoa[e], mv);
+            }
+            group_bar(bar_id, bar_n);
+            int it = 1;
+            for (; it + 1 < p.T; it += 2) {
+                lean_iteration<128>(p, me, ms, mi, st_lane, tb, mybits);
+                group_bar(bar_id, bar_n);
+                lean_iteration<0>(p, me, ms, mi, st_lane, tb, mybits);
+                group_bar(bar_id, bar_n);
+            }
+            if (it < p.T) {
+                lean_iteration<128>(p, me, ms, mi, st_lane, tb, mybits);
+                group_bar(bar_id, bar_n);
+            }
+            // ---- read-out: logit_v = prior + sum over the variable's edges of f3(m_e); staged with an odd pitch in the free buffer ----
+            const uint32_t st_grp = st_lane - (uint32_t)lane * 4u;
+            for (int v = r; v < p.V; v += p.R) {
+                const uint2 ve = lds_u64(s_base + p.off_var + 8u * v);
+                float acc = prior;
+                if (ve.x != kNone) acc += lean_cubic<16>(rt_base, fminf(fmaxf(fmaf(lds_state_rt(st_lane + ve.x + fin), rt_inv_h, rt_off), -1.4f), (float)p.rt_n + 0.4f));
+                if (ve.y != kNone) acc += lean_cubic<16>(rt_base, fminf(fmaxf(fmaf(lds_state_rt(st_lane + ve.y + fin), rt_inv_h, rt_off), -1.4f), (float)p.rt_n + 0.4f));
+                const uint32_t q = (uint32_t)lane * (uint32_t)p.P + (uint32_t)v;
+                sts_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth, acc);
+            }
+            group_bar(bar_id, bar_n);
+            // ---- outputs: the tile's syndromes sit anywhere in the batch; a warp writes whole rows (V contiguous values) ----
+            const int nvalid = min(32, cnt - j * 32);
+            for (int s = r; s < nvalid; s += p.R) {
+                const long long row = __shfl_sync(0xffffffffu, sg, s);
+                for (int w = 0; w < p.vw; ++w) {
+                    const int v = w * 32 + lane;
+                    const uint32_t q = (uint32_t)s * (uint32_t)p.P + (uint32_t)v;
+                    const float lv = v < p.V ? lds_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth) : 1.0f;
+                    const float pr = sigmoid_neg(lv);
+                    if (v < p.V) {
+                        if (p.prob) p.prob[row * p.V + v] = pr;
+                        if (p.logit) p.logit[row * p.V + v] = lv;
+                        if (p.hard) p.hard[row * p.V + v] = pr > 0.5f;
+                    }
+                    if (p.hard_bits) {                          // packed hard decisions: bit v of the row
+                        const uint32_t word = __ballot_sync(0xffffffffu, pr > 0.5f);
+                        if (lane == 0) p.hard_bits[row * p.vw + w] = word;
+                    }
+                }
+            }
+            group_bar(bar_id, bar_n);                           // the staged logits are consumed before the next tile writes
+        }
     }
 }
 
@@ -420,8 +421,8 @@ __device__ void build_chunk(const MlpD& M, double prior, bool tanh_fold, double 
 // prior look-up / insertion into the header's slot list; returns the slot or -1 (list full).  `mirror` is the CTA's copy of
 // the list in shared memory: after the first few syndromes every look-up is answered there (all warps of the grid polling
 // the one global cache line serialises on a single L2 slice: 125 us for 65536 syndromes, measured).
-__device__ __forceinline__ int slot_of(LeanHeader* H, unsigned int* mirror, unsigned int bits, int vt_k) {
-    for (int k = 0; k < vt_k; ++k) {
+__device__ __forceinline__ int slot_of(LeanHeader* H, unsigned int* mirror, unsigned int bits) {
+    for (int k = 0; k < kMaxSlots; ++k) {
         unsigned int cur = *reinterpret_cast<volatile unsigned int*>(&mirror[k]);
         if (cur == bits) return k;
         if (cur != kNone) continue;
@@ -478,28 +479,46 @@ __device__ void lean_hash_check(const float* weights, int n_w, int T, int ct_n, 
 struct PrepParams {
     const float* x;              // [B, N] or NULL (packed inputs given)
     const float* weights;
-    float* prior_out;            // [B]   (x given)
-    uint32_t* sgn_out;           // [B][nw]
-    const float* prior_in;       // [B]   (packed inputs)
-    int* slot; int* defer_idx;
+    uint32_t* sgn_out;           // [B][nw]  (x given)
+    const float* prior_in;       // [B]      (packed inputs)
+    short* slot;                 // [B] table slot of the syndrome, -1: not table-eligible (deferred) or no slot left
+    int* pos;                    // [B] its rank among the syndromes of that slot (any order: a syndrome's result does not depend on its neighbours)
+    int* defer_idx;
     LeanHeader* hdr;
     LeanCall* call;
     long long B;
-    int V, C, N, nw, vt_k;
+    int V, C, N, nw, rows_per_block;
     int n_w, T, ct_n, rt_n, vt_n;   // what the content hash covers
 };
 
-// x [B, V+C] rows -> packed form, L lanes per row (see lean_prep_kernel)
+constexpr int kPrepRows = 256;     // most rows a prep CTA handles (its shared-memory lists)
+
+// The tail every prep CTA runs: its rows' slots were counted in cnt_sh (the rank inside the CTA came from that atomicAdd);
+// one global atomicAdd per (CTA, slot) reserves a range of the slot's list.
+__device__ __forceinline__ void prep_publish(const PrepParams& p, long long r0, int n_rows, const short* slot_sh, const int* rank_sh,
+                                             int* cnt_sh, int* base_sh) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < kMaxSlots; k += blockDim.x) base_sh[k] = cnt_sh[k] ? atomicAdd(&p.call->count[k], cnt_sh[k]) : 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
+        const int k = slot_sh[i];
+        p.slot[r0 + i] = (short)k;
+        p.pos[r0 + i] = k >= 0 ? base_sh[k] + rank_sh[i] : 0;
+    }
+}
+
+// x [B, V+C] rows [r0, r0 + n_rows) -> packed form, L lanes per row (see lean_prep_kernel)
 template <int L>
 __device__ __forceinline__ void pack_rows(const PrepParams& p, LeanHeader* H, volatile unsigned int* mirror_v, unsigned int* mirror,
-                                          long long wid, long long nwarps) {
+                                          long long r0, int n_rows, short* slot_sh, int* rank_sh, int* cnt_sh) {
     constexpr int G = 32 / L;                                   // rows per warp
     constexpr unsigned int kMask = L == 32 ? 0xFFFFFFFFu : ((1u << (L & 31)) - 1u);
-    const int lane = threadIdx.x & 31, sub = lane % L, grp = lane / L, sh = grp * L;
-    for (long long s0 = wid * G; s0 < p.B; s0 += nwarps * G) {
-        const long long s = s0 + grp;
-        const bool valid = s < p.B;
-        const float* row = p.x + (valid ? s : p.B - 1) * p.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, sub = lane % L, grp = lane / L, sh = grp * L;
+    for (int i0 = warp * G; i0 < n_rows; i0 += nwarp * G) {
+        const int i = i0 + grp;
+        const bool valid = i < n_rows;
+        const long long s = r0 + (valid ? i : 0);
+        const float* row = p.x + s * p.N;
         // every load of a pass is issued before its first use (the SM issues in order: load -> use -> load would pay one
         // memory latency per load)
         const unsigned int p0b = __float_as_uint(__ldg(row));
@@ -530,14 +549,15 @@ __device__ __forceinline__ void pack_rows(const PrepParams& p, LeanHeader* H, vo
         const float p0 = __uint_as_float(p0b);
         const bool good = ((__ballot_sync(0xffffffffu, bad != 0u) >> sh) & kMask) == 0u && isfinite(p0);
         int slot = -1;
-#pragma unroll
-        for (int j = 0; j < (16 + L - 1) / L; ++j) {             // the prior list, L slots per vote
+        for (int j = 0; j * L < kMaxSlots; ++j) {                // the prior list, L slots per vote; free slots end it
             const int k = j * L + sub;
-            const uint32_t b = __ballot_sync(0xffffffffu, k < p.vt_k && mirror_v[k & 15] == p0b);
+            const unsigned int cur = mirror_v[k & (kMaxSlots - 1)];
+            const uint32_t b = __ballot_sync(0xffffffffu, k < kMaxSlots && cur == p0b);
             const uint32_t gb = (b >> sh) & kMask;
             if (gb && slot < 0) slot = j * L + __ffs(gb) - 1;
+            if (__all_sync(0xffffffffu, slot >= 0 || cur == kNone)) break;
         }
-        if (good && slot < 0 && sub == 0 && valid) slot = slot_of(H, mirror, p0b, p.vt_k);    // first sight of this prior in this CTA
+        if (good && slot < 0 && sub == 0 && valid) slot = slot_of(H, mirror, p0b);    // first sight of this prior in this CTA
         slot = __shfl_sync(0xffffffffu, slot, sh);
         if (sub == 0 && valid) {
             if (good && slot < 0) p.call->overflow = 1;
@@ -545,47 +565,54 @@ __device__ __forceinline__ void pack_rows(const PrepParams& p, LeanHeader* H, vo
                 slot = -1;
                 p.defer_idx[atomicAdd(&p.call->defer_count, 1)] = (int)s;
             }
-            p.prior_out[s] = p0;
-            p.slot[s] = slot;
+            slot_sh[i] = (short)slot;
+            rank_sh[i] = slot >= 0 ? atomicAdd(&cnt_sh[slot], 1) : 0;
         }
     }
 }
 
-// Prep kernel: CTA 0 checks the weights' content hash; the others bring the inputs into packed form -- prior value, table
-// slot, check-sign bits -- discover the distinct priors and list the syndromes the tables cannot serve.
+// Prep kernel: CTA 0 checks the weights' content hash; every other CTA takes a contiguous block of rows, brings them into
+// packed form (table slot of the prior, check-sign bits), discovers new priors, lists the rows the tables cannot serve and
+// reserves the rows' places in the per-prior lists the decode kernel walks.
 __global__ void __launch_bounds__(256, 6) lean_prep_kernel(const PrepParams p) {
-    __shared__ volatile unsigned int mirror_v[16];
+    __shared__ volatile unsigned int mirror_v[kMaxSlots];
+    __shared__ short slot_sh[kPrepRows];
+    __shared__ int rank_sh[kPrepRows];
+    __shared__ int cnt_sh[kMaxSlots], base_sh[kMaxSlots];
     unsigned int* mirror = const_cast<unsigned int*>(mirror_v);
     LeanHeader* H = p.hdr;
     if (blockIdx.x == 0) {
         lean_hash_check(p.weights, p.n_w, p.T, p.ct_n, p.rt_n, p.vt_n, H);
         return;
     }
-    if (threadIdx.x < 16) mirror[threadIdx.x] = threadIdx.x < p.vt_k ? H->slot_bits[threadIdx.x] : 0u;
+    for (int k = threadIdx.x; k < kMaxSlots; k += blockDim.x) { mirror[k] = H->slot_bits[k]; cnt_sh[k] = 0; }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const long long wid = (long long)(blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)(gridDim.x - 1) * (blockDim.x >> 5);
+    const long long r0 = (long long)(blockIdx.x - 1) * p.rows_per_block;
+    const int n_rows = (int)min((long long)p.rows_per_block, p.B - r0);
+    if (n_rows <= 0) return;
     if (p.x) {
         // L lanes per syndrome (8 up to 128 nodes, 16 up to 512, else 32): the per-row overhead -- address arithmetic, votes,
-        // the prior look-up, three stores -- is shared by the 32 / L rows a warp handles at once (issue-bound otherwise:
+        // the prior look-up, the stores -- is shared by the 32 / L rows a warp handles at once (issue-bound otherwise:
         // ~200 warp instructions per row, 19 us for 65536 rows of the d = 5 code)
-        if (p.N <= 128) pack_rows<8>(p, H, mirror_v, mirror, wid, nwarps);
-        else if (p.N <= 512) pack_rows<16>(p, H, mirror_v, mirror, wid, nwarps);
-        else pack_rows<32>(p, H, mirror_v, mirror, wid, nwarps);
+        if (p.N <= 128) pack_rows<8>(p, H, mirror_v, mirror, r0, n_rows, slot_sh, rank_sh, cnt_sh);
+        else if (p.N <= 512) pack_rows<16>(p, H, mirror_v, mirror, r0, n_rows, slot_sh, rank_sh, cnt_sh);
+        else pack_rows<32>(p, H, mirror_v, mirror, r0, n_rows, slot_sh, rank_sh, cnt_sh);
     } else {
-        for (long long s = wid * 32 + lane; s < p.B; s += nwarps * 32) {   // a thread per syndrome
+        for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {     // packed inputs: a thread per syndrome
+            const long long s = r0 + i;
             const float p0 = __ldg(p.prior_in + s);
             int slot = -1;
             if (isfinite(p0)) {
-                slot = slot_of(H, mirror, __float_as_uint(p0), p.vt_k);
+                slot = slot_of(H, mirror, __float_as_uint(p0));
                 if (slot < 0) p.call->overflow = 1;
             } else {
                 p.defer_idx[atomicAdd(&p.call->defer_count, 1)] = (int)s;
             }
-            p.slot[s] = slot;
+            slot_sh[i] = (short)slot;
+            rank_sh[i] = slot >= 0 ? atomicAdd(&cnt_sh[slot], 1) : 0;
         }
     }
+    prep_publish(p, r0, n_rows, slot_sh, rank_sh, cnt_sh, base_sh);
 }
 
 struct TabParams {
@@ -593,7 +620,9 @@ struct TabParams {
     LeanHeader* hdr;
     const LeanCall* call;
     float4* ctab; float4* rtab; float4* vtab;
-    int hid, T, ct_n, rt_n, vt_n, vt_k, ct_blocks, rt_blocks, vt_blocks_per_slot;
+    const short* slot; const int* pos; int* idx;      // per-syndrome slot and rank -> the prior-sorted list
+    long long B;
+    int hid, T, ct_n, rt_n, vt_n, ct_blocks, rt_blocks, vt_blocks_per_slot, scatter_blocks;
 };
 
 // Table kernel.  In the steady state (same weights, no new prior) every CTA returns at once.  After a weight change the
@@ -605,15 +634,30 @@ __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
     __shared__ double2 nodes[kChunk + 1];
     __shared__ unsigned int fmax_sh;
     LeanHeader* H = p.hdr;
+    if ((int)blockIdx.x < p.scatter_blocks) {
+        // the prior-sorted syndrome list: slot k's syndromes start at the sum of the earlier slots' counts
+        __shared__ int off_sh[kMaxSlots];
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int k = 0; k < kMaxSlots; ++k) { off_sh[k] = acc; acc += p.call->count[k]; }
+        }
+        __syncthreads();
+        if (p.call->overflow) return;
+        for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < p.B; s += (long long)p.scatter_blocks * blockDim.x) {
+            const int k = p.slot[s];
+            if (k >= 0) p.idx[off_sh[k] + p.pos[s]] = (int)s;
+        }
+        return;
+    }
     const int rebuild = H->rebuild;
-    const int bid = blockIdx.x;
+    const int bid = blockIdx.x - p.scatter_blocks;
     const bool is_ct = bid < p.ct_blocks, is_rt = !is_ct && bid < p.ct_blocks + p.rt_blocks;
     int k = -1, cb = 0;
     if (!is_ct && !is_rt) {
         const int b = bid - p.ct_blocks - p.rt_blocks;
         k = b / p.vt_blocks_per_slot;
         cb = b - k * p.vt_blocks_per_slot;
-        if (k >= H->n_slots || p.call->overflow || ((H->built_mask >> k) & 1u)) return;   // nothing new to tabulate
+        if (k >= H->n_slots || p.call->overflow || ((H->built_mask >> k) & 1ull)) return;   // nothing new to tabulate
     } else if (!rebuild) {
         return;
     }
@@ -688,14 +732,14 @@ struct LeanMeta {
     int off_ms = 0, off_mi = 0, off_var = 0;   // byte offsets inside the blob (me at 0)
     double balance = 0.0;
 };
-struct LeanGeom { int R = 0, G = 0, NCH = 0, rt_n = 0, vt_k = 0, ct_n = 0, vt_n = 0; long long opt_epoch = -1; bool valid = false; };
+struct LeanGeom { int R = 0, G = 0, NCH = 0, rt_n = 0, ct_n = 0, vt_n = 0; long long opt_epoch = -1; bool valid = false; };
 // One table set on the device, keyed on the host by (stream, weights pointer, T, table sizes) and VALIDATED on the device
 // by a content hash (lean_begin_kernel): a stale or recycled entry simply rebuilds itself.  An entry is only ever used in
 // stream order; when the least recently used one is handed to another stream, that stream first waits for its last use.
 struct LeanEntry {
     cudaStream_t st = nullptr;
     const float* w = nullptr;
-    int T = 0, hid = 0, ct_n = 0, rt_n = 0, vt_n = 0, vt_k = 0;
+    int T = 0, hid = 0, ct_n = 0, rt_n = 0, vt_n = 0;
     unsigned char* dev = nullptr;          // header | ctab | rtab | vtab
     size_t o_ct = 0, o_rt = 0, o_vt = 0;
     cudaEvent_t ev = nullptr;
@@ -714,7 +758,7 @@ struct LeanCtx {
 
 struct LeanPlan {
     LeanParams p;
-    int threads, grid, smem;
+    int threads, grid, smem, n_tiles;
     const LeanMeta* meta;
 };
 
@@ -820,12 +864,12 @@ static bool lean_search(gd_graph* g, LeanGeom* out) {
     const int ct_n = (int)std::min<long long>(1024, std::max<long long>(32, opt_int(OPT_LEAN_CTAB_N, 128)));
     const int vt_n = (int)std::min<long long>(4096, std::max<long long>(64, opt_int(OPT_LEAN_VTAB_N, 512)));
     const int state = E * 256;
-    const int smem_max = g->max_smem_optin;
-    struct Cand { int R, G, NCH, rt_n, vt_k; double score; };
-    Cand best{0, 0, 0, 0, 0, -1.0};
-    static const int rts[] = {2048, 1024}, ks[] = {12, 10, 8, 6};
+    const int smem_max = g->max_smem_optin - 1024;              // the kernel's static shared memory (tile / row prefixes)
+    struct Cand { int R, G, NCH, rt_n; double score; };
+    Cand best{0, 0, 0, 0, -1.0};
+    static const int rts[] = {2048, 1024};
     const long long force_R = opt_int(OPT_LEAN_R, 0), force_G = opt_int(OPT_LEAN_G, 0);
-    const long long force_rt = opt_int(OPT_LEAN_RTAB_N, 0), force_k = opt_int(OPT_LEAN_VTAB_K, 0);
+    const long long force_rt = opt_int(OPT_LEAN_RTAB_N, 0);
     for (int R = 1; R <= 32; ++R) {
         if (force_R > 0 && R != force_R) continue;
         std::vector<std::vector<int>> own;
@@ -834,24 +878,26 @@ static bool lean_search(gd_graph* g, LeanGeom* out) {
         assign_owners(g, R, own, &nch, &bal);
         if (nch > 32 || nch == 0) continue;                      // sign bits of the owned checks live in one register
         const int meta = align_up_i(align_up_i(2 * R * nch * 16 + R * nch * 4, 16) + V * 8, 16);
-        for (int ri = 0; ri < 2; ++ri)
-            for (int ki = 0; ki < 4; ++ki) {
-                const int rt_n = force_rt > 0 ? (int)force_rt : rts[ri], vt_k = force_k > 0 ? (int)std::min<long long>(force_k, kMaxSlots) : ks[ki];
-                const int fixed = align_up_i(meta + (ct_n + 2) * 128 + (rt_n + 2) * 16 + vt_k * (vt_n + 2) * 16, 128);
-                int G = (smem_max - fixed) / state;
-                G = std::min(G, std::min(32 / R, 15));
-                if (force_G > 0) G = G >= force_G ? (int)force_G : 0;
-                if (G < 1) continue;
-                const int warps = G * R;
-                // enough warps to cover the look-up latency, balanced owners, then: keep the big tables, more groups
-                double score = std::min(1.0, warps / 24.0) * (0.4 + 0.6 * bal);
-                score *= 1.0 - 0.03 * ri - 0.02 * ki;
-                score *= 1.0 + 0.01 * std::min(G, 8);
-                if (score > best.score) best = Cand{R, G, nch, rt_n, vt_k, score};
-            }
+        for (int ri = 0; ri < 2; ++ri) {
+            // shared memory: metadata, check table and ONE variable-phase table replicated per bank group, read-out table
+            const int rt_n = force_rt > 0 ? (int)force_rt : rts[ri];
+            const int fixed = align_up_i(meta + (ct_n + 2) * 128 + (rt_n + 2) * 16 + (vt_n + 2) * 128, 128);
+            int G = (smem_max - fixed) / state;
+            G = std::min(G, std::min(32 / R, 15));
+            if (force_G > 0) G = G >= force_G ? (int)force_G : 0;
+            if (G < 1) continue;
+            const int warps = G * R;
+            // measured (B200, rotated d = 5 / toric L = 5 / rotated d = 11, profiles/r02_lean_geometry_sweep.txt): what counts is
+            // filling all 32 warp slots with balanced owners -- (R, G) = (8, 4) 0.162 ms vs (5, 5) 0.188 vs (16, 2) 0.185;
+            // then: keep the big read-out table, more groups (independent barrier domains)
+            double score = (0.25 + 0.75 * warps / 32.0) * (0.4 + 0.6 * bal);
+            score *= 1.0 - 0.03 * ri;
+            score *= 1.0 + 0.005 * std::min(G, 8);
+            if (score > best.score) best = Cand{R, G, nch, rt_n, score};
+        }
     }
     out->valid = true;                                          // "does not fit" is a cached answer too (R == 0)
-    out->R = best.R; out->G = best.G; out->NCH = best.NCH; out->rt_n = best.rt_n; out->vt_k = best.vt_k;
+    out->R = best.R; out->G = best.G; out->NCH = best.NCH; out->rt_n = best.rt_n;
     out->ct_n = ct_n; out->vt_n = vt_n;
     return true;
 }
@@ -864,19 +910,19 @@ static bool lean_fill(gd_graph* g, const gd_model* m, int64_t B, const LeanGeom&
     p.B = B; p.T = m->iters; p.V = V; p.C = g->C; p.E = E;
     p.nw = (g->C + 31) / 32; p.vw = (V + 31) / 32; p.P = V | 1;
     p.R = best.R; p.G = best.G; p.NCH = meta->NCH;
-    p.ct_n = ct_n; p.rt_n = best.rt_n; p.vt_n = vt_n; p.vt_k = best.vt_k;
-    p.n_tiles = (int)((B + 31) / 32);
+    p.ct_n = ct_n; p.rt_n = best.rt_n; p.vt_n = vt_n;
     p.meta = meta->dev;
     p.off_me = 0; p.off_ms = meta->off_ms; p.off_mi = meta->off_mi; p.off_var = meta->off_var;
     p.off_ct = (int)meta->bytes;
     p.off_rt = p.off_ct + (ct_n + 2) * 128;
     p.off_vt = p.off_rt + (best.rt_n + 2) * 16;
-    p.off_state = align_up_i(p.off_vt + best.vt_k * (vt_n + 2) * 16, 128);
+    p.off_state = align_up_i(p.off_vt + (vt_n + 2) * 128, 128);
     out->smem = p.off_state + best.G * state;
     out->threads = 32 * best.G * best.R;
-    out->grid = std::min(g->sm_count, std::max(1, p.n_tiles));
+    out->n_tiles = (int)((B + 31) / 32);                       // (+ at most one partial tile per distinct prior)
+    out->grid = std::min(g->sm_count, std::max(1, out->n_tiles));
     out->meta = meta;
-    return out->smem <= smem_max;
+    return out->smem <= smem_max - 1024;
 }
 
 // Geometry: R owners (warps) per group of 32 syndromes, G groups per CTA.  The kernel is bound by the shared-memory
@@ -907,7 +953,7 @@ bool lean_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_la
     LeanPlan pl;
     if (!lean_plan(const_cast<gd_graph*>(g), model, B, &pl)) return false;
     out->tile = 32 * pl.p.G; out->threads = pl.threads; out->grid = pl.grid; out->smem_bytes = pl.smem;
-    out->resident = 1; out->n_tiles = (pl.p.n_tiles + pl.p.G - 1) / pl.p.G;
+    out->resident = 1; out->n_tiles = (pl.n_tiles + pl.p.G - 1) / pl.p.G;
     return true;
 }
 
@@ -939,12 +985,12 @@ static LeanEntry* lean_entry(gd_graph* g, LeanCtx* ctx, const LeanParams& p, con
     LeanEntry* lru = nullptr;
     for (LeanEntry* e : ctx->entries) {
         if (e->st == st && e->w == w && e->T == model->iters && e->hid == model->hidden && e->ct_n == p.ct_n && e->rt_n == p.rt_n &&
-            e->vt_n == p.vt_n && e->vt_k == p.vt_k)
+            e->vt_n == p.vt_n)
             hit = e;
         if (!lru || e->last_use < lru->last_use) lru = e;
     }
     if (!hit) {
-        const bool same_shape = lru && lru->ct_n == p.ct_n && lru->rt_n == p.rt_n && lru->vt_n == p.vt_n && lru->vt_k == p.vt_k;
+        const bool same_shape = lru && lru->ct_n == p.ct_n && lru->rt_n == p.rt_n && lru->vt_n == p.vt_n;
         if ((int)ctx->entries.size() < kMaxEntries || !same_shape) {
             if ((int)ctx->entries.size() >= kMaxEntries) {          // table sizes changed (options): drop the oldest entry
                 cudaEventSynchronize(lru->ev);
@@ -959,7 +1005,7 @@ static LeanEntry* lean_entry(gd_graph* g, LeanCtx* ctx, const LeanParams& p, con
             take(kHdrBytes);
             hit->o_ct = take((size_t)(p.ct_n + 2) * 16);
             hit->o_rt = take((size_t)(p.rt_n + 2) * 16);
-            hit->o_vt = take((size_t)p.vt_k * (p.vt_n + 2) * 16);
+            hit->o_vt = take((size_t)kMaxSlots * (p.vt_n + 2) * 16);
             if (cudaMalloc((void**)&hit->dev, off) != cudaSuccess || cudaMemsetAsync(hit->dev, 0, kHdrBytes, st) != cudaSuccess ||
                 cudaMemsetAsync(hit->dev + offsetof(LeanHeader, slot_bits), 0xFF, sizeof(LeanHeader::slot_bits), st) != cudaSuccess ||
                 cudaEventCreateWithFlags(&hit->ev, cudaEventDisableTiming) != cudaSuccess) {
@@ -974,7 +1020,7 @@ static LeanEntry* lean_entry(gd_graph* g, LeanCtx* ctx, const LeanParams& p, con
             if (hit->st != st && cudaStreamWaitEvent(st, hit->ev, 0) != cudaSuccess) return nullptr;
         }
         hit->st = st; hit->w = w; hit->T = model->iters; hit->hid = model->hidden;
-        hit->ct_n = p.ct_n; hit->rt_n = p.rt_n; hit->vt_n = p.vt_n; hit->vt_k = p.vt_k;
+        hit->ct_n = p.ct_n; hit->rt_n = p.rt_n; hit->vt_n = p.vt_n;
     }
     hit->last_use = ++ctx->tick;
     return hit;
@@ -993,11 +1039,11 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
     LeanEntry* ent = lean_entry(g, ctx, p, model, weights_dev, st);
     if (!ent) return -1;
     const int N = g->N;
-    // per-call workspace: slot | prior | sgn | defer_idx | (x for the deferred pass of packed calls)
+    // per-call workspace: slot | pos | idx | sgn | defer_idx | (x for the deferred pass of packed calls)
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_slot = take((size_t)B * 4);
-    const size_t o_prior = take(x_dev ? (size_t)B * 4 : 0), o_sgn = take(x_dev ? (size_t)B * p.nw * 4 : 0);
+    const size_t o_slot = take((size_t)B * 2), o_pos = take((size_t)B * 4), o_idx = take((size_t)B * 4);
+    const size_t o_sgn = take(x_dev ? (size_t)B * p.nw * 4 : 0);
     const size_t o_defer = take((size_t)B * 4), o_x = take(x_dev ? 0 : (size_t)B * N * 4);
     unsigned char* ws = nullptr;
     GD_CUDA(cudaMallocFromPoolAsync((void**)&ws, off, pool, st));
@@ -1014,29 +1060,36 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         PrepParams pp;
         memset(&pp, 0, sizeof(pp));
         pp.x = x_dev; pp.weights = weights_dev; pp.hdr = hdr; pp.call = call;
-        pp.prior_out = reinterpret_cast<float*>(ws + o_prior); pp.sgn_out = reinterpret_cast<uint32_t*>(ws + o_sgn);
-        pp.prior_in = prior_dev; pp.slot = reinterpret_cast<int*>(ws + o_slot); pp.defer_idx = reinterpret_cast<int*>(ws + o_defer);
-        pp.B = B; pp.V = g->V; pp.C = g->C; pp.N = N; pp.nw = p.nw; pp.vt_k = p.vt_k;
+        pp.sgn_out = reinterpret_cast<uint32_t*>(ws + o_sgn);
+        pp.prior_in = prior_dev; pp.slot = reinterpret_cast<short*>(ws + o_slot); pp.pos = reinterpret_cast<int*>(ws + o_pos);
+        pp.defer_idx = reinterpret_cast<int*>(ws + o_defer);
+        pp.B = B; pp.V = g->V; pp.C = g->C; pp.N = N; pp.nw = p.nw;
         pp.n_w = (int)gd_weights_size(model); pp.T = model->iters; pp.ct_n = p.ct_n; pp.rt_n = p.rt_n; pp.vt_n = p.vt_n;
-        const long long units = x_dev ? B : (B + 31) / 32;       // warps of work
-        const int pack_blocks = (int)std::min<long long>((units + 7) / 8, (long long)g->sm_count * 8);
-        lean_prep_kernel<<<1 + std::max(1, pack_blocks), 256, 0, st>>>(pp);
+        // rows per CTA: 64 (x given: 8 warps x 4 rows, twice) or 256 (packed: a thread per row), more only for batches beyond 2^24
+        pp.rows_per_block = x_dev ? 64 : kPrepRows;
+        while ((B + pp.rows_per_block - 1) / pp.rows_per_block > (1 << 18) && pp.rows_per_block < kPrepRows) pp.rows_per_block *= 2;
+        const long long blocks = (B + pp.rows_per_block - 1) / pp.rows_per_block;
+        GD_CHECK_ARG(blocks < (1ll << 30), "gd_decode_fwd: batch too large for the table kernel's prep pass");
+        lean_prep_kernel<<<(unsigned int)(1 + blocks), 256, 0, st>>>(pp);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) {
         TabParams tp;
+        memset(&tp, 0, sizeof(tp));
         tp.weights = weights_dev; tp.hdr = hdr; tp.call = call; tp.ctab = ctab; tp.rtab = rtab; tp.vtab = vtab;
-        tp.hid = model->hidden; tp.T = model->iters; tp.ct_n = p.ct_n; tp.rt_n = p.rt_n; tp.vt_n = p.vt_n; tp.vt_k = p.vt_k;
+        tp.slot = reinterpret_cast<const short*>(ws + o_slot); tp.pos = reinterpret_cast<const int*>(ws + o_pos);
+        tp.idx = reinterpret_cast<int*>(ws + o_idx); tp.B = B;
+        tp.hid = model->hidden; tp.T = model->iters; tp.ct_n = p.ct_n; tp.rt_n = p.rt_n; tp.vt_n = p.vt_n;
         tp.ct_blocks = (p.ct_n + 2 + kChunk - 1) / kChunk;
         tp.rt_blocks = (p.rt_n + 2 + kChunk - 1) / kChunk;
         tp.vt_blocks_per_slot = (p.vt_n + 2 + kChunk - 1) / kChunk;
-        lean_tables_kernel<<<tp.ct_blocks + tp.rt_blocks + p.vt_k * tp.vt_blocks_per_slot, 256, 0, st>>>(tp);
+        tp.scatter_blocks = (int)std::min<long long>((B + 1023) / 1024, (long long)g->sm_count * 4);
+        lean_tables_kernel<<<tp.scatter_blocks + tp.ct_blocks + tp.rt_blocks + kMaxSlots * tp.vt_blocks_per_slot, 256, 0, st>>>(tp);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) {
-        p.prior = x_dev ? reinterpret_cast<const float*>(ws + o_prior) : prior_dev;
+        p.idx = reinterpret_cast<const int*>(ws + o_idx);
         p.sgn = x_dev ? reinterpret_cast<const uint32_t*>(ws + o_sgn) : synd_dev;
-        p.slot = reinterpret_cast<const int*>(ws + o_slot);
         p.prob = prob_dev; p.logit = logit_dev; p.hard = hard_dev; p.hard_bits = hard_bits_dev;
         p.hdr = hdr; p.call = call; p.next_call = next_call;
         p.ctab = ctab; p.rtab = rtab; p.vtab = vtab;

@@ -4,27 +4,29 @@
 
 namespace gd {
 
+constexpr int kLeanMaxSlots = 64;   // distinct priors a table set can hold (one 8 KB variable-phase table each, in global memory)
+
 // per call: two of them live in the header and alternate, so that call n's decode kernel can clear the one call n + 1 will
 // use (nobody else touches it in between: its last reader, the deferred pass of call n - 1, is long done) -- no memset launch
 struct LeanCall {
     int overflow;                // more distinct priors than table slots: the whole batch takes the edge-owner kernel
     int defer_count;             // syndromes listed in defer_idx; -1 = all of them, in batch order
+    int count[kLeanMaxSlots];    // syndromes of this batch that carry the prior of slot k
 };
 
 // Device-side state of one table set (lives in a cache entry of the graph, persists across calls): the tables are rebuilt
 // only when the content hash of (weights, T, table sizes) changes, variable-phase tables are added as new priors show up.
 struct LeanHeader {
     unsigned long long hash;     // what the tables were built from
-    int rebuild;                 // this call found other weights: check / read-out tables are rebuilt, the prior list was reset
-    int n_slots;                 // distinct priors in the list (<= slots of the plan)
-    unsigned int built_mask;     // slots whose variable-phase table is complete
-    int pad0;
+    unsigned long long built_mask;   // slots whose variable-phase table is complete
+    int rebuild;                 // this call found other weights: every table is rebuilt
+    int n_slots;                 // distinct priors in the list
     unsigned int fmax_bits;      // max |mlp2| over the check table's nodes (float bits, rounded up)
     unsigned int f3max_bits;     // max |mlp3| over the read-out table's nodes
     unsigned int err_c_bits;     // a-posteriori interpolation error of the check table (sampled interval midpoints)
     unsigned int err_r_bits;     // ... of the read-out table
-    unsigned int err_v_bits[16]; // ... of each variable-phase table (in units of tanh output)
-    unsigned int slot_bits[16];  // prior value (float bits) of table slot k; 0xFFFFFFFF = free
+    unsigned int err_v_bits[kLeanMaxSlots];  // ... of each variable-phase table (in units of tanh output)
+    unsigned int slot_bits[kLeanMaxSlots];   // prior value (float bits) of table slot k; 0xFFFFFFFF = free
     LeanCall calls[2];
 };
 
