@@ -516,8 +516,8 @@ def run_workload(name, args, dev, rank, world, clocks, headline):
     n_kernels = 1
     if info["resident"]:
         alg_bytes = io_bytes
-        kname = "gd::lean_decode_kernel (+ begin / prep / tables / deferred-pass launches)" if lean else "gd::decode_kernel<%s, resident>" % program
-        n_kernels = 5 if lean else 1
+        kname = "gd::lean_decode_kernel (+ prep / tables / deferred-pass launches)" if lean else "gd::decode_kernel<%s, resident>" % program
+        n_kernels = 4 if lean else 1
         note = "fused resident kernel: ~%d B/syndrome of HBM traffic, so HBM is not the binding resource; see pipe" % (alg_bytes // B)
     else:
         # streamed path: per edge and iteration m: R,R,W  t: W,R = 20 B for the learned programs, 16 B for
@@ -546,8 +546,8 @@ def run_workload(name, args, dev, rank, world, clocks, headline):
             "achieved": wf / (med_ms * 1e-3) / 1e12, "peak": wf_peak / 1e12, "unit": "T wavefronts/s",
             "frac": wf / (med_ms * 1e-3) / wf_peak,
             "what": "ALGORITHMIC (conflict-free) wavefronts per launch = %.0f per syndrome x %d syndromes, over the time of the WHOLE "
-                    "step (5 launches: hash check, input packing, table refresh, decode, deferred pass); bank conflicts of the "
-                    "variable-phase look-ups (random 16-byte indices, 8 lanes per phase) add ~40%% real wavefronts on top" % (wf / B, B),
+                    "step (4 launches: hash check + input packing, table refresh + sort by prior, decode, deferred pass); the decode "
+                    "kernel alone is ~85%% of it" % (wf / B, B),
             "peak_source": "gd_microbench kind=7 (conflict-free LDS.128 stream), measured live on this GPU",
             "ncu": measured}
     elif program == "v2_4":

@@ -182,8 +182,7 @@ __device__ __forceinline__ void lean_iteration(const LeanParams& p, uint32_t me,
 
 __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ int tile_pre[kMaxSlots + 1];                   // tiles of the slots before slot k, in the prior-sorted tile list
-    __shared__ int row_pre[kMaxSlots + 1];                    // syndromes of the slots before slot k
+    __shared__ int tile_pre[4];                                // this CTA's share: {slot, first tile, end tile, first syndrome of the slot in idx}
     const LeanHeader* H = p.hdr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (blockIdx.x == 0) {                                     // the next call's state: nobody reads or writes it until then
@@ -211,24 +210,83 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
     if (!ok) return;
     if (n_slots == 0) return;                                  // nothing eligible: all listed as deferred already
 
-    // ---- prologue: metadata and the prior-independent tables into shared memory ----
+    // ---- which prior does this CTA serve?  Every CTA serves ONE prior (one variable-phase table, loaded once, no barrier in
+    // the middle of the kernel): the CTAs are dealt to the priors in proportion to their tile counts (at least one each,
+    // largest remainders first; warp 0 computes it, identically in every CTA), a prior's tiles are split evenly among its CTAs.
+    if (warp == 0) {
+        const int grid = (int)gridDim.x;
+        int tl[2], nc[2];
+        int total = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = lane + 32 * h;
+            tl[h] = k < n_slots ? (p.call->count[k] + 31) >> 5 : 0;
+            total += tl[h];
+        }
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        int given = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            nc[h] = tl[h] ? max(1, (int)((long long)grid * tl[h] / max(total, 1))) : 0;
+            given += nc[h];
+        }
+        for (int o = 16; o > 0; o >>= 1) given += __shfl_xor_sync(0xffffffffu, given, o);
+        // hand out what is left (or take back what the "at least one" rule over-spent), one CTA at a time, where it changes
+        // the tiles per CTA the most
+        for (int left = grid - given; left != 0; left += left > 0 ? -1 : 1) {
+            float best = -3e38f;
+            int who = -1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool can = left > 0 ? tl[h] > 0 : nc[h] > 1;
+                const float load = left > 0 ? (float)tl[h] / (float)max(nc[h], 1) : -(float)tl[h] / (float)max(nc[h] - 1, 1);
+                if (can && load > best) { best = load; who = lane + 32 * h; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+                if (ow >= 0 && (who < 0 || ob > best || (ob == best && ow < who))) { best = ob; who = ow; }
+            }
+            if (who < 0) break;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (who == lane + 32 * h) nc[h] += left > 0 ? 1 : -1;
+        }
+        // prefix sums: CTAs and syndromes before slot k
+        int my_slot = -1, my_part = 0, my_n = 1, my_tiles = 0, my_row0 = 0;
+        int cta_acc = 0, row_acc = 0;
+        for (int k = 0; k < n_slots; ++k) {
+            const int src = k & 31, h = k >> 5;
+            const int nk = __shfl_sync(0xffffffffu, h ? nc[1] : nc[0], src), tk = __shfl_sync(0xffffffffu, h ? tl[1] : tl[0], src);
+            if (my_slot < 0 && nk > 0 && (int)blockIdx.x >= cta_acc && (int)blockIdx.x < cta_acc + nk) {
+                my_slot = k; my_part = (int)blockIdx.x - cta_acc; my_n = nk; my_tiles = tk; my_row0 = row_acc;
+            }
+            cta_acc += nk;
+            row_acc += p.call->count[k];
+        }
+        if (lane == 0) {
+            tile_pre[0] = my_slot;
+            tile_pre[1] = my_slot >= 0 ? (int)((long long)my_part * my_tiles / my_n) : 0;
+            tile_pre[2] = my_slot >= 0 ? (int)((long long)(my_part + 1) * my_tiles / my_n) : 0;
+            tile_pre[3] = my_row0;
+        }
+    }
+    __syncthreads();
+    const int k = tile_pre[0], j_lo = tile_pre[1], j_hi = tile_pre[2];
+    if (k < 0 || j_lo >= j_hi) return;                         // no work for this CTA (small batch)
+    // ---- prologue: metadata and the tables into shared memory ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.meta);
         uint4* dst = reinterpret_cast<uint4*>(smem + p.off_me);
         const int n16 = (p.off_ct - p.off_me) >> 4;
         for (int i = tid; i < n16; i += blockDim.x) dst[i] = src[i];
         float4* ct = reinterpret_cast<float4*>(smem + p.off_ct);
-        for (int i = tid; i < (p.ct_n + 2) * 8; i += blockDim.x) ct[i] = p.ctab[i >> 3];          // 8 replicas: one per bank group
+        for (int i = tid; i < (p.ct_n + 2) * 8; i += blockDim.x) ct[i] = __ldg(p.ctab + (i >> 3));   // 8 replicas: one per bank group
         float4* rt = reinterpret_cast<float4*>(smem + p.off_rt);
-        for (int i = tid; i < p.rt_n + 2; i += blockDim.x) rt[i] = p.rtab[i];
-        if (tid == 0) {
-            int acc = 0, racc = 0;
-            for (int k = 0; k < n_slots; ++k) {
-                tile_pre[k] = acc; row_pre[k] = racc;
-                acc += (p.call->count[k] + 31) >> 5; racc += p.call->count[k];
-            }
-            tile_pre[n_slots] = acc; row_pre[n_slots] = racc;
-        }
+        for (int i = tid; i < p.rt_n + 2; i += blockDim.x) rt[i] = __ldg(p.rtab + i);
+        float4* vt = reinterpret_cast<float4*>(smem + p.off_vt);
+        const float4* vsrc = p.vtab + (size_t)k * (p.vt_n + 2);
+        for (int i = tid; i < (p.vt_n + 2) * 8; i += blockDim.x) vt[i] = __ldg(vsrc + (i >> 3));     // this CTA's prior, replicated likewise
     }
     __syncthreads();
     const int grp = warp / p.R, r = warp - grp * p.R;
@@ -250,25 +308,12 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
     const uint32_t rt_base = lean_base<16>(s_base + p.off_rt + 16u);
     const int fin = (p.T & 1) * 128, oth = 128 - fin;          // buffer holding the final messages / free for the staged logits
 
-    // The batch, sorted by prior, is one list of tiles of 32 syndromes; this CTA takes a contiguous share of it.  All 32
-    // syndromes of a tile carry the SAME prior, so one variable-phase table serves the whole CTA at a time: it is loaded
-    // once per prior the share touches (usually one or two), replicated per bank group like the check table -- every table
-    // look-up of the iteration is then conflict-free -- and the CTA's groups deal that prior's tiles among themselves.
-    const int total_tiles = tile_pre[n_slots];
-    const int t_lo = (int)((long long)blockIdx.x * total_tiles / gridDim.x), t_hi = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
-    for (int k = 0; k < n_slots; ++k) {
-        const int j_lo = max(t_lo, tile_pre[k]) - tile_pre[k], j_hi = min(t_hi, tile_pre[k + 1]) - tile_pre[k];
-        if (j_lo >= j_hi) continue;                            // (CTA-uniform)
-        __syncthreads();                                       // every group is done with the previous prior's table
-        {
-            float4* vt = reinterpret_cast<float4*>(smem + p.off_vt);
-            const float4* src = p.vtab + (size_t)k * (p.vt_n + 2);
-            for (int i = tid; i < (p.vt_n + 2) * 8; i += blockDim.x) vt[i] = __ldg(src + (i >> 3));
-        }
-        __syncthreads();
+    // All 32 syndromes of a tile carry the SAME prior (the batch is walked sorted by prior), so the one variable-phase table
+    // in shared memory, replicated per bank group like the check table, serves every look-up of this CTA conflict-free.
+    {
         const float prior = __uint_as_float(H->slot_bits[k]);
         const int cnt = p.call->count[k];
-        const int* rows = p.idx + row_pre[k];
+        const int* rows = p.idx + tile_pre[3];
         tb.t0 = lean_vt(tb, 0.f);
         for (int j = j_lo + grp; j < j_hi; j += p.G) {
             const int li = j * 32 + lane;
@@ -920,7 +965,7 @@ static bool lean_fill(gd_graph* g, const gd_model* m, int64_t B, const LeanGeom&
     out->smem = p.off_state + best.G * state;
     out->threads = 32 * best.G * best.R;
     out->n_tiles = (int)((B + 31) / 32);                       // (+ at most one partial tile per distinct prior)
-    out->grid = std::min(g->sm_count, std::max(1, out->n_tiles));
+    out->grid = g->sm_count;                                   // one CTA per SM, dealt to the priors inside the kernel (idle ones exit at once)
     out->meta = meta;
     return out->smem <= smem_max - 1024;
 }
