@@ -166,6 +166,42 @@ def _v1_1_case(name, consts, T, seed=1234):
               (path, rows, cols, E, B, T, int(ns.nb_digits), out["prob"].min(), out["prob"].max()))
 
 
+def _v2_4_1_case(name, consts, T, seed=1234):
+    """quantum/decoder_v2_4_1.py: decoder_v2_4 with UN-TIED layers, per-edge-type weights and a gated residual.  The script
+    does `import decoder_v2_4` (which cannot be imported unpatched: the generate_PCM API drift) only to copy a pretrained
+    checkpoint into the new model at the very end; the import is dropped and the module is cut before that tail -- the class
+    bodies are untouched.  No shipped checkpoint matches: seeded perturbation of the script's initialisation."""
+    script = "quantum/decoder_v2_4_1.py"
+    with ref_loader.reference_session("quantum"):
+        ns = ref_loader.load_reference(script, consts=consts, seed=seed, raw_subs=[("import decoder_v2_4\n", "\n")],
+                                       truncate_at="'''\nload pretrained model")
+        rows, cols, B = int(ns.rows), int(ns.cols), int(ns.BATCH_SIZE)
+        torch.manual_seed(seed + 1)
+        dec = ns.GNNI(T)
+        with torch.no_grad():
+            for n_, p_ in dec.named_parameters():
+                if n_.endswith("W") or n_.endswith("W_p"):
+                    p_.copy_(torch.rand_like(p_) * 0.8 + 0.5)
+                elif n_ in ("alpha", "beta"):
+                    p_.copy_(torch.full_like(p_, 1.5 if n_ == "alpha" else -0.5))
+        dec.eval()
+        batch = next(iter(ns.train_loader))
+        with torch.no_grad():
+            pred = dec(batch)
+        E = batch.edge_index.size(1) // B
+        ei = batch.edge_index[:, :E].clone()
+        oh = ns.feat_onehot[:E]
+        out = dict(program="v2_4_1", script=script, V=rows, C=cols, E=E, B=B, T=T, dtype="float64",
+                   edge_index=_np(ei).astype(np.int64), H=_np(ns.H).astype(np.uint8), x=_np(batch.x.reshape(B, rows + cols)),
+                   y=_np(batch.y.reshape(B, -1)), prob=_np(pred.reshape(B, rows)), edge_types=_np(oh.argmax(1)).astype(np.int64),
+                   nb_digits=int(ns.nb_digits), m0=np.zeros((B, E)), phase_var=np.zeros((B, E)), phase_chk=np.zeros((B, E)))
+        for k, v in dec.state_dict().items():
+            out["w:" + k] = _np(v)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote %s  (V=%d C=%d E=%d B=%d T=%d, prob range %.3g..%.3g)" % (path, rows, cols, E, B, T, out["prob"].min(), out["prob"].max()))
+
+
 def _grad_case(name, consts, ckpt, T, seed=1234):
     """One train-step gradient of the reference: loss = criterion(decoder(datas), datas);
     loss.backward()  (decoder_v2_4.py:331-335) -> per-parameter gradients."""
@@ -255,6 +291,7 @@ def main():
     _ext_case("ext_neural_bp_toricL4", "quantum/neural_BP.py", "neural_bp", dict(q_small, L="4"), T=5)
     _ext_case("ext_gru_ca_toricL4", "quantum/QGNNNI_ca.py", "gru_ca", dict(q_small, L="4"), T=6)
     _v1_1_case("ext_v1_1_onehot_toricL4", dict(q_small, L="4"), T=5)
+    _v2_4_1_case("ext_v2_4_1_toricL4", dict(q_small, L="4"), T=4)
     _codes()
 
 

@@ -87,11 +87,13 @@ def _sub_const(src, name, value):
     return pat.sub("%s = %s" % (name, value), src, count=1)
 
 
-def load_reference(script, consts=None, seed=1234, raw_subs=()):
+def load_reference(script, consts=None, seed=1234, raw_subs=(), truncate_at=None):
     """Exec reference `script` (e.g. 'quantum/decoder_v2_4.py') and return its namespace.
 
     consts   : {name: python-literal-string} module-level constant substitutions
     raw_subs : [(old, new)] literal text substitutions (must each match)
+    truncate_at : literal text; the module source is cut there (scripts whose TAIL cannot run -- a training driver that
+               needs another script's checkpoint -- keep their class bodies, which is all the oracle uses)
     The namespace stays usable after return ONLY inside `reference_session()`, because the
     class bodies call `.cuda()` at forward time.
     """
@@ -104,6 +106,9 @@ def load_reference(script, consts=None, seed=1234, raw_subs=()):
     for old, new in raw_subs:
         assert old in src, "raw substitution %r did not match" % old
         src = src.replace(old, new)
+    if truncate_at is not None:
+        assert truncate_at in src, "truncation marker %r not found" % truncate_at
+        src = src[:src.index(truncate_at)]
     for k, v in (consts or {}).items():
         src = _sub_const(src, k, v)
     mod = types.ModuleType("ref_" + os.path.basename(script)[:-3])

@@ -70,6 +70,41 @@ def test_restatement_matches_live_reference(script, program):
         assert torch.equal(got["prob"].reshape(-1, 1), want)
 
 
+def test_v2_4_1_restatement_matches_golden_and_types():
+    """quantum/decoder_v2_4_1.py (un-tied layers, one-hot edge types, gated residual): the restatement reproduces the fixture
+    the reference's own classes wrote, bit for bit, and derives the same edge types from the graph alone."""
+    g = Golden("ext_v2_4_1_toricL4")
+    z = np.load(__file__.rsplit("/", 1)[0] + "/golden/ext_v2_4_1_toricL4.npz")
+    assert torch.equal(restate.edge_types_v2_4_1(g.edge_index, g.C), torch.from_numpy(z["edge_types"]))
+    out = restate.decode("v2_4_1", g.edge_index, g.V, g.C, g.x, g.weights, T=g.T, dtype=g.dtype)
+    assert torch.equal(out["prob"], g.prob)
+    from gnn_decode_b200.quantum import decoder_v2_4_1
+    dec = decoder_v2_4_1.GNNI(g.T)
+    assert list(dec.state_dict().keys()) == list(g.weights.keys())
+    dec.load_state_dict(g.weights, strict=True)
+    assert torch.equal(decoder_v2_4_1.edge_types(g.edge_index, g.C), torch.from_numpy(z["edge_types"]))
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_v2_4_1_restatement_matches_live_reference():
+    with ref_loader.reference_session("quantum"):
+        ns = ref_loader.load_reference("quantum/decoder_v2_4_1.py", consts={"BATCH_SIZE": "6", "run1": "6", "run2": "6", "L": "4"}, seed=7,
+                                       raw_subs=[("import decoder_v2_4\n", "\n")], truncate_at="'''\nload pretrained model")
+        torch.manual_seed(3)
+        dec = ns.GNNI(3)
+        with torch.no_grad():
+            for n_, p_ in dec.named_parameters():
+                if n_.endswith("W") or n_.endswith("W_p"):
+                    p_.copy_(torch.rand_like(p_) * 0.8 + 0.5)
+        batch = next(iter(ns.train_loader))
+        with torch.no_grad():
+            want = dec(batch)
+        rows, cols = int(ns.rows), int(ns.cols)
+        ei = batch.edge_index[:, : batch.edge_index.size(1) // 6]
+        got = restate.decode("v2_4_1", ei, rows, cols, batch.x.reshape(6, rows + cols), dec.state_dict(), T=3)
+    assert torch.equal(got["prob"].reshape(-1, 1), want)
+
+
 # ------------------------------------------------------------------------------------------ GPU
 def _close(got, want, rtol):
     from conftest import logit_worst
@@ -215,3 +250,26 @@ def test_v1_1_onehot_decoder_matches_reference():
     with torch.no_grad():
         dec.W.mul_(1.5)
     assert not torch.equal(dec.decode(g.x.to(dev), graph=tg), prob)
+
+
+@pytest.mark.gpu
+def test_v2_4_1_drop_in_matches_reference_fixture():
+    """decoder_v2_4_1 through the drop-in classes: every layer's propagate() is the CUDA kernel (fp32 reduce), the script's own
+    update()s are torch modules -- against the probabilities the reference itself produced."""
+    from gnn_decode_b200.quantum import decoder_v2_4_1
+    g = Golden("ext_v2_4_1_toricL4")
+    dev = torch.device("cuda", 0)
+    dec = decoder_v2_4_1.GNNI(g.T)
+    dec.load_state_dict(g.weights, strict=True)
+    dec = dec.to(dev).eval()
+    d = _Data(g, dev)
+    with torch.no_grad():
+        prob = dec(d)
+        prob2 = dec(d)
+    assert prob.shape == (g.B * g.V, 1) and prob.dtype == torch.float64 and torch.equal(prob, prob2)
+    ref = restate.decode("v2_4_1", g.edge_index, g.V, g.C, g.x, g.weights, T=g.T)
+    assert torch.equal(ref["prob"], g.prob)
+    logit = -torch.log(prob / (1 - prob)).reshape(g.B, g.V)
+    worst, max_err = _close(logit, ref["logit"], RTOL)
+    assert worst <= 1.0, "logits: %.3g x the bar (max abs err %.3g)" % (worst, max_err)
+    assert (prob.reshape(g.B, g.V).cpu() - g.prob).abs().max().item() < 1e-5
