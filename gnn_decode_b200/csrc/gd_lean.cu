@@ -29,6 +29,7 @@
 #include "gd_math.cuh"
 #include "gd_options.cuh"
 #include <algorithm>
+#include <cmath>
 #include <stddef.h>
 #include <string.h>
 
@@ -777,7 +778,7 @@ struct LeanMeta {
     int off_ms = 0, off_mi = 0, off_var = 0;   // byte offsets inside the blob (me at 0)
     double balance = 0.0;
 };
-struct LeanGeom { int R = 0, G = 0, NCH = 0, rt_n = 0, ct_n = 0, vt_n = 0; long long opt_epoch = -1; bool valid = false; };
+struct LeanGeom { int R = 0, G = 0, NCH = 0, rt_n = 0, ct_n = 0, vt_n = 0; long long opt_epoch = -1; int tpc = -1; bool valid = false; };
 // One table set on the device, keyed on the host by (stream, weights pointer, T, table sizes) and VALIDATED on the device
 // by a content hash (lean_begin_kernel): a stale or recycled entry simply rebuilds itself.  An entry is only ever used in
 // stream order; when the least recently used one is handed to another stream, that stream first waits for its last use.
@@ -794,7 +795,7 @@ struct LeanEntry {
 constexpr int kMaxEntries = 4;
 struct LeanCtx {
     std::vector<LeanMeta*> metas;          // one per R ever planned (stable addresses)
-    LeanGeom geom;                         // geometry search result, redone when an option changes
+    std::vector<LeanGeom> geoms;           // geometry search results per tiles-per-CTA count, redone when an option changes
     cudaMemPool_t pool = nullptr;
     std::mutex enq;                        // one call at a time enqueues on a graph (entries are shared state)
     std::vector<LeanEntry*> entries;
@@ -904,7 +905,7 @@ static bool lean_applicable(const gd_graph* g, const gd_model* m) {
 }
 
 // the search itself (host work proportional to C * 32^2: done once per graph and option set, not per call)
-static bool lean_search(gd_graph* g, LeanGeom* out) {
+static bool lean_search(gd_graph* g, int tpc, LeanGeom* out) {
     const int E = (int)g->E, V = g->V;
     const int ct_n = (int)std::min<long long>(1024, std::max<long long>(32, opt_int(OPT_LEAN_CTAB_N, 128)));
     const int vt_n = (int)std::min<long long>(4096, std::max<long long>(64, opt_int(OPT_LEAN_VTAB_N, 512)));
@@ -932,12 +933,14 @@ static bool lean_search(gd_graph* g, LeanGeom* out) {
             if (force_G > 0) G = G >= force_G ? (int)force_G : 0;
             if (G < 1) continue;
             const int warps = G * R;
-            // measured (B200, rotated d = 5 / toric L = 5 / rotated d = 11, profiles/r02_lean_geometry_sweep.txt): what counts is
-            // filling all 32 warp slots with balanced owners -- (R, G) = (8, 4) 0.162 ms vs (5, 5) 0.188 vs (16, 2) 0.185;
-            // then: keep the big read-out table, more groups (independent barrier domains)
-            double score = (0.25 + 0.75 * warps / 32.0) * (0.4 + 0.6 * bal);
+            // Fitted to the sweeps in profiles/r02_lean_geometry_sweep.txt (B200; rotated d = 5 / toric L = 5 / rotated d = 11,
+            // B = 65536): the kernel is latency-bound, so resident warps count (saturating), independent groups count
+            // (a group waiting at its barrier is another group's issue slot: (R, G) = (6, 5) 0.162 ms, (8, 4) 0.168,
+            // (10, 3) 0.177, (16, 2) 0.185), owners should be balanced, and the last round of a CTA's tiles should not
+            // run half empty (tpc tiles per CTA dealt to G groups).
+            const double eff = (double)tpc / (double)(((tpc + G - 1) / G) * G);
+            double score = (warps / (warps + 8.0)) * (G / (G + 0.8)) * std::sqrt(eff) * (0.4 + 0.6 * bal);
             score *= 1.0 - 0.03 * ri;
-            score *= 1.0 + 0.005 * std::min(G, 8);
             if (score > best.score) best = Cand{R, G, nch, rt_n, score};
         }
     }
@@ -976,17 +979,25 @@ static bool lean_fill(gd_graph* g, const gd_model* m, int64_t B, const LeanGeom&
 // needed to seat at least one group.
 static bool lean_plan(gd_graph* g, const gd_model* m, int64_t B, LeanPlan* out) {
     if (!lean_applicable(g, m)) return false;
+    // tiles of 32 syndromes a CTA will see (one CTA per SM; large batches: the quantisation no longer matters)
+    const int tpc = (int)std::min<long long>(64, std::max<long long>(1, ((B + 31) / 32 + g->sm_count - 1) / g->sm_count));
     LeanGeom geom;
     {
         std::lock_guard<std::mutex> lk(g->mu);
         if (!g->lean_ctx) g->lean_ctx = new LeanCtx();
-        geom = static_cast<LeanCtx*>(g->lean_ctx)->geom;
+        LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
+        if (!ctx->geoms.empty() && ctx->geoms[0].opt_epoch != opt_epoch()) ctx->geoms.clear();
+        for (const LeanGeom& q : ctx->geoms)
+            if (q.tpc == tpc) geom = q;
     }
-    if (!geom.valid || geom.opt_epoch != opt_epoch()) {
-        if (!lean_search(g, &geom)) return false;
+    if (!geom.valid) {
+        if (!lean_search(g, tpc, &geom)) return false;
         geom.opt_epoch = opt_epoch();
+        geom.tpc = tpc;
         std::lock_guard<std::mutex> lk(g->mu);
-        static_cast<LeanCtx*>(g->lean_ctx)->geom = geom;
+        LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
+        if (ctx->geoms.size() >= 64) ctx->geoms.clear();
+        ctx->geoms.push_back(geom);
     }
     if (geom.R == 0) return false;
     const LeanMeta* meta = get_meta(g, geom.R);
