@@ -17,6 +17,7 @@
 #include "gd_common.cuh"
 #include "gd_math.cuh"
 #include "gd_options.cuh"
+#include "gd_lean.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -31,6 +32,7 @@ struct BwdParams {
     const float* stash;       // [(T+1)][2][E][B]
     const float* grad_logit;  // [B, V]
     const float* weights;     // packed raw weights
+    const int* run_flag;      // NULL, or: run only if *run_flag != 0 (the stash header's old_count, gd_lean.cuh)
     float* partials;          // [grid * warps][np_pad]
     GraphTables tb;
     long long B;
@@ -194,6 +196,7 @@ __device__ __forceinline__ void store_acc(float* dst, const LaneAcc& A, int h, b
 
 __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
+    if (p.run_flag && *p.run_flag == 0) return;               // the table forward wrote this step's stash: gd_lean.cu's backward runs
     const int tile = p.tile, R = p.R, E = p.E, V = p.V, C = p.C, N = p.N, h = p.hid, T = p.T;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
     const int s = tid % tile, r = tid / tile;
@@ -475,7 +478,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
 
 // stage 2: fixed-order sum over the per-warp partials (double accumulation) -> grad[n_params]
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_rows, int np_pad, int n_params,
-                                       float* __restrict__ grad, int accumulate) {
+                                       float* __restrict__ grad, int accumulate, const int* run_flag) {
+    if (run_flag && *run_flag == 0) return;                   // the table backward (gd_lean.cu) produced this step's gradient
     const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
     if (pidx >= n_params) return;
     double a = 0.0;
@@ -561,7 +565,8 @@ extern "C" int64_t gd_bwd_workspace_floats(const gd_graph* g, const gd_model* mo
     }
     gd::BwdPlan pl;
     if (gd::plan_bwd(g, model, B, &pl) != GD_OK) return -1;
-    return (int64_t)pl.n_rows * pl.p.np_pad;
+    // per-warp partial gradient vectors of the edge-owner backward, then the adjoint bins of the table backward (gd_lean.cu)
+    return (int64_t)pl.n_rows * pl.p.np_pad + gd::lean_bwd_bins_floats(g, model) + 4;
 }
 
 extern "C" int gd_decode_bwd(const gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev,
@@ -588,6 +593,18 @@ extern "C" int gd_decode_bwd(const gd_graph* g, const gd_model* model, const flo
     int prev = 0;
     GD_CUDA(cudaGetDevice(&prev));
     if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
+    // decoder_v2_4 on surface / toric codes: when the table forward wrote the stash (its header says so, on the device), the
+    // table backward produces the gradient and the two kernels below return at once; otherwise the other way round
+    {
+        float* bins = workspace_dev + (((int64_t)pl.n_rows * pl.p.np_pad + 3) & ~(int64_t)3);   // 16-byte aligned (64-bit atomics)
+        const int lrc = gd::lean_backward(const_cast<gd_graph*>(g), model, weights_dev, x_dev, stash_dev, grad_logit_dev,
+                                          grad_weights_dev, bins, accumulate, B, st);
+        if (lrc > 0) {
+            if (prev != g->device) cudaSetDevice(prev);
+            return lrc;
+        }
+        if (lrc == 0) pl.p.run_flag = &gd::lean_train_hdr(const_cast<float*>(stash_dev), g, model, B)->old_count;
+    }
     cudaError_t e = cudaFuncSetAttribute(gd::decode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
     if (e == cudaSuccess) {
         gd::decode_bwd_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(pl.p);
@@ -595,7 +612,7 @@ extern "C" int gd_decode_bwd(const gd_graph* g, const gd_model* model, const flo
     }
     if (e == cudaSuccess) {
         gd::reduce_partials_kernel<<<(n_params + 127) / 128, 128, 0, st>>>(workspace_dev, pl.n_rows, pl.p.np_pad, n_params,
-                                                                           grad_weights_dev, accumulate ? 1 : 0);
+                                                                           grad_weights_dev, accumulate ? 1 : 0, pl.p.run_flag);
         e = cudaGetLastError();
     }
     if (prev != g->device) cudaSetDevice(prev);

@@ -1063,7 +1063,7 @@ extern "C" int64_t gd_stash_floats(const gd_graph* g, const gd_model* model, int
         gd::set_error("gd_stash_floats: invalid argument");
         return -1;
     }
-    return (int64_t)(model->iters + 1) * 2 * g->E * B;
+    return (int64_t)(model->iters + 1) * 2 * g->E * B + gd::kLeanTrainTailFloats + B;   // + the header and sorted list of gd_lean.cuh
 }
 
 extern "C" int gd_decode_fwd_train(const gd_graph* gc, const gd_model* model, const float* weights_dev,
@@ -1085,8 +1085,8 @@ extern "C" int gd_decode_fwd_train(const gd_graph* gc, const gd_model* model, co
 
 int gd::decode_fwd_deferred(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, float* prob_dev,
                             float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev, int64_t B, cudaStream_t st,
-                            const gd::DeferList& dl) {
-    return decode_fwd_impl(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, nullptr, B, (void*)st, nullptr, &dl,
+                            const gd::DeferList& dl, float* stash_dev) {
+    return decode_fwd_impl(g, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, stash_dev, B, (void*)st, nullptr, &dl,
                            hard_bits_dev);
 }
 
@@ -1108,11 +1108,12 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     int prev = 0;
     GD_CUDA(cudaGetDevice(&prev));
     if (prev != g->device) GD_CUDA(cudaSetDevice(g->device));
-    if (!stash_dev && !gate && !dl) {
+    if (!gate && !dl) {
         // decoder_v2_4 on surface / toric codes: the check-owner table kernel (gd_lean.cu); what it cannot serve comes back
-        // here through decode_fwd_deferred
+        // here through decode_fwd_deferred.  Training (stash_dev): the table kernel writes an m-only stash when it can serve
+        // EVERY row, else this kernel writes the full one; the header at the end of the stash says which (gd_lean.cuh).
         const int lrc = gd::lean_decode(g, model, weights_dev, x_dev, nullptr, nullptr, prob_dev, logit_dev, hard_dev, hard_bits_dev,
-                                        B, st);
+                                        B, st, stash_dev);
         if (lrc >= 0) {
             if (prev != g->device) cudaSetDevice(prev);
             return lrc;

@@ -52,6 +52,9 @@ struct LeanParams {
     LeanHeader* hdr;
     LeanCall* call;              // this call's state
     LeanCall* next_call;         // the next call's: cleared here
+    float* stash;                // training: m after every iteration, [T][E][B] by sorted position (NULL otherwise)
+    LeanTrainHdr* train;         // training: the header at the end of the stash buffer
+    const int* idx_src;          // training: the prior-sorted list, copied behind the header
     const float4* ctab; const float4* rtab; const float4* vtab;   // global tables: (n + 2) pieces each, piece 0 = interval -1
     const uint32_t* meta;        // device metadata blob of this (graph, R)
     long long B;
@@ -141,8 +144,9 @@ __device__ __forceinline__ float lean_ct(const LeanTabs& tb, float ext) {
 
 // one check of degree DEG whose first NSIB edges have a sibling edge at their variable (the metadata lists those first):
 // CUR = byte offset of the buffer read, NXT = written
-template <int DEG, int NSIB, int CUR, int NXT>
-__device__ __forceinline__ void lean_check(const uint4 eo, const uint4 so, uint32_t st_lane, const LeanTabs& tb, uint32_t sgn) {
+template <int DEG, int NSIB, int CUR, int NXT, bool STASH>
+__device__ __forceinline__ void lean_check(const uint4 eo, const uint4 so, uint32_t st_lane, const LeanTabs& tb, uint32_t sgn,
+                                           float* stash_q, long long Bp) {
     const uint32_t eoa[4] = {eo.x, eo.y, eo.z, eo.w}, soa[4] = {so.x, so.y, so.z, so.w};
     float t[4], mo[4];
 #pragma unroll
@@ -155,13 +159,15 @@ __device__ __forceinline__ void lean_check(const uint4 eo, const uint4 so, uint3
 #pragma unroll
     for (int j = 0; j < DEG; ++j) {
         const float o = lean_ct(tb, ext[j]);
-        sts_state<NXT>(st_lane + eoa[j], mo[j] + __uint_as_float(__float_as_uint(o) ^ sgn));
+        const float mn = mo[j] + __uint_as_float(__float_as_uint(o) ^ sgn);
+        sts_state<NXT>(st_lane + eoa[j], mn);
+        if (STASH && stash_q) stash_q[(long long)(eoa[j] >> 8) * Bp] = mn;      // training: m after this iteration
     }
 }
 
-template <int CUR>
+template <int CUR, bool STASH>
 __device__ __forceinline__ void lean_iteration(const LeanParams& p, uint32_t me, uint32_t ms, uint32_t mi, uint32_t st_lane,
-                                               const LeanTabs& tb, uint32_t mybits) {
+                                               const LeanTabs& tb, uint32_t mybits, float* stash_q) {
     constexpr int NXT = 128 - CUR;
 #pragma unroll 1
     for (int k = 0; k < p.NCH; ++k) {
@@ -170,7 +176,7 @@ __device__ __forceinline__ void lean_iteration(const LeanParams& p, uint32_t me,
         const uint4 eo = lds_u128(me + 16u * k), so = lds_u128(ms + 16u * k);
         const uint32_t sgn = (mybits >> k) << 31;
         switch (kind) {
-#define GD_LEAN_CASE(D, S) case ((D) | ((S) << 3)): lean_check<D, S, CUR, NXT>(eo, so, st_lane, tb, sgn); break;
+#define GD_LEAN_CASE(D, S) case ((D) | ((S) << 3)): lean_check<D, S, CUR, NXT, STASH>(eo, so, st_lane, tb, sgn, stash_q, p.B); break;
             GD_LEAN_CASE(4, 4) GD_LEAN_CASE(4, 3) GD_LEAN_CASE(4, 2) GD_LEAN_CASE(4, 1) GD_LEAN_CASE(4, 0)
             GD_LEAN_CASE(3, 3) GD_LEAN_CASE(3, 2) GD_LEAN_CASE(3, 1) GD_LEAN_CASE(3, 0)
             GD_LEAN_CASE(2, 2) GD_LEAN_CASE(2, 1) GD_LEAN_CASE(2, 0)
@@ -181,47 +187,18 @@ __device__ __forceinline__ void lean_iteration(const LeanParams& p, uint32_t me,
     }
 }
 
-__global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ int tile_pre[4];                                // this CTA's share: {slot, first tile, end tile, first syndrome of the slot in idx}
-    const LeanHeader* H = p.hdr;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (blockIdx.x == 0) {                                     // the next call's state: nobody reads or writes it until then
-        if (tid == 0) { p.next_call->overflow = 0; p.next_call->defer_count = 0; }
-        if (tid < kMaxSlots) p.next_call->count[tid] = 0;
-    }
-    // ---- can the tables serve this call at all? (identical decision in every thread of the grid) ----
-    const int n_slots = H->n_slots;
-    const float fmax = __uint_as_float(H->fmax_bits), f3max = __uint_as_float(H->f3max_bits);
-    const bool overflow = p.call->overflow != 0;
-    bool ok = !overflow && n_slots <= kMaxSlots && __uint_as_float(H->err_c_bits) <= kBudgetC + 6e-8f * fmax &&
-              __uint_as_float(H->err_r_bits) <= kBudgetR + 1e-7f * f3max && isfinite(fmax) && isfinite(f3max);
-    for (int k = 0; k < n_slots && k < kMaxSlots; ++k)
-        ok = ok && (p.call->count[k] == 0 || __uint_as_float(H->err_v_bits[k]) <= kBudgetV);   // (a listed prior this batch does not use cannot hurt it)
-    if (blockIdx.x == 0 && tid == 0) {
-        if (overflow) {        // the prior list is full of values this batch does not (only) use: start it afresh next call
-            p.hdr->n_slots = 0;
-            p.hdr->built_mask = 0ull;
-            for (int k = 0; k < kMaxSlots; ++k) { p.hdr->slot_bits[k] = kNone; p.hdr->err_v_bits[k] = 0u; }
-        } else {
-            p.hdr->built_mask = n_slots >= 64 ? ~0ull : ((1ull << n_slots) - 1ull);   // the table kernel finished before this one
-        }
-        if (!ok) p.call->defer_count = -1;                     // everything goes to the edge-owner kernel
-    }
-    if (!ok) return;
-    if (n_slots == 0) return;                                  // nothing eligible: all listed as deferred already
-
-    // ---- which prior does this CTA serve?  Every CTA serves ONE prior (one variable-phase table, loaded once, no barrier in
-    // the middle of the kernel): the CTAs are dealt to the priors in proportion to their tile counts (at least one each,
-    // largest remainders first; warp 0 computes it, identically in every CTA), a prior's tiles are split evenly among its CTAs.
-    if (warp == 0) {
+// Which prior does a CTA serve?  Every CTA serves ONE prior (one variable-phase table, loaded once, no barrier in the middle
+// of the kernel): the CTAs are dealt to the priors in proportion to their tile counts (at least one each, largest remainders
+// first), a prior's tiles are split evenly among its CTAs.  Called by ONE warp; identical result in every CTA.
+// out4 (shared): {slot or -1, first tile, end tile, first position of the slot in the prior-sorted list}
+__device__ __forceinline__ void lean_deal(int n_slots, const int* counts, int* out4, int lane) {
         const int grid = (int)gridDim.x;
         int tl[2], nc[2];
         int total = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int k = lane + 32 * h;
-            tl[h] = k < n_slots ? (p.call->count[k] + 31) >> 5 : 0;
+            tl[h] = k < n_slots ? (counts[k] + 31) >> 5 : 0;
             total += tl[h];
         }
         for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
@@ -263,15 +240,63 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
                 my_slot = k; my_part = (int)blockIdx.x - cta_acc; my_n = nk; my_tiles = tk; my_row0 = row_acc;
             }
             cta_acc += nk;
-            row_acc += p.call->count[k];
+            row_acc += counts[k];
         }
         if (lane == 0) {
-            tile_pre[0] = my_slot;
-            tile_pre[1] = my_slot >= 0 ? (int)((long long)my_part * my_tiles / my_n) : 0;
-            tile_pre[2] = my_slot >= 0 ? (int)((long long)(my_part + 1) * my_tiles / my_n) : 0;
-            tile_pre[3] = my_row0;
+            out4[0] = my_slot;
+            out4[1] = my_slot >= 0 ? (int)((long long)my_part * my_tiles / my_n) : 0;
+            out4[2] = my_slot >= 0 ? (int)((long long)(my_part + 1) * my_tiles / my_n) : 0;
+            out4[3] = my_row0;
         }
+}
+
+template <bool STASH>
+__global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int tile_pre[4];                                // this CTA's share: {slot, first tile, end tile, first syndrome of the slot in idx}
+    const LeanHeader* H = p.hdr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (blockIdx.x == 0) {                                     // the next call's state: nobody reads or writes it until then
+        if (tid == 0) { p.next_call->overflow = 0; p.next_call->defer_count = 0; }
+        if (tid < kMaxSlots) p.next_call->count[tid] = 0;
     }
+    // ---- can the tables serve this call at all? (identical decision in every thread of the grid) ----
+    const int n_slots = H->n_slots;
+    const float fmax = __uint_as_float(H->fmax_bits), f3max = __uint_as_float(H->f3max_bits);
+    const bool overflow = p.call->overflow != 0;
+    bool ok = !overflow && n_slots <= kMaxSlots && __uint_as_float(H->err_c_bits) <= kBudgetC + 6e-8f * fmax &&
+              __uint_as_float(H->err_r_bits) <= kBudgetR + 1e-7f * f3max && isfinite(fmax) && isfinite(f3max);
+    for (int k = 0; k < n_slots && k < kMaxSlots; ++k)
+        ok = ok && (p.call->count[k] == 0 || __uint_as_float(H->err_v_bits[k]) <= kBudgetV);   // (a listed prior this batch does not use cannot hurt it)
+    if (STASH) ok = ok && p.call->defer_count == 0;            // training: the m-only stash must cover every row
+    if (STASH && blockIdx.x == 0 && tid < kMaxSlots) {       // tell the backward which forward wrote the stash (and with what)
+        if (tid == 0) {
+            p.train->status = ok ? 1 : 0;
+            p.train->old_count = ok ? 0 : -1;
+            p.train->n_slots = n_slots;
+            p.train->fmax_bits = H->fmax_bits;
+        }
+        p.train->count[tid] = tid < n_slots ? p.call->count[tid] : 0;
+        p.train->slot_bits[tid] = H->slot_bits[tid];
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        if (overflow) {        // the prior list is full of values this batch does not (only) use: start it afresh next call
+            p.hdr->n_slots = 0;
+            p.hdr->built_mask = 0ull;
+            for (int k = 0; k < kMaxSlots; ++k) { p.hdr->slot_bits[k] = kNone; p.hdr->err_v_bits[k] = 0u; }
+        } else {
+            p.hdr->built_mask = n_slots >= 64 ? ~0ull : ((1ull << n_slots) - 1ull);   // the table kernel finished before this one
+        }
+        if (!ok) p.call->defer_count = -1;                     // everything goes to the edge-owner kernel
+    }
+    if (!ok) return;
+    if (n_slots == 0) return;                                  // nothing eligible: all listed as deferred already
+    if (STASH) {                                               // the prior-sorted list outlives this call's workspace: copy it behind the header
+        int* dst = reinterpret_cast<int*>(reinterpret_cast<float*>(p.train) + kLeanTrainTailFloats);
+        for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < p.B; i += (long long)gridDim.x * blockDim.x) dst[i] = p.idx_src[i];
+    }
+
+    if (warp == 0) lean_deal(n_slots, p.call->count, tile_pre, lane);
     __syncthreads();
     const int k = tile_pre[0], j_lo = tile_pre[1], j_hi = tile_pre[2];
     if (k < 0 || j_lo >= j_hi) return;                         // no work for this CTA (small batch)
@@ -320,6 +345,7 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
             const int li = j * 32 + lane;
             const bool live = li < cnt;
             const long long sg = live ? (long long)__ldg(rows + li) : 0;
+            float* const stash_q = (STASH && live) ? p.stash + tile_pre[3] + li : nullptr;   // + (it * E + e) * B
             uint32_t mybits = 0;                                // bit q = the sign bit of my q-th check's input
             for (int q = 0; q < p.NCH; ++q) {
                 const uint32_t info = lds_u32(mi + 4u * q);
@@ -338,18 +364,22 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
                 const uint32_t eoa[4] = {eo.x, eo.y, eo.z, eo.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (e < deg) sts_state<128>(st_lane + eoa[e], mv);
+                    if (e < deg) {
+                        sts_state<128>(st_lane + eoa[e], mv);
+                        if (STASH && stash_q) stash_q[(long long)(eoa[e] >> 8) * p.B] = mv;
+                    }
             }
             group_bar(bar_id, bar_n);
             int it = 1;
+            const long long EB = (long long)p.E * p.B;
             for (; it + 1 < p.T; it += 2) {
-                lean_iteration<128>(p, me, ms, mi, st_lane, tb, mybits);
+                lean_iteration<128, STASH>(p, me, ms, mi, st_lane, tb, mybits, stash_q ? stash_q + it * EB : nullptr);
                 group_bar(bar_id, bar_n);
-                lean_iteration<0>(p, me, ms, mi, st_lane, tb, mybits);
+                lean_iteration<0, STASH>(p, me, ms, mi, st_lane, tb, mybits, stash_q ? stash_q + (it + 1) * EB : nullptr);
                 group_bar(bar_id, bar_n);
             }
             if (it < p.T) {
-                lean_iteration<128>(p, me, ms, mi, st_lane, tb, mybits);
+                lean_iteration<128, STASH>(p, me, ms, mi, st_lane, tb, mybits, stash_q ? stash_q + it * EB : nullptr);
                 group_bar(bar_id, bar_n);
             }
             // ---- read-out: logit_v = prior + sum over the variable's edges of f3(m_e); staged with an odd pitch in the free buffer ----
@@ -748,6 +778,289 @@ __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
         build_chunk(M, prior, true, Rm, p.vt_n, i0, n_int, p.vtab + (size_t)k * (p.vt_n + 2), nullptr, &H->err_v_bits[k], nodes);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Training backward on the same scheme (BASELINE config 4; replaces autograd through quantum/decoder_v2_4.py:280-292).
+// The forward kept m after every iteration (an m-only stash, by prior-sorted position).  Going back through iteration k,
+// everything else is recomputed from m^k with the forward's own tables, and the derivatives are the tables' too:
+//     t_e = g_p(u_e), u_e = m^k_sib(e);  ext_e = sum of the other t of the check;  m^{k+1}_e = m^k_e + s_c f2(ext_e)
+//     db_e = s_c dm^{k+1}_e;  dext_e = db_e f2'(ext_e);  dt_e = sum of the other dext of the check;
+//     du_e = dt_e g_p'(u_e);  dm^k_e = dm^{k+1}_e + du_sib(e)
+// Weight gradients need no per-hidden-unit work either: sum_i g_i dF/dtheta(x_i) over all (syndrome, edge, iteration) items is
+// a weighted sum of a smooth function of x, so the ADJOINT of the Hermite interpolation is accumulated instead -- four
+// shared-memory atomics per item into (value, slope) bins over the table's nodes -- and contracted with dF/dtheta at the nodes
+// once per step in double precision (lean_contract_kernel).  Bins are 64-bit FIXED-POINT integers (2^-32 resolution): integer
+// adds commute, so the gradients are bit-reproducible.  F = mlp2 (g = db), mlp (g = dlogit), and per prior mlp1 with
+// g = da = dt (1 - t^2) / 2 (the table holds tanh(mlp1 / 2), the adjoint is taken on the same grid).
+struct LeanBwdParams {
+    const float* x;              // [B, N]: check signs
+    const float* stash;          // [T][E][B] by sorted position
+    const LeanTrainHdr* train;   // header behind the stash; idx follows it
+    const float* grad_logit;     // [B, V]
+    const float4* ctab; const float4* rtab; const float4* vtab;
+    const uint32_t* meta;
+    long long* bins;             // global: ct | rt | vt[kMaxSlots], each [2][n + 3]
+    long long B;
+    int T, V, C, E, N, R, G, NCH, ct_n, rt_n, vt_n;
+    int off_me, off_ms, off_mi, off_var, off_ct, off_rt, off_vt, off_bc, off_br, off_bv, off_state;
+};
+
+__device__ __forceinline__ void bin_add(long long* bins, int nb, int piece, float tau, float g) {
+    // piece in [-1, n]: nodes piece + 1 and piece + 2 of the (n + 3)-node grid; t in [0, 1] inside the piece
+    const float t = tau + 0.5f, t2 = t * t, t3 = t2 * t;
+    const float h01 = 3.0f * t2 - 2.0f * t3, gs = g * 4294967296.0f;
+    unsigned long long* b = reinterpret_cast<unsigned long long*>(bins) + piece + 1;
+    atomicAdd(b, (unsigned long long)__float2ll_rn(gs * (1.0f - h01)));
+    atomicAdd(b + 1, (unsigned long long)__float2ll_rn(gs * h01));
+    atomicAdd(b + nb, (unsigned long long)__float2ll_rn(gs * (t3 - 2.0f * t2 + t)));
+    atomicAdd(b + nb + 1, (unsigned long long)__float2ll_rn(gs * (t3 - t2)));
+}
+// value and d/dtau of the cubic piece holding interval coordinate w (table of 16-byte pieces at `base`, piece 0 first)
+__device__ __forceinline__ void cubic_vd(const float4* base, float w, float& val, float& dtau, int& piece, float& tau) {
+    const float v = w + 12582912.0f;
+    tau = w - (v - 12582912.0f);
+    piece = __float_as_int(v) - 0x4B400000;
+    const float4 c = base[piece];
+    val = fmaf(fmaf(fmaf(c.w, tau, c.z), tau, c.y), tau, c.x);
+    dtau = fmaf(fmaf(3.0f * c.w, tau, 2.0f * c.z), tau, c.y);
+}
+
+__global__ void __launch_bounds__(1024, 1) lean_bwd_kernel(const LeanBwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int share[4];
+    const LeanTrainHdr* H = p.train;
+    if (H->status != 1) return;                                // the edge-owner forward wrote this stash: its backward runs instead
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_slots = H->n_slots;
+    if (warp == 0) lean_deal(n_slots, H->count, share, lane);
+    __syncthreads();
+    const int k = share[0], j_lo = share[1], j_hi = share[2];
+    if (k < 0 || j_lo >= j_hi) return;
+    {   // metadata, the three tables (one copy each: the backward is bound by its atomics, not by look-up conflicts), zeroed bins
+        const uint4* src = reinterpret_cast<const uint4*>(p.meta);
+        uint4* dst = reinterpret_cast<uint4*>(smem + p.off_me);
+        for (int i = tid; i < (p.off_ct - p.off_me) >> 4; i += blockDim.x) dst[i] = src[i];
+        float4* ct = reinterpret_cast<float4*>(smem + p.off_ct);
+        for (int i = tid; i < p.ct_n + 2; i += blockDim.x) ct[i] = __ldg(p.ctab + i);
+        float4* rt = reinterpret_cast<float4*>(smem + p.off_rt);
+        for (int i = tid; i < p.rt_n + 2; i += blockDim.x) rt[i] = __ldg(p.rtab + i);
+        float4* vt = reinterpret_cast<float4*>(smem + p.off_vt);
+        for (int i = tid; i < p.vt_n + 2; i += blockDim.x) vt[i] = __ldg(p.vtab + (size_t)k * (p.vt_n + 2) + i);
+        long long* z = reinterpret_cast<long long*>(smem + p.off_bc);
+        for (int i = tid; i < (p.off_state - p.off_bc) >> 3; i += blockDim.x) z[i] = 0ll;
+    }
+    __syncthreads();
+    long long* bins_c = reinterpret_cast<long long*>(smem + p.off_bc);
+    long long* bins_r = reinterpret_cast<long long*>(smem + p.off_br);
+    long long* bins_v = reinterpret_cast<long long*>(smem + p.off_bv);
+    const float4* ct = reinterpret_cast<const float4*>(smem + p.off_ct) + 1;      // piece 0
+    const float4* rt = reinterpret_cast<const float4*>(smem + p.off_rt) + 1;
+    const float4* vt = reinterpret_cast<const float4*>(smem + p.off_vt) + 1;
+    const int grp = warp / p.R, r = warp - grp * p.R;
+    const uint32_t* me = reinterpret_cast<const uint32_t*>(smem + p.off_me) + (size_t)r * p.NCH * 4;
+    const uint32_t* ms = reinterpret_cast<const uint32_t*>(smem + p.off_ms) + (size_t)r * p.NCH * 4;
+    const uint32_t* mi = reinterpret_cast<const uint32_t*>(smem + p.off_mi) + (size_t)r * p.NCH;
+    const uint2* varm = reinterpret_cast<const uint2*>(smem + p.off_var);
+    // per group: MK (m of the iteration), DM (dL/dm), DU (dL/du per edge), each [E][32]
+    float* MK = reinterpret_cast<float*>(smem + p.off_state) + (size_t)grp * 3 * p.E * 32 + lane;
+    float* DM = MK + (size_t)p.E * 32;
+    float* DU = DM + (size_t)p.E * 32;
+    const int bar_id = 1 + grp, bar_n = 32 * p.R;
+    const float fmax = __uint_as_float(H->fmax_bits);
+    const float Rm = (float)p.T * (fmax * 1.02f + 1e-6f);
+    const float vt_inv_h = 0.5f * (float)p.vt_n / Rm, vt_off = Rm * vt_inv_h - 0.5f;
+    const float ct_inv_h = (float)p.ct_n / 6.0f, ct_off = 3.0f * ct_inv_h - 0.5f;
+    const float rt_inv_h = 0.5f * (float)p.rt_n / Rm, rt_off = Rm * rt_inv_h - 0.5f;
+    const int nbc = p.ct_n + 3, nbr = p.rt_n + 3, nbv = p.vt_n + 3;
+    const int cnt = H->count[k];
+    const int* rows = reinterpret_cast<const int*>(reinterpret_cast<const float*>(H) + kLeanTrainTailFloats) + share[3];
+    const long long EB = (long long)p.E * p.B;
+
+    for (int j = j_lo + grp; j < j_hi; j += p.G) {
+        const int li = j * 32 + lane;
+        const bool live = li < cnt;
+        const long long row = live ? (long long)__ldg(rows + li) : 0;
+        const float* st_q = p.stash + share[3] + li;            // + (it * E + e) * B: m after iteration it
+        uint32_t mybits = 0;
+        for (int q = 0; q < p.NCH; ++q) {
+            const uint32_t info = mi[q];
+            if ((info & 7u) == 0) break;
+            const int c = (int)(info >> 8);
+            mybits |= ((live && __ldg(p.x + row * p.N + p.V + c) < 0.f) ? 1u : 0u) << q;
+        }
+        // ---- read-out backward: logit_v = prior + sum_{e at v} f3(m^T_e) ----
+        for (int v = r; v < p.V; v += p.R) {
+            const uint2 ve = varm[v];
+            const float g = live ? __ldg(p.grad_logit + row * p.V + v) : 0.f;
+            const uint32_t es[2] = {ve.x, ve.y};
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (es[h] != kNone) {
+                    const int e = (int)(es[h] >> 8);
+                    const float m = live ? __ldg(st_q + (long long)(p.T - 1) * EB + (long long)e * p.B) : 0.f;
+                    float val, dtau, tau;
+                    int piece;
+                    cubic_vd(rt, fminf(fmaxf(fmaf(m, rt_inv_h, rt_off), -1.4f), (float)p.rt_n + 0.4f), val, dtau, piece, tau);
+                    DM[e * 32] = g * dtau * rt_inv_h;
+                    if (g != 0.f) bin_add(bins_r, nbr, piece, tau, g);
+                }
+        }
+        group_bar(bar_id, bar_n);
+        for (int it = p.T - 1; it >= 0; --it) {
+            // m^it of my edges (m^0 = 0) for the siblings' owners to read
+            for (int q = 0; q < p.NCH; ++q) {
+                const int deg = (int)(mi[q] & 7u);
+                if (deg == 0) break;
+                for (int e4 = 0; e4 < deg; ++e4) {
+                    const int e = (int)(me[4 * q + e4] >> 8);
+                    MK[e * 32] = (it > 0 && live) ? __ldg(st_q + (long long)(it - 1) * EB + (long long)e * p.B) : 0.f;
+                }
+            }
+            group_bar(bar_id, bar_n);
+            for (int q = 0; q < p.NCH; ++q) {
+                const uint32_t kind = mi[q] & 63u;
+                if (kind == 0) break;
+                const int deg = (int)(kind & 7u), nsib = (int)(kind >> 3);
+                float t[4], gd[4], tau_v[4], dext[4];
+                int pc_v[4];
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                    t[e4] = 0.f; gd[e4] = 0.f; tau_v[e4] = 0.f; pc_v[e4] = 0; dext[e4] = 0.f;
+                    if (e4 < deg) {
+                        const float u = e4 < nsib ? MK[(ms[4 * q + e4] >> 8) * 32] : 0.f;
+                        cubic_vd(vt, fmaf(u, vt_inv_h, vt_off), t[e4], gd[e4], pc_v[e4], tau_v[e4]);
+                    }
+                }
+                const float a = t[0] + t[1], b = t[2] + t[3];
+                const float ext[4] = {t[1] + b, t[0] + b, a + t[3], a + t[2]};
+                const float sg = ((mybits >> q) & 1u) ? -1.0f : 1.0f;
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4)
+                    if (e4 < deg) {
+                        const int e = (int)(me[4 * q + e4] >> 8);
+                        const float db = sg * DM[e * 32];
+                        float val, dtau, tau;
+                        int piece;
+                        cubic_vd(ct, fmaf(ext[e4], ct_inv_h, ct_off), val, dtau, piece, tau);
+                        dext[e4] = db * dtau * ct_inv_h;
+                        if (db != 0.f) bin_add(bins_c, nbc, piece, tau, db);
+                    }
+                const float da_ = dext[0] + dext[1], db_ = dext[2] + dext[3];
+                const float dt[4] = {dext[1] + db_, dext[0] + db_, da_ + dext[3], da_ + dext[2]};
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4)
+                    if (e4 < deg) {
+                        const int e = (int)(me[4 * q + e4] >> 8);
+                        const float da = dt[e4] * 0.5f * (1.0f - t[e4] * t[e4]);
+                        if (da != 0.f) bin_add(bins_v, nbv, pc_v[e4], tau_v[e4], da);
+                        DU[e * 32] = dt[e4] * gd[e4] * vt_inv_h;
+                    }
+            }
+            group_bar(bar_id, bar_n);
+            // dm^it_e = dm^{it+1}_e + du of the sibling edge (whose u is m_e)
+            for (int q = 0; q < p.NCH; ++q) {
+                const uint32_t kind = mi[q] & 63u;
+                if (kind == 0) break;
+                const int nsib = (int)(kind >> 3);
+                for (int e4 = 0; e4 < nsib; ++e4) {
+                    const int e = (int)(me[4 * q + e4] >> 8);
+                    DM[e * 32] += DU[(ms[4 * q + e4] >> 8) * 32];
+                }
+            }
+        }
+        group_bar(bar_id, bar_n);                              // DM / MK are rewritten by the next tile's read-out backward
+    }
+    __syncthreads();
+    // flush this CTA's bins (integer adds: any order gives the same bits)
+    {
+        unsigned long long* gc = reinterpret_cast<unsigned long long*>(p.bins);
+        unsigned long long* gr = gc + 2 * nbc;
+        unsigned long long* gv = gr + 2 * nbr + (size_t)k * 2 * nbv;
+        for (int i = tid; i < 2 * nbc; i += blockDim.x) if (bins_c[i]) atomicAdd(gc + i, (unsigned long long)bins_c[i]);
+        for (int i = tid; i < 2 * nbr; i += blockDim.x) if (bins_r[i]) atomicAdd(gr + i, (unsigned long long)bins_r[i]);
+        for (int i = tid; i < 2 * nbv; i += blockDim.x) if (bins_v[i]) atomicAdd(gv + i, (unsigned long long)bins_v[i]);
+    }
+}
+
+// Contraction of the adjoint bins with dF/dtheta at the table nodes, in double: one CTA per MLP parameter row j (hidden unit),
+// threads over the nodes; grad layout = the packed weights (ggc1.mlp: w1 [h,2] | b1 | w2 | b2; ggc2.mlp, mlp: w1 | b1 | w2 | b2).
+//   dF/dw2_j = sp(z_j), dF/db1_j = w2_j s(z_j), dF/dw1_j = w2_j s(z_j) x (second input: the prior), dF/db2 = 1, z_j = w1_j x + c_j,
+//   and their x-derivatives times the node spacing pair with the slope bins.
+struct ContractParams {
+    const float* weights; const LeanTrainHdr* train; const long long* bins; float* grad;
+    int hid, T, ct_n, rt_n, vt_n, accumulate;
+};
+__device__ __forceinline__ void sp_sig(double z, double& sp, double& sg) {
+    if (z > 20.0) { sp = z; sg = 1.0; return; }
+    const double e = exp(-fabs(z));
+    sp = fmax(z, 0.0) + log1p(e);
+    sg = z >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
+}
+__global__ void __launch_bounds__(256) lean_contract_kernel(const ContractParams p) {
+    __shared__ double red[5][8];
+    const LeanTrainHdr* H = p.train;
+    if (H->status != 1) return;
+    const int h = p.hid, j = blockIdx.x % (h + 1), which = blockIdx.x / (h + 1);     // which: 0 mlp1 (all priors), 1 mlp2, 2 mlp3; j == h: the bias b2
+    const float fmax = __uint_as_float(H->fmax_bits);
+    const double Rm = (double)((float)p.T * (fmax * 1.02f + 1e-6f));
+    const int nbc = p.ct_n + 3, nbr = p.rt_n + 3, nbv = p.vt_n + 3;
+    const double inv = 1.0 / 4294967296.0;
+    double g_w1 = 0.0, g_w1b = 0.0, g_b1 = 0.0, g_w2 = 0.0, g_b2 = 0.0;
+    const float* w = p.weights + (which == 0 ? 0 : which == 1 ? 4 * h + 1 : 7 * h + 2);
+    const int n_tab = which == 0 ? H->n_slots : 1;
+    for (int tab = 0; tab < n_tab; ++tab) {
+        const long long* bins;
+        int nb;
+        double R, hstep, prior = 0.0;
+        if (which == 0) {
+            if (H->count[tab] == 0) continue;
+            bins = p.bins + 2 * nbc + 2 * nbr + (size_t)tab * 2 * nbv; nb = nbv; R = Rm; hstep = 2.0 * Rm / p.vt_n;
+            prior = (double)__uint_as_float(H->slot_bits[tab]);
+        } else if (which == 1) { bins = p.bins; nb = nbc; R = 3.0; hstep = 6.0 / p.ct_n; }
+        else { bins = p.bins + 2 * nbc; nb = nbr; R = Rm; hstep = 2.0 * Rm / p.rt_n; }
+        double a = 0.0, c = 0.0, w2 = 0.0;
+        if (j < h) {
+            if (which == 0) { a = (double)w[2 * j]; c = (double)w[2 * h + j] + (double)w[2 * j + 1] * prior; w2 = (double)w[3 * h + j]; }
+            else { a = (double)w[j]; c = (double)w[h + j]; w2 = (double)w[2 * h + j]; }
+        }
+        for (int n = threadIdx.x; n < nb; n += blockDim.x) {
+            const long long bA = bins[n], bD = bins[nb + n];
+            if (!bA && !bD) continue;
+            const double A = (double)bA * inv, D = (double)bD * inv * hstep, x = -R + hstep * (double)(n - 1);
+            if (j == h) { g_b2 += A; continue; }
+            double sp, sg;
+            sp_sig(a * x + c, sp, sg);
+            const double dsg = sg * (1.0 - sg) * a;                 // d sigma / dx
+            g_w2 += A * sp + D * (a * sg);
+            g_b1 += w2 * (A * sg + D * dsg);
+            g_w1 += w2 * (A * sg * x + D * (sg + x * dsg));
+            g_w1b += w2 * prior * (A * sg + D * dsg);
+        }
+    }
+    double vals[5] = {g_w1, g_w1b, g_b1, g_w2, g_b2};
+    for (int q = 0; q < 5; ++q) {
+        double v = vals[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 5; ++q) {
+            double v = 0.0;
+            for (int i = 0; i < 8; ++i) v += red[q][i];
+            vals[q] = v;
+        }
+        float* g = p.grad + (which == 0 ? 0 : which == 1 ? 4 * h + 1 : 7 * h + 2);
+        auto put = [&](int at, double v) { g[at] = p.accumulate ? g[at] + (float)v : (float)v; };
+        if (which == 0) {
+            if (j < h) { put(2 * j, vals[0]); put(2 * j + 1, vals[1]); put(2 * h + j, vals[2]); put(3 * h + j, vals[3]); }
+            else put(4 * h, vals[4]);
+        } else {
+            if (j < h) { put(j, vals[0]); put(h + j, vals[2]); put(2 * h + j, vals[3]); }
+            else put(3 * h, vals[4]);
+        }
+    }
+}
+
 // packed inputs -> x rows for the syndromes the edge-owner kernel has to redo (gd_decode_packed_*)
 __global__ void lean_unpack_kernel(const float* prior, const uint32_t* sgn, const LeanCall* H, const int* defer_idx, float* x,
                                    long long B, int V, int C, int nw) {
@@ -1084,7 +1397,7 @@ static LeanEntry* lean_entry(gd_graph* g, LeanCtx* ctx, const LeanParams& p, con
 
 int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* prior_dev,
                 const uint32_t* synd_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev,
-                int64_t B, cudaStream_t st) {
+                int64_t B, cudaStream_t st, float* stash_dev) {
     LeanPlan pl;
     if (!lean_plan(g, model, B, &pl)) return -1;
     cudaMemPool_t pool = lean_pool(g);
@@ -1149,9 +1462,13 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         p.prob = prob_dev; p.logit = logit_dev; p.hard = hard_dev; p.hard_bits = hard_bits_dev;
         p.hdr = hdr; p.call = call; p.next_call = next_call;
         p.ctab = ctab; p.rtab = rtab; p.vtab = vtab;
-        e = cudaFuncSetAttribute(lean_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
+        p.stash = stash_dev;
+        p.train = stash_dev ? lean_train_hdr(stash_dev, g, model, B) : nullptr;
+        p.idx_src = p.idx;
+        auto kern = stash_dev ? lean_decode_kernel<true> : lean_decode_kernel<false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
         if (e == cudaSuccess) {
-            lean_decode_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(p);
+            kern<<<pl.grid, pl.threads, pl.smem, st>>>(p);
             e = cudaGetLastError();
         }
     }
@@ -1166,8 +1483,10 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         x_for_deferred = xw;
     }
     if (e == cudaSuccess) {
-        const DeferList dl{&call->defer_count, reinterpret_cast<const int*>(ws + o_defer)};
-        rc = decode_fwd_deferred(g, model, weights_dev, x_for_deferred, prob_dev, logit_dev, hard_dev, hard_bits_dev, B, st, dl);
+        // training: all rows or none (the header's old_count is 0 or -1), and the edge-owner kernel writes its own stash layout
+        const DeferList dl{stash_dev ? &lean_train_hdr(stash_dev, g, model, B)->old_count : &call->defer_count,
+                           reinterpret_cast<const int*>(ws + o_defer)};
+        rc = decode_fwd_deferred(g, model, weights_dev, x_for_deferred, prob_dev, logit_dev, hard_dev, hard_bits_dev, B, st, dl, stash_dev);
     }
     cudaError_t ef = cudaFreeAsync(ws, st);
     if (rc != GD_OK) return rc;
@@ -1194,6 +1513,83 @@ int packed_via_unpack(gd_graph* g, const float* prior_dev, const uint32_t* synd_
     if (rc != GD_OK) return rc;
     GD_CUDA(e);
     GD_CUDA(ef);
+    return GD_OK;
+}
+
+int64_t lean_bwd_bins_floats(const gd_graph* g, const gd_model* model) {
+    if (!lean_applicable(g, model)) return 0;
+    const int ct_n = (int)std::min<long long>(1024, std::max<long long>(32, opt_int(OPT_LEAN_CTAB_N, 128)));
+    const int vt_n = (int)std::min<long long>(4096, std::max<long long>(64, opt_int(OPT_LEAN_VTAB_N, 512)));
+    return 2 * 2 * ((int64_t)(ct_n + 3) + (2048 + 3) + (int64_t)kMaxSlots * (vt_n + 3));
+}
+
+int lean_backward(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* stash_dev,
+                  const float* grad_logit_dev, float* grad_weights_dev, float* bins_dev, int accumulate, int64_t B, cudaStream_t st) {
+    LeanPlan fwd;
+    if (!lean_plan(g, model, B, &fwd)) return -1;              // the forward took the edge-owner kernel as well
+    LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
+    std::lock_guard<std::mutex> enq(ctx->enq);
+    // the table set the forward of this step used (same stream, same weights): it is not touched in between
+    LeanEntry* ent = nullptr;
+    for (LeanEntry* e : ctx->entries)
+        if (e->st == st && e->w == weights_dev && e->T == model->iters && e->hid == model->hidden && e->ct_n == fwd.p.ct_n &&
+            e->rt_n == fwd.p.rt_n && e->vt_n == fwd.p.vt_n)
+            ent = e;
+    if (!ent) {
+        set_error("gd_decode_bwd: no table set of a matching gd_decode_fwd_train on this stream (call the forward first)");
+        return GD_ERR_INVALID;
+    }
+    LeanBwdParams p;
+    memset(&p, 0, sizeof(p));
+    const int E = (int)g->E, ct_n = fwd.p.ct_n, rt_n = fwd.p.rt_n, vt_n = fwd.p.vt_n;
+    // geometry: three [E][32] arrays per group; one copy of each table; the bins
+    const int smem_max = g->max_smem_optin - 1024;
+    int bestR = 0, bestG = 0;
+    double best = -1.0;
+    for (int R = 1; R <= 32; ++R) {
+        std::vector<std::vector<int>> own;
+        int nch;
+        double bal;
+        assign_owners(g, R, own, &nch, &bal);
+        if (nch == 0 || nch > 32) continue;
+        const int meta = align_up_i(align_up_i(2 * R * nch * 16 + R * nch * 4, 16) + g->V * 8, 16);
+        const int fixed = align_up_i(meta + (ct_n + 2 + rt_n + 2 + vt_n + 2) * 16 + 16 * (ct_n + 3 + rt_n + 3 + vt_n + 3), 128);
+        int G = (smem_max - fixed) / (3 * E * 128);
+        G = std::min(G, std::min(32 / R, 15));
+        if (G < 1) continue;
+        const int warps = G * R;
+        const double score = (warps / (warps + 8.0)) * (G / (G + 0.8)) * (0.4 + 0.6 * bal);
+        if (score > best) { best = score; bestR = R; bestG = G; }
+    }
+    if (!bestR) return -1;
+    const LeanMeta* meta = get_meta(g, bestR);
+    if (!meta) return -1;
+    const LeanTrainHdr* hdr = lean_train_hdr(const_cast<float*>(stash_dev), g, model, B);
+    p.x = x_dev; p.stash = stash_dev; p.train = hdr; p.grad_logit = grad_logit_dev;
+    p.ctab = reinterpret_cast<const float4*>(ent->dev + ent->o_ct);
+    p.rtab = reinterpret_cast<const float4*>(ent->dev + ent->o_rt);
+    p.vtab = reinterpret_cast<const float4*>(ent->dev + ent->o_vt);
+    p.meta = meta->dev; p.bins = reinterpret_cast<long long*>(bins_dev);
+    p.B = B; p.T = model->iters; p.V = g->V; p.C = g->C; p.E = E; p.N = g->N; p.R = bestR; p.G = bestG; p.NCH = meta->NCH;
+    p.ct_n = ct_n; p.rt_n = rt_n; p.vt_n = vt_n;
+    p.off_me = 0; p.off_ms = meta->off_ms; p.off_mi = meta->off_mi; p.off_var = meta->off_var;
+    p.off_ct = (int)meta->bytes;
+    p.off_rt = p.off_ct + (ct_n + 2) * 16;
+    p.off_vt = p.off_rt + (rt_n + 2) * 16;
+    p.off_bc = align_up_i(p.off_vt + (vt_n + 2) * 16, 16);
+    p.off_br = p.off_bc + 16 * (ct_n + 3);
+    p.off_bv = p.off_br + 16 * (rt_n + 3);
+    p.off_state = align_up_i(p.off_bv + 16 * (vt_n + 3), 128);
+    const int smem = p.off_state + bestG * 3 * E * 128;
+    const size_t bins_bytes = (size_t)2 * 8 * ((ct_n + 3) + (rt_n + 3) + (size_t)kMaxSlots * (vt_n + 3));
+    GD_CUDA(cudaMemsetAsync(bins_dev, 0, bins_bytes, st));
+    GD_CUDA(cudaFuncSetAttribute(lean_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    lean_bwd_kernel<<<g->sm_count, 32 * bestG * bestR, smem, st>>>(p);
+    GD_CUDA(cudaGetLastError());
+    ContractParams cp{weights_dev, hdr, reinterpret_cast<const long long*>(bins_dev), grad_weights_dev, model->hidden, model->iters,
+                      ct_n, rt_n, vt_n, accumulate};
+    lean_contract_kernel<<<3 * (model->hidden + 1), 256, 0, st>>>(cp);
+    GD_CUDA(cudaGetLastError());
     return GD_OK;
 }
 

@@ -30,6 +30,24 @@ struct LeanHeader {
     LeanCall calls[2];
 };
 
+// Training (decoder_v2_4): the header at the END of the stash buffer (gd_stash_floats() reserves kLeanTrainTailFloats + B floats
+// behind the edge-owner kernel's [(T+1)][2][E][B] layout).  It says which forward wrote the stash, so the matching backward runs:
+// both forwards / both backwards are launched every step and the one whose turn it is not returns at once -- the choice is made
+// on the device, no host synchronisation.
+constexpr int kLeanTrainTailFloats = 512;
+struct LeanTrainHdr {
+    int status;                  // 1: the table kernel wrote an m-only stash [T][E][B] (sorted positions) for ALL rows; 0: edge-owner layout
+    int old_count;               // DeferList count of the edge-owner forward / backward: 0 when status == 1, -1 (all rows) otherwise
+    int n_slots;
+    int pad;
+    unsigned int fmax_bits;      // max |mlp2| the tables' domains were built from
+    unsigned int pad1[3];
+    int count[kLeanMaxSlots];
+    unsigned int slot_bits[kLeanMaxSlots];
+    // followed (at float offset kLeanTrainTailFloats) by idx[B]: the prior-sorted syndrome list
+};
+static_assert(sizeof(LeanTrainHdr) <= kLeanTrainTailFloats * 4, "training header");
+
 // Edge-owner kernel pass over the syndromes the lean kernel deferred (gd_decode.cu).
 struct DeferList {
     const int* count;            // &LeanCall::defer_count
@@ -40,7 +58,15 @@ struct DeferList {
 // otherwise a gd_status.  Exactly one of x_dev / (prior_dev, synd_dev) is given.
 int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* prior_dev,
                 const uint32_t* synd_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev,
-                int64_t B, cudaStream_t st);
+                int64_t B, cudaStream_t st, float* stash_dev = nullptr);
+// training: the table backward (returns -1 when the lean path does not apply to (graph, model)); it runs only if the stash header
+// says the table forward wrote it.  grad_weights_dev receives (or accumulates) the 10h+3 gradients; bins_dev: lean_bwd_bins_floats() floats.
+int lean_backward(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* stash_dev,
+                  const float* grad_logit_dev, float* grad_weights_dev, float* bins_dev, int accumulate, int64_t B, cudaStream_t st);
+int64_t lean_bwd_bins_floats(const gd_graph* g, const gd_model* model);
+inline LeanTrainHdr* lean_train_hdr(float* stash, const gd_graph* g, const gd_model* m, int64_t B) {
+    return reinterpret_cast<LeanTrainHdr*>(stash + (int64_t)(m->iters + 1) * 2 * g->E * B);
+}
 int packed_via_unpack(gd_graph* g, const float* prior_dev, const uint32_t* synd_dev, int64_t B, cudaStream_t st,
                       int (*run)(void* ctx, const float* x_dev), void* ctx);
 bool lean_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out);
@@ -49,6 +75,6 @@ bool lean_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_la
 // evaluation, so a deferred syndrome's result never depends on what else was deferred)
 int decode_fwd_deferred(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, float* prob_dev,
                         float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev, int64_t B, cudaStream_t st,
-                        const DeferList& dl);
+                        const DeferList& dl, float* stash_dev = nullptr);
 
 }  // namespace gd

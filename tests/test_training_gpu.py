@@ -208,3 +208,28 @@ def test_p2p_allreduce_two_gpus():
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "p2p all-reduce ok on 2 GPUs" in res.stdout
+
+
+@pytest.mark.parametrize("name", ["grad_v2_4_toricL4_epoch1", "grad_v2_4_toricL5_epoch3_T6"])
+def test_table_backward_runs_and_agrees_with_the_edge_owner_backward(name, gd_opt):
+    """On surface / toric codes the training step goes through the table kernels (csrc/gd_lean.cu: m-only stash, derivatives from
+    the tables, weight gradients as adjoint bins): its gradients match the edge-owner kernels' (GD_NO_LEAN) far inside the bar,
+    are NOT bit-identical to them (so the table path really ran), and are bit-reproducible."""
+    from gnn_decode_b200.quantum import decoder_v2_4
+    case = _Case(name)
+    dec = decoder_v2_4.GNNI(case.T)
+    dec.load_state_dict(case.weights)
+    dec = dec.to(DEV).train()
+    loss_a, ga, _ = _train_step(case, dec, reps=5)
+    loss_a2, ga2, _ = _train_step(case, dec, reps=5)
+    assert loss_a == loss_a2 and all(torch.equal(ga[k], ga2[k]) for k in ga)
+    gd_opt.set("GD_NO_LEAN")
+    loss_b, gb, _ = _train_step(case, dec, reps=5)
+    gd_opt.unset("GD_NO_LEAN")
+    assert abs(loss_a - loss_b) <= 1e-6 * abs(loss_b)
+    same = True
+    for k in ga:
+        scale = gb[k].abs().max().item()
+        assert (ga[k] - gb[k]).abs().max().item() <= 2e-5 * scale + 1e-12, k
+        same = same and torch.equal(ga[k], gb[k])
+    assert not same
