@@ -12,6 +12,8 @@ struct LeanCall {
     int overflow;                // more distinct priors than table slots: the whole batch takes the edge-owner kernel
     int defer_count;             // syndromes listed in defer_idx; -1 = all of them, in batch order
     int count[kLeanMaxSlots];    // syndromes of this batch that carry the prior of slot k
+    unsigned int fmax_new;       // max |mlp2| over the check table's nodes, gathered by the prep kernel when the weights changed
+    int pad[3];
 };
 
 // Device-side state of one table set (lives in a cache entry of the graph, persists across calls): the tables are rebuilt
@@ -19,12 +21,17 @@ struct LeanCall {
 struct LeanHeader {
     unsigned long long hash;     // what the tables were built from
     unsigned long long built_mask;   // slots whose variable-phase table is complete
+    unsigned long long pending_hash; // hash of this call's weights; becomes `hash` once the table kernel has rebuilt
     int rebuild;                 // this call found other weights: every table is rebuilt
     int n_slots;                 // distinct priors in the list
+    int vt_n_eff;                // pieces of the variable-phase tables: base * 2^k, finer for wider message domains
+    int vt_mult;                 // ... at least base * vt_mult: raised by the decode kernel when a table set missed its budget (0 = 1)
     unsigned int fmax_bits;      // max |mlp2| over the check table's nodes (float bits, rounded up)
     unsigned int f3max_bits;     // max |mlp3| over the read-out table's nodes
     unsigned int err_c_bits;     // a-posteriori interpolation error of the check table (sampled interval midpoints)
     unsigned int err_r_bits;     // ... of the read-out table
+    unsigned int d2max_bits;     // max |mlp2'| and max |mlp3'| over the nodes: how much a table error is amplified on its way
+    unsigned int d3max_bits;     //   to the logits (the variable-phase tables' budget shrinks with their product)
     unsigned int err_v_bits[kLeanMaxSlots];  // ... of each variable-phase table (in units of tanh output)
     unsigned int slot_bits[kLeanMaxSlots];   // prior value (float bits) of table slot k; 0xFFFFFFFF = free
     LeanCall calls[2];
@@ -41,7 +48,8 @@ struct LeanTrainHdr {
     int n_slots;
     int pad;
     unsigned int fmax_bits;      // max |mlp2| the tables' domains were built from
-    unsigned int pad1[3];
+    int vt_n_eff;                // pieces of the variable-phase tables
+    unsigned int pad1[2];
     int count[kLeanMaxSlots];
     unsigned int slot_bits[kLeanMaxSlots];
     // followed (at float offset kLeanTrainTailFloats) by idx[B]: the prior-sorted syndrome list

@@ -34,6 +34,7 @@ def build_table(a, c, w2, b2, Rdom, n, tanh_fold=False):
     x = -Rdom + h * np.arange(-1, n + 2)
     f, df = mlp_f_df(a, c, w2, b2, x)
     fmax = float(np.abs(f).max())
+    build_table.last_dmax = float(np.abs(df).max())              # max |f'| over the nodes (the kernel keeps it for mlp2 and mlp3)
     if tanh_fold:
         g = np.tanh(0.5 * f)
         df = 0.5 * (1.0 - g * g) * df
@@ -66,8 +67,27 @@ def eval_table(coef, inv_h, off, x, clamp=None):
     return r
 
 
-def decode(edge_index, V, C, x, w, T, ct_n=128, vt_n=512, rt_n=2048):
-    """x [B, V+C] with one prior per syndrome and +-1 check inputs -> dict(logit, errs).  w: reference state_dict (numpy)."""
+def vt_pieces(base, Rm, mult=1):
+    """Pieces of the variable-phase tables (gd_lean.cu: lean_vt_pieces): the base count, doubled (up to 8x) until a piece is
+    narrower than 0.172 and there are at least base * mult of them."""
+    n = base
+    while n < 8 * base and (2.0 * Rm / n > 0.172 or n < base * mult):
+        n *= 2
+    return n
+
+
+def budget_v(T, d2max, d3max):
+    """Error budget of the variable-phase tables (gd_lean.cu: lean_decode_kernel): 1e-6, less when the model amplifies an error in
+    t by more than 400 on its way to the logits (first order: 6 T max|mlp2'| max|mlp3'|)."""
+    gain = 6.0 * T * d2max * d3max
+    return 4e-4 / gain if gain > 400.0 else BUDGET_V
+
+
+def decode(edge_index, V, C, x, w, T, ct_n=128, vt_n=512, rt_n=2048, adaptive=True):
+    """x [B, V+C] with one prior per syndrome and +-1 check inputs -> dict(logit, errs).  w: reference state_dict (numpy).
+    vt_n is the BASE piece count of the variable-phase tables; adaptive=False keeps it whatever the message domain, otherwise the
+    kernel's rule applies: the piece-width rule first, then doubled while a table of the batch misses budget_v (the kernel does that
+    from one call to the next; the calls in between are served by the edge-owner kernel)."""
     ei = np.asarray(edge_index)
     var, chk = ei[0], ei[1]
     E = ei.shape[1]
@@ -81,10 +101,21 @@ def decode(edge_index, V, C, x, w, T, ct_n=128, vt_n=512, rt_n=2048):
     a2, c2_, w22, b22 = g("ggc2.mlp.0.weight")[:, 0], g("ggc2.mlp.0.bias"), g("ggc2.mlp.2.weight")[0], float(g("ggc2.mlp.2.bias")[0])
     a3, c3_, w23, b23 = g("mlp.0.weight")[:, 0], g("mlp.0.bias"), g("mlp.2.weight")[0], float(g("mlp.2.bias")[0])
     ctab, err_c, fmax = build_table(a2, c2_, w22, b22, 3.0, ct_n)
+    d2max = build_table.last_dmax
     fmax32 = np.nextafter(np.float32(fmax), np.float32(np.inf)) if np.float32(fmax) < fmax else np.float32(fmax)
     Rm = float(np.float32(T) * (fmax32 * np.float32(1.02) + np.float32(1e-6)))
     rtab, err_r, f3max = build_table(a3, c3_, w23, b23, Rm, rt_n)
-    errs = {"c": err_c, "r": err_r, "v": {}, "Rm": Rm, "f3max": f3max}
+    d3max = build_table.last_dmax
+    bv = budget_v(T, d2max, d3max)
+    if adaptive:
+        base, mult = vt_n, 1
+        while True:
+            vt_n = vt_pieces(base, Rm, mult)
+            worst = max(build_table(W1[:, 0], W1[:, 1] * float(p) + b1, w2v, b2v, Rm, vt_n, tanh_fold=True)[1] for p in np.unique(prior))
+            if worst <= bv or vt_n >= 8 * base:
+                break
+            mult = 2 * vt_n // base
+    errs = {"c": err_c, "r": err_r, "v": {}, "Rm": Rm, "f3max": f3max, "vt_n": vt_n, "budget_v": bv}
     # sibling edge of each edge at its variable, other edges of each edge at its check
     sib = -np.ones(E, np.int64)
     for v in range(V):

@@ -23,16 +23,33 @@ def test_table_recurrence_matches_the_oracle(name):
     fmax = e["Rm"] / g.T / 1.02
     assert e["c"] <= lean_model.BUDGET_C + 6e-8 * fmax           # check table: 1e-7 + half an fp32 ulp of its values
     assert e["r"] <= lean_model.BUDGET_R + 1e-7 * e["f3max"]
-    assert max(e["v"].values()) <= lean_model.BUDGET_V
+    assert max(e["v"].values()) <= e["budget_v"] == lean_model.BUDGET_V and e["vt_n"] == 512
 
 
-def test_collapsed_checkpoint_misses_the_variable_table_budget():
-    """epoch67 (T max|mlp2| = 70): 512 pieces cannot hold tanh(mlp1 / 2) to 1e-6 -- the kernel must notice (it then hands the
-    batch to the edge-owner kernel; tests/test_lean_gpu.py)."""
+def test_collapsed_checkpoint_needs_finer_variable_tables():
+    """epoch67 (T max|mlp2| = 70, max|mlp3'| = 20: a table error is amplified ~4000 x on its way to the logits, the shipped
+    checkpoints: ~200 x).  512 pieces on [-72, 72] miss even the plain 1e-6 budget; the piece-width rule's 1024 meet that (3.8e-7) but
+    not the logit bar (1.1 x) -- the amplification-aware budget (1e-7 here) sends the kernel on to 2048 pieces, which do (0.43 x)."""
     g = Golden("v2_4_toricL4_epoch67")
     w = {k: v.numpy() for k, v in g.weights.items()}
-    out = lean_model.decode(g.edge_index.numpy(), g.V, g.C, g.x.numpy()[:4], w, g.T)
+    ref = restate.decode("v2_4", g.edge_index, g.V, g.C, g.x, g.weights, T=g.T)["logit"]
+    out = lean_model.decode(g.edge_index.numpy(), g.V, g.C, g.x.numpy()[:4], w, g.T, adaptive=False)
     assert max(out["errs"]["v"].values()) > lean_model.BUDGET_V
+    out = lean_model.decode(g.edge_index.numpy(), g.V, g.C, g.x.numpy(), w, g.T, vt_n=1024, adaptive=False)
+    e = out["errs"]
+    assert e["budget_v"] < max(e["v"].values()) <= lean_model.BUDGET_V
+    assert logit_worst(torch.from_numpy(out["logit"]), ref)[0] > 1.0          # the reason the budget has to know about the gain
+    out = lean_model.decode(g.edge_index.numpy(), g.V, g.C, g.x.numpy(), w, g.T)
+    e = out["errs"]
+    assert e["vt_n"] == 2048 and max(e["v"].values()) <= e["budget_v"] < 2e-7
+    worst, max_err = logit_worst(torch.from_numpy(out["logit"]), ref)
+    assert worst <= 0.5, (worst, max_err)
+
+
+def test_piece_rule_keeps_the_shipped_checkpoints_on_the_base_tables():
+    assert lean_model.vt_pieces(512, 34.0) == 512 and lean_model.vt_pieces(512, 43.9) == 512
+    assert lean_model.vt_pieces(512, 71.0) == 1024 and lean_model.vt_pieces(512, 96.0) == 2048
+    assert lean_model.vt_pieces(512, 1e4) == 4096                # capped: the error check then sends the batch to the edge-owner kernel
 
 
 def test_midpoint_error_estimate_is_the_true_error():
