@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
     if (blockIdx.x == 0 && tid == 0 && ok && !overflow) {
         // finer tables next time (this batch goes to the edge-owner kernel), or coarser ones when the finer ones are not needed any more
         const int mult = max(1, H->vt_mult);
-        if (!ok_v && vt_n < vt_n_max) { p.hdr->vt_mult = 2 * vt_n / p.vt_n; p.hdr->hash = 0ull; }
+        if (!ok_v && vt_n < vt_n_max) { p.hdr->vt_mult = 2 * vt_n / p.vt_n; p.hdr->hash = 0ull; p.hdr->forced = 1; }
         else if (ok_v && mult > 1 && vt_n == mult * p.vt_n && worst_v * 32.0f < budget_v) p.hdr->vt_mult = mult / 2;
     }
     ok = ok && ok_v;
@@ -592,6 +592,7 @@ struct PrepParams {
     LeanCall* call;
     long long B;
     int V, C, N, nw, rows_per_block, fm_blocks, hid;
+    int keep_mult;               // training: other weights every step, the table resolution found so far stays a hint
     int n_w, T, ct_n, rt_n, vt_n;   // what the content hash covers
 };
 
@@ -695,6 +696,10 @@ __global__ void __launch_bounds__(256, 6) lean_prep_kernel(const PrepParams p) {
             if (threadIdx.x == 0) {
                 H->pending_hash = h;
                 H->rebuild = rebuild ? 1 : 0;
+                // other weights (not a rebuild the decode kernel asked for): the table resolution starts from the piece-width rule
+                // again, so that what a call returns depends on the weights and not on what this entry served before
+                if (rebuild && !H->forced && !p.keep_mult) H->vt_mult = 0;
+                H->forced = 0;
                 if (rebuild) {
                     H->built_mask = 0ull;
                     H->f3max_bits = H->err_c_bits = H->err_r_bits = H->d2max_bits = H->d3max_bits = 0u;
@@ -1285,7 +1290,9 @@ static const LeanMeta* get_meta(gd_graph* g, int R) {
 }
 
 static bool lean_applicable(const gd_graph* g, const gd_model* m) {
-    if (m->program != GD_PROG_V2_4 || m->flags != 0 || m->iters < 1 || opt_on(OPT_NO_LEAN)) return false;
+    // T <= 32: the messages grow to T max|mlp2| and fp32 accumulation at that magnitude has been checked against the oracle up to
+    // there only (numpy emulation at T = 15 / 24 / 32 / 45: <= 0.26 of the bar; T = 60: 1.7 x on two golden syndromes)
+    if (m->program != GD_PROG_V2_4 || m->flags != 0 || m->iters < 1 || m->iters > 32 || opt_on(OPT_NO_LEAN)) return false;
     if (g->max_var_deg > 2 || g->max_chk_deg > 4 || g->E >= (1 << 23) / 256) return false;
     if ((g->V | 1) > g->E) return false;                        // the staged logits reuse the free message buffer
     return true;
@@ -1303,15 +1310,30 @@ static bool lean_search(gd_graph* g, int tpc, LeanGeom* out) {
     static const int rts[] = {2048, 1024};
     const long long force_R = opt_int(OPT_LEAN_R, 0), force_G = opt_int(OPT_LEAN_G, 0);
     const long long force_rt = opt_int(OPT_LEAN_RTAB_N, 0);
+    // The read-out table's size is part of what a call returns (its last bits), so it must not depend on the batch size: it is
+    // chosen per graph from what shared memory can seat at all -- 2048 pieces unless that costs more than one of the (up to 4)
+    // groups 1024 pieces would allow -- and never traded against the geometry below.
+    int g_cap[2] = {0, 0};
+    std::vector<int> nchs(33, 0);
+    std::vector<double> bals(33, 0.0);
+    for (int R = 1; R <= 32; ++R) {
+        std::vector<std::vector<int>> own;
+        assign_owners(g, R, own, &nchs[R], &bals[R]);
+        if (nchs[R] > 32 || nchs[R] == 0) continue;
+        const int meta = align_up_i(align_up_i(2 * R * nchs[R] * 16 + R * nchs[R] * 4, 16) + V * 8, 16);
+        for (int ri = 0; ri < 2; ++ri) {
+            const int fixed = align_up_i(meta + (ct_n + 2) * 128 + (rts[ri] + 2) * 16 + (vt_n + 2) * 128, 128);
+            g_cap[ri] = std::max(g_cap[ri], std::min((smem_max - fixed) / state, std::min(32 / R, 15)));
+        }
+    }
+    const int ri_fixed = g_cap[0] >= std::min(g_cap[1], 3) && g_cap[0] >= 1 ? 0 : 1;
     for (int R = 1; R <= 32; ++R) {
         if (force_R > 0 && R != force_R) continue;
-        std::vector<std::vector<int>> own;
-        int nch;
-        double bal;
-        assign_owners(g, R, own, &nch, &bal);
+        const int nch = nchs[R];
+        const double bal = bals[R];
         if (nch > 32 || nch == 0) continue;                      // sign bits of the owned checks live in one register
         const int meta = align_up_i(align_up_i(2 * R * nch * 16 + R * nch * 4, 16) + V * 8, 16);
-        for (int ri = 0; ri < 2; ++ri) {
+        for (int ri = ri_fixed; ri <= ri_fixed; ++ri) {
             // shared memory: metadata, check table and ONE variable-phase table replicated per bank group, read-out table
             const int rt_n = force_rt > 0 ? (int)force_rt : rts[ri];
             const int fixed = align_up_i(meta + (ct_n + 2) * 128 + (rt_n + 2) * 16 + (vt_n + 2) * 128, 128);
@@ -1327,7 +1349,6 @@ static bool lean_search(gd_graph* g, int tpc, LeanGeom* out) {
             // run half empty (tpc tiles per CTA dealt to G groups).
             const double eff = (double)tpc / (double)(((tpc + G - 1) / G) * G);
             double score = (warps / (warps + 8.0)) * (G / (G + 0.8)) * std::sqrt(eff) * (0.4 + 0.6 * bal);
-            score *= 1.0 - 0.03 * ri;
             if (score > best.score) best = Cand{R, G, nch, rt_n, score};
         }
     }
@@ -1362,8 +1383,7 @@ static bool lean_fill(gd_graph* g, const gd_model* m, int64_t B, const LeanGeom&
 
 // Geometry: R owners (warps) per group of 32 syndromes, G groups per CTA.  The kernel is bound by the shared-memory
 // crossbar, so what matters is enough resident warps (>= ~24) with balanced owners; more groups = more independent
-// barrier domains.  Table sizes shrink (read-out 2048 -> 1024 intervals, slots 12 -> 10 -> 8 -> 6) only as far as
-// needed to seat at least one group.
+// barrier domains.  The read-out table's size (2048 or 1024 pieces) is fixed per graph (lean_search).
 static bool lean_plan(gd_graph* g, const gd_model* m, int64_t B, LeanPlan* out) {
     if (!lean_applicable(g, m)) return false;
     // tiles of 32 syndromes a CTA will see (one CTA per SM; large batches: the quantisation no longer matters)
@@ -1511,8 +1531,12 @@ static LeanEntry* lean_entry(gd_graph* g, LeanCtx* ctx, const LeanParams& p, con
             }
             ctx->entries.push_back(hit);
         } else {
-            hit = lru;                                            // recycle: its hash will not match, so it rebuilds itself
+            hit = lru;                                            // recycle: back to the state of a new entry, after its last use
             if (hit->st != st && cudaStreamWaitEvent(st, hit->ev, 0) != cudaSuccess) return nullptr;
+            if (cudaMemsetAsync(hit->dev, 0, kHdrBytes, st) != cudaSuccess ||
+                cudaMemsetAsync(hit->dev + offsetof(LeanHeader, slot_bits), 0xFF, sizeof(LeanHeader::slot_bits), st) != cudaSuccess)
+                return nullptr;
+            hit->calls = 0;
         }
         hit->st = st; hit->w = w; hit->T = model->iters; hit->hid = model->hidden;
         hit->ct_n = p.ct_n; hit->rt_n = p.rt_n; hit->vt_n = p.vt_n;
@@ -1566,6 +1590,7 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         const long long blocks = (B + pp.rows_per_block - 1) / pp.rows_per_block;
         GD_CHECK_ARG(blocks < (1ll << 30), "gd_decode_fwd: batch too large for the table kernel's prep pass");
         pp.hid = model->hidden;
+        pp.keep_mult = stash_dev ? 1 : 0;
         pp.fm_blocks = (p.ct_n + 3 + 7) / 8;                      // 8 warps = 8 check-table nodes per CTA
         lean_prep_kernel<<<(unsigned int)(1 + pp.fm_blocks + blocks), 256, 0, st>>>(pp);
         e = cudaGetLastError();

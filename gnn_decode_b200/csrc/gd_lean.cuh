@@ -26,6 +26,8 @@ struct LeanHeader {
     int n_slots;                 // distinct priors in the list
     int vt_n_eff;                // pieces of the variable-phase tables: base * 2^k, finer for wider message domains
     int vt_mult;                 // ... at least base * vt_mult: raised by the decode kernel when a table set missed its budget (0 = 1)
+    int forced;                  // the decode kernel asked for the rebuild (hash cleared): keep vt_mult
+    int pad0;
     unsigned int fmax_bits;      // max |mlp2| over the check table's nodes (float bits, rounded up)
     unsigned int f3max_bits;     // max |mlp3| over the read-out table's nodes
     unsigned int err_c_bits;     // a-posteriori interpolation error of the check table (sampled interval midpoints)

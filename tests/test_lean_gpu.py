@@ -56,7 +56,7 @@ def test_per_item_routing_and_batch_invariance():
     with options.option("GD_NO_LEAN"), options.option("GD_NO_VTAB"):
         p_dir = dec.decode(xm)
     assert torch.equal(p_mix[special], p_dir[special])                                       # deferred rows: exactly the direct evaluation
-    # slices of the batch give the same bits
+    # slices of the batch give the same bits (whatever geometry their size selects)
     for lo, n in ((0, 8), (100, 1000), (B - 333, 333)):
         assert torch.equal(dec.decode(xm[lo:lo + n].contiguous()), p_mix[lo:lo + n])
     # and everything matches the oracle
@@ -127,6 +127,24 @@ def test_tables_follow_the_weights():
         p_old = dec.decode(x)
     assert float((p - p_old).abs().max()) < 1e-4
     assert not torch.equal(p, outs["v2_4_toricL5_epoch3"])
+
+
+def test_results_do_not_depend_on_the_geometry_a_batch_size_selects():
+    """Toric L = 4 (E = 128): one group of 30 owner warps for a small batch, four groups of 8 for a large one -- and no table size
+    may follow the geometry (the read-out table once shrank to seat the fourth group, which changed the last bits)."""
+    gold = Golden("v2_4_toricL4_epoch1")
+    g = TannerGraph(gold.edge_index, gold.V, gold.C, DEV)
+    dec = decoder_v2_4.GNNI(15)
+    dec.load_state_dict(gold.weights)
+    dec = dec.to(DEV).eval().bind_graph(g)
+    x = gold.x.float().repeat(1100, 1).contiguous().to(DEV)
+    full = dec.decode(x)
+    shapes = set()
+    for n in (16, 64, 4096, 8800):
+        info = g.launch_info(dec.gd_model(), n)
+        shapes.add((info["tile"], info["threads"]))
+        assert torch.equal(dec.decode(x[:n].contiguous()), full[:n]), n
+    assert len(shapes) >= 2
 
 
 def test_wide_message_domains_get_finer_variable_tables():
