@@ -10,6 +10,7 @@ from .build import LIB_PATH
 GD_OK, GD_ERR_INVALID, GD_ERR_CUDA, GD_ERR_UNSUPPORTED = 0, 1, 2, 3
 PROG_CGNNI, PROG_QGNNI, PROG_V2_4, PROG_BP_QUANTUM, PROG_BP_CLASSICAL = 0, 1, 2, 3, 4
 PROG_NEURAL_BP, PROG_GRU_CA = 5, 6
+PROG_V3_0, PROG_V1_2_2 = 7, 8
 FLAG_ALL_ITERS = 1
 PHASE_VAR, PHASE_CHK = 0, 1
 ABI_VERSION = 1
@@ -44,6 +45,7 @@ _SIGNATURES = {
     "gd_propagate_features": (C.c_int, [C.c_int32, C.c_int32]),
     "gd_propagate_fwd": (C.c_int, [_p, C.POINTER(GdModel), C.c_int32, C.c_int32, _p, _p, _p, _p, C.c_int64, _p]),
     "gd_decode_fwd": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, _p, C.c_int64, _p]),
+    "gd_decode_fwd_aux": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, _p, _p, _p, C.c_int64, _p]),
     "gd_decode_packed_fwd": (C.c_int, [_p, C.POINTER(GdModel), _p, _p, _p, _p, _p, C.c_int64, _p]),
     "gd_pipeline_create": (C.c_int, [_p, C.POINTER(GdModel), _p, C.c_int64, C.c_int32, C.POINTER(_p)]),
     "gd_pipeline_destroy": (None, [_p]),

@@ -71,9 +71,11 @@ struct gd_graph {
 static inline bool gd_model_valid(const gd_model* m) {
     if (!m) return false;
     if (m->iters < 0) return false;
-    if (m->flags != 0 && !(m->flags == GD_FLAG_ALL_ITERS && m->program == GD_PROG_GRU_CA)) return false;
+    if (m->flags != 0 && !(m->flags == GD_FLAG_ALL_ITERS && (m->program == GD_PROG_GRU_CA || m->program == GD_PROG_V1_2_2))) return false;
     switch (m->program) {
         case GD_PROG_GRU_CA:
+        case GD_PROG_V3_0:
+        case GD_PROG_V1_2_2:
             return m->hidden >= 1 && m->hidden <= 256;
         case GD_PROG_NEURAL_BP:
             return m->hidden >= 1;          // = E, checked against the graph at launch

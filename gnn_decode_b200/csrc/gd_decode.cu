@@ -65,6 +65,7 @@ struct DecodeParams {
     const int* defer_count;
     const int* defer_idx;
     uint32_t* hard_bits;    // optional packed hard decisions [B][ceil(V/32)]
+    float* aux_prob; float* aux_logit;   // GD_PROG_V3_0: the check-node read-out [B][C]
 };
 
 // ---------------- PTX helpers: mbarrier + bulk async copy (TMA 1-D) ----------------
@@ -134,6 +135,8 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     constexpr bool kSoftplus = (PROG == GD_PROG_V2_4);
     constexpr bool kNBP = (PROG == GD_PROG_NEURAL_BP);   // sum-product + per-edge weights (quantum/neural_BP.py)
     constexpr bool kGRU = (PROG == GD_PROG_GRU_CA);      // MLP + GRUCell updates (quantum/QGNNNI_ca.py)
+    constexpr bool kV3 = (PROG == GD_PROG_V3_0);         // 2-input ReLU MLPs + GRUCell updates, second read-out at the checks (quantum/decoder_v3_0.py)
+    constexpr bool kV122 = (PROG == GD_PROG_V1_2_2);     // Tanh-MLP variable phase, sum-product check phase, a read-out per iteration (quantum/decoder_v1_2_2.py)
     // ReLU programs: NPOLY carries NPAD -- > 0 evaluates their 1->h->1 MLPs as piecewise-linear tables (gd_math.cuh)
     constexpr int kNPAD = (PROG == GD_PROG_CGNNI || PROG == GD_PROG_QGNNI || kGRU) ? (NPOLY > 0 ? NPOLY : 0) : 0;
 
@@ -242,6 +245,35 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             }
         }
         gru = gs;
+    } else if constexpr (kV3) {
+        // ggc1.mlp1 (2 -> h -> 1) | ggc1.rnn1 | ggc2.mlp2 (2 -> h -> 1) | ggc2.rnn2 | mlp (1 -> h -> 1)
+        const float* w = p.weights;
+        const int h = p.hid;
+        float* slot = wsm;
+        float* gs = wsm + 3 * p.wslot;
+        for (int k = 0; k < 2; ++k) {
+            stage_mlp(slot, hp, h, w, 2, true, w + 2 * h, w + 3 * h, 1.f, 1.f, tid, nthr);
+            const MlpSmem Wk{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[4 * h]};
+            if (k == 0) W1 = Wk; else W2 = Wk;
+            w += 4 * h + 1;
+            slot += p.wslot;
+            if (tid < 12) gs[k * 12 + tid] = w[tid];
+            w += 12;
+        }
+        stage_mlp(slot, hp, h, w, 1, false, w + h, w + 2 * h, 1.f, 1.f, tid, nthr);
+        W3 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
+        gru = gs;
+    } else if constexpr (kV122) {
+        // ggc1.mlp | mlp, both 2 -> h -> 1 Tanh: first layers pre-scaled by 2 log2(e) (mlp_tanh2)
+        const float* w = p.weights;
+        const int h = p.hid;
+        const float s1 = 2.0f * kLog2e;
+        stage_mlp(wsm, hp, h, w, 2, true, w + 2 * h, w + 3 * h, s1, 1.f, tid, nthr);
+        W1 = MlpSmem{wsm, wsm + hp, wsm + 2 * hp, wsm + 3 * hp, w[4 * h]};
+        w += 4 * h + 1;
+        float* slot = wsm + p.wslot;
+        stage_mlp(slot, hp, h, w, 2, true, w + 2 * h, w + 3 * h, s1, 1.f, tid, nthr);
+        W3 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[4 * h]};
     } else if constexpr (!kIsBP && !kNBP) {
         const float* w = p.weights;
         const int h = p.hid;
@@ -465,7 +497,17 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         acc += src[(size_t)e * tile + s];
                     }
                 }
-                float lg = kNBP ? acc + acc_p : (kGRU ? acc : acc + xrow[v]);   // QGNNNI_ca.py:241-245: mlp(sum), no prior
+                float lg = kNBP ? acc + acc_p : ((kGRU || kV3 || kV122) ? acc : acc + xrow[v]);   // QGNNNI_ca.py:241-245: mlp(sum), no prior
+                if constexpr (kV3) {            // decoder_v3_0.py:275: mlp(sum) + x
+                    float xi[1] = {lg}, oo[1];
+                    mlp_relu<1>(W3, hp, xi, oo);
+                    lg = oo[0] + xrow[v];
+                }
+                if constexpr (kV122) {          // decoder_v1_2_2.py:275-278: mlp([sum, prior])
+                    float xi[1] = {lg}, xp[1] = {xrow[v]}, oo[1];
+                    mlp_tanh2<1>(W3, hp, xi, xp, oo);
+                    lg = oo[0];
+                }
                 if constexpr (kGRU) {
                     float xi[1] = {lg}, oo[1];
                     if constexpr (kNPAD > 0) oo[0] = pwl_eval<kNPAD>(P3, xi[0]);
@@ -608,6 +650,20 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                             t_st[(size_t)e * tile + s] = a < 0.f ? -tv : tv;                 // sign flag rides in the sign bit
                             continue;
                         }
+                        if constexpr (kV3) {           // decoder_v3_0.py:103-108,229-232,246-247: rnn1(m, mlp1([sum - m, prior]))
+                            const float mo = m_st[(size_t)e * tile + s];
+                            float ai[1] = {node[v * tile + s] - mo}, ap[1] = {xrow[v]}, oo[1];
+                            mlp_relu2<1>(W1, hp, ai, ap, oo);
+                            m_st[(size_t)e * tile + s] = gru_cell(gru, mo, oo[0]);
+                            continue;
+                        }
+                        if constexpr (kV122) {         // decoder_v1_2_2.py:120-124,232-233: mlp([sum - m, prior]); m itself stays = m_p
+                            float ai[1] = {node[v * tile + s] - m_st[(size_t)e * tile + s]}, ap[1] = {xrow[v]}, oo[1];
+                            mlp_tanh2<1>(W1, hp, ai, ap, oo);
+                            const float tv = bp_log_abs_tanh_half<false>(oo[0], -46.0517019f);  // < 0 always
+                            t_st[(size_t)e * tile + s] = oo[0] < 0.f ? -tv : tv;                 // sign flag rides in the sign bit
+                            continue;
+                        }
                         if constexpr (kGRU) {          // QGNNNI_ca.py:103-106,197-198,208-209
                             const float mo = m_st[(size_t)e * tile + s];
                             float ai[1] = {node[v * tile + s] - mo + xrow[v]}, oo[1];
@@ -635,11 +691,11 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                 float acc = 0.f, cnt = 0.f;
                 for (int i = b; i < e_end; ++i) {
                     const int e = tb.ld(tb.chk_edges, i);
-                    if constexpr (kNBP) {
+                    if constexpr (kNBP || kV122) {
                         const float tv = t_st[(size_t)e * tile + s];
                         acc -= fabsf(tv);
                         cnt += tv > 0.f ? 1.f : 0.f;
-                    } else if constexpr (kGRU) {
+                    } else if constexpr (kGRU || kV3) {
                         acc += m_st[(size_t)e * tile + s];          // no tanh in this script's check phase
                     } else {
                         acc += t_st[(size_t)e * tile + s];
@@ -647,9 +703,23 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                     }
                 }
                 node[c * tile + s] = acc;
-                if constexpr (kIsBP || kNBP) node2[c * tile + s] = cnt;
+                if constexpr (kIsBP || kNBP || kV122) node2[c * tile + s] = cnt;
             }
             __syncthreads();
+            }
+            if constexpr (kV3) {
+                // the second read-out (decoder_v3_0.py:267-268, 276): mlp(sum at the check of the messages after the LAST variable phase)
+                if (it == p.T - 1 && (p.aux_prob || p.aux_logit)) {
+                    for (int c = r; c < C; c += R) {
+                        float xi[1] = {node[c * tile + s]}, oo[1];
+                        mlp_relu<1>(W3, hp, xi, oo);
+                        if (s < nvalid) {
+                            const long long row = didx ? (long long)__ldg(didx + s0 + s) : s0 + s;
+                            if (p.aux_logit) p.aux_logit[row * C + c] = oo[0];
+                            if (p.aux_prob) p.aux_prob[row * C + c] = sigmoid_neg(oo[0]);
+                        }
+                    }
+                }
             }
             // ---- C2: check-phase message, residual ----
             if constexpr (kNBP) {          // neural_BP.py:108-122 (eps2 = 1e-15) and :304 (+ alpha * m_p)
@@ -663,6 +733,30 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         cnt += xrow[V + c] < 0.f ? 1 : 0;
                         float* mp = m_st + (size_t)e * tile + s;
                         *mp = fmaf(alpha, *mp, bp_check_out(node[c * tile + s] + fabsf(tv), cnt & 1, 1e-15f));
+                    }
+                }
+            } else if constexpr (kV122) {  // decoder_v1_2_2.py:105-119 (eps 1e-20 / 1e-12, no input clamp) and :266 (+ m_p)
+                for (int i = 0; i < n_iter; ++i) {
+                    const int e = r + i * R;
+                    if (e < E) {
+                        const int c = tb.ld(tb.edge_chk, e);
+                        const float tv = t_st[(size_t)e * tile + s];
+                        int cnt = (int)(node2[c * tile + s] - (tv > 0.f ? 1.f : 0.f));
+                        cnt += xrow[V + c] < 0.f ? 1 : 0;
+                        float* mp = m_st + (size_t)e * tile + s;
+                        *mp = *mp + bp_check_out(node[c * tile + s] + fabsf(tv), cnt & 1, 1e-12f);
+                    }
+                }
+            } else if constexpr (kV3) {    // decoder_v3_0.py:109-112,229-231,242-243: rnn2(m, mlp2([sum - m, syndrome]))
+                for (int i = 0; i < n_iter; ++i) {
+                    const int e = r + i * R;
+                    if (e < E) {
+                        const int c = tb.ld(tb.edge_chk, e);
+                        float* mp = m_st + (size_t)e * tile + s;
+                        const float mo = *mp;
+                        float ai[1] = {node[c * tile + s] - mo}, ap[1] = {xrow[V + c]}, oo[1];
+                        mlp_relu2<1>(W2, hp, ai, ap, oo);
+                        *mp = gru_cell(gru + 12, mo, oo[0]);
                     }
                 }
             } else if constexpr (kGRU) {   // QGNNNI_ca.py:109,197-198,206-207
@@ -731,11 +825,11 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                 }
             }
             __syncthreads();
-            if constexpr (kGRU) {
+            if constexpr (kGRU || kV122) {
                 if (p.all_iters) emit((long long)it * p.B * V);
             }
         }
-        if (!(kGRU && p.all_iters)) emit(0);
+        if (!((kGRU || kV122) && p.all_iters)) emit(0);
         if (p.gate_out) {   // gated launch: publish the tile so the chunk's device->host copy can go
             __syncthreads();
             if (tid == 0) {
@@ -779,7 +873,8 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     const bool bp = m->program == GD_PROG_BP_QUANTUM || m->program == GD_PROG_BP_CLASSICAL || m->program == GD_PROG_NEURAL_BP;
     const int hid = bp ? 0 : m->hidden;
     const int hp = align_up(hid, 8);
-    const bool gru = m->program == GD_PROG_GRU_CA;
+    const bool gru = m->program == GD_PROG_GRU_CA || m->program == GD_PROG_V3_0;      // three MLP slots + two GRU cells
+    const bool sp2 = bp || m->program == GD_PROG_V1_2_2;                             // sum-product check phase: a second node array (sign counts)
     const int n_slots = bp ? 0 : ((m->program == GD_PROG_V2_4 || gru) ? 3 : 2);
     const int maxvc = V > C ? V : C;
     DecodeParams& p = out->p;
@@ -799,7 +894,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     const int thr_max = out->cps == 1 ? kMaxThreads : (kMaxThreads / out->cps) / 32 * 32;
     int off = 16;                                  // mbarrier
     // ReLU programs with h < 32: piecewise-linear tables (3 * NPAD floats per MLP) instead of the SoA weight rows
-    const bool relu_prog = m->program == GD_PROG_CGNNI || m->program == GD_PROG_QGNNI || gru;
+    const bool relu_prog = m->program == GD_PROG_CGNNI || m->program == GD_PROG_QGNNI || m->program == GD_PROG_GRU_CA;   // 1-input ReLU MLPs
     out->npad = (relu_prog && hid < 32 && !opt_on(OPT_NO_PWL)) ? (hid < 16 ? 16 : 32) : 0;
     p.wslot = 4 * hp > 3 * out->npad ? 4 * hp : 3 * out->npad;
     p.off_w = off; off += n_slots * p.wslot * 4 + (gru ? 24 * 4 : 0); off = align_up(off, 16);
@@ -849,7 +944,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     int tile = 0, resident = 0, R = 0;
     if (fits16 && off + tab_bytes < smem_max) {
         const int fixed = align_up(off + tab_bytes, 128);
-        const int64_t per_syn = ((int64_t)N + (int64_t)maxvc * (bp ? 2 : 1) + 2 * E64) * 4;
+        const int64_t per_syn = ((int64_t)N + (int64_t)maxvc * (sp2 ? 2 : 1) + 2 * E64) * 4;
         const int64_t tmax = (smem_max - fixed) / per_syn;
         if (tmax >= 8) {
             // Pick (tile, R, EB): tile = syndromes per CTA, R = threads per syndrome.  Score =
@@ -881,7 +976,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
                     const int n_iter = (E + r - 1) / r;
                     // per-thread cost of one iteration in issue slots: EB-blocked per-edge update
                     // (c_edge each) + the node sums this thread owns (c_ld per summed edge)
-                    const double c_edge = m->program == GD_PROG_V2_4 ? 16.0 * hp : (bp ? 200.0 : 40.0 + 6.0 * hp);
+                    const double c_edge = (m->program == GD_PROG_V2_4 || m->program == GD_PROG_V1_2_2) ? 16.0 * hp : (bp ? 200.0 : 40.0 + 6.0 * hp);
                     const double c_ld = 4.0;
                     const double node_cost = (double)((V + r - 1) / r) * g->max_var_deg + (double)((Cn + r - 1) / r) * g->max_chk_deg;
                     const double ideal = E * c_edge + 2.0 * E * c_ld;
@@ -903,7 +998,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
             p.off_tab = off;
             int o2 = fixed;
             p.off_x = o2; o2 += tile * N * 4; o2 = align_up(o2, 16);
-            p.off_node = o2; o2 += maxvc * tile * 4 * (bp ? 2 : 1);
+            p.off_node = o2; o2 += maxvc * tile * 4 * (sp2 ? 2 : 1);
             p.off_m = o2; o2 += (int)E64 * tile * 4;
             p.off_t = o2; o2 += (int)E64 * tile * 4;
             out->smem = o2;
@@ -983,7 +1078,7 @@ extern "C" int gd_decode_tables_info(const gd_graph* g, const gd_model* model, i
 static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
                            float* prob_dev, float* logit_dev, uint8_t* hard_dev, float* stash_dev, int64_t B,
                            void* stream, const gd::Gate* gate = nullptr, const gd::DeferList* dl = nullptr,
-                           uint32_t* hard_bits_dev = nullptr);
+                           uint32_t* hard_bits_dev = nullptr, float* aux_prob_dev = nullptr, float* aux_logit_dev = nullptr);
 
 bool gd::gated_plan(const gd_graph* g, const gd_model* model, int64_t B, int* tile, int* n_tiles) {
     gd::DecodePlan pl;
@@ -1007,6 +1102,17 @@ extern "C" int gd_decode_fwd(const gd_graph* gc, const gd_model* model, const fl
                              const float* x_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, int64_t B,
                              void* stream) {
     return decode_fwd_impl(gc, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, nullptr, B, stream);
+}
+
+extern "C" int gd_decode_fwd_aux(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
+                                 float* prob_dev, float* logit_dev, uint8_t* hard_dev, float* aux_prob_dev, float* aux_logit_dev,
+                                 int64_t B, void* stream) {
+    if ((aux_prob_dev || aux_logit_dev) && (!model || model->program != GD_PROG_V3_0)) {
+        gd::set_error("gd_decode_fwd_aux: program %d has no second read-out (GD_PROG_V3_0 only)", model ? model->program : -1);
+        return GD_ERR_UNSUPPORTED;
+    }
+    return decode_fwd_impl(gc, model, weights_dev, x_dev, prob_dev, logit_dev, hard_dev, nullptr, B, stream, nullptr, nullptr, nullptr,
+                           aux_prob_dev, aux_logit_dev);
 }
 
 // ---- packed form of the same decode (include/gnn_decode.h): what the reference's x actually carries per syndrome is ONE
@@ -1092,7 +1198,8 @@ int gd::decode_fwd_deferred(gd_graph* g, const gd_model* model, const float* wei
 
 static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const float* weights_dev, const float* x_dev,
                            float* prob_dev, float* logit_dev, uint8_t* hard_dev, float* stash_dev, int64_t B,
-                           void* stream, const gd::Gate* gate, const gd::DeferList* dl, uint32_t* hard_bits_dev) {
+                           void* stream, const gd::Gate* gate, const gd::DeferList* dl, uint32_t* hard_bits_dev, float* aux_prob_dev,
+                           float* aux_logit_dev) {
     gd_graph* g = const_cast<gd_graph*>(gc);
     GD_CHECK_ARG(g != nullptr, "gd_decode_fwd: graph is NULL");
     GD_CHECK_ARG(gd_model_valid(model), "gd_decode_fwd: invalid model (program=%d hidden=%d iters=%d)",
@@ -1127,6 +1234,7 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     }
     pl.p.x = x_dev; pl.p.prob = prob_dev; pl.p.logit = logit_dev; pl.p.hard = hard_dev; pl.p.weights = weights_dev;
     pl.p.stash = stash_dev; pl.p.hard_bits = hard_bits_dev;
+    pl.p.aux_prob = aux_prob_dev; pl.p.aux_logit = aux_logit_dev;
     if (dl) { pl.p.defer_count = dl->count; pl.p.defer_idx = dl->idx; }
     if (gate) {
         GD_CHECK_ARG(pl.resident && gate->chunk_tiles > 0, "gd_decode_host: gated launch needs the resident kernel");
@@ -1140,7 +1248,8 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     GD_CHECK_ARG(model->program != GD_PROG_NEURAL_BP || model->hidden == g->E,
                  "gd_decode_fwd: GD_PROG_NEURAL_BP needs model.hidden == E (%lld per-edge weights), got %d",
                  (long long)g->E, model->hidden);
-    if (!pl.resident && (model->program == GD_PROG_NEURAL_BP || model->program == GD_PROG_GRU_CA)) {
+    if (!pl.resident && (model->program == GD_PROG_NEURAL_BP || model->program == GD_PROG_GRU_CA || model->program == GD_PROG_V3_0 ||
+                         model->program == GD_PROG_V1_2_2)) {
         gd::set_error("gd_decode_fwd: program %d has a resident kernel only and this code's edge state does not fit "
                       "shared memory", model->program);
         return GD_ERR_UNSUPPORTED;
@@ -1165,6 +1274,8 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
         case GD_PROG_BP_QUANTUM: rc = gd::launch_decode<GD_PROG_BP_QUANTUM>(pl, st); break;
         case GD_PROG_NEURAL_BP: rc = gd::launch_decode<GD_PROG_NEURAL_BP>(pl, st); break;
         case GD_PROG_GRU_CA: rc = gd::launch_decode<GD_PROG_GRU_CA>(pl, st); break;
+        case GD_PROG_V3_0: rc = gd::launch_decode<GD_PROG_V3_0>(pl, st); break;
+        case GD_PROG_V1_2_2: rc = gd::launch_decode<GD_PROG_V1_2_2>(pl, st); break;
         default: rc = gd::launch_decode<GD_PROG_BP_CLASSICAL>(pl, st); break;
     }
     if (prev != g->device) cudaSetDevice(prev);

@@ -34,6 +34,8 @@ extern "C" int64_t gd_weights_size(const gd_model* m) {
         case GD_PROG_QGNNI: return 6 * h + 2;
         case GD_PROG_NEURAL_BP: return (2 * (int64_t)m->iters + 2) * h + 1;
         case GD_PROG_GRU_CA: return 9 * h + 27;
+        case GD_PROG_V3_0: return 11 * h + 27;
+        case GD_PROG_V1_2_2: return 8 * h + 2;
         default: return 0;
     }
 }

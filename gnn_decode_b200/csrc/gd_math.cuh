@@ -199,6 +199,63 @@ __device__ __forceinline__ void mlp_relu(const MlpSmem& W, int hp, const float (
     for (int j = 0; j < EB; ++j) out[j] = acc[j] + W.b2;
 }
 
+// 2 -> h -> 1 ReLU MLP (decoder_v3_0.py:217-222: [sum over the other edges, node input]); W.w1b holds the second input's weights
+template <int EB>
+__device__ __forceinline__ void mlp_relu2(const MlpSmem& W, int hp, const float (&x0)[EB], const float (&x1)[EB], float (&out)[EB]) {
+    float acc[EB];
+#pragma unroll
+    for (int j = 0; j < EB; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < hp; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(W.w1a + k);
+        const float4 d4 = *reinterpret_cast<const float4*>(W.w1b + k);
+        const float4 b4 = *reinterpret_cast<const float4*>(W.b1 + k);
+        const float4 c4 = *reinterpret_cast<const float4*>(W.w2 + k);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float b[4] = {b4.x, b4.y, b4.z, b4.w}, c[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < EB; ++j) {
+                const float z = fmaf(a[u], x0[j], fmaf(d[u], x1[j], b[u]));
+                acc[j] = fmaf(c[u], fmaxf(z, 0.f), acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < EB; ++j) out[j] = acc[j] + W.b2;
+}
+
+__device__ __forceinline__ float rcp_fast(float x);
+// 2 -> h -> 1 Tanh MLP (decoder_v1_2_2.py:216-220, 245-248; h = 256).  The staged first layer is pre-scaled by 2 log2(e), so that
+// tanh(z) = 1 - 2 / (1 + 2^(z')) costs one ex2 and one rcp (abs. error ~2e-7, as tanh_half_fast); padded units have w2 = 0.
+template <int EB>
+__device__ __forceinline__ void mlp_tanh2(const MlpSmem& W, int hp, const float (&x0)[EB], const float (&x1)[EB], float (&out)[EB]) {
+    float acc[EB];
+#pragma unroll
+    for (int j = 0; j < EB; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < hp; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(W.w1a + k);
+        const float4 d4 = *reinterpret_cast<const float4*>(W.w1b + k);
+        const float4 b4 = *reinterpret_cast<const float4*>(W.b1 + k);
+        const float4 c4 = *reinterpret_cast<const float4*>(W.w2 + k);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float b[4] = {b4.x, b4.y, b4.z, b4.w}, c[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < EB; ++j) {
+                const float z2 = fmaf(a[u], x0[j], fmaf(d[u], x1[j], b[u]));         // = 2 log2(e) z
+                const float th = fmaf(-2.0f, rcp_fast(1.0f + ex2_approx(z2)), 1.0f);
+                acc[j] = fmaf(c[u], th, acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < EB; ++j) out[j] = acc[j] + W.b2;
+}
+
 // ---- 1 -> h -> 1 ReLU MLP as the piecewise-linear function it is --------------------------------
 // f(x) = b2 + sum_u c_u relu(a_u x + b_u) has at most h breakpoints t_u = -b_u / a_u; between two
 // consecutive breakpoints it is one line S_j x + I_j.  One warp builds the sorted breakpoints and

@@ -27,7 +27,10 @@ __global__ void __launch_bounds__(128) propagate_kernel(const PropParams p) {
     constexpr bool kIsBP = (PROG == GD_PROG_BP_QUANTUM || PROG == GD_PROG_BP_CLASSICAL);
     constexpr bool kNBP = (PROG == GD_PROG_NEURAL_BP);
     constexpr bool kGRU = (PROG == GD_PROG_GRU_CA);
-    constexpr bool kHasMlp = (PROG == GD_PROG_V2_4) || kGRU || (!kIsBP && !kNBP && PHASE == GD_PHASE_CHK);
+    constexpr bool kV3 = (PROG == GD_PROG_V3_0);         // decoder_v3_0.py:103-112: plain sums, cat the node input in both phases
+    constexpr bool kV122 = (PROG == GD_PROG_V1_2_2);     // decoder_v1_2_2.py:105-124: cat prior / sum-product check rule
+    // (V3_0 / V1_2_2: the un-fused form only -- their update()s run in the caller, or everything in the fused decoder)
+    constexpr bool kHasMlp = (PROG == GD_PROG_V2_4) || kGRU || (!kIsBP && !kNBP && !kV3 && !kV122 && PHASE == GD_PHASE_CHK);
     const int hp = p.hp, h = p.hid;
     MlpSmem W{};
     if (kHasMlp && p.fuse) {
@@ -59,9 +62,9 @@ __global__ void __launch_bounds__(128) propagate_kernel(const PropParams p) {
         float acc = 0.f, cnt = 0.f;
         for (int i = e0; i < e1; ++i) {
             const float v = mb[ids[i]];
-            if constexpr (PHASE == GD_PHASE_VAR || kGRU) {
+            if constexpr (PHASE == GD_PHASE_VAR || kGRU || kV3) {
                 acc += v;                                      // QGNNNI_ca.py:101: no tanh in either phase
-            } else if constexpr (kNBP) {
+            } else if constexpr (kNBP || kV122) {
                 acc += bp_log_abs_tanh_half<false>(v, -46.0517019f);
                 cnt += v < 0.f ? 1.f : 0.f;
             } else if constexpr (kIsBP) {
@@ -85,6 +88,8 @@ __global__ void __launch_bounds__(128) propagate_kernel(const PropParams p) {
                         mlp_softplus<1, true>(W, hp, a0, a1, o);
                         res0 = o[0];
                     } else { res0 = ext; two_out = true; }
+                } else if constexpr (kV3 || kV122) {          // cat[ext, prior]; update() is the caller's
+                    res0 = ext; two_out = true;
                 } else if constexpr (kNBP) {                  // neural_BP.py:122-124,253-255: cat[ext, prior]; update = ext + prior * W_p
                     if (p.fuse) res0 = ext + extra * p.w[e];
                     else { res0 = ext; two_out = true; }
@@ -98,6 +103,13 @@ __global__ void __launch_bounds__(128) propagate_kernel(const PropParams p) {
                 } else {
                     res0 = ext + extra;                        // + post / extra; update = identity
                 }
+            } else if constexpr (kV3) {                       // decoder_v3_0.py:103,111: cat[sum - self, syndrome]
+                res0 = acc - v; two_out = true;
+            } else if constexpr (kV122) {                     // decoder_v1_2_2.py:105-119: eps 1e-20 / 1e-12, no input clamp; identity update
+                const float lg = bp_log_abs_tanh_half<false>(v, -46.0517019f);
+                int k = (int)(cnt - (v < 0.f ? 1.f : 0.f));
+                k += extra < 0.f ? 1 : 0;
+                res0 = bp_check_out(acc - lg, k & 1, 1e-12f);
             } else if constexpr (kGRU) {                      // QGNNNI_ca.py:109,206-207: mlp2((sum - self) * s)
                 res0 = (acc - v) * extra;
                 if (p.fuse) {
@@ -149,8 +161,9 @@ static int launch_prop(const PropParams& p, int phase, int grid, int smem, cudaS
 }  // namespace gd
 
 extern "C" int gd_propagate_features(int32_t program, int32_t phase) {
-    if (phase == GD_PHASE_VAR) return (program == GD_PROG_V2_4 || program == GD_PROG_NEURAL_BP) ? 2 : 1;
-    if (phase == GD_PHASE_CHK) return (program == GD_PROG_V2_4 || program == GD_PROG_QGNNI) ? 2 : 1;
+    if (phase == GD_PHASE_VAR)
+        return (program == GD_PROG_V2_4 || program == GD_PROG_NEURAL_BP || program == GD_PROG_V3_0 || program == GD_PROG_V1_2_2) ? 2 : 1;
+    if (phase == GD_PHASE_CHK) return (program == GD_PROG_V2_4 || program == GD_PROG_QGNNI || program == GD_PROG_V3_0) ? 2 : 1;
     return -1;
 }
 
@@ -166,7 +179,12 @@ extern "C" int gd_propagate_fwd(const gd_graph* g, const gd_model* model, int32_
     const int prog = model->program;
     const bool x_optional = (prog == GD_PROG_CGNNI || prog == GD_PROG_BP_CLASSICAL) && phase == GD_PHASE_CHK;
     GD_CHECK_ARG(x_dev || x_optional, "gd_propagate_fwd: x (extra/post) is NULL");
-    const bool bp = prog == GD_PROG_BP_QUANTUM || prog == GD_PROG_BP_CLASSICAL || prog == GD_PROG_NEURAL_BP;
+    const bool ext_only = prog == GD_PROG_V3_0 || prog == GD_PROG_V1_2_2;     // update() of these scripts is not part of this kernel
+    if (ext_only && fuse_update && !(prog == GD_PROG_V1_2_2 && phase == GD_PHASE_CHK)) {
+        gd::set_error("gd_propagate_fwd: program %d has no fused update in the propagate kernel (use fuse_update = 0 or gd_decode_fwd)", prog);
+        return GD_ERR_UNSUPPORTED;
+    }
+    const bool bp = prog == GD_PROG_BP_QUANTUM || prog == GD_PROG_BP_CLASSICAL || prog == GD_PROG_NEURAL_BP || ext_only;
     const bool has_mlp = fuse_update && ((!bp && (prog == GD_PROG_V2_4 || prog == GD_PROG_GRU_CA || phase == GD_PHASE_CHK)) ||
                                          (prog == GD_PROG_NEURAL_BP && phase == GD_PHASE_VAR));   // W_p[E] there
     GD_CHECK_ARG(!has_mlp || weights_dev, "gd_propagate_fwd: weights is NULL");
@@ -191,6 +209,8 @@ extern "C" int gd_propagate_fwd(const gd_graph* g, const gd_model* model, int32_
         case GD_PROG_BP_QUANTUM: rc = gd::launch_prop<GD_PROG_BP_QUANTUM>(p, phase, (int)blocks, smem, st); break;
         case GD_PROG_NEURAL_BP: rc = gd::launch_prop<GD_PROG_NEURAL_BP>(p, phase, (int)blocks, smem, st); break;
         case GD_PROG_GRU_CA: rc = gd::launch_prop<GD_PROG_GRU_CA>(p, phase, (int)blocks, smem, st); break;
+        case GD_PROG_V3_0: rc = gd::launch_prop<GD_PROG_V3_0>(p, phase, (int)blocks, smem, st); break;
+        case GD_PROG_V1_2_2: rc = gd::launch_prop<GD_PROG_V1_2_2>(p, phase, (int)blocks, smem, st); break;
         default: rc = gd::launch_prop<GD_PROG_BP_CLASSICAL>(p, phase, (int)blocks, smem, st); break;
     }
     if (prev != g->device) cudaSetDevice(prev);

@@ -50,14 +50,18 @@ enum gd_program {
     /* the "next" update programs; resident kernel only: */
     GD_PROG_NEURAL_BP = 5,    /* quantum/neural_BP.py:236-314    sum-product + per-edge learned weights,
                                  2*Nc un-tied layers, gated residual alpha * m_p, weighted read-out */
-    GD_PROG_GRU_CA = 6        /* quantum/QGNNNI_ca.py:177-251    hidden 20 ReLU MLPs + GRUCell(1,1) updates,
+    GD_PROG_GRU_CA = 6,       /* quantum/QGNNNI_ca.py:177-251    hidden 20 ReLU MLPs + GRUCell(1,1) updates,
                                  sign-multiplied check phase, one read-out per iteration              */
+    GD_PROG_V3_0 = 7,         /* quantum/decoder_v3_0.py:199-290 hidden 10 ReLU MLPs of [sum, node input] + GRUCell(1,1)
+                                 per phase, no tanh; a SECOND read-out at the check nodes (gd_decode_fwd_aux) */
+    GD_PROG_V1_2_2 = 8        /* quantum/decoder_v1_2_2.py:212-278 hidden 256 Tanh MLP of [sum, prior] (variable phase),
+                                 sum-product check phase + residual, Tanh-MLP read-out of EVERY iteration */
 };
 
 /* gd_model.flags */
-#define GD_FLAG_ALL_ITERS 1   /* GD_PROG_GRU_CA only: the reference returns a LIST of Nc predictions
-                                 (deep supervision, QGNNNI_ca.py:239-249); prob / logit / hard are then
-                                 [iters, B, V] instead of [B, V] (the last iteration otherwise) */
+#define GD_FLAG_ALL_ITERS 1   /* GD_PROG_GRU_CA / GD_PROG_V1_2_2: the reference returns a LIST of Nc predictions
+                                 (deep supervision, QGNNNI_ca.py:239-249, decoder_v1_2_2.py:267-278); prob / logit /
+                                 hard are then [iters, B, V] instead of [B, V] (the last iteration otherwise) */
 
 /* flow of one propagate(): which node type the reduce runs over. */
 enum gd_phase {
@@ -81,12 +85,16 @@ typedef struct gd_graph gd_graph;
  *                ((2 iters + 2) E + 1 floats; `hidden` carries E, checked against the graph)
  *   GRU_CA     : ggc1.mlp1{0.weight[h,1],0.bias[h],2.weight[1,h],2.bias[1]}, ggc1.rnn{weight_ih[3],
  *                weight_hh[3],bias_ih[3],bias_hh[3]}, ggc2.mlp2{...}, ggc2.rnn{...}, mlp{...}   (9h+27)
+ *   V3_0       : ggc1.mlp1{0.weight[h,2],0.bias[h],2.weight[1,h],2.bias[1]}, ggc1.rnn1{weight_ih[3],weight_hh[3],
+ *                bias_ih[3],bias_hh[3]}, ggc2.mlp2{0.weight[h,2],...}, ggc2.rnn2{...}, mlp{0.weight[h,1],...}   (11h+27)
+ *                (the state_dict's ggc1.mlp2 / ggc1.rnn2 / ggc2.mlp1 / ggc2.rnn1 are never used by the forward)
+ *   V1_2_2     : ggc1.mlp{0.weight[h,2],0.bias[h],2.weight[1,h],2.bias[1]}, mlp{0.weight[h,2],...}              (8h+2)
  */
 typedef struct gd_model {
     int32_t program;   /* enum gd_program                                   */
     int32_t hidden;    /* h: 128 for V2_4, 10 for CGNNI/QGNNI, 0 for BP, 20 for GRU_CA; E for NEURAL_BP */
     int32_t iters;     /* Nc (T) message-passing iterations                  */
-    int32_t flags;     /* 0, or GD_FLAG_ALL_ITERS (GRU_CA)                   */
+    int32_t flags;     /* 0, or GD_FLAG_ALL_ITERS (GRU_CA, V1_2_2)           */
 } gd_model;
 
 const char* gd_last_error(void);
@@ -149,6 +157,16 @@ int gd_propagate_fwd(const gd_graph* g, const gd_model* model, int32_t phase, in
 int gd_decode_fwd(const gd_graph* g, const gd_model* model, const float* weights_dev,
                   const float* x_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev,
                   int64_t B, void* stream);
+
+/* gd_decode_fwd plus the SECOND read-out of the programs that have one (any output may be NULL):
+ *   GD_PROG_V3_0: aux_prob_dev / aux_logit_dev [B, C] = the check-node prediction res_p = mlp(sum over the check's edges of
+ *   the messages after the LAST variable phase) (decoder_v3_0.py:267-268, 276); prob = sigmoid(-logit).
+ * The reference returns both read-outs over all V+C nodes; the remaining rows are constants of the inputs (res at a check
+ * row = mlp(0) + its syndrome input, res_p at a variable row = mlp(0)) that the caller's drop-in class fills in.
+ * Other programs: GD_ERR_UNSUPPORTED when an aux pointer is given. */
+int gd_decode_fwd_aux(const gd_graph* g, const gd_model* model, const float* weights_dev,
+                      const float* x_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev,
+                      float* aux_prob_dev, float* aux_logit_dev, int64_t B, void* stream);
 
 /* The same decode with PACKED inputs and outputs.  What the reference's x carries per syndrome (gen_syn,
  * quantum/error_generate.py:258, 270-276) is ONE prior value log((1-p)/p), repeated on all V variables, and C check signs:

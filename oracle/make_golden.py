@@ -202,6 +202,48 @@ def _v2_4_1_case(name, consts, T, seed=1234):
         print("wrote %s  (V=%d C=%d E=%d B=%d T=%d, prob range %.3g..%.3g)" % (path, rows, cols, E, B, T, out["prob"].min(), out["prob"].max()))
 
 
+def _v3_v122_case(name, script, program, consts, T, seed=1234):
+    """quantum/decoder_v3_0.py (2-input ReLU MLPs + GRUCell per phase, a second read-out at the check nodes) and
+    quantum/decoder_v1_2_2.py (Tanh MLPs, sum-product check phase, one prediction per iteration).  No shipped checkpoint matches
+    either: the script's own initialisation, biases perturbed with seeded noise so that no term is identically zero.
+    decoder_v3_0 compares the loop index with the script's GLOBAL Nc (:267), so that constant is substituted too."""
+    if program == "v3_0":
+        consts = dict(consts, Nc=str(T))
+    with ref_loader.reference_session("quantum"):
+        ns = ref_loader.load_reference(script, consts=consts, seed=seed)
+        rows, cols, B = int(ns.rows), int(ns.cols), int(ns.BATCH_SIZE)
+        torch.manual_seed(seed + 1)
+        dec = ns.GNNI(T)
+        with torch.no_grad():
+            for n_, p_ in dec.named_parameters():
+                if "bias" in n_:
+                    p_.add_(0.2 * torch.randn_like(p_))
+                if program == "v3_0" and ("rnn" in n_ or n_.endswith(".2.weight")):
+                    p_.mul_(3.0)        # default-initialised GRUCell(1,1) + 10-unit MLPs barely move the output: make the messages matter
+        dec.eval()
+        batch = next(iter(ns.train_loader))
+        with torch.no_grad():
+            pred = dec(batch)
+        E = batch.edge_index.size(1) // B
+        ei = batch.edge_index[:, :E].clone()
+        N = rows + cols
+        out = dict(program=program, script=script, V=rows, C=cols, E=E, B=B, T=T, dtype="float64",
+                   edge_index=_np(ei).astype(np.int64), H=_np(ns.H).astype(np.uint8), x=_np(batch.x.reshape(B, N)),
+                   y=_np(batch.y.reshape(B, -1)), m0=np.zeros((B, E)), phase_var=np.zeros((B, E)), phase_chk=np.zeros((B, E)))
+        if program == "v3_0":           # the reference returns [sigmoid(-res), sigmoid(-res_p)], both over ALL V+C nodes
+            out["prob_all"] = _np(pred[0].reshape(B, N))
+            out["prob_p_all"] = _np(pred[1].reshape(B, N))
+            out["prob"] = out["prob_all"][:, :rows]
+        else:                           # a list of Nc predictions [B*V, 1]
+            out["all_prob"] = np.stack([_np(p_.reshape(B, rows)) for p_ in pred], 0)
+            out["prob"] = out["all_prob"][-1]
+        for k, v in dec.state_dict().items():
+            out["w:" + k] = _np(v)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote %s  (V=%d C=%d E=%d B=%d T=%d, prob range %.3g..%.3g)" % (path, rows, cols, E, B, T, out["prob"].min(), out["prob"].max()))
+
+
 def _grad_case(name, consts, ckpt, T, seed=1234):
     """One train-step gradient of the reference: loss = criterion(decoder(datas), datas);
     loss.backward()  (decoder_v2_4.py:331-335) -> per-parameter gradients."""
@@ -292,6 +334,8 @@ def main():
     _ext_case("ext_gru_ca_toricL4", "quantum/QGNNNI_ca.py", "gru_ca", dict(q_small, L="4"), T=6)
     _v1_1_case("ext_v1_1_onehot_toricL4", dict(q_small, L="4"), T=5)
     _v2_4_1_case("ext_v2_4_1_toricL4", dict(q_small, L="4"), T=4)
+    _v3_v122_case("ext_v3_0_toricL4", "quantum/decoder_v3_0.py", "v3_0", dict(q_small, L="4"), T=6)
+    _v3_v122_case("ext_v1_2_2_toricL4", "quantum/decoder_v1_2_2.py", "v1_2_2", dict(q_small, L="4"), T=5)
     _codes()
 
 

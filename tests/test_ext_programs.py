@@ -117,6 +117,11 @@ class _Data(object):
         self.edge_index = g.batched_edge_index().to(dev)
 
 
+def _graph(g, dev):
+    from gnn_decode_b200.graph import TannerGraph
+    return TannerGraph(g.edge_index, g.V, g.C, dev)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_fused_decoder_matches_reference(name):
@@ -273,3 +278,131 @@ def test_v2_4_1_drop_in_matches_reference_fixture():
     worst, max_err = _close(logit, ref["logit"], RTOL)
     assert worst <= 1.0, "logits: %.3g x the bar (max abs err %.3g)" % (worst, max_err)
     assert (prob.reshape(g.B, g.V).cpu() - g.prob).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("name,prog", [("ext_v3_0_toricL4", "v3_0"), ("ext_v1_2_2_toricL4", "v1_2_2")])
+def test_v3_0_and_v1_2_2_restatements_match_golden(name, prog):
+    """quantum/decoder_v3_0.py (2-input ReLU MLPs + GRUCell per phase, two read-outs over all V+C nodes) and
+    quantum/decoder_v1_2_2.py (Tanh MLP variable phase, sum-product check phase, a prediction per iteration): the restatements
+    reproduce what the reference's own classes produced, bit for bit."""
+    g = Golden(name)
+    z = np.load(__file__.rsplit("/", 1)[0] + "/golden/%s.npz" % name)
+    out = restate.decode(prog, g.edge_index, g.V, g.C, g.x, g.weights, T=g.T, dtype=g.dtype)
+    if prog == "v3_0":
+        assert torch.equal(out["prob_all"], torch.from_numpy(z["prob_all"])) and torch.equal(out["prob_p_all"], torch.from_numpy(z["prob_p_all"]))
+        assert torch.equal(out["prob"], g.prob)
+    else:
+        assert torch.equal(out["all_prob"], torch.from_numpy(z["all_prob"])) and out["all_prob"].shape == (g.T, g.B, g.V)
+
+
+@pytest.mark.parametrize("script,prog,T", [("quantum/decoder_v3_0.py", "v3_0", 3), ("quantum/decoder_v1_2_2.py", "v1_2_2", 3)])
+def test_v3_0_and_v1_2_2_restatements_match_live_reference(script, prog, T):
+    if not ref_loader.reference_available():
+        pytest.skip("reference tree not mounted")
+    consts = {"BATCH_SIZE": "6", "run1": "6", "run2": "6", "L": "4"}
+    if prog == "v3_0":
+        consts["Nc"] = str(T)                                  # the script compares the loop index with its GLOBAL Nc (:267)
+    with ref_loader.reference_session("quantum"):
+        ns = ref_loader.load_reference(script, consts=consts, seed=11)
+        torch.manual_seed(12)
+        dec = ns.GNNI(T)
+        with torch.no_grad():
+            for n_, p_ in dec.named_parameters():
+                if "bias" in n_:
+                    p_.add_(0.3 * torch.randn_like(p_))
+        batch = next(iter(ns.train_loader))
+        with torch.no_grad():
+            pred = dec(batch)
+        rows, cols = int(ns.rows), int(ns.cols)
+        E = batch.edge_index.size(1) // 6
+        got = restate.decode(prog, batch.edge_index[:, :E].clone(), rows, cols, batch.x.reshape(6, rows + cols), dec.state_dict(), T=T)
+        if prog == "v3_0":
+            assert torch.equal(got["prob_all"].reshape(-1, 1), pred[0]) and torch.equal(got["prob_p_all"].reshape(-1, 1), pred[1])
+        else:
+            assert len(pred) == T
+            for i in range(T):
+                assert torch.equal(got["all_prob"][i].reshape(-1, 1), pred[i])
+
+
+@pytest.mark.gpu
+def test_v1_2_2_fused_decoder_matches_reference_fixture():
+    """decoder_v1_2_2 through the drop-in GNNI (fused kernel, GD_PROG_V1_2_2 with a read-out per iteration): the list of predictions
+    against what the reference itself produced, logits against the fp64 restatement."""
+    from gnn_decode_b200.quantum import decoder_v1_2_2
+    g = Golden("ext_v1_2_2_toricL4")
+    z = np.load(__file__.rsplit("/", 1)[0] + "/golden/ext_v1_2_2_toricL4.npz")
+    dev = torch.device("cuda", 0)
+    dec = decoder_v1_2_2.GNNI(g.T)
+    dec.load_state_dict(g.weights, strict=True)
+    dec = dec.to(dev).eval()
+    with torch.no_grad():
+        preds = dec(_Data(g, dev))
+    assert isinstance(preds, list) and len(preds) == g.T and preds[0].shape == (g.B * g.V, 1) and preds[0].dtype == torch.float64
+    ref = restate.decode("v1_2_2", g.edge_index, g.V, g.C, g.x, g.weights, T=g.T)
+    _, logits = dec.decode_all(g.x.to(dev), graph=_graph(g, dev), return_logits=True)
+    for i in range(g.T):
+        worst, max_err = _close(logits[i], ref["all_logit"][i], RTOL)
+        assert worst <= 1.0, "iteration %d logits: %.3g x the bar (max abs err %.3g)" % (i, worst, max_err)
+        assert (preds[i].reshape(g.B, g.V).cpu() - torch.from_numpy(z["all_prob"][i])).abs().max().item() < 2e-5
+    assert torch.equal(dec.decode(g.x.to(dev), graph=_graph(g, dev)), dec.decode_all(g.x.to(dev), graph=_graph(g, dev))[-1])
+
+
+@pytest.mark.gpu
+def test_v1_2_2_layers_run_the_propagate_kernel():
+    """The per-layer classes (the reference's plugin API): ggc1 = propagate kernel + this script's Tanh MLP in torch, ggc2 = the
+    sum-product check rule in the kernel; iterated by hand as GNNI.forward does (:264-267), the messages match the restatement."""
+    from gnn_decode_b200.quantum import decoder_v1_2_2
+    g = Golden("ext_v1_2_2_toricL4")
+    dev = torch.device("cuda", 0)
+    dec = decoder_v1_2_2.GNNI(g.T)
+    dec.load_state_dict(g.weights, strict=True)
+    dec = dec.to(dev).eval().bind_code(g.V, g.C)
+    d = _Data(g, dev)
+    ei = torch.cat([d.edge_index[0].unsqueeze(0), d.edge_index[1].unsqueeze(0).add(g.V)], 0)
+    m = torch.zeros((ei.size(1), 1), dtype=torch.float64, device=dev)
+    with torch.no_grad():
+        for _ in range(g.T):
+            m_p = m.clone()
+            m = dec.ggc1(m, ei, d.x)
+            m = dec.ggc2(m, ei, d.x) + m_p
+    ref = restate.decode("v1_2_2", g.edge_index, g.V, g.C, g.x, g.weights, T=g.T)["m"]
+    err = (m.reshape(g.B, g.E).cpu() - ref).abs()
+    assert float((err / ref.abs().clamp_min(1.0)).max()) <= 1e-4, err.max().item()
+
+
+@pytest.mark.gpu
+def test_v3_0_fused_decoder_matches_reference_fixture():
+    """decoder_v3_0 through the drop-in GNNI (fused kernel GD_PROG_V3_0 + its second read-out): the reference's two [B*(V+C), 1]
+    outputs, logits of both read-outs against the fp64 restatement; the per-layer classes (propagate kernel + torch MLP + GRUCell)
+    reproduce the messages."""
+    from gnn_decode_b200.quantum import decoder_v3_0
+    g = Golden("ext_v3_0_toricL4")
+    z = np.load(__file__.rsplit("/", 1)[0] + "/golden/ext_v3_0_toricL4.npz")
+    dev = torch.device("cuda", 0)
+    dec = decoder_v3_0.GNNI(g.T)
+    dec.load_state_dict(g.weights, strict=True)
+    dec = dec.to(dev).eval()
+    d = _Data(g, dev)
+    with torch.no_grad():
+        out = dec(d)
+    N = g.V + g.C
+    assert isinstance(out, list) and len(out) == 2 and out[0].shape == (g.B * N, 1) and out[0].dtype == torch.float64
+    assert (out[0].reshape(g.B, N).cpu() - torch.from_numpy(z["prob_all"])).abs().max().item() < 1e-5
+    assert (out[1].reshape(g.B, N).cpu() - torch.from_numpy(z["prob_p_all"])).abs().max().item() < 1e-5
+    ref = restate.decode("v3_0", g.edge_index, g.V, g.C, g.x, g.weights, T=g.T)
+    tg = _graph(g, dev)
+    prob, prob_c, logit, logit_c = dec.decode_aux(g.x.to(dev), graph=tg, return_logits=True)
+    for got, want in ((logit, ref["logit"]), (logit_c, ref["logit_chk"])):
+        worst, max_err = _close(got, want, RTOL)
+        assert worst <= 1.0, "logits: %.3g x the bar (max abs err %.3g)" % (worst, max_err)
+    assert torch.equal(dec.decode(g.x.to(dev), graph=tg), prob)
+    # per-layer classes, iterated as GNNI.forward does (:264-270)
+    ei = torch.cat([d.edge_index[0].unsqueeze(0), d.edge_index[1].unsqueeze(0).add(g.V)], 0)
+    m = torch.zeros((ei.size(1), 1), dtype=torch.float64, device=dev)
+    dec.bind_code(g.V, g.C)
+    with torch.no_grad():
+        for _ in range(g.T):
+            m = dec.ggc1(m, ei, d.x)
+            m = dec.ggc2(m, ei, d.x)
+    err = (m.reshape(g.B, g.E).cpu() - ref["m"]).abs()
+    assert float((err / ref["m"].abs().clamp_min(1.0)).max()) <= 1e-4, err.max().item()

@@ -25,7 +25,7 @@ def _random_pcm(rng, C, V, max_row):
 
 
 def _decoder(program, T, E):
-    from gnn_decode_b200.quantum import decoder_v2_4, QGNNI, BP, neural_BP, QGNNNI_ca
+    from gnn_decode_b200.quantum import decoder_v2_4, QGNNI, BP, neural_BP, QGNNNI_ca, decoder_v3_0, decoder_v1_2_2
     from gnn_decode_b200.classical import CGNNI, BP as CBP
     if program == "neural_bp":
         dec = neural_BP.GNNI(T, n_edges=E)
@@ -34,11 +34,11 @@ def _decoder(program, T, E):
                 p_.copy_(torch.full_like(p_, 0.25) if n_ == "alpha" else torch.rand_like(p_) * 0.6 + 0.6)
         return dec
     return {"v2_4": decoder_v2_4.GNNI, "qgnni": QGNNI.GNNI, "bp_quantum": BP.GNNI, "cgnni": CGNNI.GNNI,
-            "bp_classical": CBP.GNNI, "gru_ca": QGNNNI_ca.GNNI}[program](T)
+            "bp_classical": CBP.GNNI, "gru_ca": QGNNNI_ca.GNNI, "v3_0": decoder_v3_0.GNNI, "v1_2_2": decoder_v1_2_2.GNNI}[program](T)
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
-@pytest.mark.parametrize("program", ["v2_4", "qgnni", "cgnni", "bp_quantum", "bp_classical", "neural_bp", "gru_ca"])
+@pytest.mark.parametrize("program", ["v2_4", "qgnni", "cgnni", "bp_quantum", "bp_classical", "neural_bp", "gru_ca", "v3_0", "v1_2_2"])
 def test_random_graph_matches_oracle(program, seed, gd_opt):
     rng = np.random.RandomState(100 * seed + 7)
     C, V = rng.randint(3, 14), rng.randint(6, 40)
@@ -54,11 +54,26 @@ def test_random_graph_matches_oracle(program, seed, gd_opt):
     else:
         x[:, V:] = 0.0
     dec = _decoder(program, T, E).to(DEV).eval()
+    if program == "v3_0":                                      # default GRUCell(1,1) / 10-unit MLPs barely move anything: make the messages matter
+        with torch.no_grad():
+            for n_, p_ in dec.named_parameters():
+                if "rnn" in n_ or n_.endswith(".2.weight"):
+                    p_.mul_(3.0)
     w = {k: v.detach().cpu() for k, v in dec.state_dict().items()}
-    ref = restate.decode(program, ei, V, C, x, w, T=T, dtype=torch.float64)["logit"]
-    bp = "bp" in program
+    ref_all = restate.decode(program, ei, V, C, x, w, T=T, dtype=torch.float64)
+    ref = ref_all["logit"]
+    bp = "bp" in program or program == "v1_2_2"
     rtol = 2e-3 if bp else 1e-4
-    modes = ["resident"] + (["streamed"] if program not in ("neural_bp", "gru_ca") else [])
+    modes = ["resident"] + (["streamed"] if program not in ("neural_bp", "gru_ca", "v3_0", "v1_2_2") else [])
+    if program == "v3_0":                                      # the second read-out, at the check nodes
+        _, _, _, logit_c = dec.decode_aux(x.to(DEV), graph=g, return_logits=True)
+        rc = ref_all["logit_chk"]
+        assert bool(((logit_c.double().cpu() - rc).abs() <= 1e-4 * rc.abs().clamp_min(1.0)).all())
+    if program == "v1_2_2":                                    # every iteration's read-out
+        _, la = dec.decode_all(x.to(DEV), graph=g, return_logits=True)
+        ra = ref_all["all_logit"]
+        ok_all = (la.double().cpu() - ra).abs() <= 2e-3 * ra.abs().clamp_min(1.0)
+        assert bool((ok_all | (ra.abs() > 30)).all()), (la.double().cpu() - ra).abs().max().item()
     for mode in modes:
         if mode == "streamed":
             gd_opt.set("GD_FORCE_STREAMED")
