@@ -58,7 +58,8 @@ struct LeanParams {
     const float4* ctab; const float4* rtab; const float4* vtab;   // global tables: (n + 2) pieces each, piece 0 = interval -1
     const uint32_t* meta;        // device metadata blob of this (graph, R)
     long long B;
-    int T, V, C, E, nw, vw, P;   // P = odd pitch of the staged logits
+    int T, V, C, E, nw, vw, P;   // P = odd pitch of the staged logits; E = edges of THIS launch's part of the graph
+    int v_lo, nv, part;          // the part's variables [v_lo, v_lo + nv); part = 1: one of several launches (connected components)
     int R, G, NCH;               // owners per group, groups per CTA, checks per owner (padded)
     int ct_n, rt_n, vt_n;        // vt_n: BASE piece count of the variable-phase tables (the header holds the one in use)
     int train_vt_max;            // training: most pieces the backward kernel can seat
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
             }
             // ---- read-out: logit_v = prior + sum over the variable's edges of f3(m_e); staged with an odd pitch in the free buffer ----
             const uint32_t st_grp = st_lane - (uint32_t)lane * 4u;
-            for (int v = r; v < p.V; v += p.R) {
+            for (int v = r; v < p.nv; v += p.R) {              // v: index into this part's variables
                 const uint2 ve = lds_u64(s_base + p.off_var + 8u * v);
                 float acc = prior;
                 if (ve.x != kNone) acc += lean_cubic<16>(rt_base, fminf(fmaxf(fmaf(lds_state_rt(st_lane + ve.x + fin), rt_inv_h, rt_off), -1.4f), (float)p.rt_n + 0.4f));
@@ -432,19 +433,21 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
             const int nvalid = min(32, cnt - j * 32);
             for (int s = r; s < nvalid; s += p.R) {
                 const long long row = __shfl_sync(0xffffffffu, sg, s);
-                for (int w = 0; w < p.vw; ++w) {
-                    const int v = w * 32 + lane;
-                    const uint32_t q = (uint32_t)s * (uint32_t)p.P + (uint32_t)v;
-                    const float lv = v < p.V ? lds_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth) : 1.0f;
+                for (int w = p.v_lo >> 5; w <= (p.v_lo + p.nv - 1) >> 5; ++w) {
+                    const int v = w * 32 + lane, vl = v - p.v_lo;       // global variable, its index in this part
+                    const bool mine = vl >= 0 && vl < p.nv;
+                    const uint32_t q = (uint32_t)s * (uint32_t)p.P + (uint32_t)(mine ? vl : 0);
+                    const float lv = mine ? lds_state_rt(st_grp + (q >> 5) * 256u + (q & 31u) * 4u + oth) : 1.0f;
                     const float pr = sigmoid_neg(lv);
-                    if (v < p.V) {
+                    if (mine) {
                         if (p.prob) p.prob[row * p.V + v] = pr;
                         if (p.logit) p.logit[row * p.V + v] = lv;
                         if (p.hard) p.hard[row * p.V + v] = pr > 0.5f;
                     }
                     if (p.hard_bits) {                          // packed hard decisions: bit v of the row
-                        const uint32_t word = __ballot_sync(0xffffffffu, pr > 0.5f);
-                        if (lane == 0) p.hard_bits[row * p.vw + w] = word;
+                        const uint32_t word = __ballot_sync(0xffffffffu, mine && pr > 0.5f);
+                        // (parts share the words at their borders: the buffer was cleared, every part ORs its bits in)
+                        if (lane == 0) { if (p.part) atomicOr(p.hard_bits + row * p.vw + w, word); else p.hard_bits[row * p.vw + w] = word; }
                     }
                 }
             }
@@ -1160,14 +1163,24 @@ __global__ void lean_unpack_kernel(const float* prior, const uint32_t* sgn, cons
 
 // ------------------------------------------------------------------------------------------------------------------
 // host side: owner assignment, metadata, plan, workspace
+// The part of the graph one decode launch covers: the whole graph, or one connected component of it.  Every CSS code of the
+// reference splits in two (X and Z halves: toric L = 11 is 2 x 480 edges): half the edge state per group of syndromes, so twice
+// the groups per CTA -- or a code that fits shared memory at all.
+struct LeanSub {
+    int id = -1;                           // -1: the whole graph
+    int v_lo = 0, nv = 0, E = 0;
+    std::vector<int> checks;               // global check ids, ascending
+    std::vector<int> edge_local;           // [E of the graph] -> edge index inside the part, -1 elsewhere
+};
 struct LeanMeta {
+    int sub = -1;
     int R = 0, NCH = 0;
     uint32_t* dev = nullptr;
     size_t bytes = 0;
     int off_ms = 0, off_mi = 0, off_var = 0;   // byte offsets inside the blob (me at 0)
     double balance = 0.0;
 };
-struct LeanGeom { int R = 0, G = 0, NCH = 0, rt_n = 0, ct_n = 0, vt_n = 0; long long opt_epoch = -1; int tpc = -1; bool valid = false; };
+struct LeanGeom { int R = 0, G = 0, NCH = 0, rt_n = 0, ct_n = 0, vt_n = 0; long long opt_epoch = -1; int tpc = -1, sub = -1; bool valid = false; };
 // geometry of the training backward: (R, G) for the base table size, and the finest variable-phase table that still seats one group
 struct LeanBwdGeom { int R = 0, G = 0, vt_max = 0, ct_n = 0, rt_n = 0, vt_n = 0, tpc = 0; long long opt_epoch = -1; bool valid = false; };
 // One table set on the device, keyed on the host by (stream, weights pointer, T, table sizes) and VALIDATED on the device
@@ -1185,7 +1198,11 @@ struct LeanEntry {
 };
 constexpr int kMaxEntries = 4;
 struct LeanCtx {
-    std::vector<LeanMeta*> metas;          // one per R ever planned (stable addresses)
+    std::vector<LeanMeta*> metas;          // one per (part, R) ever planned (stable addresses)
+    std::vector<LeanSub*> subs;            // [0] = the whole graph, [1 ..] = its connected components (when they can be decoded apart)
+    bool subs_done = false;
+    long long mode_epoch = -1;             // parts decision per option set: [0] inference, [1] training (whole graph only)
+    int mode[2] = {-2, -2}, mode_ri[2] = {-1, -1};
     std::vector<LeanGeom> geoms;           // geometry search results per tiles-per-CTA count, redone when an option changes
     std::vector<LeanBwdGeom> bwd;          // ... of the training backward
     cudaMemPool_t pool = nullptr;
@@ -1198,14 +1215,15 @@ struct LeanPlan {
     LeanParams p;
     int threads, grid, smem, n_tiles;
     const LeanMeta* meta;
+    int n_parts = 1;                       // launches this plan is one of
 };
 
 static int align_up_i(int x, int a) { return (x + a - 1) / a * a; }
 
 // owners' check lists: longest-processing-time assignment by degree (ties: ascending check id) -> balanced edge counts
-static void assign_owners(const gd_graph* g, int R, std::vector<std::vector<int>>& own, int* nch, double* balance) {
+static void assign_owners(const gd_graph* g, const LeanSub* sub, int R, std::vector<std::vector<int>>& own, int* nch, double* balance) {
     std::vector<int> order;
-    for (int c = 0; c < g->C; ++c)
+    for (int c : sub->checks)
         if (g->h_chk_ptr[c + 1] > g->h_chk_ptr[c]) order.push_back(c);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         return g->h_chk_ptr[a + 1] - g->h_chk_ptr[a] > g->h_chk_ptr[b + 1] - g->h_chk_ptr[b];
@@ -1225,25 +1243,85 @@ static void assign_owners(const gd_graph* g, int R, std::vector<std::vector<int>
         mxn = std::max(mxn, (int)own[r].size());
     }
     *nch = mxn;
-    *balance = mx ? (double)g->E / ((double)R * mx) : 0.0;
+    *balance = mx ? (double)sub->E / ((double)R * mx) : 0.0;
 }
 
-static const LeanMeta* get_meta(gd_graph* g, int R) {
+// parts of the graph: [0] the whole graph; [1 ..] its connected components, kept only when there are several, each holds a
+// contiguous range of variables (the output rows are written range by range) and at least one check
+static const std::vector<LeanSub*>& lean_subs(gd_graph* g) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (!g->lean_ctx) g->lean_ctx = new LeanCtx();
+    LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
+    if (ctx->subs_done) return ctx->subs;
+    const int E = (int)g->E, V = g->V, C = g->C;
+    LeanSub* whole = new LeanSub();
+    whole->v_lo = 0; whole->nv = V; whole->E = E;
+    for (int c = 0; c < C; ++c) whole->checks.push_back(c);
+    whole->edge_local.resize(E);
+    for (int e = 0; e < E; ++e) whole->edge_local[e] = e;
+    ctx->subs.push_back(whole);
+    // union-find over the nodes (variables 0 .. V-1, checks V .. V+C-1)
+    std::vector<int> parent(V + C);
+    for (int i = 0; i < V + C; ++i) parent[i] = i;
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (int e = 0; e < E; ++e) {
+        const int a = find(g->h_edge_var[e]), b = find(V + g->h_edge_chk[e]);
+        if (a != b) parent[std::max(a, b)] = std::min(a, b);
+    }
+    std::vector<int> comp_of(V + C, -1);
+    std::vector<LeanSub*> comps;
+    bool ok = true;
+    for (int c = 0; c < C; ++c) {
+        if (g->h_chk_ptr[c + 1] == g->h_chk_ptr[c]) continue;   // an empty check belongs nowhere (and does nothing)
+        const int root = find(V + c);
+        if (comp_of[root] < 0) { comp_of[root] = (int)comps.size(); comps.push_back(new LeanSub()); comps.back()->edge_local.assign(E, -1); }
+        comps[comp_of[root]]->checks.push_back(c);
+    }
+    std::vector<int> vmin(comps.size(), V), vmax(comps.size(), -1), vcnt(comps.size(), 0);
+    for (int v = 0; v < V; ++v) {
+        if (g->h_var_ptr[v + 1] == g->h_var_ptr[v]) continue;   // isolated variable: logit = prior; only the whole-graph part writes it
+        const int k = comp_of[find(v)];
+        if (k < 0) { ok = false; break; }
+        vmin[k] = std::min(vmin[k], v); vmax[k] = std::max(vmax[k], v); ++vcnt[k];
+    }
+    for (int v = 0; v < V && ok; ++v)
+        if (g->h_var_ptr[v + 1] == g->h_var_ptr[v]) ok = false; // (isolated variables: keep to the whole graph)
+    for (size_t k = 0; k < comps.size() && ok; ++k) ok = vcnt[k] > 0 && vmax[k] - vmin[k] + 1 == vcnt[k];
+    if (ok && comps.size() >= 2 && comps.size() <= 8) {
+        for (size_t k = 0; k < comps.size(); ++k) {
+            LeanSub* s = comps[k];
+            s->id = (int)k; s->v_lo = vmin[k]; s->nv = vcnt[k];
+            int n = 0;
+            for (int e = 0; e < E; ++e)
+                if (comp_of[find(V + g->h_edge_chk[e])] == (int)k) s->edge_local[e] = n++;
+            s->E = n;
+            ctx->subs.push_back(s);
+        }
+    } else {
+        for (LeanSub* s : comps) delete s;
+    }
+    ctx->subs_done = true;
+    return ctx->subs;
+}
+
+static const LeanMeta* get_meta(gd_graph* g, const LeanSub* sub, int R) {
     std::lock_guard<std::mutex> lk(g->mu);
     if (!g->lean_ctx) g->lean_ctx = new LeanCtx();
     LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
     for (const LeanMeta* q : ctx->metas)
-        if (q->R == R) return q->dev ? q : nullptr;
+        if (q->R == R && q->sub == sub->id) return q->dev ? q : nullptr;
     LeanMeta* mp = new LeanMeta();
     LeanMeta& m = *mp;
     m.R = R;
+    m.sub = sub->id;
     std::vector<std::vector<int>> own;
-    assign_owners(g, R, own, &m.NCH, &m.balance);
+    assign_owners(g, sub, R, own, &m.NCH, &m.balance);
     const int n = R * m.NCH;
     m.off_ms = n * 16;
     m.off_mi = 2 * n * 16;
     m.off_var = align_up_i(m.off_mi + n * 4, 16);
-    m.bytes = (size_t)align_up_i(m.off_var + g->V * 8, 16);
+    m.bytes = (size_t)align_up_i(m.off_var + sub->nv * 8, 16);
+    const std::vector<int>& loc = sub->edge_local;           // edge offsets are those of the part's own state array
     std::vector<uint32_t> blob(m.bytes / 4, 0u);
     uint32_t* me = blob.data();
     uint32_t* ms = blob.data() + m.off_ms / 4;
@@ -1252,7 +1330,7 @@ static const LeanMeta* get_meta(gd_graph* g, int R) {
     auto sibling = [&](int e) -> uint32_t {
         const int v = g->h_edge_var[e], b = g->h_var_ptr[v], d = g->h_var_ptr[v + 1] - b;
         if (d < 2) return kNone;
-        return (uint32_t)(g->h_var_edges[b] == e ? g->h_var_edges[b + 1] : g->h_var_edges[b]) * 256u;
+        return (uint32_t)loc[g->h_var_edges[b] == e ? g->h_var_edges[b + 1] : g->h_var_edges[b]] * 256u;
     };
     for (int r = 0; r < R; ++r)
         for (int k = 0; k < m.NCH; ++k) {
@@ -1267,17 +1345,17 @@ static const LeanMeta* get_meta(gd_graph* g, int R) {
                     const int e = g->h_chk_edges[b + q];
                     const uint32_t sb = sibling(e);
                     if ((sb != kNone) != (pass == 0)) continue;
-                    me[4 * i + j] = (uint32_t)e * 256u;
+                    me[4 * i + j] = (uint32_t)loc[e] * 256u;
                     ms[4 * i + j] = sb;
                     nsib += sb != kNone;
                     ++j;
                 }
             mi[i] = (uint32_t)d | ((uint32_t)nsib << 3) | ((uint32_t)c << 8);
         }
-    for (int v = 0; v < g->V; ++v) {
-        const int b = g->h_var_ptr[v], d = g->h_var_ptr[v + 1] - b;
-        var[2 * v] = d > 0 ? (uint32_t)g->h_var_edges[b] * 256u : kNone;
-        var[2 * v + 1] = d > 1 ? (uint32_t)g->h_var_edges[b + 1] * 256u : kNone;
+    for (int i = 0; i < sub->nv; ++i) {
+        const int v = sub->v_lo + i, b = g->h_var_ptr[v], d = g->h_var_ptr[v + 1] - b;
+        var[2 * i] = d > 0 ? (uint32_t)loc[g->h_var_edges[b]] * 256u : kNone;
+        var[2 * i + 1] = d > 1 ? (uint32_t)loc[g->h_var_edges[b + 1]] * 256u : kNone;
     }
     if (cudaMalloc((void**)&m.dev, m.bytes) != cudaSuccess ||
         cudaMemcpy(m.dev, blob.data(), m.bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1294,39 +1372,54 @@ static bool lean_applicable(const gd_graph* g, const gd_model* m) {
     // there only (numpy emulation at T = 15 / 24 / 32 / 45: <= 0.26 of the bar; T = 60: 1.7 x on two golden syndromes)
     if (m->program != GD_PROG_V2_4 || m->flags != 0 || m->iters < 1 || m->iters > 32 || opt_on(OPT_NO_LEAN)) return false;
     if (g->max_var_deg > 2 || g->max_chk_deg > 4 || g->E >= (1 << 23) / 256) return false;
-    if ((g->V | 1) > g->E) return false;                        // the staged logits reuse the free message buffer
     return true;
 }
 
-// the search itself (host work proportional to C * 32^2: done once per graph and option set, not per call)
-static bool lean_search(gd_graph* g, int tpc, LeanGeom* out) {
-    const int E = (int)g->E, V = g->V;
+// The read-out table's size is part of what a call returns (its last bits), so it must not depend on the batch size: it is
+// chosen per graph (and set of parts) from what shared memory can seat at all -- 2048 pieces unless that costs more than one of
+// the (up to 4) groups 1024 pieces would allow -- and never traded against the geometry.  Returns 0 (2048), 1 (1024) or -1.
+static const int kLeanRts[] = {2048, 1024};
+static int lean_rt_choice(gd_graph* g, const std::vector<const LeanSub*>& parts, int ct_n, int vt_n) {
+    const int smem_max = g->max_smem_optin - 1024;
+    int ri_all = 0;
+    for (const LeanSub* sub : parts) {
+        int g_cap[2] = {0, 0};
+        for (int R = 1; R <= 32; ++R) {
+            std::vector<std::vector<int>> own;
+            int nch;
+            double bal;
+            assign_owners(g, sub, R, own, &nch, &bal);
+            if (nch > 32 || nch == 0) continue;
+            const int meta = align_up_i(align_up_i(2 * R * nch * 16 + R * nch * 4, 16) + sub->nv * 8, 16);
+            for (int ri = 0; ri < 2; ++ri) {
+                const int fixed = align_up_i(meta + (ct_n + 2) * 128 + (kLeanRts[ri] + 2) * 16 + (vt_n + 2) * 128, 128);
+                g_cap[ri] = std::max(g_cap[ri], std::min((smem_max - fixed) / (sub->E * 256), std::min(32 / R, 15)));
+            }
+        }
+        if (g_cap[1] < 1) return -1;                            // this part does not fit at all
+        if (!(g_cap[0] >= std::min(g_cap[1], 3) && g_cap[0] >= 1)) ri_all = 1;
+    }
+    return ri_all;
+}
+
+// the search itself (host work proportional to C * 32^2: done once per graph part and option set, not per call)
+static bool lean_search(gd_graph* g, const LeanSub* sub, int tpc, int ri_fixed, LeanGeom* out) {
+    const int E = sub->E, V = sub->nv;
     const int ct_n = (int)std::min<long long>(1024, std::max<long long>(32, opt_int(OPT_LEAN_CTAB_N, 128)));
     const int vt_n = (int)std::min<long long>(4096, std::max<long long>(64, opt_int(OPT_LEAN_VTAB_N, 512)));
     const int state = E * 256;
     const int smem_max = g->max_smem_optin - 1024;              // the kernel's static shared memory (tile / row prefixes)
     struct Cand { int R, G, NCH, rt_n; double score; };
     Cand best{0, 0, 0, 0, -1.0};
-    static const int rts[] = {2048, 1024};
+    const int* rts = kLeanRts;
     const long long force_R = opt_int(OPT_LEAN_R, 0), force_G = opt_int(OPT_LEAN_G, 0);
     const long long force_rt = opt_int(OPT_LEAN_RTAB_N, 0);
-    // The read-out table's size is part of what a call returns (its last bits), so it must not depend on the batch size: it is
-    // chosen per graph from what shared memory can seat at all -- 2048 pieces unless that costs more than one of the (up to 4)
-    // groups 1024 pieces would allow -- and never traded against the geometry below.
-    int g_cap[2] = {0, 0};
     std::vector<int> nchs(33, 0);
     std::vector<double> bals(33, 0.0);
     for (int R = 1; R <= 32; ++R) {
         std::vector<std::vector<int>> own;
-        assign_owners(g, R, own, &nchs[R], &bals[R]);
-        if (nchs[R] > 32 || nchs[R] == 0) continue;
-        const int meta = align_up_i(align_up_i(2 * R * nchs[R] * 16 + R * nchs[R] * 4, 16) + V * 8, 16);
-        for (int ri = 0; ri < 2; ++ri) {
-            const int fixed = align_up_i(meta + (ct_n + 2) * 128 + (rts[ri] + 2) * 16 + (vt_n + 2) * 128, 128);
-            g_cap[ri] = std::max(g_cap[ri], std::min((smem_max - fixed) / state, std::min(32 / R, 15)));
-        }
+        assign_owners(g, sub, R, own, &nchs[R], &bals[R]);
     }
-    const int ri_fixed = g_cap[0] >= std::min(g_cap[1], 3) && g_cap[0] >= 1 ? 0 : 1;
     for (int R = 1; R <= 32; ++R) {
         if (force_R > 0 && R != force_R) continue;
         const int nch = nchs[R];
@@ -1358,13 +1451,14 @@ static bool lean_search(gd_graph* g, int tpc, LeanGeom* out) {
     return true;
 }
 
-static bool lean_fill(gd_graph* g, const gd_model* m, int64_t B, const LeanGeom& best, const LeanMeta* meta, LeanPlan* out) {
-    const int E = (int)g->E, V = g->V, ct_n = best.ct_n, vt_n = best.vt_n, state = E * 256;
+static bool lean_fill(gd_graph* g, const LeanSub* sub, const gd_model* m, int64_t B, const LeanGeom& best, const LeanMeta* meta, LeanPlan* out) {
+    const int E = sub->E, V = g->V, ct_n = best.ct_n, vt_n = best.vt_n, state = E * 256;
     const int smem_max = g->max_smem_optin;
     LeanParams& p = out->p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.T = m->iters; p.V = V; p.C = g->C; p.E = E;
-    p.nw = (g->C + 31) / 32; p.vw = (V + 31) / 32; p.P = V | 1;
+    p.nw = (g->C + 31) / 32; p.vw = (V + 31) / 32; p.P = sub->nv | 1;
+    p.v_lo = sub->v_lo; p.nv = sub->nv; p.part = sub->id >= 0 ? 1 : 0;
     p.R = best.R; p.G = best.G; p.NCH = meta->NCH;
     p.ct_n = ct_n; p.rt_n = best.rt_n; p.vt_n = vt_n;
     p.meta = meta->dev;
@@ -1383,40 +1477,81 @@ static bool lean_fill(gd_graph* g, const gd_model* m, int64_t B, const LeanGeom&
 
 // Geometry: R owners (warps) per group of 32 syndromes, G groups per CTA.  The kernel is bound by the shared-memory
 // crossbar, so what matters is enough resident warps (>= ~24) with balanced owners; more groups = more independent
-// barrier domains.  The read-out table's size (2048 or 1024 pieces) is fixed per graph (lean_search).
-static bool lean_plan(gd_graph* g, const gd_model* m, int64_t B, LeanPlan* out) {
+// barrier domains.  The read-out table's size (2048 or 1024 pieces) is fixed per graph (lean_rt_choice).
+//
+// Parts: the whole graph in one launch, or its connected components in one launch each (same tables, same arithmetic per edge,
+// so the same results) -- when the whole graph's edge state does not fit shared memory (toric L = 11: 960 edges x 256 B per group),
+// or when halving the state seats more groups (GD_LEAN_PARTS).  Training always takes the whole graph (its stash is laid out by
+// global edge id).
+static bool lean_plan(gd_graph* g, const gd_model* m, int64_t B, std::vector<LeanPlan>* out, bool whole_only = false) {
+    out->clear();
     if (!lean_applicable(g, m)) return false;
+    const std::vector<LeanSub*>& subs = lean_subs(g);
+    const int ct_n = (int)std::min<long long>(1024, std::max<long long>(32, opt_int(OPT_LEAN_CTAB_N, 128)));
+    const int vt_n = (int)std::min<long long>(4096, std::max<long long>(64, opt_int(OPT_LEAN_VTAB_N, 512)));
     // tiles of 32 syndromes a CTA will see (one CTA per SM; large batches: the quantisation no longer matters)
     const int tpc = (int)std::min<long long>(64, std::max<long long>(1, ((B + 31) / 32 + g->sm_count - 1) / g->sm_count));
-    LeanGeom geom;
+    LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
+    // which parts, and the read-out table they share (cached per option set)
+    int mode = -2, ri = -1;                                    // mode: 0 whole graph, 1 components, -1 neither fits
     {
         std::lock_guard<std::mutex> lk(g->mu);
-        if (!g->lean_ctx) g->lean_ctx = new LeanCtx();
-        LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
-        if (!ctx->geoms.empty() && ctx->geoms[0].opt_epoch != opt_epoch()) ctx->geoms.clear();
-        for (const LeanGeom& q : ctx->geoms)
-            if (q.tpc == tpc) geom = q;
+        if (ctx->mode_epoch == opt_epoch()) { mode = ctx->mode[whole_only ? 1 : 0]; ri = ctx->mode_ri[whole_only ? 1 : 0]; }
     }
-    if (!geom.valid) {
-        if (!lean_search(g, tpc, &geom)) return false;
-        geom.opt_epoch = opt_epoch();
-        geom.tpc = tpc;
+    if (mode == -2) {
+        int modes[2], ris[2];
+        // (nv | 1) <= E: the staged logits reuse the free message buffer
+        const int ri_whole = (subs[0]->nv | 1) <= subs[0]->E ? lean_rt_choice(g, {subs[0]}, ct_n, vt_n) : -1;
+        std::vector<const LeanSub*> comps(subs.begin() + 1, subs.end());
+        bool comps_ok = !comps.empty();
+        for (const LeanSub* c : comps) comps_ok = comps_ok && (c->nv | 1) <= c->E;
+        const int ri_comps = comps_ok ? lean_rt_choice(g, comps, ct_n, vt_n) : -1;
+        const long long want = opt_int(OPT_LEAN_PARTS, -1);
+        modes[1] = ri_whole >= 0 ? 0 : -1; ris[1] = ri_whole;                       // training: whole graph or nothing
+        if (ri_comps >= 0 && (ri_whole < 0 || want == 1) && want != 0) { modes[0] = 1; ris[0] = ri_comps; }
+        else { modes[0] = modes[1]; ris[0] = ri_whole; }
         std::lock_guard<std::mutex> lk(g->mu);
-        LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
-        if (ctx->geoms.size() >= 64) ctx->geoms.clear();
-        ctx->geoms.push_back(geom);
+        ctx->mode_epoch = opt_epoch();
+        for (int i = 0; i < 2; ++i) { ctx->mode[i] = modes[i]; ctx->mode_ri[i] = ris[i]; }
+        mode = modes[whole_only ? 1 : 0]; ri = ris[whole_only ? 1 : 0];
     }
-    if (geom.R == 0) return false;
-    const LeanMeta* meta = get_meta(g, geom.R);
-    if (!meta) return false;
-    return lean_fill(g, m, B, geom, meta, out);
+    if (mode < 0) return false;
+    const size_t first = mode == 0 ? 0 : 1, last = mode == 0 ? 1 : subs.size();
+    for (size_t si = first; si < last; ++si) {
+        const LeanSub* sub = subs[si];
+        LeanGeom geom;
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            if (!ctx->geoms.empty() && ctx->geoms[0].opt_epoch != opt_epoch()) ctx->geoms.clear();
+            for (const LeanGeom& q : ctx->geoms)
+                if (q.tpc == tpc && q.sub == sub->id) geom = q;
+        }
+        if (!geom.valid) {
+            if (!lean_search(g, sub, tpc, ri, &geom)) return false;
+            geom.opt_epoch = opt_epoch();
+            geom.tpc = tpc;
+            geom.sub = sub->id;
+            std::lock_guard<std::mutex> lk(g->mu);
+            if (ctx->geoms.size() >= 128) ctx->geoms.clear();
+            ctx->geoms.push_back(geom);
+        }
+        if (geom.R == 0) return false;
+        const LeanMeta* meta = get_meta(g, sub, geom.R);
+        if (!meta) return false;
+        LeanPlan pl;
+        if (!lean_fill(g, sub, m, B, geom, meta, &pl)) return false;
+        pl.n_parts = (int)(last - first);
+        out->push_back(pl);
+    }
+    return !out->empty();
 }
 
 bool lean_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_launch_info* out) {
-    LeanPlan pl;
-    if (!lean_plan(const_cast<gd_graph*>(g), model, B, &pl)) return false;
+    std::vector<LeanPlan> pls;
+    if (!lean_plan(const_cast<gd_graph*>(g), model, B, &pls)) return false;
+    const LeanPlan& pl = pls[0];                               // (parts: the first launch's geometry; tiles of all launches)
     out->tile = 32 * pl.p.G; out->threads = pl.threads; out->grid = pl.grid; out->smem_bytes = pl.smem;
-    out->resident = 1; out->n_tiles = (pl.n_tiles + pl.p.G - 1) / pl.p.G;
+    out->resident = 1; out->n_tiles = (int)pls.size() * ((pl.n_tiles + pl.p.G - 1) / pl.p.G);
     return true;
 }
 
@@ -1467,7 +1602,7 @@ static bool lean_bwd_geom(gd_graph* g, const LeanParams& fp, LeanBwdGeom* out) {
         std::vector<std::vector<int>> own;
         int nch;
         double bal;
-        assign_owners(g, R, own, &nch, &bal);
+        assign_owners(g, lean_subs(g)[0], R, own, &nch, &bal);
         if (nch == 0 || nch > 32) continue;
         const int meta = align_up_i(align_up_i(2 * R * nch * 16 + R * nch * 4, 16) + g->V * 8, 16);
         int G = (smem_max - fixed_bytes(meta, vt_n)) / (3 * E * 128);
@@ -1548,13 +1683,13 @@ static LeanEntry* lean_entry(gd_graph* g, LeanCtx* ctx, const LeanParams& p, con
 int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* prior_dev,
                 const uint32_t* synd_dev, float* prob_dev, float* logit_dev, uint8_t* hard_dev, uint32_t* hard_bits_dev,
                 int64_t B, cudaStream_t st, float* stash_dev) {
-    LeanPlan pl;
-    if (!lean_plan(g, model, B, &pl)) return -1;
+    std::vector<LeanPlan> pls;
+    if (!lean_plan(g, model, B, &pls, stash_dev != nullptr)) return -1;
     cudaMemPool_t pool = lean_pool(g);
     if (!pool) return -1;
     LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
     std::lock_guard<std::mutex> enq(ctx->enq);
-    LeanParams& p = pl.p;
+    LeanParams& p = pls[0].p;                                   // table sizes and batch layout are the same for every part
     LeanEntry* ent = lean_entry(g, ctx, p, model, weights_dev, st);
     if (!ent) return -1;
     const int N = g->N;
@@ -1609,23 +1744,27 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         lean_tables_kernel<<<tp.scatter_blocks + tp.ct_blocks + tp.rt_blocks + kVtSlotGroups * tp.vt_chunks, 256, 0, st>>>(tp);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) {
-        p.idx = reinterpret_cast<const int*>(ws + o_idx);
-        p.sgn = x_dev ? reinterpret_cast<const uint32_t*>(ws + o_sgn) : synd_dev;
-        p.prob = prob_dev; p.logit = logit_dev; p.hard = hard_dev; p.hard_bits = hard_bits_dev;
-        p.hdr = hdr; p.call = call; p.next_call = next_call;
-        p.ctab = ctab; p.rtab = rtab; p.vtab = vtab;
-        p.stash = stash_dev;
-        p.train = stash_dev ? lean_train_hdr(stash_dev, g, model, B) : nullptr;
+    if (e == cudaSuccess && pls.size() > 1 && hard_bits_dev)    // parts share the words at their borders and OR their bits in
+        e = cudaMemsetAsync(hard_bits_dev, 0, (size_t)B * p.vw * sizeof(uint32_t), st);
+    for (size_t pi = 0; pi < pls.size() && e == cudaSuccess; ++pi) {
+        LeanPlan& pl = pls[pi];
+        LeanParams& q = pl.p;
+        q.idx = reinterpret_cast<const int*>(ws + o_idx);
+        q.sgn = x_dev ? reinterpret_cast<const uint32_t*>(ws + o_sgn) : synd_dev;
+        q.prob = prob_dev; q.logit = logit_dev; q.hard = hard_dev; q.hard_bits = hard_bits_dev;
+        q.hdr = hdr; q.call = call; q.next_call = next_call;
+        q.ctab = ctab; q.rtab = rtab; q.vtab = vtab;
+        q.stash = stash_dev;
+        q.train = stash_dev ? lean_train_hdr(stash_dev, g, model, B) : nullptr;
         if (stash_dev) {
             LeanBwdGeom bg;
-            p.train_vt_max = lean_bwd_geom(g, p, &bg) ? bg.vt_max : 0;   // 0: the backward has no room at all -> edge-owner kernels
+            q.train_vt_max = lean_bwd_geom(g, q, &bg) ? bg.vt_max : 0;   // 0: the backward has no room at all -> edge-owner kernels
         }
-        p.idx_src = p.idx;
+        q.idx_src = q.idx;
         auto kern = stash_dev ? lean_decode_kernel<true> : lean_decode_kernel<false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
         if (e == cudaSuccess) {
-            kern<<<pl.grid, pl.threads, pl.smem, st>>>(p);
+            kern<<<pl.grid, pl.threads, pl.smem, st>>>(q);
             e = cudaGetLastError();
         }
     }
@@ -1682,8 +1821,9 @@ int64_t lean_bwd_bins_floats(const gd_graph* g, const gd_model* model) {
 
 int lean_backward(gd_graph* g, const gd_model* model, const float* weights_dev, const float* x_dev, const float* stash_dev,
                   const float* grad_logit_dev, float* grad_weights_dev, float* bins_dev, int accumulate, int64_t B, cudaStream_t st) {
-    LeanPlan fwd;
-    if (!lean_plan(g, model, B, &fwd)) return -1;              // the forward took the edge-owner kernel as well
+    std::vector<LeanPlan> fwds;
+    if (!lean_plan(g, model, B, &fwds, true)) return -1;       // the forward took the edge-owner kernel as well
+    const LeanPlan& fwd = fwds[0];
     LeanCtx* ctx = static_cast<LeanCtx*>(g->lean_ctx);
     std::lock_guard<std::mutex> enq(ctx->enq);
     // the table set the forward of this step used (same stream, same weights): it is not touched in between
@@ -1702,7 +1842,7 @@ int lean_backward(gd_graph* g, const gd_model* model, const float* weights_dev, 
     LeanBwdGeom bg;
     if (!lean_bwd_geom(g, fwd.p, &bg)) return -1;              // (the forward saw the same answer and left the stash to the edge-owner kernel)
     const int bestR = bg.R, bestG = bg.G;
-    const LeanMeta* meta = get_meta(g, bestR);
+    const LeanMeta* meta = get_meta(g, lean_subs(g)[0], bestR);
     if (!meta) return -1;
     const LeanTrainHdr* hdr = lean_train_hdr(const_cast<float*>(stash_dev), g, model, B);
     p.x = x_dev; p.stash = stash_dev; p.train = hdr; p.grad_logit = grad_logit_dev;
@@ -1739,6 +1879,7 @@ void gd_lean_ctx_destroy(gd_graph* g) {
         if (m->dev) cudaFree(m->dev);
         delete m;
     }
+    for (gd::LeanSub* sb : ctx->subs) delete sb;
     for (gd::LeanEntry* e : ctx->entries) {
         if (e->ev) { cudaEventSynchronize(e->ev); cudaEventDestroy(e->ev); }
         if (e->dev) cudaFree(e->dev);

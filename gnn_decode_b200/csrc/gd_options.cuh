@@ -42,7 +42,7 @@ enum Opt {
     OPT_LEAN_VTAB_N,      // GD_LEAN_VTAB_N    its variable-phase table intervals (512)
     OPT_LEAN_CTAB_N,      // GD_LEAN_CTAB_N    its check-phase table intervals (128, replicated per bank group)
     OPT_LEAN_RTAB_N,      // GD_LEAN_RTAB_N    its read-out table intervals (2048)
-    OPT_LEAN_VTAB_K,      // GD_LEAN_VTAB_K    its variable-phase table slots (<= 12)
+    OPT_LEAN_PARTS,       // GD_LEAN_PARTS     1: decode the graph's connected components in separate launches, 0: never (unset: when that seats more groups)
     OPT_LAUNCH_BLOCKING,  // (derived) a tool that makes launches block the host is attached (ncu / sanitizer / CUDA_LAUNCH_BLOCKING)
     OPT_COUNT
 };

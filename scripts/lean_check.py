@@ -48,10 +48,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--codes", default="rot5,toric5,rot7,rot11")
+    ap.add_argument("--parts", type=int, default=-1, help="GD_LEAN_PARTS: 1 = decode connected components apart, 0 = never")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "lean_check.json"))
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     w = weights()
+    if args.parts >= 0:
+        options.set_option("GD_LEAN_PARTS", args.parts)
     res = {}
     for name in args.codes.split(","):
         mk, noise, B = CODES[name]
@@ -95,7 +98,7 @@ def main():
                     if R * G > 32:
                         continue
                     for K in (12,):
-                        options.set_option("GD_LEAN_R", R); options.set_option("GD_LEAN_G", G); options.set_option("GD_LEAN_VTAB_K", K)
+                        options.set_option("GD_LEAN_R", R); options.set_option("GD_LEAN_G", G)
                         li = g.launch_info(model, B)
                         if li["threads"] != 32 * R * G:          # geometry refused (does not fit): the fallback kernel answered
                             continue
@@ -106,7 +109,7 @@ def main():
                             continue
                         sw.append({"R": R, "G": G, "K": K, "ms": t, "Msyn_s": B / t / 1e3, "smem": li["smem_bytes"]})
                         print("   R=%2d G=%d K=%d  %.3f ms  %.1f M/s" % (R, G, K, t, B / t / 1e3), flush=True)
-            for o in ("GD_LEAN_R", "GD_LEAN_G", "GD_LEAN_VTAB_K"):
+            for o in ("GD_LEAN_R", "GD_LEAN_G"):
                 options.unset_option(o)
             rec["sweep"] = sw
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

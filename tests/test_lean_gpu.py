@@ -147,6 +147,52 @@ def test_results_do_not_depend_on_the_geometry_a_batch_size_selects():
     assert len(shapes) >= 2
 
 
+def test_connected_components_are_decoded_apart_with_identical_results(gd_opt):
+    """Every CSS code of the reference splits into an X and a Z half.  Decoding the halves in separate launches (GD_LEAN_PARTS=1:
+    half the edge state per group, twice the groups) is the same arithmetic per edge: bit-identical outputs, fp32 and packed --
+    including the hard-decision words the two halves share (V / 2 = 25 is not a multiple of 32)."""
+    g, dec, _ = _setup()
+    B = 4100
+    x, _ = sample_syndromes(g, B, P10, noise=1, seed=21)
+    prob, logit, hard = dec.decode(x, return_logits=True, return_hard=True)
+    prior, bits = packing.pack_x(x, g.V)
+    hb = dec.decode_packed(prior, bits)
+    info = g.launch_info(dec.gd_model(), B)
+    gd_opt.set("GD_LEAN_PARTS", 1)
+    info_p = g.launch_info(dec.gd_model(), B)
+    assert info_p != info                                       # another geometry: the halves' own
+    prob_p, logit_p, hard_p = dec.decode(x, return_logits=True, return_hard=True)
+    hb_p, pp = dec.decode_packed(prior, bits, return_prob=True)
+    assert torch.equal(prob_p, prob) and torch.equal(logit_p, logit) and torch.equal(hard_p, hard)
+    assert torch.equal(hb_p, hb) and torch.equal(pp, prob)
+    assert torch.equal(packing.unpack_bits(hb_p, g.V), hard)
+
+
+def test_toric_L11_runs_on_the_table_kernel_by_components():
+    """Toric L = 11 (E = 960): the whole graph's edge state does not fit shared memory (245 KB per group of 32 syndromes), its two
+    components do -- the table kernel, not the edge-owner kernel, decodes it; against the fp64 oracle and the edge-owner kernel."""
+    pcm = codes.toric_pcm(11)
+    g = TannerGraph.from_pcm(pcm, DEV)
+    dec = decoder_v2_4.GNNI(15)
+    w = Golden("v2_4_toricL5_epoch3").weights
+    dec.load_state_dict(w)
+    dec = dec.to(DEV).eval().bind_graph(g)
+    assert _lean_runs(g, dec, 9000)
+    x, _ = sample_syndromes(g, 9000, P10[:5], noise=0, seed=5)
+    prob, logit, hard = dec.decode(x, return_logits=True, return_hard=True)
+    with options.option("GD_NO_LEAN"):
+        p_old, l_old, h_old = dec.decode(x, return_logits=True, return_hard=True)
+    assert float((prob - p_old).abs().max()) < 1e-4
+    ei = torch.from_numpy(codes.edge_index_of(pcm))
+    ref = restate.decode("v2_4", ei, g.V, g.C, x[:24].double().cpu(), w, T=15)["logit"]
+    worst, max_err = logit_worst(logit[:24].cpu(), ref)
+    assert worst <= 1.0, (worst, max_err)
+    decided = ref.abs() > 1e-3
+    assert torch.equal(hard[:24].cpu().bool()[decided], (ref < 0)[decided])
+    # slices: same bits
+    assert torch.equal(dec.decode(x[1000:1777].contiguous()), prob[1000:1777])
+
+
 def test_wide_message_domains_get_finer_variable_tables():
     """epoch67 (|logit| up to ~600, T max|mlp2| = 70, errors amplified ~4000 x) and freshly initialised weights (T max|mlp2| ~ 140):
     512 pieces miss the budget of the variable-phase tables on such a domain.  The piece-width rule doubles them at once; where the
