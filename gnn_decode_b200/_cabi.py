@@ -10,7 +10,7 @@ from .build import LIB_PATH
 GD_OK, GD_ERR_INVALID, GD_ERR_CUDA, GD_ERR_UNSUPPORTED = 0, 1, 2, 3
 PROG_CGNNI, PROG_QGNNI, PROG_V2_4, PROG_BP_QUANTUM, PROG_BP_CLASSICAL = 0, 1, 2, 3, 4
 PROG_NEURAL_BP, PROG_GRU_CA = 5, 6
-PROG_V3_0, PROG_V1_2_2 = 7, 8
+PROG_V3_0, PROG_V1_2_2, PROG_V2_4_1 = 7, 8, 9
 FLAG_ALL_ITERS = 1
 PHASE_VAR, PHASE_CHK = 0, 1
 ABI_VERSION = 1

@@ -76,6 +76,7 @@ static inline bool gd_model_valid(const gd_model* m) {
         case GD_PROG_GRU_CA:
         case GD_PROG_V3_0:
         case GD_PROG_V1_2_2:
+        case GD_PROG_V2_4_1:
             return m->hidden >= 1 && m->hidden <= 256;
         case GD_PROG_NEURAL_BP:
             return m->hidden >= 1;          // = E, checked against the graph at launch

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     constexpr bool kGRU = (PROG == GD_PROG_GRU_CA);      // MLP + GRUCell updates (quantum/QGNNNI_ca.py)
     constexpr bool kV3 = (PROG == GD_PROG_V3_0);         // 2-input ReLU MLPs + GRUCell updates, second read-out at the checks (quantum/decoder_v3_0.py)
     constexpr bool kV122 = (PROG == GD_PROG_V1_2_2);     // Tanh-MLP variable phase, sum-product check phase, a read-out per iteration (quantum/decoder_v1_2_2.py)
+    constexpr bool kV241 = (PROG == GD_PROG_V2_4_1);     // decoder_v2_4 with un-tied layers, per-edge-type weights, gated residual (quantum/decoder_v2_4_1.py)
     // ReLU programs: NPOLY carries NPAD -- > 0 evaluates their 1->h->1 MLPs as piecewise-linear tables (gd_math.cuh)
     constexpr int kNPAD = (PROG == GD_PROG_CGNNI || PROG == GD_PROG_QGNNI || kGRU) ? (NPOLY > 0 ? NPOLY : 0) : 0;
 
@@ -263,6 +264,29 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         stage_mlp(slot, hp, h, w, 1, false, w + h, w + 2 * h, 1.f, 1.f, tid, nthr);
         W3 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
         gru = gs;
+    } else if constexpr (kV241) {
+        // per iteration (staged at its start): layers.{2l}.mlp1 | W[8] | W_p[8] | layers.{2l+1}.mlp; once: mlp | W[8] | W_p[8] | alpha | beta
+        const int h = p.hid;
+        const float* w = p.weights + (size_t)p.T * (6 * h + 18);
+        float* slot = wsm + 2 * p.wslot;
+        stage_mlp(slot, hp, h, w, 1, false, w + h, w + 2 * h, kLog2e, kLn2, tid, nthr);
+        W3 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
+        float* tw = wsm + 3 * p.wslot;                 // [0..15] this layer's W | W_p, [16..31] the read-out's, [32..33] the gates
+        if (tid < 16) tw[16 + tid] = w[3 * h + 1 + tid];
+        if (tid < 2) tw[32 + tid] = sigmoid_fast(w[3 * h + 17 + tid]);
+        // edge types (decoder_v2_4_1.py:211-236): rank of the edge among its check's edges in ascending variable order, + 4 for
+        // the second half of the checks (`idx > cols / 2 - 1`)
+        __syncthreads();                               // the 16-bit graph tables are complete
+        uint16_t* et = const_cast<uint16_t*>(tb.csib);
+        for (int e = tid; e < E; e += nthr) {
+            const int c = tb.edge_chk[e], v = tb.edge_var[e];
+            int rank = 0;
+            for (int i = tb.chk_ptr[c]; i < tb.chk_ptr[c + 1]; ++i) {
+                const int e2 = tb.chk_edges[i], v2 = tb.edge_var[e2];
+                rank += (v2 < v || (v2 == v && e2 < e)) ? 1 : 0;
+            }
+            et[e] = (uint16_t)((rank & 3) + (2 * c > C - 2 ? 4 : 0));
+        }
     } else if constexpr (kV122) {
         // ggc1.mlp | mlp, both 2 -> h -> 1 Tanh: first layers pre-scaled by 2 log2(e) (mlp_tanh2)
         const float* w = p.weights;
@@ -457,6 +481,28 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         // read-out as a callable: GRU_CA with GD_FLAG_ALL_ITERS emits one prediction per iteration
         auto emit = [&](const long long out_off) {
             // ---- read-out: logits staged as [tile][V] in the node region ----
+            if constexpr (kV241) {                 // decoder_v2_4_1.py:341-345: mlp(m) W[type], summed at the variable with prior W_p[type]
+                const float* tw = wsm + 3 * p.wslot;
+                const uint16_t* et = tb.csib;
+                for (int i0 = 0; i0 < n_iter; i0 += kEB) {
+                    float x0[kEB], o[kEB];
+                    int ee[kEB];
+#pragma unroll
+                    for (int j = 0; j < kEB; ++j) {
+                        const int e = r + (i0 + j) * R;
+                        ee[j] = e;
+                        x0[j] = m_st[(size_t)(e < E ? e : E - 1) * tile + s];
+                    }
+                    mlp_softplus<kEB, false>(W3, hp, x0, x0, o);
+#pragma unroll
+                    for (int j = 0; j < kEB; ++j)
+                        if (ee[j] < E) {
+                            const int ty = et[ee[j]];
+                            t_st[(size_t)ee[j] * tile + s] = fmaf(o[j], tw[16 + ty], xrow[tb.ld(tb.edge_var, ee[j])] * tw[24 + ty]);
+                        }
+                }
+                __syncthreads();
+            }
             if constexpr (PROG == GD_PROG_V2_4) {  // per-EDGE MLP, then sum at the variable
                 for (int i0 = 0; i0 < n_iter; i0 += kEB) {
                     float x0[kEB], o[kEB];
@@ -485,7 +531,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
             float* stage = node;  // [tile][V]
             for (int v = r; v < V; v += R) {
                 const int b = tb.ld(tb.var_ptr, v), e_end = tb.ld(tb.var_ptr, v + 1);
-                const float* src = PROG == GD_PROG_V2_4 ? t_st : m_st;
+                const float* src = (PROG == GD_PROG_V2_4 || kV241) ? t_st : m_st;
                 float acc = 0.f, acc_p = 0.f;
                 for (int i = b; i < e_end; ++i) {
                     const int e = tb.ld(tb.var_edges, i);
@@ -497,7 +543,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         acc += src[(size_t)e * tile + s];
                     }
                 }
-                float lg = kNBP ? acc + acc_p : ((kGRU || kV3 || kV122) ? acc : acc + xrow[v]);   // QGNNNI_ca.py:241-245: mlp(sum), no prior
+                float lg = kNBP ? acc + acc_p : ((kGRU || kV3 || kV122 || kV241) ? acc : acc + xrow[v]);   // QGNNNI_ca.py:241-245: mlp(sum), no prior
                 if constexpr (kV3) {            // decoder_v3_0.py:275: mlp(sum) + x
                     float xi[1] = {lg}, oo[1];
                     mlp_relu<1>(W3, hp, xi, oo);
@@ -574,6 +620,19 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
         for (int it = 0; it < p.T; ++it) {
             // NEURAL_BP: this layer's per-edge weights W_l[E] | W_p,l[E] (warp-uniform reads)
             const float* wl = kNBP ? p.weights + (size_t)it * 2 * E : nullptr;
+            if constexpr (kV241) {     // un-tied layers: this iteration's two MLPs and type tables (the last readers of the old ones are behind a barrier)
+                const int h = p.hid;
+                const float* w = p.weights + (size_t)it * (6 * h + 18);
+                stage_mlp(wsm, hp, h, w, 1, false, w + h, w + 2 * h, kLog2e, kLn2, tid, nthr);
+                W1 = MlpSmem{wsm, wsm + hp, wsm + 2 * hp, wsm + 3 * hp, w[3 * h]};
+                float* tw = wsm + 3 * p.wslot;
+                if (tid < 16) tw[tid] = w[3 * h + 1 + tid];
+                w += 3 * h + 17;
+                float* slot = wsm + p.wslot;
+                stage_mlp(slot, hp, h, w, 1, false, w + h, w + 2 * h, kLog2e, kLn2, tid, nthr);
+                W2 = MlpSmem{slot, slot + hp, slot + 2 * hp, slot + 3 * hp, w[3 * h]};
+                __syncthreads();
+            }
             // ---- V1: per-variable sums of m (ascending edge id) ----
             if (!vdir) {
             for (int v = r; v < V; v += R) {
@@ -583,6 +642,7 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                     const int e = tb.ld(tb.var_edges, i);
                     float mv = m_st[(size_t)e * tile + s];
                     if constexpr (kNBP) mv *= __ldg(wl + e);
+                    if constexpr (kV241) mv *= (wsm + 3 * p.wslot)[tb.csib[e]];
                     acc += mv;
                 }
                 node[v * tile + s] = acc;
@@ -648,6 +708,14 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                             const float a = node[v * tile + s] - mw + xrow[v] * __ldg(wl + E + e);
                             const float tv = bp_log_abs_tanh_half<false>(a, -46.0517019f);    // < 0 always
                             t_st[(size_t)e * tile + s] = a < 0.f ? -tv : tv;                 // sign flag rides in the sign bit
+                            continue;
+                        }
+                        if constexpr (kV241) {         // decoder_v2_4_1.py:275-276, 283-286: mlp1(sum of (m W) - own) + prior W_p; m itself stays = m_p
+                            const float* tw = wsm + 3 * p.wslot;
+                            const int ty = tb.csib[e];
+                            float ai[1] = {node[v * tile + s] - m_st[(size_t)e * tile + s] * tw[ty]}, oo[1];
+                            mlp_softplus<1, false>(W1, hp, ai, ai, oo);
+                            t_st[(size_t)e * tile + s] = tanh_half_fast(fmaf(xrow[v], tw[8 + ty], oo[0]));
                             continue;
                         }
                         if constexpr (kV3) {           // decoder_v3_0.py:103-108,229-232,246-247: rnn1(m, mlp1([sum - m, prior]))
@@ -734,6 +802,27 @@ __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
                         float* mp = m_st + (size_t)e * tile + s;
                         *mp = fmaf(alpha, *mp, bp_check_out(node[c * tile + s] + fabsf(tv), cnt & 1, 1e-15f));
                     }
+                }
+            } else if constexpr (kV241) {  // decoder_v2_4_1.py:287-288 (mlp(sum - own) * sign) and :337-339 (gated residual)
+                const float* tw = wsm + 3 * p.wslot;
+                const float ga = tw[32], gb = tw[33];
+                for (int i0 = 0; i0 < n_iter; i0 += kEB) {
+                    float x0[kEB], o[kEB];
+                    int ee[kEB];
+#pragma unroll
+                    for (int j = 0; j < kEB; ++j) {
+                        const int e = r + (i0 + j) * R;
+                        ee[j] = e;
+                        const int ec = e < E ? e : E - 1;
+                        x0[j] = node[tb.ld(tb.edge_chk, ec) * tile + s] - t_st[(size_t)ec * tile + s];
+                    }
+                    mlp_softplus<kEB, false>(W2, hp, x0, x0, o);
+#pragma unroll
+                    for (int j = 0; j < kEB; ++j)
+                        if (ee[j] < E) {
+                            float* mp = m_st + (size_t)ee[j] * tile + s;
+                            *mp = fmaf(o[j] * xrow[V + tb.ld(tb.edge_chk, ee[j])], ga, *mp * gb);
+                        }
                 }
             } else if constexpr (kV122) {  // decoder_v1_2_2.py:105-119 (eps 1e-20 / 1e-12, no input clamp) and :266 (+ m_p)
                 for (int i = 0; i < n_iter; ++i) {
@@ -873,7 +962,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     const bool bp = m->program == GD_PROG_BP_QUANTUM || m->program == GD_PROG_BP_CLASSICAL || m->program == GD_PROG_NEURAL_BP;
     const int hid = bp ? 0 : m->hidden;
     const int hp = align_up(hid, 8);
-    const bool gru = m->program == GD_PROG_GRU_CA || m->program == GD_PROG_V3_0;      // three MLP slots + two GRU cells
+    const bool gru = m->program == GD_PROG_GRU_CA || m->program == GD_PROG_V3_0 || m->program == GD_PROG_V2_4_1;   // three MLP slots + 24 (V2_4_1: 34) extra floats
     const bool sp2 = bp || m->program == GD_PROG_V1_2_2;                             // sum-product check phase: a second node array (sign counts)
     const int n_slots = bp ? 0 : ((m->program == GD_PROG_V2_4 || gru) ? 3 : 2);
     const int maxvc = V > C ? V : C;
@@ -897,7 +986,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
     const bool relu_prog = m->program == GD_PROG_CGNNI || m->program == GD_PROG_QGNNI || m->program == GD_PROG_GRU_CA;   // 1-input ReLU MLPs
     out->npad = (relu_prog && hid < 32 && !opt_on(OPT_NO_PWL)) ? (hid < 16 ? 16 : 32) : 0;
     p.wslot = 4 * hp > 3 * out->npad ? 4 * hp : 3 * out->npad;
-    p.off_w = off; off += n_slots * p.wslot * 4 + (gru ? 24 * 4 : 0); off = align_up(off, 16);
+    p.off_w = off; off += n_slots * p.wslot * 4 + (gru ? 40 * 4 : 0); off = align_up(off, 16);
     if (m->program == GD_PROG_V2_4 && !opt_on(OPT_NO_CTAB) && !opt_on(OPT_NO_RTAB)) {
         p.rtab_n = (int)opt_int(OPT_RTAB_N, 2048);
         if (p.rtab_n < 16 || p.rtab_n > 8192) p.rtab_n = 2048;
@@ -976,7 +1065,7 @@ static int plan_decode(const gd_graph* g, const gd_model* m, int64_t B, DecodePl
                     const int n_iter = (E + r - 1) / r;
                     // per-thread cost of one iteration in issue slots: EB-blocked per-edge update
                     // (c_edge each) + the node sums this thread owns (c_ld per summed edge)
-                    const double c_edge = (m->program == GD_PROG_V2_4 || m->program == GD_PROG_V1_2_2) ? 16.0 * hp : (bp ? 200.0 : 40.0 + 6.0 * hp);
+                    const double c_edge = (m->program == GD_PROG_V2_4 || m->program == GD_PROG_V1_2_2 || m->program == GD_PROG_V2_4_1) ? 16.0 * hp : (bp ? 200.0 : 40.0 + 6.0 * hp);
                     const double c_ld = 4.0;
                     const double node_cost = (double)((V + r - 1) / r) * g->max_var_deg + (double)((Cn + r - 1) / r) * g->max_chk_deg;
                     const double ideal = E * c_edge + 2.0 * E * c_ld;
@@ -1245,11 +1334,16 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
     pl.p.n_vact = gd::opt_on(gd::OPT_NO_VSKIP) ? (int)g->E : g->n_vact;
     pl.p.vdirect = (g->max_var_deg <= 2 && !gd::opt_on(gd::OPT_NO_DIRECT)) ? 1 : 0;
     pl.p.cdirect = (g->max_chk_deg <= 4 && !gd::opt_on(gd::OPT_NO_DIRECT)) ? 1 : 0;
+    if (model->program == GD_PROG_V2_4_1) {
+        bool all4 = true;
+        for (int c = 0; c < g->C && all4; ++c) all4 = g->h_chk_ptr[c + 1] - g->h_chk_ptr[c] == 4;
+        GD_CHECK_ARG(all4, "gd_decode_fwd: GD_PROG_V2_4_1 needs every check to have exactly 4 edges (decoder_v2_4_1.py:211-236)");
+    }
     GD_CHECK_ARG(model->program != GD_PROG_NEURAL_BP || model->hidden == g->E,
                  "gd_decode_fwd: GD_PROG_NEURAL_BP needs model.hidden == E (%lld per-edge weights), got %d",
                  (long long)g->E, model->hidden);
     if (!pl.resident && (model->program == GD_PROG_NEURAL_BP || model->program == GD_PROG_GRU_CA || model->program == GD_PROG_V3_0 ||
-                         model->program == GD_PROG_V1_2_2)) {
+                         model->program == GD_PROG_V1_2_2 || model->program == GD_PROG_V2_4_1)) {
         gd::set_error("gd_decode_fwd: program %d has a resident kernel only and this code's edge state does not fit "
                       "shared memory", model->program);
         return GD_ERR_UNSUPPORTED;
@@ -1276,6 +1370,7 @@ static int decode_fwd_impl(const gd_graph* gc, const gd_model* model, const floa
         case GD_PROG_GRU_CA: rc = gd::launch_decode<GD_PROG_GRU_CA>(pl, st); break;
         case GD_PROG_V3_0: rc = gd::launch_decode<GD_PROG_V3_0>(pl, st); break;
         case GD_PROG_V1_2_2: rc = gd::launch_decode<GD_PROG_V1_2_2>(pl, st); break;
+        case GD_PROG_V2_4_1: rc = gd::launch_decode<GD_PROG_V2_4_1>(pl, st); break;
         default: rc = gd::launch_decode<GD_PROG_BP_CLASSICAL>(pl, st); break;
     }
     if (prev != g->device) cudaSetDevice(prev);

@@ -36,6 +36,7 @@ extern "C" int64_t gd_weights_size(const gd_model* m) {
         case GD_PROG_GRU_CA: return 9 * h + 27;
         case GD_PROG_V3_0: return 11 * h + 27;
         case GD_PROG_V1_2_2: return 8 * h + 2;
+        case GD_PROG_V2_4_1: return (int64_t)m->iters * (6 * h + 18) + 3 * h + 19;
         default: return 0;
     }
 }

@@ -4,11 +4,11 @@ target_to_source layer a 1 -> 128 -> 1 `mlp`), one-hot edge types, and a gated r
 `m = chk * sigmoid(alpha) + m_p * sigmoid(beta)`.  Reference: GraphConv decoder_v2_4_1.py:255-288, GNNI :291-349.
 Same class names, signatures and state_dict keys (44 tensors for Nc = 3).
 
-How it runs: the propagate() of every layer -- tanh pre, "sum over siblings minus self", cat with extra[edge_index[j]]
-(decoder_v2_4_1.py:134-146, identical to decoder_v2_4's) -- is the CUDA propagate kernel (C ABI gd_propagate_fwd); this
-script's `update()`s (the un-tied MLPs and type tables) run as the torch modules they are, exactly as the reference's
-plugin API intends for a subclass that overrides update().  It is NOT one of the fused programs: there is no tuned kernel
-for un-tied 128-wide layers yet (out of scope).
+How it runs: `GNNI.forward` / `decode()` is the fused persistent kernel (GD_PROG_V2_4_1: the layer's two MLPs and type tables are
+re-staged in shared memory at the start of every iteration, edge types are derived from the graph inside the kernel).  The per-layer
+classes keep the reference's plugin API: the propagate() of every layer -- tanh pre, "sum over siblings minus self", cat with
+extra[edge_index[j]] (decoder_v2_4_1.py:134-146, identical to decoder_v2_4's) -- is the CUDA propagate kernel (C ABI
+gd_propagate_fwd) and the layer's `update()` (the un-tied MLP and type tables) runs in torch on its result (`forward_layers`).
 
 The reference derives the edge types from H at import time (`feat_onehot`, :211-236: position of the edge among its
 check's four edges, + 4 for the second half of the checks); here they are computed from edge_index on first use.  Every
@@ -17,7 +17,7 @@ import torch
 
 from .. import _cabi
 from ..graph import graph_from_batched
-from ..message_passing import MessagePassingBase, _require_cuda
+from ..message_passing import DecoderBase, MessagePassingBase, pack_mlp, _require_cuda
 
 nb_digits = 8
 
@@ -87,12 +87,11 @@ class GraphConv(MessagePassing):
         return 128
 
 
-class GNNI(torch.nn.Module):
+class GNNI(DecoderBase):
+    _gd_program = _cabi.PROG_V2_4_1
+
     def __init__(self, Nc, *, rows=None, cols=None):
-        super(GNNI, self).__init__()
-        self.Nc = Nc
-        self._gd_rows = None if rows is None else int(rows)
-        self._gd_cols = None if cols is None else int(cols)
+        super(GNNI, self).__init__(Nc, rows, cols)
         self.layers = self._make_layer()
         self.mlp = _mlp()
         self.mlp.apply(init_weights_2)
@@ -117,8 +116,18 @@ class GNNI(torch.nn.Module):
             layer.bind_code(rows, cols)
         return self
 
-    def forward(self, data):
-        """data.x [B*(V+C), 1], data.edge_index [2, B*E] (check ids not yet offset) -> P(flip) [B*V, 1]."""
+    def _gd_hidden(self):
+        return self.mlp[0].out_features
+
+    def _gd_params(self):
+        ps = []
+        for i in range(0, len(self.layers), 2):
+            ps += pack_mlp(self.layers[i].mlp1) + [self.layers[i].W, self.layers[i].W_p] + pack_mlp(self.layers[i + 1].mlp)
+        return ps + pack_mlp(self.mlp) + [self.W, self.W_p, self.alpha, self.beta]
+
+    def forward_layers(self, data):
+        """The reference's forward spelled out on the per-layer classes (CUDA propagate kernel + torch update() per layer):
+        data.x [B*(V+C), 1], data.edge_index [2, B*E] (check ids not yet offset) -> P(flip) [B*V, 1]."""
         x, ei0 = data.x, data.edge_index
         _require_cuda(x, "data.x")
         _require_cuda(ei0, "data.edge_index")

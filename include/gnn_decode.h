@@ -54,8 +54,11 @@ enum gd_program {
                                  sign-multiplied check phase, one read-out per iteration              */
     GD_PROG_V3_0 = 7,         /* quantum/decoder_v3_0.py:199-290 hidden 10 ReLU MLPs of [sum, node input] + GRUCell(1,1)
                                  per phase, no tanh; a SECOND read-out at the check nodes (gd_decode_fwd_aux) */
-    GD_PROG_V1_2_2 = 8        /* quantum/decoder_v1_2_2.py:212-278 hidden 256 Tanh MLP of [sum, prior] (variable phase),
+    GD_PROG_V1_2_2 = 8,       /* quantum/decoder_v1_2_2.py:212-278 hidden 256 Tanh MLP of [sum, prior] (variable phase),
                                  sum-product check phase + residual, Tanh-MLP read-out of EVERY iteration */
+    GD_PROG_V2_4_1 = 9        /* quantum/decoder_v2_4_1.py:255-349 decoder_v2_4 with 2*Nc UN-TIED layers (hidden 128 Softplus),
+                                 per-edge-type weights (8 types, derived from the graph: every check must have 4 edges) and a
+                                 gated residual sigmoid(alpha) / sigmoid(beta) */
 };
 
 /* gd_model.flags */
@@ -89,6 +92,9 @@ typedef struct gd_graph gd_graph;
  *                bias_ih[3],bias_hh[3]}, ggc2.mlp2{0.weight[h,2],...}, ggc2.rnn2{...}, mlp{0.weight[h,1],...}   (11h+27)
  *                (the state_dict's ggc1.mlp2 / ggc1.rnn2 / ggc2.mlp1 / ggc2.rnn1 are never used by the forward)
  *   V1_2_2     : ggc1.mlp{0.weight[h,2],0.bias[h],2.weight[1,h],2.bias[1]}, mlp{0.weight[h,2],...}              (8h+2)
+ *   V2_4_1     : for l in 0..iters-1: layers.{2l}.mlp1{0.weight[h,1],0.bias[h],2.weight[1,h],2.bias[1]}, layers.{2l}.W[8],
+ *                layers.{2l}.W_p[8], layers.{2l+1}.mlp{...}; then mlp{...}, W[8], W_p[8], alpha, beta
+ *                (iters (6h+18) + 3h+19; the W / W_p of the target_to_source layers are never used by the forward)
  */
 typedef struct gd_model {
     int32_t program;   /* enum gd_program                                   */

@@ -258,9 +258,10 @@ def test_v1_1_onehot_decoder_matches_reference():
 
 
 @pytest.mark.gpu
-def test_v2_4_1_drop_in_matches_reference_fixture():
-    """decoder_v2_4_1 through the drop-in classes: every layer's propagate() is the CUDA kernel (fp32 reduce), the script's own
-    update()s are torch modules -- against the probabilities the reference itself produced."""
+def test_v2_4_1_fused_and_per_layer_match_reference_fixture():
+    """decoder_v2_4_1: (a) GNNI.forward = the fused kernel (GD_PROG_V2_4_1: un-tied layers re-staged per iteration, edge types derived
+    in the kernel), (b) forward_layers = every layer's propagate() on the CUDA propagate kernel with the script's own update()s in
+    torch -- both against the probabilities the reference itself produced and the fp64 restatement's logits."""
     from gnn_decode_b200.quantum import decoder_v2_4_1
     g = Golden("ext_v2_4_1_toricL4")
     dev = torch.device("cuda", 0)
@@ -268,16 +269,30 @@ def test_v2_4_1_drop_in_matches_reference_fixture():
     dec.load_state_dict(g.weights, strict=True)
     dec = dec.to(dev).eval()
     d = _Data(g, dev)
-    with torch.no_grad():
-        prob = dec(d)
-        prob2 = dec(d)
-    assert prob.shape == (g.B * g.V, 1) and prob.dtype == torch.float64 and torch.equal(prob, prob2)
     ref = restate.decode("v2_4_1", g.edge_index, g.V, g.C, g.x, g.weights, T=g.T)
     assert torch.equal(ref["prob"], g.prob)
-    logit = -torch.log(prob / (1 - prob)).reshape(g.B, g.V)
+    with torch.no_grad():
+        outs = {"fused": dec(d), "fused again": dec(d), "layers": dec.forward_layers(d)}
+    assert torch.equal(outs["fused"], outs["fused again"])
+    for name, prob in outs.items():
+        assert prob.shape == (g.B * g.V, 1) and prob.dtype == torch.float64, name
+        logit = -torch.log(prob / (1 - prob)).reshape(g.B, g.V)
+        worst, max_err = _close(logit, ref["logit"], RTOL)
+        assert worst <= 1.0, "%s logits: %.3g x the bar (max abs err %.3g)" % (name, worst, max_err)
+        assert (prob.reshape(g.B, g.V).cpu() - g.prob).abs().max().item() < 1e-5, name
+    # logits straight from the kernel (no sigmoid round trip), hard decisions
+    tg = _graph(g, dev)
+    prob, logit, hard = dec.decode(g.x.to(dev), graph=tg, return_logits=True, return_hard=True)
     worst, max_err = _close(logit, ref["logit"], RTOL)
-    assert worst <= 1.0, "logits: %.3g x the bar (max abs err %.3g)" % (worst, max_err)
-    assert (prob.reshape(g.B, g.V).cpu() - g.prob).abs().max().item() < 1e-5
+    assert worst <= 1.0, (worst, max_err)
+    decided = ref["logit"].abs() > LOGIT_TIE
+    assert torch.equal(hard.cpu().bool()[decided], (ref["logit"] < 0)[decided])
+    # a code whose checks do not all have four edges is refused, as the reference's feat_onehot construction would fail on it
+    from gnn_decode_b200 import codes
+    from gnn_decode_b200.graph import TannerGraph
+    rot = TannerGraph.from_pcm(codes.rotated_surface_pcm(3), dev)
+    with pytest.raises(_cabi.GdError):
+        dec.decode(torch.ones(4, rot.N, device=dev), graph=rot)
 
 
 @pytest.mark.parametrize("name,prog", [("ext_v3_0_toricL4", "v3_0"), ("ext_v1_2_2_toricL4", "v1_2_2")])
