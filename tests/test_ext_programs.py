@@ -291,7 +291,7 @@ def test_v2_4_1_fused_and_per_layer_match_reference_fixture():
     from gnn_decode_b200 import codes
     from gnn_decode_b200.graph import TannerGraph
     rot = TannerGraph.from_pcm(codes.rotated_surface_pcm(3), dev)
-    with pytest.raises(_cabi.GdError):
+    with pytest.raises(ValueError, match="exactly 4 edges"):
         dec.decode(torch.ones(4, rot.N, device=dev), graph=rot)
 
 
