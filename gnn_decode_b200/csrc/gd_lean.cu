@@ -1445,6 +1445,20 @@ static bool lean_search(gd_graph* g, const LeanSub* sub, int tpc, int ri_fixed, 
             if (score > best.score) best = Cand{R, G, nch, rt_n, score};
         }
     }
+    // More owners at the same critical path never hurt: while the most loaded owner's edge count and the checks per owner stay what
+    // they are, the groups still fit and the CTA stays within 32 warps, take them (rotated d = 11: R = 30 -> 32, 75.6 -> 80.5 M
+    // syndromes/s; toric L = 11: 35.9 -> 37.4 M; profiles/r02_lean_geometry_sweep.txt).
+    if (best.R > 0 && force_R <= 0) {
+        auto max_load = [&](int R) { return bals[R] > 0.0 ? (int)std::lround((double)E / ((double)R * bals[R])) : 0; };
+        const int mx0 = max_load(best.R);
+        for (int R = best.R + 1; R <= 32 && R * best.G <= 32; ++R) {
+            if (nchs[R] == 0 || nchs[R] > best.NCH || max_load(R) > mx0) continue;
+            const int meta = align_up_i(align_up_i(2 * R * nchs[R] * 16 + R * nchs[R] * 4, 16) + V * 8, 16);
+            const int fixed = align_up_i(meta + (ct_n + 2) * 128 + (best.rt_n + 2) * 16 + (vt_n + 2) * 128, 128);
+            if ((smem_max - fixed) / state < best.G) continue;
+            best.R = R; best.NCH = nchs[R];
+        }
+    }
     out->valid = true;                                          // "does not fit" is a cached answer too (R == 0)
     out->R = best.R; out->G = best.G; out->NCH = best.NCH; out->rt_n = best.rt_n;
     out->ct_n = ct_n; out->vt_n = vt_n;

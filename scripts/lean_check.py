@@ -93,7 +93,7 @@ def main():
         res[name] = rec
         if args.sweep:
             sw = []
-            for R in (2, 3, 4, 5, 6, 8, 10, 12, 15, 16, 20, 24):
+            for R in (2, 3, 4, 5, 6, 8, 10, 12, 15, 16, 20, 24, 28, 30, 32):
                 for G in (1, 2, 3, 4, 5, 6, 8):
                     if R * G > 32:
                         continue
