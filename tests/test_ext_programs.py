@@ -35,12 +35,22 @@ def test_restatement_matches_golden_bit_exact(name):
         assert torch.equal(out["all_prob"], _all_prob(name))          # every iteration's prediction
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+MORE = {"ext_v3_0_toricL4": "quantum.decoder_v3_0", "ext_v1_2_2_toricL4": "quantum.decoder_v1_2_2", "ext_v2_4_1_toricL4": "quantum.decoder_v2_4_1"}
+
+
+@pytest.mark.parametrize("name", sorted(CASES) + sorted(MORE))
 def test_state_dict_and_weight_count(name):
+    """The drop-in modules carry the reference's state_dict keys in the reference's order (the fixtures hold what the reference's own
+    classes saved), and the packed weight buffer has the size the C ABI expects."""
     import ctypes as C
+    import importlib
     from gnn_decode_b200 import _cabi
     g = Golden(name)
-    mod, dec = _make(g, name)
+    if name in MORE:
+        dec = importlib.import_module("gnn_decode_b200." + MORE[name]).GNNI(g.T)
+        dec.load_state_dict(g.weights, strict=True)
+    else:
+        mod, dec = _make(g, name)
     assert list(dec.state_dict().keys()) == list(g.weights.keys())
     assert sum(p.numel() for p in dec._gd_params()) == _cabi.lib().gd_weights_size(C.byref(dec.gd_model()))
 
