@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p
     const LeanHeader* H = p.hdr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (blockIdx.x == 0) {                                     // the next call's state: nobody reads or writes it until then
-        if (tid == 0) { p.next_call->overflow = 0; p.next_call->defer_count = 0; p.next_call->fmax_new = 0u; }
+        if (tid == 0) { p.next_call->overflow = 0; p.next_call->defer_count = 0; p.next_call->fmax_new = 0u; p.next_call->d2_new = 0u; p.next_call->d3_new = 0u; }
         if (tid < kMaxSlots) p.next_call->count[tid] = 0;
     }
     // ---- can the tables serve this call at all? (identical decision in every thread of the grid) ----
@@ -600,6 +600,8 @@ struct PrepParams {
 };
 
 constexpr int kPrepRows = 256;     // most rows a prep CTA handles (its shared-memory lists)
+constexpr int kD3Points = 1025;    // grid of the prep kernel's max |mlp3'| estimate
+constexpr double kD3Range = 352.0; // = 0.172 x 4096 / 2
 
 // The tail every prep CTA runs: its rows' slots were counted in cnt_sh (the rank inside the CTA came from that atomicAdd);
 // one global atomicAdd per (CTA, slot) reserves a range of the slot's list.
@@ -716,7 +718,16 @@ __global__ void __launch_bounds__(256, 6) lean_prep_kernel(const PrepParams p) {
             if (j < p.ct_n + 3) {
                 double f, df;
                 mlp_eval_warp(M2, 0.0, -3.0 + (6.0 / (double)p.ct_n) * (double)(j - 1), threadIdx.x & 31, f, df);
-                if ((threadIdx.x & 31) == 0) atomic_max_float_up(&p.call->fmax_new, f);
+                if ((threadIdx.x & 31) == 0) { atomic_max_float_up(&p.call->fmax_new, f); atomic_max_float_up(&p.call->d2_new, df); }
+            } else if (j < p.ct_n + 3 + kD3Points) {
+                // max |mlp3'| on a coarse grid over [-kD3Range, kD3Range], the widest message domain 4096 pieces can take: an
+                // ESTIMATE of how much the read-out amplifies a message error, for the table kernel's first choice of resolution
+                const float* w3 = p.weights + 7 * p.hid + 2;
+                const MlpD M3{w3, 1, nullptr, w3 + p.hid, w3 + 2 * p.hid, w3[3 * p.hid], p.hid};
+                const int i = j - (p.ct_n + 3);
+                double f, df;
+                mlp_eval_warp(M3, 0.0, -kD3Range + (2.0 * kD3Range / (double)(kD3Points - 1)) * (double)i, threadIdx.x & 31, f, df);
+                if ((threadIdx.x & 31) == 0) atomic_max_float_up(&p.call->d3_new, df);
             }
         }
         return;
@@ -766,9 +777,13 @@ constexpr int kVtSlotGroups = 16;   // variable-table CTAs: vt_chunks x 16, CTA 
 // 34 .. 43) at 2e-7 .. 6e-7; wider domains (fresh kaiming weights: 96, the collapsed epoch-67 checkpoint: 70) double it until the
 // piece width is back under 0.172.  The a-posteriori error check has the last word: a decode kernel that finds a table over its
 // budget hands the batch to the edge-owner kernel and raises LeanHeader::vt_mult, so the NEXT call rebuilds with finer tables.
-__device__ __forceinline__ int lean_vt_pieces(int base, double Rm, int mult) {
+__device__ __forceinline__ int lean_vt_pieces(int base, double Rm, int mult, int T, float d2, float d3) {
+    // widest piece: 0.172 meets the plain 1e-6 budget; a model that amplifies table errors more (lean_decode_kernel's budget_v:
+    // 4e-4 / amplification) needs pieces narrower by the fourth root of the budget's ratio (Hermite error ~ width^4)
+    const double gain = 6.0 * (double)T * (double)d2 * (double)d3;
+    const double wmax = gain > 400.0 && isfinite(gain) ? 0.172 * sqrt(sqrt(400.0 / gain)) : 0.172;
     int n = base;
-    while (n < 8 * base && (2.0 * Rm / (double)n > 0.172 || n < base * mult)) n *= 2;
+    while (n < 8 * base && (2.0 * Rm / (double)n > wmax || n < base * mult)) n *= 2;
     return n;
 }
 
@@ -790,7 +805,7 @@ __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
                 H->hash = H->pending_hash;
                 H->fmax_bits = p.call->fmax_new;
                 const float fm = __uint_as_float(p.call->fmax_new);
-                H->vt_n_eff = lean_vt_pieces(p.vt_n, (double)((float)p.T * (fm * 1.02f + 1e-6f)), H->vt_mult);
+                H->vt_n_eff = lean_vt_pieces(p.vt_n, (double)((float)p.T * (fm * 1.02f + 1e-6f)), H->vt_mult, p.T, __uint_as_float(p.call->d2_new), __uint_as_float(p.call->d3_new));
             }
         }
         __syncthreads();
@@ -823,7 +838,7 @@ __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
     }
     if (p.call->overflow) return;
     const int b = bid - p.ct_blocks - p.rt_blocks, cb = b % p.vt_chunks, sg = b / p.vt_chunks;
-    const int vt_n = rebuild ? lean_vt_pieces(p.vt_n, Rm, H->vt_mult) : H->vt_n_eff;
+    const int vt_n = rebuild ? lean_vt_pieces(p.vt_n, Rm, H->vt_mult, p.T, __uint_as_float(p.call->d2_new), __uint_as_float(p.call->d3_new)) : H->vt_n_eff;
     const int i0 = cb * kChunk, n_int = min(kChunk, vt_n + 2 - i0);
     if (n_int <= 0) return;
     const int n_slots = H->n_slots;
@@ -1740,7 +1755,7 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         GD_CHECK_ARG(blocks < (1ll << 30), "gd_decode_fwd: batch too large for the table kernel's prep pass");
         pp.hid = model->hidden;
         pp.keep_mult = stash_dev ? 1 : 0;
-        pp.fm_blocks = (p.ct_n + 3 + 7) / 8;                      // 8 warps = 8 check-table nodes per CTA
+        pp.fm_blocks = (p.ct_n + 3 + kD3Points + 7) / 8;          // 8 warps = 8 points per CTA (check-table nodes, then the mlp3' grid)
         lean_prep_kernel<<<(unsigned int)(1 + pp.fm_blocks + blocks), 256, 0, st>>>(pp);
         e = cudaGetLastError();
     }

@@ -13,7 +13,9 @@ struct LeanCall {
     int defer_count;             // syndromes listed in defer_idx; -1 = all of them, in batch order
     int count[kLeanMaxSlots];    // syndromes of this batch that carry the prior of slot k
     unsigned int fmax_new;       // max |mlp2| over the check table's nodes, gathered by the prep kernel when the weights changed
-    int pad[3];
+    unsigned int d2_new;         // ... max |mlp2'| there, and max |mlp3'| on a coarse grid over the widest domain the tables can take:
+    unsigned int d3_new;         //   the amplification estimate the table kernel sizes the variable-phase tables with
+    int pad[1];
 };
 
 // Device-side state of one table set (lives in a cache entry of the graph, persists across calls): the tables are rebuilt

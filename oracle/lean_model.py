@@ -67,11 +67,13 @@ def eval_table(coef, inv_h, off, x, clamp=None):
     return r
 
 
-def vt_pieces(base, Rm, mult=1):
+def vt_pieces(base, Rm, mult=1, gain=0.0):
     """Pieces of the variable-phase tables (gd_lean.cu: lean_vt_pieces): the base count, doubled (up to 8x) until a piece is
-    narrower than 0.172 and there are at least base * mult of them."""
+    narrower than 0.172 -- narrower by (400 / gain)^(1/4) for a model that amplifies table errors by more than 400 -- and there are
+    at least base * mult of them."""
+    wmax = 0.172 * (400.0 / gain) ** 0.25 if gain > 400.0 else 0.172
     n = base
-    while n < 8 * base and (2.0 * Rm / n > 0.172 or n < base * mult):
+    while n < 8 * base and (2.0 * Rm / n > wmax or n < base * mult):
         n *= 2
     return n
 
@@ -109,13 +111,16 @@ def decode(edge_index, V, C, x, w, T, ct_n=128, vt_n=512, rt_n=2048, adaptive=Tr
     bv = budget_v(T, d2max, d3max)
     if adaptive:
         base, mult = vt_n, 1
+        # the kernel's first choice uses max |mlp3'| on a coarse grid over [-352, 352] (the prep kernel's estimate)
+        d3_est = float(np.abs(mlp_f_df(a3, c3_, w23, b23, np.linspace(-352.0, 352.0, 1025))[1]).max())
+        errs_first = vt_pieces(base, Rm, 1, 6.0 * T * d2max * d3_est)
         while True:
-            vt_n = vt_pieces(base, Rm, mult)
+            vt_n = vt_pieces(base, Rm, mult, 6.0 * T * d2max * d3_est)
             worst = max(build_table(W1[:, 0], W1[:, 1] * float(p) + b1, w2v, b2v, Rm, vt_n, tanh_fold=True)[1] for p in np.unique(prior))
             if worst <= bv or vt_n >= 8 * base:
                 break
             mult = 2 * vt_n // base
-    errs = {"c": err_c, "r": err_r, "v": {}, "Rm": Rm, "f3max": f3max, "vt_n": vt_n, "budget_v": bv}
+    errs = {"c": err_c, "r": err_r, "v": {}, "Rm": Rm, "f3max": f3max, "vt_n": vt_n, "budget_v": bv, "vt_n_first": errs_first if adaptive else vt_n}
     # sibling edge of each edge at its variable, other edges of each edge at its check
     sib = -np.ones(E, np.int64)
     for v in range(V):

@@ -38,6 +38,11 @@ def main():
         ref = restate.decode("v2_4", ei, g.V, g.C, x.double().cpu(), w, T=15)["logit"]
         with options.option("GD_NO_LEAN"):
             l_old = dec.decode(x, return_logits=True)[1]
+            with options.option("GD_NO_VTAB"):
+                l_nv = dec.decode(x, return_logits=True)[1]
+                with options.option("GD_NO_CTAB"):
+                    l_dir = dec.decode(x, return_logits=True)[1]
+        print(name, "edge-owner without variable tables: worst %.3f | all-direct: worst %.3f" % (logit_worst(l_nv.cpu(), ref)[0], logit_worst(l_dir.cpu(), ref)[0]))
         ls = [dec.decode(x, return_logits=True)[1] for _ in range(4)]
         print(name, "edge-owner: worst %.3f (max abs %.2e)" % logit_worst(l_old.cpu(), ref),
               "| table calls:", ["%.3f%s" % (logit_worst(l.cpu(), ref)[0], "=" if torch.equal(l, l_old) else "") for l in ls],

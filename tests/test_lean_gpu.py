@@ -195,9 +195,9 @@ def test_toric_L11_runs_on_the_table_kernel_by_components():
 
 def test_wide_message_domains_get_finer_variable_tables():
     """epoch67 (|logit| up to ~600, T max|mlp2| = 70, errors amplified ~4000 x) and freshly initialised weights (T max|mlp2| ~ 140):
-    512 pieces miss the budget of the variable-phase tables on such a domain.  The piece-width rule doubles them at once; where the
-    a-posteriori check still finds a table over its (amplification-aware) budget, THAT call is decoded by the edge-owner kernel --
-    bit-identical to running it directly -- and the next one rebuilds with finer tables (epoch67: 1024 -> 2048)."""
+    512 pieces miss the budget of the variable-phase tables on such a domain.  The piece-width rule -- which knows the model's
+    amplification from the prep pass -- doubles them at once (epoch67: 2048); only where the a-posteriori check still finds a table
+    over its budget would a call go to the edge-owner kernel and the next one rebuild finer."""
     g, dec, _ = _setup(case="v2_4_toricL4_epoch67")
     x, _ = sample_syndromes(g, 2000, P10[:6], noise=1, seed=8)
     ei = torch.from_numpy(codes.edge_index_of(codes.rotated_surface_pcm(5)))
@@ -208,9 +208,8 @@ def test_wide_message_domains_get_finer_variable_tables():
         with options.option("GD_NO_LEAN"):
             p_old, l_old = dec.decode(x, return_logits=True)
         l_first = dec.decode(x, return_logits=True)[1]
-        if not fresh:
-            assert torch.equal(l_first, l_old)                    # 1024 pieces: 3.8e-7 > the 1e-7 this checkpoint needs
         p, l = dec.decode(x, return_logits=True)
+        assert torch.equal(l_first, l)                            # served by the tables from the first call on
         assert not torch.equal(l, l_old)                          # the tables served it
         assert torch.equal(dec.decode(x, return_logits=True)[1], l)
         w = {k: v.detach().cpu() for k, v in dec.state_dict().items()}

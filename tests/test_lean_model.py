@@ -29,7 +29,7 @@ def test_table_recurrence_matches_the_oracle(name):
 def test_collapsed_checkpoint_needs_finer_variable_tables():
     """epoch67 (T max|mlp2| = 70, max|mlp3'| = 20: a table error is amplified ~4000 x on its way to the logits, the shipped
     checkpoints: ~200 x).  512 pieces on [-72, 72] miss even the plain 1e-6 budget; the piece-width rule's 1024 meet that (3.8e-7) but
-    not the logit bar (1.1 x) -- the amplification-aware budget (1e-7 here) sends the kernel on to 2048 pieces, which do (0.43 x)."""
+    not the logit bar (1.1 x) -- the amplification-aware budget (1e-7 here) and piece width (0.097 instead of 0.172) make it 2048 pieces, which do (0.43 x)."""
     g = Golden("v2_4_toricL4_epoch67")
     w = {k: v.numpy() for k, v in g.weights.items()}
     ref = restate.decode("v2_4", g.edge_index, g.V, g.C, g.x, g.weights, T=g.T)["logit"]
@@ -42,6 +42,7 @@ def test_collapsed_checkpoint_needs_finer_variable_tables():
     out = lean_model.decode(g.edge_index.numpy(), g.V, g.C, g.x.numpy(), w, g.T)
     e = out["errs"]
     assert e["vt_n"] == 2048 and max(e["v"].values()) <= e["budget_v"] < 2e-7
+    assert e["vt_n_first"] == 2048            # ... at once: the piece-width rule knows the amplification (estimated in the prep pass)
     worst, max_err = logit_worst(torch.from_numpy(out["logit"]), ref)
     assert worst <= 0.5, (worst, max_err)
 
