@@ -66,6 +66,12 @@ struct LeanParams {
     int off_me, off_ms, off_mi, off_var, off_ct, off_rt, off_vt, off_state;   // shared-memory byte offsets
 };
 
+// Programmatic dependent launch: the four kernels of a decode call are launched with programmatic stream serialisation, so a
+// kernel's CTAs are scheduled while the previous kernel drains; pdl_wait() returns once that kernel has completed and its writes
+// are visible (a no-op in a launch without the attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------------------------
 // shared-memory access by 32-bit address
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -265,6 +271,8 @@ template <bool STASH>
 __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int tile_pre[4];                                // this CTA's share: {slot, first tile, end tile, first syndrome of the slot in idx}
+    pdl_launch_dependents();
+    pdl_wait();
     const LeanHeader* H = p.hdr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (blockIdx.x == 0) {                                     // the next call's state: nobody reads or writes it until then
@@ -691,6 +699,8 @@ __global__ void __launch_bounds__(256, 6) lean_prep_kernel(const PrepParams p) {
     __shared__ int cnt_sh[kMaxSlots], base_sh[kMaxSlots];
     unsigned int* mirror = const_cast<unsigned int*>(mirror_v);
     LeanHeader* H = p.hdr;
+    pdl_launch_dependents();
+    pdl_wait();
     if ((int)blockIdx.x <= p.fm_blocks) {
         // CTA 0: does the cached table set belong to these weights?  H->hash itself is only replaced by the table kernel, so the
         // CTAs 1 .. fm_blocks, which make the same comparison, see the same answer: when the weights changed they gather
@@ -793,6 +803,8 @@ __device__ __forceinline__ int lean_vt_pieces(int base, double Rm, int mult, int
 // iteration); max|mlp2| was gathered by the prep kernel.  The first CTAs scatter the rows into the prior-sorted list.
 __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
     __shared__ double2 nodes[kChunk + 1];
+    pdl_launch_dependents();
+    pdl_wait();
     LeanHeader* H = p.hdr;
     const int rebuild = H->rebuild;
     if ((int)blockIdx.x < p.scatter_blocks) {
@@ -1584,6 +1596,19 @@ bool lean_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_la
     return true;
 }
 
+// launch with programmatic stream serialisation (see pdl_wait)
+template <typename P>
+static cudaError_t pdl_launch(void (*kern)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P& params) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = opt_on(OPT_NO_PDL) ? 0 : 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, params);
+}
+
 static cudaMemPool_t lean_pool(gd_graph* g) {
     std::lock_guard<std::mutex> lk(g->mu);
     if (!g->lean_ctx) g->lean_ctx = new LeanCtx();
@@ -1756,8 +1781,7 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         pp.hid = model->hidden;
         pp.keep_mult = stash_dev ? 1 : 0;
         pp.fm_blocks = (p.ct_n + 3 + kD3Points + 7) / 8;          // 8 warps = 8 points per CTA (check-table nodes, then the mlp3' grid)
-        lean_prep_kernel<<<(unsigned int)(1 + pp.fm_blocks + blocks), 256, 0, st>>>(pp);
-        e = cudaGetLastError();
+        e = pdl_launch(lean_prep_kernel, dim3((unsigned int)(1 + pp.fm_blocks + blocks)), dim3(256), 0, st, pp);
     }
     if (e == cudaSuccess) {
         TabParams tp;
@@ -1770,8 +1794,7 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         tp.rt_blocks = (p.rt_n + 2 + kChunk - 1) / kChunk;
         tp.vt_chunks = (8 * p.vt_n + 2 + kChunk - 1) / kChunk;
         tp.scatter_blocks = (int)std::max<long long>(1, std::min<long long>((B + 1023) / 1024, (long long)g->sm_count * 4));
-        lean_tables_kernel<<<tp.scatter_blocks + tp.ct_blocks + tp.rt_blocks + kVtSlotGroups * tp.vt_chunks, 256, 0, st>>>(tp);
-        e = cudaGetLastError();
+        e = pdl_launch(lean_tables_kernel, dim3(tp.scatter_blocks + tp.ct_blocks + tp.rt_blocks + kVtSlotGroups * tp.vt_chunks), dim3(256), 0, st, tp);
     }
     if (e == cudaSuccess && pls.size() > 1 && hard_bits_dev)    // parts share the words at their borders and OR their bits in
         e = cudaMemsetAsync(hard_bits_dev, 0, (size_t)B * p.vw * sizeof(uint32_t), st);
@@ -1792,10 +1815,7 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         q.idx_src = q.idx;
         auto kern = stash_dev ? lean_decode_kernel<true> : lean_decode_kernel<false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
-        if (e == cudaSuccess) {
-            kern<<<pl.grid, pl.threads, pl.smem, st>>>(q);
-            e = cudaGetLastError();
-        }
+        if (e == cudaSuccess) e = pdl_launch(kern, dim3(pl.grid), dim3(pl.threads), (size_t)pl.smem, st, q);
     }
     cudaEventRecord(ent->ev, st);                                // the entry's tables are free again after this point of the stream
     // the syndromes the tables could not serve: edge-owner kernel, direct evaluation, per item

@@ -43,6 +43,7 @@ enum Opt {
     OPT_LEAN_CTAB_N,      // GD_LEAN_CTAB_N    its check-phase table intervals (128, replicated per bank group)
     OPT_LEAN_RTAB_N,      // GD_LEAN_RTAB_N    its read-out table intervals (2048)
     OPT_LEAN_PARTS,       // GD_LEAN_PARTS     1: decode the graph's connected components in separate launches, 0: never (unset: when that seats more groups)
+    OPT_NO_PDL,           // GD_NO_PDL         launch the table kernel's passes without programmatic dependent launch
     OPT_LAUNCH_BLOCKING,  // (derived) a tool that makes launches block the host is attached (ncu / sanitizer / CUDA_LAUNCH_BLOCKING)
     OPT_COUNT
 };
