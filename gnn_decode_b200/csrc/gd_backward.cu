@@ -196,6 +196,7 @@ __device__ __forceinline__ void store_acc(float* dst, const LaneAcc& A, int h, b
 
 __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
+    pdl_enter();
     if (p.run_flag && *p.run_flag == 0) return;               // the table forward wrote this step's stash: gd_lean.cu's backward runs
     const int tile = p.tile, R = p.R, E = p.E, V = p.V, C = p.C, N = p.N, h = p.hid, T = p.T;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
@@ -479,6 +480,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decode_bwd_kernel(const BwdPar
 // stage 2: fixed-order sum over the per-warp partials (double accumulation) -> grad[n_params]
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_rows, int np_pad, int n_params,
                                        float* __restrict__ grad, int accumulate, const int* run_flag) {
+    pdl_enter();
     if (run_flag && *run_flag == 0) return;                   // the table backward (gd_lean.cu) produced this step's gradient
     const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
     if (pidx >= n_params) return;
@@ -607,13 +609,11 @@ extern "C" int gd_decode_bwd(const gd_graph* g, const gd_model* model, const flo
     }
     cudaError_t e = cudaFuncSetAttribute(gd::decode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
     if (e == cudaSuccess) {
-        gd::decode_bwd_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(pl.p);
-        e = cudaGetLastError();
+        e = gd::pdl_launch_on(!gd::opt_on(gd::OPT_NO_PDL), gd::decode_bwd_kernel, dim3(pl.grid), dim3(pl.threads), (size_t)pl.smem, st, pl.p);
     }
     if (e == cudaSuccess) {
-        gd::reduce_partials_kernel<<<(n_params + 127) / 128, 128, 0, st>>>(workspace_dev, pl.n_rows, pl.p.np_pad, n_params,
-                                                                           grad_weights_dev, accumulate ? 1 : 0, pl.p.run_flag);
-        e = cudaGetLastError();
+        e = gd::pdl_launch_on(!gd::opt_on(gd::OPT_NO_PDL), gd::reduce_partials_kernel, dim3((n_params + 127) / 128), dim3(128), 0, st, workspace_dev,
+                              pl.n_rows, pl.p.np_pad, n_params, grad_weights_dev, accumulate ? 1 : 0, pl.p.run_flag);
     }
     if (prev != g->device) cudaSetDevice(prev);
     GD_CUDA(e);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include <vector>
 #include <mutex>
 
@@ -41,6 +42,28 @@ struct GraphTables {
     const int32_t* chk_edges;  // [E]
     const int32_t* vlist;      // [E]   edge ids: first the n_vact edges whose variable has degree >= 2, then the rest
 };
+
+// Programmatic dependent launch.  Kernels that follow one another on a stream (the passes of a decode call, the launches of a
+// training step) are launched with programmatic stream serialisation and begin with pdl_enter(): the next kernel's CTAs are
+// scheduled while this one drains, and nothing of this kernel runs before its predecessor has completed and its writes are visible.
+// In a launch without the attribute both instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pdl_launch_on(bool enable, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = enable ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace gd
 

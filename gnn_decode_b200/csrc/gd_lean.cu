@@ -926,6 +926,7 @@ __device__ __forceinline__ void cubic_vd(const float4* base, float w, float& val
 __global__ void __launch_bounds__(1024, 1) lean_bwd_kernel(const LeanBwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int share[4];
+    pdl_enter();
     const LeanTrainHdr* H = p.train;
     if (H->status != 1) return;                                // the edge-owner forward wrote this stash: its backward runs instead
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1102,6 +1103,7 @@ __device__ __forceinline__ void sp_sig(double z, double& sp, double& sg) {
 }
 __global__ void __launch_bounds__(256) lean_contract_kernel(const ContractParams p) {
     __shared__ double red[5][8];
+    pdl_enter();
     const LeanTrainHdr* H = p.train;
     if (H->status != 1) return;
     const int h = p.hid, j = blockIdx.x % (h + 1), which = blockIdx.x / (h + 1);     // which: 0 mlp1 (all priors), 1 mlp2, 2 mlp3; j == h: the bias b2
@@ -1910,12 +1912,10 @@ int lean_backward(gd_graph* g, const gd_model* model, const float* weights_dev, 
     const size_t bins_bytes = (size_t)2 * 8 * ((ct_n + 3) + (rt_n + 3) + (size_t)kMaxSlots * (4 * vt_n + 3));
     GD_CUDA(cudaMemsetAsync(bins_dev, 0, bins_bytes, st));
     GD_CUDA(cudaFuncSetAttribute(lean_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    lean_bwd_kernel<<<g->sm_count, 32 * bestG * bestR, smem, st>>>(p);
-    GD_CUDA(cudaGetLastError());
+    GD_CUDA(pdl_launch_on(!opt_on(OPT_NO_PDL), lean_bwd_kernel, dim3(g->sm_count), dim3(32 * bestG * bestR), (size_t)smem, st, p));
     ContractParams cp{weights_dev, hdr, reinterpret_cast<const long long*>(bins_dev), grad_weights_dev, model->hidden, model->iters,
                       ct_n, rt_n, vt_n, accumulate};
-    lean_contract_kernel<<<3 * (model->hidden + 1), 256, 0, st>>>(cp);
-    GD_CUDA(cudaGetLastError());
+    GD_CUDA(pdl_launch_on(!opt_on(OPT_NO_PDL), lean_contract_kernel, dim3(3 * (model->hidden + 1)), dim3(256), 0, st, cp));
     return GD_OK;
 }
 

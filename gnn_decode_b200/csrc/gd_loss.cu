@@ -7,6 +7,7 @@
 // directly in the layout the backward kernel reads.  Per-syndrome losses are written out and summed
 // by the caller in a fixed order (deterministic).
 #include "gd_common.cuh"
+#include "gd_options.cuh"
 
 namespace gd {
 
@@ -15,6 +16,7 @@ __global__ void __launch_bounds__(128) loss_kernel(const float* __restrict__ pro
                                                    long long B, int V, int C, float* __restrict__ loss_per,
                                                    float* __restrict__ grad_prob, float* __restrict__ grad_logit) {
     extern __shared__ float lsm[];   // [4 warps][V + C + K]
+    pdl_enter();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float* z = lsm + (size_t)wib * (V + C + K);
     float* gc = z + V;               // d loss / d s_c  per check
@@ -78,10 +80,8 @@ extern "C" int gd_loss_v2_4(const gd_graph* g, const uint8_t* logical_dev, int32
     cudaError_t e = cudaSuccess;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(gd::loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) {
-        gd::loss_kernel<<<(int)blocks, 128, smem, (cudaStream_t)stream>>>(prob_dev, y_dev, logical_dev, K, g->t, B, g->V,
-                                                                         g->C, loss_per_syndrome_dev, grad_prob_dev,
-                                                                         grad_logit_dev);
-        e = cudaGetLastError();
+        e = gd::pdl_launch_on(!gd::opt_on(gd::OPT_NO_PDL), gd::loss_kernel, dim3((unsigned)blocks), dim3(128), (size_t)smem, (cudaStream_t)stream,
+                              prob_dev, y_dev, logical_dev, K, g->t, B, g->V, g->C, loss_per_syndrome_dev, grad_prob_dev, grad_logit_dev);
     }
     if (prev != g->device) cudaSetDevice(prev);
     GD_CUDA(e);
