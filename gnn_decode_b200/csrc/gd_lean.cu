@@ -1654,6 +1654,13 @@ static bool lean_bwd_geom(gd_graph* g, const LeanParams& fp, LeanBwdGeom* out) {
     };
     LeanBwdGeom b;
     double best = -1.0;
+    std::vector<int> nchs(33, 0), mxs(33, 0), metas(33, 0);
+    auto take = [&](int R, int G) {
+        b.R = R; b.G = G;
+        b.vt_max = vt_n;
+        for (int mult = 2; mult <= 4; mult *= 2)
+            if (fixed_bytes(metas[R], mult * vt_n) + 3 * E * 128 <= smem_max) b.vt_max = mult * vt_n;
+    };
     for (int R = 1; R <= 32; ++R) {
         std::vector<std::vector<int>> own;
         int nch;
@@ -1661,6 +1668,7 @@ static bool lean_bwd_geom(gd_graph* g, const LeanParams& fp, LeanBwdGeom* out) {
         assign_owners(g, lean_subs(g)[0], R, own, &nch, &bal);
         if (nch == 0 || nch > 32) continue;
         const int meta = align_up_i(align_up_i(2 * R * nch * 16 + R * nch * 4, 16) + g->V * 8, 16);
+        nchs[R] = nch; metas[R] = meta; mxs[R] = bal > 0.0 ? (int)std::lround((double)E / ((double)R * bal)) : 0;
         int G = (smem_max - fixed_bytes(meta, vt_n)) / (3 * E * 128);
         G = std::min(G, std::min(32 / R, 15));
         if (G < 1) continue;
@@ -1668,11 +1676,15 @@ static bool lean_bwd_geom(gd_graph* g, const LeanParams& fp, LeanBwdGeom* out) {
         const int warps = G * R;
         const double eff = (double)tpc / (double)(((tpc + G - 1) / G) * G);
         const double score = (warps / (warps + 8.0)) * (G / (G + 0.8)) * std::sqrt(eff) * (0.4 + 0.6 * bal);
-        if (score > best) {
-            best = score; b.R = R; b.G = G;
-            b.vt_max = vt_n;
-            for (int mult = 2; mult <= 4; mult *= 2)
-                if (fixed_bytes(meta, mult * vt_n) + 3 * E * 128 <= smem_max) b.vt_max = mult * vt_n;
+        if (score > best) { best = score; take(R, G); }
+    }
+    // as in the forward's search: more owners at the same critical path (most loaded owner, checks per owner) never hurt
+    if (b.R > 0) {
+        const int r0 = b.R;
+        for (int R = r0 + 1; R <= 32 && R * b.G <= 32; ++R) {
+            if (nchs[R] == 0 || nchs[R] > nchs[r0] || mxs[R] > mxs[r0]) continue;
+            if ((smem_max - fixed_bytes(metas[R], vt_n)) / (3 * E * 128) < b.G) continue;
+            take(R, b.G);
         }
     }
     b.ct_n = ct_n; b.rt_n = rt_n; b.vt_n = vt_n; b.tpc = tpc; b.opt_epoch = opt_epoch(); b.valid = true;
