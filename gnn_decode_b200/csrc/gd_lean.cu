@@ -781,7 +781,6 @@ struct TabParams {
     long long B;
     int hid, T, ct_n, rt_n, vt_n, ct_blocks, rt_blocks, vt_chunks, scatter_blocks;
 };
-constexpr int kVtSlotGroups = 16;   // variable-table CTAs: vt_chunks x 16, CTA (chunk, g) serves the slots g, g + 16, g + 32, g + 48
 
 // pieces of the variable-phase tables for a message domain [-Rm, Rm]: the base count (512) serves Rm <= 44 (the shipped checkpoints:
 // 34 .. 43) at 2e-7 .. 6e-7; wider domains (fresh kaiming weights: 96, the collapsed epoch-67 checkpoint: 70) double it until the
@@ -810,9 +809,18 @@ __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
     if ((int)blockIdx.x < p.scatter_blocks) {
         // the prior-sorted syndrome list: slot k's syndromes start at the sum of the earlier slots' counts
         __shared__ int off_sh[kMaxSlots];
+        if (threadIdx.x < 32) {                                 // exclusive prefix sum of the 64 counts by one warp
+            const int lane = threadIdx.x, c0 = p.call->count[lane], c1 = p.call->count[32 + lane];
+            int a0 = c0, a1 = c1;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u0 = __shfl_up_sync(0xffffffffu, a0, o), u1 = __shfl_up_sync(0xffffffffu, a1, o);
+                if (lane >= o) { a0 += u0; a1 += u1; }
+            }
+            const int tot0 = __shfl_sync(0xffffffffu, a0, 31);
+            off_sh[lane] = a0 - c0;
+            off_sh[32 + lane] = tot0 + a1 - c1;
+        }
         if (threadIdx.x == 0) {
-            int acc = 0;
-            for (int k = 0; k < kMaxSlots; ++k) { off_sh[k] = acc; acc += p.call->count[k]; }
             if (blockIdx.x == 0 && rebuild) {                   // commit what the prep kernel found (nobody reads these concurrently)
                 H->hash = H->pending_hash;
                 H->fmax_bits = p.call->fmax_new;
@@ -849,16 +857,23 @@ __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
         return;
     }
     if (p.call->overflow) return;
-    const int b = bid - p.ct_blocks - p.rt_blocks, cb = b % p.vt_chunks, sg = b / p.vt_chunks;
-    const int vt_n = rebuild ? lean_vt_pieces(p.vt_n, Rm, H->vt_mult, p.T, __uint_as_float(p.call->d2_new), __uint_as_float(p.call->d3_new)) : H->vt_n_eff;
-    const int i0 = cb * kChunk, n_int = min(kChunk, vt_n + 2 - i0);
-    if (n_int <= 0) return;
+    // variable-phase tables: p.vt_chunks CTAs (a fixed number: in the steady state they all return here) walk the
+    // (prior without a table, chunk of 32 pieces) jobs
     const int n_slots = H->n_slots;
-    const unsigned long long built = rebuild ? 0ull : H->built_mask;
+    const unsigned long long all = n_slots >= 64 ? ~0ull : ((1ull << n_slots) - 1ull);
+    const unsigned long long todo = all & ~(rebuild ? 0ull : H->built_mask);
+    if (!todo) return;
+    const int vt_n = rebuild ? lean_vt_pieces(p.vt_n, Rm, H->vt_mult, p.T, __uint_as_float(p.call->d2_new), __uint_as_float(p.call->d3_new)) : H->vt_n_eff;
+    const int chunks = (vt_n + 2 + kChunk - 1) / kChunk, n_jobs = __popcll(todo) * chunks;
     const float* w = p.weights;                                 // ggc1.mlp: w1 [h, 2] | b1 | w2 | b2
     const MlpD M{w, 2, w + 1, w + 2 * p.hid, w + 3 * p.hid, w[4 * p.hid], p.hid};
-    for (int k = sg; k < n_slots; k += kVtSlotGroups) {
-        if ((built >> k) & 1ull) continue;                      // nothing new to tabulate for this prior
+    for (int job = bid - p.ct_blocks - p.rt_blocks; job < n_jobs; job += p.vt_chunks) {
+        int q = job / chunks;                                   // the q-th prior of `todo`
+        const int cb = job - q * chunks;
+        unsigned long long rest = todo;
+        while (q-- > 0) rest &= rest - 1ull;
+        const int k = __ffsll((long long)rest) - 1;
+        const int i0 = cb * kChunk, n_int = min(kChunk, vt_n + 2 - i0);
         const double prior = (double)__uint_as_float(H->slot_bits[k]);
         __syncthreads();                                        // `nodes` is reused
         build_chunk(M, prior, true, Rm, vt_n, i0, n_int, p.vtab + (size_t)k * (8 * p.vt_n + 2), nullptr, nullptr, &H->err_v_bits[k], nodes);
@@ -1806,9 +1821,9 @@ int lean_decode(gd_graph* g, const gd_model* model, const float* weights_dev, co
         tp.hid = model->hidden; tp.T = model->iters; tp.ct_n = p.ct_n; tp.rt_n = p.rt_n; tp.vt_n = p.vt_n;
         tp.ct_blocks = (p.ct_n + 2 + kChunk - 1) / kChunk;
         tp.rt_blocks = (p.rt_n + 2 + kChunk - 1) / kChunk;
-        tp.vt_chunks = (8 * p.vt_n + 2 + kChunk - 1) / kChunk;
+        tp.vt_chunks = 2 * g->sm_count;                          // CTAs that walk the variable-phase table jobs
         tp.scatter_blocks = (int)std::max<long long>(1, std::min<long long>((B + 1023) / 1024, (long long)g->sm_count * 4));
-        e = pdl_launch(lean_tables_kernel, dim3(tp.scatter_blocks + tp.ct_blocks + tp.rt_blocks + kVtSlotGroups * tp.vt_chunks), dim3(256), 0, st, tp);
+        e = pdl_launch(lean_tables_kernel, dim3(tp.scatter_blocks + tp.ct_blocks + tp.rt_blocks + tp.vt_chunks), dim3(256), 0, st, tp);
     }
     if (e == cudaSuccess && pls.size() > 1 && hard_bits_dev)    // parts share the words at their borders and OR their bits in
         e = cudaMemsetAsync(hard_bits_dev, 0, (size_t)B * p.vw * sizeof(uint32_t), st);
