@@ -311,3 +311,48 @@ def test_pipeline_matches_the_device_path():
     p_new = dec.decode(x).cpu()
     pipe.wait(pipe.submit(rec["x"], prob_out=rec["prob_out2"]))
     assert torch.equal(rec["prob_out2"], p_new) and not torch.equal(p_new, rec["prob"])
+
+
+def test_random_call_sequences_keep_the_table_cache_consistent():
+    """The table set is a small state machine on the device (content hash, prior list, two alternating per-call records, table
+    resolution, deferred lists).  80 calls in random order -- batch sizes 1 .. 6000, prior pools of 3 .. 90 values (more than the 64
+    slots), rows the tables cannot serve, weights edited in place or swapped, two streams, fp32 and packed inputs -- each checked
+    against the edge-owner kernel run on the same inputs."""
+    rng = np.random.RandomState(7)
+    g, dec, _ = _setup()
+    other = Golden("v2_4_toricL4_epoch1").weights
+    mine = Golden("v2_4_toricL5_epoch3").weights
+    pool = [0.004 + 0.0011 * i for i in range(90)]
+    streams = [torch.cuda.current_stream(DEV), torch.cuda.Stream(DEV)]
+    for step in range(80):
+        B = int(rng.choice([1, 7, 32, 33, 500, 2049, 6000]))
+        n_pri = int(rng.choice([3, 10, 40, 64, 65, 90]))
+        ps = [pool[i] for i in rng.choice(90, n_pri, replace=False)]
+        parts = [sample_syndromes(g, max(1, (B + len(ps) // 50) // (len(ps) // 50 + 1)), ps[k:k + 50], noise=1, seed=1000 + 7 * step + k)[0]
+                 for k in range(0, len(ps), 50)]
+        x = torch.cat(parts)[:B].contiguous()
+        B = x.size(0)
+        what = rng.randint(0, 6)
+        if what == 0:
+            with torch.no_grad():
+                dec.mlp[2].bias.add_(0.05)                      # weights edited in place
+        elif what == 1:
+            dec.load_state_dict(other if step % 2 else mine)    # another checkpoint, same buffers
+        elif what == 2 and B > 4:
+            x[::3, :g.V] += 0.01 * torch.arange(g.V, device=DEV, dtype=torch.float32)      # rows the tables cannot serve
+        torch.cuda.synchronize()                                # (the inputs and weight edits above ran on the default stream)
+        st = streams[step % 2]
+        with torch.cuda.stream(st):
+            if what == 3:
+                prior, bits = packing.pack_x(x, g.V)
+                hb, p = dec.decode_packed(prior, bits, return_prob=True)
+                h = packing.unpack_bits(hb, g.V)
+            else:
+                p, h = dec.decode(x, return_hard=True)
+            with options.option("GD_NO_LEAN"):
+                p_old, h_old = dec.decode(x, return_hard=True)
+        st.synchronize()
+        assert float((p - p_old).abs().max()) < 1e-4, (step, what, B, n_pri)
+        decided = (p_old - 0.5).abs() > 1e-4
+        assert torch.equal(h.bool()[decided], h_old.bool()[decided]), (step, what, B, n_pri)
+
