@@ -233,3 +233,32 @@ def test_table_backward_runs_and_agrees_with_the_edge_owner_backward(name, gd_op
         assert (ga[k] - gb[k]).abs().max().item() <= 2e-5 * scale + 1e-12, k
         same = same and torch.equal(ga[k], gb[k])
     assert not same
+
+
+def test_training_steps_switch_between_table_and_edge_owner_kernels_on_the_device(gd_opt):
+    """Which forward / backward pair takes a training step is decided on the device, per step (the stash header): a batch the tables
+    cannot serve -- here: one row with per-variable priors -- trains through the edge-owner kernels, the next one is back on the
+    tables.  Every step's gradients match the edge-owner-only run (GD_NO_LEAN) of the same batch."""
+    from gnn_decode_b200.quantum import decoder_v2_4
+    case = _Case("grad_v2_4_toricL4_epoch1")
+    dec = decoder_v2_4.GNNI(case.T)
+    dec.load_state_dict(case.weights)
+    dec = dec.to(DEV).train()
+    clean = case.x.clone()
+    dirty = case.x.clone()
+    dirty[2, :case.V] += 0.01 * torch.arange(case.V, dtype=dirty.dtype)
+    for step, xs in enumerate([clean, dirty, clean, clean, dirty, dirty, clean]):
+        case.x = xs
+        with torch.no_grad():
+            dec.mlp[2].bias.add_(0.01)                            # the weights move between steps, as in training
+        loss_a, ga, _ = _train_step(case, dec, reps=4)
+        gd_opt.set("GD_NO_LEAN")
+        loss_b, gb, _ = _train_step(case, dec, reps=4)
+        gd_opt.unset("GD_NO_LEAN")
+        assert abs(loss_a - loss_b) <= 1e-6 * abs(loss_b), step
+        identical = all(torch.equal(ga[k], gb[k]) for k in ga)
+        assert identical == (xs is dirty), step                   # dirty batches: the very same kernels ran
+        for k in ga:
+            # (each path is within 1e-4 of the fp64 reference; measured against each other here: up to ~3e-5)
+            assert (ga[k] - gb[k]).abs().max().item() <= 1e-4 * gb[k].abs().max().item() + 1e-12, (step, k)
+
