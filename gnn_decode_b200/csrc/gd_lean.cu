@@ -7,9 +7,10 @@
 //                                             (no sibling: ext == 0 in every iteration, t_e = g_p(0))
 //     m_e  += s_c * f2(sum of t over the other edges of c)          f2 = ggc2.mlp, s_c = the check's +-1 input
 // and the read-out (decoder_v2_4.py:291-292) to logit_v = prior + sum_{e at v} f3(m_e), f3 = mlp.  g_p, f2 and f3 are
-// smooth scalar functions on compact, known domains (|ext| <= 3, |m| <= T max|f2|): they are tabulated ONCE per call in
-// double precision (exact node values AND derivatives -> cubic Hermite pieces, a-posteriori error measured at the
-// interval midpoints and checked against a budget), by two small kernels, and the decode kernel evaluates nothing else:
+// smooth scalar functions on compact, known domains (|ext| <= 3, |m| <= T max|f2|): they are tabulated once per WEIGHT SET
+// (cached on the device, validated by a content hash every call) in double precision (exact node values AND derivatives ->
+// cubic Hermite pieces, a-posteriori error measured at the interval midpoints and checked against a budget), by two small
+// kernels, and the decode kernel evaluates nothing else:
 //   * a thread owns CHECKS of one syndrome (lanes = 32 syndromes of a group, a group's R warps = its check owners);
 //     the whole iteration is one fused pass over the owned checks -- read the sibling messages, look up t, sum, look up
 //     f2, update m -- against a double-buffered message array in shared memory: ONE barrier per iteration, and it is a
@@ -1228,7 +1229,7 @@ struct LeanGeom { int R = 0, G = 0, NCH = 0, rt_n = 0, ct_n = 0, vt_n = 0; long 
 // geometry of the training backward: (R, G) for the base table size, and the finest variable-phase table that still seats one group
 struct LeanBwdGeom { int R = 0, G = 0, vt_max = 0, ct_n = 0, rt_n = 0, vt_n = 0, tpc = 0; long long opt_epoch = -1; bool valid = false; };
 // One table set on the device, keyed on the host by (stream, weights pointer, T, table sizes) and VALIDATED on the device
-// by a content hash (lean_begin_kernel): a stale or recycled entry simply rebuilds itself.  An entry is only ever used in
+// by a content hash (lean_prep_kernel): a stale entry simply rebuilds itself, a recycled one is reset first.  An entry is only ever used in
 // stream order; when the least recently used one is handed to another stream, that stream first waits for its last use.
 struct LeanEntry {
     cudaStream_t st = nullptr;
