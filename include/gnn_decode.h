@@ -157,6 +157,13 @@ int gd_propagate_fwd(const gd_graph* g, const gd_model* model, int32_t phase, in
  * when an error bound computed from the weights is below 1e-7 / 4e-6, else the direct sum) -- logits stay
  * within 1e-4 relative of the fp64 reference (tests/test_parity_gpu.py).  Results are deterministic and do
  * not depend on how the batch is tiled or sharded.
+ * GD_PROG_V2_4 on graphs with variable degree <= 2 and check degree <= 4 (every surface / toric code) and iters <= 32 takes
+ * the check-owner table kernel (csrc/gd_lean.cu): all three MLPs and the tanh as cubic tables built in double precision
+ * once per weight set and kept in a per-(stream, weights pointer) cache on the device that a content hash validates on every
+ * call -- editing the weights in place is fine.  Rows the tables cannot serve (priors that differ inside a row, check
+ * inputs other than +-1, non-finite priors) are decoded by the direct evaluation, per row; a batch with more than 64
+ * distinct priors, or weights whose tables miss their error budget, as a whole.  gd_decode_launch_info() tells which
+ * kernel a call takes; GD_NO_LEAN=1 (gd_set_option) keeps to the edge-owner kernel.
  * Codes whose edge state does not fit shared memory run the streamed global-memory kernel, whose
  * per-graph state slab is allocated lazily and is NOT re-entrant: serialise streamed decodes of
  * one gd_graph across streams (gd_decode_launch_info().resident == 0 tells which path is taken). */
