@@ -433,7 +433,7 @@ def run_workload(name, args, dev, rank, world, clocks, headline):
     pipe = DecodePipeline(dec, g, max_B=B, depth=depth)
     xh = x.cpu().pin_memory()
     e2e = {}
-    if program == "v2_4":
+    if program == "v2_4" and g.launch_info(dec.gd_model(), B)["resident"]:       # (gd_decode_packed_fwd: resident codes only)
         # packed form: what x carries per syndrome is one prior float + C check-sign bits; V hard-decision bits come back
         prior_d, synd_d = packing.pack_x(x, V)
         prior_h, synd_h = prior_d.cpu().pin_memory(), synd_d.cpu().pin_memory()

@@ -35,6 +35,11 @@ struct NodeMath {
     MlpSmem W1, W2, W3;
     PwlSmem P2, P3;
     int hp;
+    // decoder_v2_4 in the streamed kernel: the two 1 -> h -> 1 Softplus MLPs as cubic tables (gd_math.cuh, CubicTab), used when
+    // the kernel's error bound allows; the 2-input variable-phase MLP stays a direct evaluation there
+    CubicTab ctab, rtab;
+    bool use_ctab, use_rtab;
+    float rtab_R;
 
     // variable phase: ext = (sum of siblings) - own, prior -> the value the check phase sums
     __device__ __forceinline__ void var_update(const float (&ext)[4], const float (&pr)[4], float (&out)[4]) const {
@@ -58,12 +63,29 @@ struct NodeMath {
     // check phase (learned programs): mlp(ext)
     __device__ __forceinline__ void chk_mlp(const float (&ext)[4], float (&oo)[4]) const {
         if constexpr (kSoftplus) {
-            mlp_softplus_x2<4, false, 2>(W2, hp, ext, ext, oo);
+            if (use_ctab) {                  // |ext| <= check degree - 1 by construction: always inside the table
+#pragma unroll
+                for (int j = 0; j < 4; ++j) oo[j] = cubic_tab_eval(ctab, ext[j]);
+            } else {
+                mlp_softplus_x2<4, false, 2>(W2, hp, ext, ext, oo);
+            }
         } else if constexpr (NPAD > 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) oo[j] = pwl_eval<NPAD>(P2, ext[j]);
         } else {
             mlp_relu<4>(W2, hp, ext, oo);
+        }
+    }
+    // decoder_v2_4's per-edge read-out mlp(m) (decoder_v2_4.py:291)
+    __device__ __forceinline__ void readout_edge(const float (&m)[4], float (&oo)[4]) const {
+        bool in_range = use_rtab;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) in_range = in_range && fabsf(m[j]) <= rtab_R;
+        if (in_range) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oo[j] = cubic_tab_eval(rtab, m[j]);
+        } else {
+            mlp_softplus_x2<4, false, 2>(W3, hp, m, m, oo);
         }
     }
     __device__ __forceinline__ void readout_mlp(float (&lg)[4]) const {

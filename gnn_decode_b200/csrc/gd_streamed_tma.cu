@@ -48,6 +48,8 @@ struct StreamTmaParams {
     int vchunk;              // variables per variable-phase item
     int vrows;               // row index of the first prior row inside a variable-phase stage
     int off_w, off_stage;    // shared-memory byte offsets (mbarriers sit at 0)
+    int off_ctab, off_rtab, ctab_n, rtab_n;   // decoder_v2_4: cubic tables of the check-phase and read-out MLPs (0: none)
+    float ctab_R;
 };
 
 namespace tma {
@@ -147,6 +149,37 @@ __global__ void __launch_bounds__(512, 1) decode_streamed_tma_kernel(const Strea
         tma::fence_bar_init();
     }
     __syncthreads();
+    nm.use_ctab = nm.use_rtab = false;
+    nm.rtab_R = 0.f;
+    if constexpr (PROG == GD_PROG_V2_4) {
+        // the same tables, bounds and decisions as the resident kernel (gd_decode.cu): check phase on |ext| <= max check degree - 1,
+        // read-out on |m| <= T max|mlp2|; the stage area is idle here and serves as scratch
+        if (p.ctab_n > 0 && p.ctab_n + 8 <= scratch_floats) {
+            const float step = 2.0f * p.ctab_R / (float)p.ctab_n;
+            nm.use_ctab = cubic_tab_bound(p.weights + 4 * p.hid + 1, p.hid, step) <= 1e-7f;
+            if (nm.use_ctab) {
+                float4* dst = reinterpret_cast<float4*>(smem + p.off_ctab);
+                const float fm = cubic_tab_build(nm.W2, nm.hp, p.ctab_R, p.ctab_n, dst, scratch, tid, nthr);
+                nm.ctab = CubicTab{dst, 1.0f / step, p.ctab_R / step, (float)p.ctab_n - 0.001f};
+                if (p.rtab_n > 0 && p.T > 0 && p.rtab_n + 8 <= scratch_floats) {
+                    __shared__ unsigned int fmax_bits;
+                    if (tid == 0) fmax_bits = 0u;
+                    __syncthreads();
+                    atomicMax(&fmax_bits, __float_as_uint(fm));           // non-negative floats order like uints
+                    __syncthreads();
+                    nm.rtab_R = (float)p.T * (__uint_as_float(fmax_bits) * 1.02f + 1e-6f);
+                    const float rstep = 2.0f * nm.rtab_R / (float)p.rtab_n;
+                    nm.use_rtab = cubic_tab_bound(p.weights + 7 * p.hid + 2, p.hid, rstep) <= 4e-6f;
+                    if (nm.use_rtab) {
+                        float4* rdst = reinterpret_cast<float4*>(smem + p.off_rtab);
+                        cubic_tab_build(nm.W3, nm.hp, nm.rtab_R, p.rtab_n, rdst, scratch, tid, nthr);
+                        nm.rtab = CubicTab{rdst, 1.0f / rstep, nm.rtab_R / rstep, (float)p.rtab_n - 0.001f};
+                    }
+                }
+            }
+            __syncthreads();                                              // tables complete; the scratch is free again
+        }
+    }
 
     const int K = p.vchunk, n_vchunks = (V + K - 1) / K;
 
@@ -238,7 +271,7 @@ __global__ void __launch_bounds__(512, 1) decode_streamed_tma_kernel(const Strea
                                         const float4 mv = lds4(rows + k * tile);
                                         if constexpr (PROG == GD_PROG_V2_4) {     // per-EDGE read-out MLP, then the sum
                                             float xi[4] = {mv.x, mv.y, mv.z, mv.w}, oo[4];
-                                            mlp_softplus_x2<4, false, 2>(nm.W3, nm.hp, xi, xi, oo);
+                                            nm.readout_edge(xi, oo);
 #pragma unroll
                                             for (int j = 0; j < 4; ++j) acc[j] += oo[j];
                                         } else {
@@ -479,6 +512,14 @@ static void plan_streamed_tma(const gd_graph* g, const gd_model* m, int64_t B, S
     int off = 16 * 4 * 8;                              // up to 16 warps x 4 mbarriers
     p.off_w = off; off += out->npad ? 2 * pwl_smem_floats(out->npad) * 4 : n_slots * 4 * p.hp * 4;
     off = align_up_i(off, 128);
+    if (m->program == GD_PROG_V2_4 && !opt_on(OPT_NO_CTAB)) {
+        // check-phase table on |ext| <= max check degree - 1 at the resident kernel's node spacing (512 pieces per +-3), read-out 2048
+        p.ctab_R = (float)(g->max_chk_deg > 1 ? g->max_chk_deg - 1 : 1);
+        p.ctab_n = (int)(512.0f * p.ctab_R / 3.0f + 0.5f);
+        if (p.ctab_n < 512) p.ctab_n = 512;
+        p.off_ctab = off; off += p.ctab_n * 16;
+        if (!opt_on(OPT_NO_RTAB)) { p.rtab_n = 2048; p.off_rtab = off; off += p.rtab_n * 16; }
+    }
     p.off_stage = off;
     // stages per warp (2..4, GD_SSTAGES): 2 unless deeper still leaves room for all 16 warps at this stage size
     int S = 2;
