@@ -2,7 +2,7 @@
 Philox syndromes of the headline workload (decoder_v2_4, rotated surface code d = 5, depolarizing, reference checkpoint):
 hard decisions compared bit by bit, failure counters (neural_BP.py:338-348 semantics) computed for both.
 
-    python scripts/ler_vs_oracle.py [n_samples=262144] > profiles/r02_ler_vs_oracle.txt
+    python scripts/ler_vs_oracle.py [n_samples=262144] [d=5] > profiles/r02_ler_vs_oracle.txt
 
 Developer script / test helper: the oracle is the checker here, never the thing measured."""
 import os
@@ -35,7 +35,7 @@ def run(n, d=5, seed=2025, chunk=4096, log=None):
     dec = decoder_v2_4.GNNI(15)
     dec.load_state_dict(w)
     dec = dec.to(dev).eval().bind_graph(g)
-    x, err = sample_syndromes(g, n, P10, noise=1, seed=seed)
+    x, err = sample_syndromes(g, n, P10 if d <= 7 else P10[:5], noise=1, seed=seed)
     t0 = time.time()
     prob, logit, hard = dec.decode(x, return_logits=True, return_hard=True)
     torch.cuda.synchronize()
@@ -62,7 +62,7 @@ def run(n, d=5, seed=2025, chunk=4096, log=None):
            "worst_over_bar": float((dl / (1e-4 * logit_ref.abs().clamp_min(1.0))).max()),
            "failures_gpu": cnt_gpu, "failures_oracle": cnt_ref, "t_gpu_s": t_gpu, "t_cpu_s": t_cpu}
     if log:
-        print("decoder_v2_4, rotated surface code d = %d, depolarizing p in %s, T = 15, checkpoint quantum/new_model epoch3" % (d, P10), file=log)
+        print("decoder_v2_4, rotated surface code d = %d, depolarizing p in %s, T = 15, checkpoint quantum/new_model epoch3" % (d, P10 if d <= 7 else P10[:5]), file=log)
         print("%d Philox syndromes (seed %d), %d hard decisions: GPU (fp32 tables) vs oracle (fp64, oracle/restate.py)" % (n, seed, hard.numel()), file=log)
         print("  differing hard decisions: %d   (largest |reference logit| where they differ: %.3g)" %
               (out["hard_mismatches"], out["max_abs_ref_logit_at_mismatch"]), file=log)
@@ -76,4 +76,4 @@ def run(n, d=5, seed=2025, chunk=4096, log=None):
 
 
 if __name__ == "__main__":
-    run(int(sys.argv[1]) if len(sys.argv) > 1 else 262144, log=sys.stdout)
+    run(int(sys.argv[1]) if len(sys.argv) > 1 else 262144, d=int(sys.argv[2]) if len(sys.argv) > 2 else 5, log=sys.stdout)
