@@ -132,8 +132,7 @@ template <int PROG, int MAXT, int kEB, int NPOLY>
 __global__ void __launch_bounds__(MAXT, 1) decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     // (the deferred pass of the table kernel is launched with programmatic stream serialisation: a no-op otherwise)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    gd::pdl_enter();
     constexpr bool kIsBP = (PROG == GD_PROG_BP_QUANTUM || PROG == GD_PROG_BP_CLASSICAL);
     constexpr bool kSoftplus = (PROG == GD_PROG_V2_4);
     constexpr bool kNBP = (PROG == GD_PROG_NEURAL_BP);   // sum-product + per-edge weights (quantum/neural_BP.py)
@@ -1133,14 +1132,7 @@ static int launch_decode(const DecodePlan& pl, cudaStream_t st) {
     }
     GD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     if (pl.p.defer_count && !gd::opt_on(gd::OPT_NO_PDL)) {          // deferred pass of the table kernel: overlap its launch with that kernel's tail
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(pl.threads); cfg.dynamicSmemBytes = (size_t)pl.smem; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        GD_CUDA(cudaLaunchKernelEx(&cfg, k, pl.p));
+        GD_CUDA(gd::pdl_launch_on(true, k, dim3(pl.grid), dim3(pl.threads), (size_t)pl.smem, st, pl.p));
     } else {
         k<<<pl.grid, pl.threads, pl.smem, st>>>(pl.p);
         GD_CUDA(cudaGetLastError());

@@ -67,12 +67,6 @@ struct LeanParams {
     int off_me, off_ms, off_mi, off_var, off_ct, off_rt, off_vt, off_state;   // shared-memory byte offsets
 };
 
-// Programmatic dependent launch: the four kernels of a decode call are launched with programmatic stream serialisation, so a
-// kernel's CTAs are scheduled while the previous kernel drains; pdl_wait() returns once that kernel has completed and its writes
-// are visible (a no-op in a launch without the attribute).
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 // ------------------------------------------------------------------------------------------------------------------
 // shared-memory access by 32-bit address
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -272,8 +266,7 @@ template <bool STASH>
 __global__ void __launch_bounds__(1024, 1) lean_decode_kernel(const LeanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int tile_pre[4];                                // this CTA's share: {slot, first tile, end tile, first syndrome of the slot in idx}
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_enter();                                               // programmatic dependent launch (gd_common.cuh)
     const LeanHeader* H = p.hdr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (blockIdx.x == 0) {                                     // the next call's state: nobody reads or writes it until then
@@ -700,8 +693,7 @@ __global__ void __launch_bounds__(256, 6) lean_prep_kernel(const PrepParams p) {
     __shared__ int cnt_sh[kMaxSlots], base_sh[kMaxSlots];
     unsigned int* mirror = const_cast<unsigned int*>(mirror_v);
     LeanHeader* H = p.hdr;
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_enter();                                               // programmatic dependent launch (gd_common.cuh)
     if ((int)blockIdx.x <= p.fm_blocks) {
         // CTA 0: does the cached table set belong to these weights?  H->hash itself is only replaced by the table kernel, so the
         // CTAs 1 .. fm_blocks, which make the same comparison, see the same answer: when the weights changed they gather
@@ -803,8 +795,7 @@ __device__ __forceinline__ int lean_vt_pieces(int base, double Rm, int mult, int
 // iteration); max|mlp2| was gathered by the prep kernel.  The first CTAs scatter the rows into the prior-sorted list.
 __global__ void __launch_bounds__(256) lean_tables_kernel(const TabParams p) {
     __shared__ double2 nodes[kChunk + 1];
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_enter();                                               // programmatic dependent launch (gd_common.cuh)
     LeanHeader* H = p.hdr;
     const int rebuild = H->rebuild;
     if ((int)blockIdx.x < p.scatter_blocks) {
@@ -1614,17 +1605,10 @@ bool lean_launch_info(const gd_graph* g, const gd_model* model, int64_t B, gd_la
     return true;
 }
 
-// launch with programmatic stream serialisation (see pdl_wait)
+// the passes of a decode call follow one another by programmatic dependent launch (gd_common.cuh: pdl_enter / pdl_launch_on)
 template <typename P>
 static cudaError_t pdl_launch(void (*kern)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P& params) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = opt_on(OPT_NO_PDL) ? 0 : 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, params);
+    return pdl_launch_on(!opt_on(OPT_NO_PDL), kern, grid, block, smem, st, params);
 }
 
 static cudaMemPool_t lean_pool(gd_graph* g) {
