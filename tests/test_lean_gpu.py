@@ -356,3 +356,19 @@ def test_random_call_sequences_keep_the_table_cache_consistent():
         decided = (p_old - 0.5).abs() > 1e-4
         assert torch.equal(h.bool()[decided], h_old.bool()[decided]), (step, what, B, n_pri)
 
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 32])
+def test_iteration_counts_at_the_edges(T):
+    """T = 1 (only the special-cased first iteration), even / odd counts (the double buffer's final side), and the largest T the
+    table kernel takes (32), against the fp64 oracle."""
+    g, dec, w = _setup(T=T)
+    assert _lean_runs(g, dec, 700)
+    x, _ = sample_syndromes(g, 700, P10, noise=1, seed=40 + T)
+    _, logit, hard = dec.decode(x, return_logits=True, return_hard=True)
+    ei = torch.from_numpy(codes.edge_index_of(codes.rotated_surface_pcm(5)))
+    ref = restate.decode("v2_4", ei, g.V, g.C, x[:96].double().cpu(), w, T=T)["logit"]
+    worst, max_err = logit_worst(logit[:96].cpu(), ref)
+    assert worst <= 1.0, (T, worst, max_err)
+    decided = ref.abs() > 1e-3
+    assert torch.equal(hard[:96].cpu().bool()[decided], (ref < 0)[decided])
+
