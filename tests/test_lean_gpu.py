@@ -372,3 +372,46 @@ def test_iteration_counts_at_the_edges(T):
     decided = ref.abs() > 1e-3
     assert torch.equal(hard[:96].cpu().bool()[decided], (ref < 0)[decided])
 
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_random_low_degree_graphs(seed):
+    """Random Tanner graphs the table kernel takes (variable degree <= 2, check degree <= 4) that look nothing like a surface code:
+    isolated variables, variables and checks of degree 1, every (check degree, number of edges with a sibling) combination,
+    several connected components in no particular order -- against the fp64 oracle and the edge-owner kernel."""
+    rng = np.random.RandomState(900 + seed)
+    C = int(rng.randint(5, 30))
+    V = int(rng.randint(C, 3 * C))
+    pcm = np.zeros((C, V), dtype=np.uint8)
+    for v in range(V):
+        for c in rng.permutation(C)[:rng.randint(0, 3)]:                 # 0, 1 or 2 checks per variable
+            if pcm[c].sum() < 4:
+                pcm[c, v] = 1
+    for c in range(C):                                                   # no empty check
+        if pcm[c].sum() == 0:
+            free = [v for v in range(V) if pcm[:, v].sum() < 2]
+            pcm[c, free[rng.randint(len(free))] if free else rng.randint(V)] = 1
+    if pcm.sum(0).max() > 2:
+        pytest.skip("could not keep the variable degrees at 2")
+    g = TannerGraph.from_pcm(pcm, DEV)
+    dec = decoder_v2_4.GNNI(15)
+    w = Golden("v2_4_toricL5_epoch3").weights
+    dec.load_state_dict(w)
+    dec = dec.to(DEV).eval().bind_graph(g)
+    B = 1500 + 37 * seed
+    if (g.V | 1) > g.E:
+        assert not _lean_runs(g, dec, B)                                 # too few edges to stage the logits: edge-owner kernel
+        return
+    assert _lean_runs(g, dec, B)
+    priors = torch.tensor([2.2, 2.9, 3.5, 4.6], dtype=torch.float64)[torch.from_numpy(rng.randint(0, 4, B))]
+    x = torch.cat([priors[:, None].expand(B, g.V), torch.from_numpy(1.0 - 2.0 * rng.randint(0, 2, (B, g.C)))], 1).float().to(DEV)
+    prob, logit, hard = dec.decode(x, return_logits=True, return_hard=True)
+    with options.option("GD_NO_LEAN"):
+        p_old = dec.decode(x)
+    assert float((prob - p_old).abs().max()) < 1e-4
+    ei = torch.from_numpy(codes.edge_index_of(pcm))
+    ref = restate.decode("v2_4", ei, g.V, g.C, x[:64].double().cpu(), w, T=15)["logit"]
+    worst, max_err = logit_worst(logit[:64].cpu(), ref)
+    assert worst <= 1.0, (seed, worst, max_err)
+    decided = ref.abs() > 1e-3
+    assert torch.equal(hard[:64].cpu().bool()[decided], (ref < 0)[decided])
+
