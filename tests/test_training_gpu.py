@@ -262,3 +262,46 @@ def test_training_steps_switch_between_table_and_edge_owner_kernels_on_the_devic
             # (each path is within 1e-4 of the fp64 reference; measured against each other here: up to ~3e-5)
             assert (ga[k] - gb[k]).abs().max().item() <= 1e-4 * gb[k].abs().max().item() + 1e-12, (step, k)
 
+
+@pytest.mark.parametrize("seed", [2, 3, 4])
+def test_table_training_on_random_low_degree_graphs(seed, gd_opt):
+    """The table forward / backward on Tanner graphs that look nothing like a surface code (isolated variables, degree-1 nodes,
+    every check kind; the generator of tests/test_lean_gpu.py): gradients against the edge-owner training kernels on the same step."""
+    from gnn_decode_b200 import codes
+    from gnn_decode_b200.graph import TannerGraph
+    from gnn_decode_b200.quantum import decoder_v2_4
+    from gnn_decode_b200.train import train_step_grads
+    rng = np.random.RandomState(900 + seed)
+    C = int(rng.randint(5, 30))
+    V = int(rng.randint(C, 3 * C))
+    pcm = np.zeros((C, V), dtype=np.uint8)
+    for v in range(V):
+        for c in rng.permutation(C)[:rng.randint(0, 3)]:
+            if pcm[c].sum() < 4:
+                pcm[c, v] = 1
+    for c in range(C):
+        if pcm[c].sum() == 0:
+            free = [v for v in range(V) if pcm[:, v].sum() < 2]
+            pcm[c, free[rng.randint(len(free))] if free else rng.randint(V)] = 1
+    assert pcm.sum(0).max() <= 2 and (V | 1) <= int(pcm.sum())
+    g = TannerGraph.from_pcm(pcm, DEV)
+    case = _Case("grad_v2_4_toricL4_epoch1")
+    dec = decoder_v2_4.GNNI(case.T)
+    dec.load_state_dict(case.weights)
+    dec = dec.to(DEV).train()
+    B = 600
+    priors = torch.tensor([2.2, 2.9, 3.5, 4.6])[torch.from_numpy(rng.randint(0, 4, B))]
+    x = torch.cat([priors[:, None].expand(B, V), torch.from_numpy(1.0 - 2.0 * rng.randint(0, 2, (B, C))).float()], 1).to(DEV)
+    y = torch.from_numpy(rng.randint(0, 2, (B, V)).astype(np.uint8)).to(DEV)
+    logical = rng.randint(0, 2, (3, V)).astype(np.uint8)
+    loss_a, _ = train_step_grads(dec, g, x, y, logical)
+    ga = {k: p.grad.clone() for k, p in dec.named_parameters()}
+    gd_opt.set("GD_NO_LEAN")
+    loss_b, _ = train_step_grads(dec, g, x, y, logical)
+    gd_opt.unset("GD_NO_LEAN")
+    gb = {k: p.grad.clone() for k, p in dec.named_parameters()}
+    assert abs(loss_a.item() - loss_b.item()) <= 1e-6 * abs(loss_b.item())
+    assert not all(torch.equal(ga[k], gb[k]) for k in ga)                 # the table kernels really ran
+    for k in ga:
+        assert (ga[k] - gb[k]).abs().max().item() <= 1e-4 * gb[k].abs().max().item() + 1e-12, k
+
