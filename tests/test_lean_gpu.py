@@ -191,6 +191,10 @@ def test_toric_L11_runs_on_the_table_kernel_by_components():
     assert torch.equal(hard[:24].cpu().bool()[decided], (ref < 0)[decided])
     # slices: same bits
     assert torch.equal(dec.decode(x[1000:1777].contiguous()), prob[1000:1777])
+    # packed entry point: the two components OR their bits into the words they share (V / 2 = 242 is not a multiple of 32)
+    prior, bits = packing.pack_x(x, g.V)
+    hb, pp = dec.decode_packed(prior, bits, return_prob=True)
+    assert torch.equal(pp, prob) and torch.equal(packing.unpack_bits(hb, g.V), hard)
 
 
 def test_wide_message_domains_get_finer_variable_tables():
